@@ -1,0 +1,120 @@
+"""ctypes binding of ``libelimrec_b200.so`` (the C-ABI declared in ``include/elimrec_b200.h``).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  The library
+is built in-tree by ``python -m elimrec_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libelimrec_b200.so")
+
+MAX_LAYERS = 8
+MAX_MODS = 3
+D = 64
+
+vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+
+class MeanEpilogue(C.Structure):
+    _fields_ = [("n_prev", i32), ("prev", vp * MAX_LAYERS), ("prev_ld", i64 * MAX_LAYERS),
+                ("prev_width", i32 * MAX_LAYERS), ("mean_out", vp), ("mean_ld", i64), ("mean_width", i32),
+                ("mean_scale", f32)]
+
+
+class RankTables(C.Structure):
+    _fields_ = [("num_users", i32), ("num_items", i32), ("n_mod", i32), ("mode", i32), ("f_user", vp),
+                ("f_item", vp), ("s_user", vp * MAX_MODS), ("s_item", vp * MAX_MODS)]
+
+
+_SIGS = {
+    "elimrec_spmm": [i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
+    "elimrec_scatter_add_rows": [i32, vp, i32, i32, i32, vp, i64, i32, vp, i64, i32, f32, vp],
+    "elimrec_gather_rows": [i32, vp, vp, i64, vp, i64, i32, vp],
+    "elimrec_broadcast_cols": [i64, vp, i64, vp, i64, i32, vp],
+    "elimrec_copy_2d": [i64, i32, vp, i64, vp, i64, vp],
+    "elimrec_gemm": [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, vp, vp, vp],
+    "elimrec_colsum": [i64, i64, vp, i64, vp, vp, i32, vp, vp],
+    "elimrec_linear_tf32_fwd": [i64, i64, vp, i64, vp, vp, vp, i64, vp],
+    "elimrec_linear_tf32_wgrad": [i64, i64, vp, i64, vp, i64, vp, vp, vp],
+    "elimrec_bpr_forward_backward": [i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],
+    "elimrec_adam_tick": [vp, vp, f64, f64, f64, vp],
+    "elimrec_adam_apply": [i64, vp, vp, i64, i64, vp, vp, vp, f64, f64, f32, f32, vp],
+    "elimrec_sample_epoch_compat": [vp, i32, vp, vp, vp, i32, i64, vp, vp, vp],
+    "elimrec_sample_triples_device": [C.c_uint64, C.c_uint64, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp],
+    "elimrec_row_normalize": [i64, vp, vp, vp],
+    "elimrec_rank_rowmean": [C.POINTER(RankTables), i32, vp, vp, vp],
+    "elimrec_rank_scores": [C.POINTER(RankTables), i32, vp, vp, vp, vp],
+    "elimrec_rank_topk": [C.POINTER(RankTables), i32, vp, vp, vp, vp, i32, vp, vp, vp],
+    "elimrec_topk_matrix": [i32, i32, vp, i32, vp, vp, vp],
+    "elimrec_metric_rows": [i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp],
+}
+_I64_RET = {
+    "elimrec_gemm_workspace_floats": [i64, i64, i32],
+    "elimrec_colsum_workspace_floats": [i64, i64],
+    "elimrec_linear_tf32_wgrad_workspace_floats": [i64, i64],
+}
+# every symbol include/elimrec_b200.h declares (tests/test_abi.py checks the header against this)
+EXPORTS = sorted(list(_SIGS) + list(_I64_RET) + ["elimrec_last_error", "elimrec_abi_version",
+                                                   "elimrec_compat_rng_seed", "elimrec_compat_rng_next"])
+
+_lib = None
+
+
+class ElimrecError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ElimrecError(f"{LIB_PATH} is missing - build it with `python -m elimrec_b200.build` "
+                               "(there is no CPU / eager fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(l, name)
+            fn.argtypes, fn.restype = args, C.c_int
+        for name, args in _I64_RET.items():
+            fn = getattr(l, name)
+            fn.argtypes, fn.restype = args, i64
+        l.elimrec_last_error.restype = C.c_char_p
+        l.elimrec_abi_version.restype = C.c_int
+        l.elimrec_compat_rng_seed.argtypes = [vp, C.c_uint32]
+        l.elimrec_compat_rng_seed.restype = None
+        l.elimrec_compat_rng_next.argtypes = [vp]
+        l.elimrec_compat_rng_next.restype = C.c_uint32
+        _lib = l
+    return _lib
+
+
+# count of kernel-launching C-ABI calls (bench.py reports launches per step from this)
+CALLS = {"n": 0}
+
+
+def call(name: str, *args):
+    rc = getattr(lib(), name)(*args)
+    CALLS["n"] += 1
+    if rc != 0:
+        raise ElimrecError(f"{name} failed ({rc}): {lib().elimrec_last_error().decode()}")
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, dtype=None, allow_none=False):
+    """Device pointer of a CUDA tensor (no copy, no sync).  ``None`` -> NULL if allowed."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ElimrecError("NULL tensor passed where a device buffer is required")
+    if not t.is_cuda:
+        raise ElimrecError("expected a CUDA tensor - this path has no CPU implementation")
+    if dtype is not None and t.dtype != dtype:
+        raise ElimrecError(f"expected dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()

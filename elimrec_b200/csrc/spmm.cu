@@ -1,0 +1,284 @@
+// Graph propagation: Y = A_hat * X over a CSR half of the normalised bipartite adjacency.
+// Replaces torch.sparse.mm(norm_adj, all_emb) (reference models/EliMRec.py:244) and its backward.
+//
+// Mapping: one warp per SEGMENT (<= seg_len consecutive edges of one row).  A lane owns 4 (F=64,
+// two edges per warp-iteration on the two half-warps), 4 (F=128) or 8 (F=256) consecutive-by-128
+// output columns, so every neighbour row is fetched as fully coalesced 16-byte vector loads
+// (256 B / 512 B / 1 KB per row).  UNR independent row fetches are kept in flight per lane to cover
+// L2 latency - the operand slab (48-115 MB at the single-GPU shapes) is L2 resident.
+// Rows longer than seg_len are split; the last-arriving segment reduces the partial sums in a FIXED
+// order, so results are bit-reproducible run to run (no float atomics).
+#include "common.cuh"
+
+namespace {
+
+struct MeanEpi {
+    int n_prev;
+    const float* prev[ELIMREC_MAX_LAYERS];
+    long long prev_ld[ELIMREC_MAX_LAYERS];
+    int prev_width[ELIMREC_MAX_LAYERS];
+    float* out;
+    long long ld;
+    int width;
+    float scale;
+};
+
+template <int F>
+__global__ void __launch_bounds__(256)
+spmm_seg_kernel(int n_seg, const int4* __restrict__ seg, const int2* __restrict__ heavy, int* __restrict__ counter,
+                const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
+                long long ldx, float* __restrict__ Y, long long ldy, float* __restrict__ partial, MeanEpi epi) {
+    constexpr int EPW = (F == 64) ? 2 : 1;          // edges per warp-iteration
+    constexpr int NV = (F >= 128) ? F / 128 : 1;    // float4 per lane
+    constexpr int UNR = (F == 256) ? 4 : 8;         // row fetches in flight per lane
+    const unsigned full = 0xffffffffu;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_seg) return;
+    const int4 sg = __ldg(seg + warp);
+    const int sub = (F == 64) ? (lane >> 4) : 0;
+    const int l = (F == 64) ? (lane & 15) : lane;
+
+    float4 acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int base = sg.y; base < sg.z; base += 32) {
+        const int e = base + lane;
+        int c = 0;
+        float w = 0.f;
+        if (e < sg.z) {
+            c = __ldg(col + e);
+            w = __ldg(val + e);
+        }
+        const int cnt = min(32, sg.z - base);
+        for (int j = 0; j < cnt; j += UNR * EPW) {
+            float4 v[UNR][NV];
+            float ww[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int jj = j + u * EPW + sub;
+                const int cc = __shfl_sync(full, c, jj & 31);
+                const float wv = __shfl_sync(full, w, jj & 31);
+                const bool ok = jj < cnt;
+                ww[u] = ok ? wv : 0.f;
+                const float4* p = reinterpret_cast<const float4*>(X + (long long)cc * ldx) + l;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) v[u][i] = ok ? __ldg(p + i * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                for (int i = 0; i < NV; ++i) fma4(acc[i], ww[u], v[u][i]);
+        }
+    }
+    if (F == 64) {  // fold the two half-warps; afterwards both halves hold the full row
+        acc[0].x += __shfl_xor_sync(full, acc[0].x, 16);
+        acc[0].y += __shfl_xor_sync(full, acc[0].y, 16);
+        acc[0].z += __shfl_xor_sync(full, acc[0].z, 16);
+        acc[0].w += __shfl_xor_sync(full, acc[0].w, 16);
+    }
+
+    if (sg.w >= 0) {  // split row: publish partial, last arriver reduces in segment order
+        float4* pp = reinterpret_cast<float4*>(partial + (long long)warp * F);
+        if (F != 64 || lane < 16) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) pp[l + i * 32] = acc[i];
+        }
+        __threadfence();
+        const int2 hv = __ldg(heavy + sg.w);
+        int old = 0;
+        if (lane == 0) old = atomicAdd(counter + sg.w, 1);
+        old = __shfl_sync(full, old, 0);
+        if (old != hv.y - 1) return;
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* ps = reinterpret_cast<const float4*>(partial + (long long)hv.x * F) + l;
+        constexpr int RU = 8;
+        for (int s = 0; s < hv.y; s += RU) {
+            float4 t[RU][NV];
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+                    t[u][i] = (s + u < hv.y) ? __ldcg(ps + (long long)(s + u) * (F / 4) + i * 32)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+#pragma unroll
+                for (int i = 0; i < NV; ++i) add4(acc[i], t[u][i]);
+        }
+        if (lane == 0) counter[sg.w] = 0;  // leave the counter ready for the next launch
+    }
+
+    const int row = sg.x;
+    if (Y != nullptr && (F != 64 || lane < 16)) {
+        float4* yp = reinterpret_cast<float4*>(Y + (long long)row * ldy) + l;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) yp[i * 32] = acc[i];
+    }
+    if (epi.out != nullptr) {
+        // fused torch.mean(torch.stack(layers, 1), 1): ((x0 + x1) + ...) + x_L, then * 1/(L+1)
+        if (F == 64) {
+            const int c = l * 4;
+            for (int g = sub; g * 64 < epi.width; g += 2) {
+                const int oc = g * 64 + c;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < epi.n_prev; ++k) {
+                    const int pc = (epi.prev_width[k] == 64) ? c : oc;
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(epi.prev[k] + (long long)row * epi.prev_ld[k] + pc));
+                    if (k == 0) s = t; else add4(s, t);
+                }
+                add4(s, acc[0]);
+                s.x *= epi.scale; s.y *= epi.scale; s.z *= epi.scale; s.w *= epi.scale;
+                *reinterpret_cast<float4*>(epi.out + (long long)row * epi.ld + oc) = s;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int oc = (l + i * 32) * 4;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < epi.n_prev; ++k) {
+                    const int pc = (epi.prev_width[k] == 64) ? (oc & 63) : oc;
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(epi.prev[k] + (long long)row * epi.prev_ld[k] + pc));
+                    if (k == 0) s = t; else add4(s, t);
+                }
+                add4(s, acc[i]);
+                s.x *= epi.scale; s.y *= epi.scale; s.z *= epi.scale; s.w *= epi.scale;
+                *reinterpret_cast<float4*>(epi.out + (long long)row * epi.ld + oc) = s;
+            }
+        }
+    }
+}
+
+__global__ void scatter_add_rows_kernel(int n_rows, const int* __restrict__ rows, int row_lo, int row_hi, int row_off,
+                                        const float* __restrict__ src, long long src_ld, int fold, float* dst,
+                                        long long dst_ld, int width, float scale) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const int node = __ldg(rows + r);
+    if (node < row_lo || node >= row_hi) return;
+    const float* s = src + (long long)r * src_ld;
+    float* d = dst + (long long)(node - row_off) * dst_ld;
+    for (int c = lane; c < width; c += 32) {
+        float v = 0.f;
+        for (int f = 0; f < fold; ++f) v += s[f * width + c];
+        atomicAdd(d + c, scale * v);
+    }
+}
+
+__global__ void gather_rows_kernel(int n_rows, const int* __restrict__ rows, const float* __restrict__ src,
+                                   long long src_ld, float* __restrict__ dst, long long dst_ld, int width4) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const float4* s = reinterpret_cast<const float4*>(src + (long long)__ldg(rows + r) * src_ld);
+    float4* d = reinterpret_cast<float4*>(dst + (long long)r * dst_ld);
+    for (int c = lane; c < width4; c += 32) d[c] = __ldg(s + c);
+}
+
+__global__ void broadcast_cols_kernel(long long n_rows, const float* __restrict__ src, long long src_ld,
+                                      float* __restrict__ dst, long long dst_ld, int n_rep) {
+    // one thread per (row, float4 of the 64 source columns)
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t >> 4;
+    const int c = (int)(t & 15) * 4;
+    if (r >= n_rows) return;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * src_ld + c));
+    for (int g = 0; g < n_rep; ++g) *reinterpret_cast<float4*>(dst + r * dst_ld + g * 64 + c) = v;
+}
+
+__global__ void copy_2d_kernel(long long n_rows, int width4, const float* __restrict__ src, long long src_ld,
+                               float* __restrict__ dst, long long dst_ld) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t / width4;
+    const int c = (int)(t % width4) * 4;
+    if (r >= n_rows) return;
+    *reinterpret_cast<float4*>(dst + r * dst_ld + c) = __ldg(reinterpret_cast<const float4*>(src + r * src_ld + c));
+}
+
+}  // namespace
+
+ELIMREC_API int elimrec_spmm(int width, int n_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
+                             const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                             float* partial, const elimrec_mean_epilogue_t* epi, elimrec_stream_t stream) {
+    ER_CHECK_ARG(width == 64 || width == 128 || width == 256, "width must be 64, 128 or 256");
+    ER_CHECK_ARG(ldx % 4 == 0 && (Y == nullptr || ldy % 4 == 0), "row strides must be multiples of 4 floats");
+    ER_CHECK_ARG(Y != nullptr || (epi != nullptr && epi->mean_out != nullptr), "no output requested");
+    if (n_seg <= 0) return 0;
+    MeanEpi me{};
+    if (epi != nullptr && epi->mean_out != nullptr) {
+        ER_CHECK_ARG(epi->n_prev >= 0 && epi->n_prev <= ELIMREC_MAX_LAYERS, "too many layers");
+        ER_CHECK_ARG(epi->mean_width == width || width == 64, "mean epilogue: width mismatch");
+        ER_CHECK_ARG(epi->mean_width % 64 == 0 && epi->mean_ld % 4 == 0, "mean epilogue: bad output shape");
+        me.n_prev = epi->n_prev;
+        for (int k = 0; k < epi->n_prev; ++k) {
+            ER_CHECK_ARG(epi->prev_width[k] == 64 || epi->prev_width[k] == epi->mean_width, "mean epilogue: layer width");
+            me.prev[k] = epi->prev[k];
+            me.prev_ld[k] = epi->prev_ld[k];
+            me.prev_width[k] = epi->prev_width[k];
+        }
+        me.out = epi->mean_out;
+        me.ld = epi->mean_ld;
+        me.width = epi->mean_width;
+        me.scale = epi->mean_scale;
+    }
+    const int threads = 256;
+    const int blocks = (n_seg + 7) / 8;
+    const int4* sg = reinterpret_cast<const int4*>(seg);
+    const int2* hv = reinterpret_cast<const int2*>(heavy);
+    cudaStream_t st = er_stream(stream);
+    if (width == 64)
+        spmm_seg_kernel<64><<<blocks, threads, 0, st>>>(n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me);
+    else if (width == 128)
+        spmm_seg_kernel<128><<<blocks, threads, 0, st>>>(n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me);
+    else
+        spmm_seg_kernel<256><<<blocks, threads, 0, st>>>(n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_scatter_add_rows(int n_rows, const int32_t* rows, int32_t row_lo, int32_t row_hi,
+                                         int32_t row_offset, const float* src, int64_t src_ld, int src_width,
+                                         float* dst, int64_t dst_ld, int width, float scale, elimrec_stream_t stream) {
+    ER_CHECK_ARG(width > 0 && src_width % width == 0, "src_width must be a multiple of width");
+    if (n_rows <= 0) return 0;
+    const int blocks = (n_rows + 7) / 8;
+    scatter_add_rows_kernel<<<blocks, 256, 0, er_stream(stream)>>>(n_rows, rows, row_lo, row_hi, row_offset, src, src_ld,
+                                                                   src_width / width, dst, dst_ld, width, scale);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_gather_rows(int n_rows, const int32_t* rows, const float* src, int64_t src_ld, float* dst,
+                                    int64_t dst_ld, int width, elimrec_stream_t stream) {
+    ER_CHECK_ARG(width % 4 == 0 && src_ld % 4 == 0 && dst_ld % 4 == 0, "width/strides must be multiples of 4");
+    if (n_rows <= 0) return 0;
+    gather_rows_kernel<<<(n_rows + 7) / 8, 256, 0, er_stream(stream)>>>(n_rows, rows, src, src_ld, dst, dst_ld, width / 4);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_broadcast_cols(int64_t n_rows, const float* src, int64_t src_ld, float* dst, int64_t dst_ld,
+                                       int n_rep, elimrec_stream_t stream) {
+    ER_CHECK_ARG(src_ld % 4 == 0 && dst_ld % 4 == 0, "strides must be multiples of 4");
+    if (n_rows <= 0) return 0;
+    const long long threads = n_rows * 16;
+    broadcast_cols_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, er_stream(stream)>>>(n_rows, src, src_ld, dst,
+                                                                                             dst_ld, n_rep);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_copy_2d(int64_t n_rows, int width, const float* src, int64_t src_ld, float* dst, int64_t dst_ld,
+                                elimrec_stream_t stream) {
+    ER_CHECK_ARG(width % 4 == 0 && src_ld % 4 == 0 && dst_ld % 4 == 0, "width/strides must be multiples of 4");
+    if (n_rows <= 0) return 0;
+    const long long threads = n_rows * (width / 4);
+    copy_2d_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, er_stream(stream)>>>(n_rows, width / 4, src, src_ld, dst,
+                                                                                     dst_ld);
+    ER_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,155 @@
+"""Full-ranking evaluator - drop-in for the reference's ``evaluator/`` package
+(``proxy_evaluator.py:41-108``, ``backend/cpp/uni_evaluator.py:37-203``) with the C++/Cython backend
+(``cpp_evaluate_matrix``) replaced by the fused CUDA rank path.
+
+Same constructor signatures, ``metrics_info()`` and ``evaluate(model) -> (ndarray, str)``.
+Differences underneath: no [B x I] score matrix is ever copied to the host; per user batch the device
+computes scores, masks the user's training items, keeps the top-K and the metric curves; only the
+final ``[n_metrics * K]`` means come back.  Users are processed in the same order (keys of the test
+dict) and the result is independent of ``batch_size`` / ``num_thread`` (kept for API parity).
+
+Multi-GPU: pass ``rank`` / ``world_size`` (or initialise torch.distributed) and users are sharded
+across ranks; the per-column sums are all-reduced (eval shards embarrassingly).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+metric_dict = {"Precision": 1, "Recall": 2, "MAP": 3, "NDCG": 4, "MRR": 5}
+re_metric_dict = {v: k for k, v in metric_dict.items()}
+
+
+class AbstractEvaluator(object):
+    def metrics_info(self):
+        raise NotImplementedError
+
+    def evaluate(self, model):
+        raise NotImplementedError
+
+
+def _dict_to_csr(d: dict, keys):
+    lens = np.fromiter((len(d.get(k, ())) for k in keys), dtype=np.int64, count=len(keys))
+    ptr = np.zeros(len(keys) + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    flat = np.empty(int(ptr[-1]), dtype=np.int32)
+    for j, k in enumerate(keys):
+        if lens[j]:
+            flat[ptr[j]:ptr[j + 1]] = np.sort(np.asarray(d[k], dtype=np.int32))
+    return ptr, flat
+
+
+class UniEvaluator(AbstractEvaluator):
+    def __init__(self, dataset, user_train_dict, user_test_dict, user_neg_test=None, metric=None, top_k=50,
+                 batch_size=1024, num_thread=8):
+        if not isinstance(user_train_dict, dict) or not isinstance(user_test_dict, (dict, type(None))):
+            raise TypeError("user_train_dict / user_test_dict must be dict")
+        if metric is None:
+            metric = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
+        elif isinstance(metric, str):
+            metric = [metric]
+        elif not isinstance(metric, (set, tuple, list)):
+            raise TypeError("The type of 'metric' (%s) is invalid!" % metric.__class__.__name__)
+        for m in metric:
+            if m not in metric_dict:
+                raise ValueError("There is not the metric named '%s'!" % metric)
+        if user_neg_test is not None:
+            raise NotImplementedError("candidate-negatives evaluation (uni_evaluator.py:132-140) is SURVEY.md row f3")
+        self.dataset = dataset
+        self.user_pos_train = user_train_dict
+        self.user_pos_test = user_test_dict
+        self.user_neg_test = None
+        self.metrics_num = len(metric)
+        self.metrics = [metric_dict[m] for m in metric]
+        self.num_thread = num_thread
+        self.batch_size = batch_size
+        self.max_top = top_k if isinstance(top_k, int) else max(top_k)
+        self.top_show = np.arange(top_k) + 1 if isinstance(top_k, int) else np.sort(top_k)
+        self._dev = None  # device copies of the CSRs, built on first use
+
+    def metrics_info(self):
+        show = ['\t'.join([("%s@" % re_metric_dict[m] + str(k)).ljust(12) for k in self.top_show]) for m in self.metrics]
+        return "metrics:\t%s" % '\t'.join(show)
+
+    def _device_state(self, model):
+        if self._dev is None:
+            dev = model.device_
+            users = list(self.user_pos_test.keys())
+            tptr, titems = _dict_to_csr(self.user_pos_test, users)
+            U = model.num_users
+            trptr, tritems = _dict_to_csr(self.user_pos_train, range(U))
+            self._dev = dict(
+                users=torch.tensor(users, dtype=torch.int32, device=dev),
+                truth_ptr=torch.from_numpy(tptr).to(dev), truth_items=torch.from_numpy(titems).to(dev),
+                train_ptr=torch.from_numpy(trptr).to(dev), train_items=torch.from_numpy(tritems).to(dev))
+        return self._dev
+
+    @torch.no_grad()
+    def evaluate(self, model, test_users=None, rank=None, world_size=None, return_rows=False):
+        K = self.max_top
+        st = self._device_state(model)
+        dev = model.device_
+        if test_users is not None:
+            if not isinstance(test_users, (list, tuple, set, np.ndarray)):
+                raise TypeError("'test_user' must be a list, tuple, set or numpy array!")
+            users_l = list(test_users)
+            users = torch.tensor(users_l, dtype=torch.int32, device=dev)
+            tptr, titems = _dict_to_csr(self.user_pos_test, users_l)
+            truth_ptr, truth_items = torch.from_numpy(tptr).to(dev), torch.from_numpy(titems).to(dev)
+        else:
+            users, truth_ptr, truth_items = st["users"], st["truth_ptr"], st["truth_items"]
+        n_all = users.numel()
+        if world_size is None and torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world_size = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        lo, hi = 0, n_all
+        if world_size and world_size > 1:
+            per = (n_all + world_size - 1) // world_size
+            lo, hi = min(n_all, rank * per), min(n_all, (rank + 1) * per)
+        n = hi - lo
+        ncol = self.metrics_num * K
+        sums = torch.zeros(ncol, dtype=torch.float64, device=dev)
+        rows = torch.empty(max(n, 1), ncol, dtype=torch.float32, device=dev)
+        if n > 0:
+            u = users[lo:hi]
+            tables = model.rank_tables()
+            mean = None
+            if model.predict_type == "TIE":
+                mean = torch.empty(n, dtype=torch.float32, device=dev)
+                ops.rank_rowmean(tables, u, mean)
+            idx = torch.empty(n, K, dtype=torch.int32, device=dev)
+            val = torch.empty(n, K, dtype=torch.float32, device=dev)
+            ops.rank_topk(tables, u, mean, st["train_ptr"], st["train_items"], K, idx, val)
+            # truth CSR re-based to the shard
+            tp = (truth_ptr[lo:hi + 1] - truth_ptr[lo]).contiguous()
+            ti = truth_items[int(truth_ptr[lo]):int(truth_ptr[hi])] if n_all else truth_items
+            if ti.numel() == 0:
+                ti = torch.zeros(1, dtype=torch.int32, device=dev)
+            ops.metric_rows(idx, tp, ti.contiguous(), self.metrics, K, rows, sums)
+            self.last_topk = (idx, val)
+        if world_size and world_size > 1:
+            torch.distributed.all_reduce(sums)
+        final = (sums / max(n_all, 1)).cpu().numpy().astype(np.float32)
+        final = final.reshape(self.metrics_num, K)[:, self.top_show - 1].reshape(-1)
+        buf = '\t'.join([("%.8f" % x).ljust(12) for x in final])
+        if return_rows:
+            return final, buf, rows[:n]
+        return final, buf
+
+
+class ProxyEvaluator(AbstractEvaluator):
+    def __init__(self, dataset, user_train_dict, user_test_dict, user_neg_test=None, metric=None, group_view=None,
+                 top_k=50, batch_size=1024, num_thread=8):
+        if not isinstance(user_train_dict, dict) or not isinstance(user_test_dict, dict):
+            raise TypeError("user_train_dict / user_test_dict must be dict")
+        if group_view is not None:
+            raise NotImplementedError("GroupedEvaluator (broken as shipped in the reference) is SURVEY.md row f3")
+        self.evaluator = UniEvaluator(dataset, user_train_dict, user_test_dict, user_neg_test, metric=metric,
+                                      top_k=top_k, batch_size=batch_size, num_thread=num_thread)
+
+    def metrics_info(self):
+        return self.evaluator.metrics_info()
+
+    def evaluate(self, model):
+        return self.evaluator.evaluate(model)

@@ -1,0 +1,444 @@
+"""``BasicModel`` / ``EliMRec`` - drop-in for the reference's ``models/BasicModel.py`` and
+``models/EliMRec.py``, running entirely on hand-written sm_100a kernels (``libelimrec_b200.so``).
+
+Same constructor, parameter names/shapes/init order (so ``state_dict()`` interchanges and
+``torch.manual_seed`` gives the same initial weights), same public methods:
+
+    EliMRec(config, dataset)                     models/EliMRec.py:32-36
+    .bpr_loss(users, pos, neg) -> scalar Tensor  :115-142   (supports .backward(retain_graph=True))
+    .predict(user_ids, candidate_items=None)     :96-113    ([B x I] fp32 CPU tensor)
+    .evaluate() / .test() / .getFileName()       models/BasicModel.py:34-50
+    .predict_type = 'TIE' | 'TE' | 'normal'      main.py:121,140
+    .all_users / .all_items / .all_s_embs        tables cached by the last training forward
+
+What is different underneath:
+  * the 4 modality graphs are propagated as ONE wide SpMM per layer plus one 64-wide SpMM for the
+    rows that are identical across graphs (bipartite dedup, 0.625x the edge work), with the layer
+    mean fused into the last layer's epilogue;
+  * the BPR losses and their backward are one fused kernel that emits a ROW-SPARSE gradient
+    (3B instance rows); the dense [N x 64] table gradients of the reference never exist;
+  * ``train_step`` = forward + backward + fused Adam without going through autograd at all
+    (and is CUDA-graph capturable); ``bpr_loss`` wraps the same kernels in one autograd.Function
+    for the unmodified ``main.py`` loop.
+
+There is no CPU path: constructing the model without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from ._lib import CALLS, ElimrecError
+from .graph import BipartiteGraph
+
+D = 64
+PREDICT_MODE = {"normal": 0, "TE": 1, "TIE": 2}
+
+
+def _cfg(config, key, default):
+    return config[key] if key in config else default
+
+
+class BasicModel(nn.Module):
+    """models/BasicModel.py:9-50 (constructor, evaluate/test, getFileName)."""
+
+    def __init__(self, dataset, config):
+        super().__init__()
+        from .evaluator import ProxyEvaluator
+        self.config = config
+        self.dataset = dataset
+        train = dataset.get_user_train_dict()
+        kw = dict(metric=config["metric"], group_view=config["group_view"], top_k=config["topks"],
+                  batch_size=config["test_batch_size"], num_thread=config["num_thread"])
+        self.valid_evaluator = ProxyEvaluator(dataset, train, dataset.get_user_valid_dict(), None, **kw)
+        self.test_evaluator = ProxyEvaluator(dataset, train, dataset.get_user_test_dict(), None, **kw)
+
+    def getFileName(self):
+        suffix = self.config["suffix"]
+        if not os.path.exists(self.config.path):
+            os.mkdir(self.config.path)
+        file = f"{self.config.recommender}-{self.config['data.input.dataset']}-{self.config['loss']}-{suffix}.pth.tar"
+        return os.path.join(self.config.path, file)
+
+    def predict(self, user_ids, candidate_items=None):
+        raise NotImplementedError
+
+    def evaluate(self):
+        return self.valid_evaluator.evaluate(self)
+
+    def test(self):
+        return self.test_evaluator.evaluate(self)
+
+
+class _StepFunction(torch.autograd.Function):
+    """One autograd node for the whole training forward; backward runs the fused backward chain."""
+
+    @staticmethod
+    def forward(ctx, model, users, pos, neg, *params):
+        ctx.model = model
+        ctx.names = model._param_names
+        return model._forward(users, pos, neg).clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model = ctx.model
+        grads = model._backward(grad_out.contiguous().float())
+        # autograd may keep what we return as .grad -> hand out copies, never workspace views
+        return (None, None, None, None) + tuple(
+            (grads[n].clone() if grads.get(n) is not None else None) for n in ctx.names)
+
+
+class EliMRec(BasicModel):
+    def __init__(self, config, dataset):
+        super().__init__(dataset, config)
+        self._init_weight()
+
+    # ------------------------------------------------------------------------------------------
+    # construction: same order of parameter creation / initialisation as EliMRec.py:38-93,356-407
+    # ------------------------------------------------------------------------------------------
+    def _init_weight(self):
+        cfg, ds = self.config, self.dataset
+        self.num_users, self.num_items = int(ds.num_users), int(ds.num_items)
+        self.latent_dim = cfg["recdim"]
+        if self.latent_dim != D:
+            raise ElimrecError(f"recdim={self.latent_dim}: kernels are built for recdim=64 (conf/EliMRec.properties:6)")
+        self.n_layers = cfg["layer_num"]
+        if not 1 <= self.n_layers <= 8:
+            raise ElimrecError("layer_num must be in [1, 8]")
+        self.predict_type = _cfg(cfg, "predict_type", "TIE")
+        self.mm_fusion_mode = _cfg(cfg, "mm_fusion_mode", "concat")
+        self.fusion_mode = _cfg(cfg, "s_fusion_mode", "rubi")
+        if self.mm_fusion_mode != "concat" or self.fusion_mode != "rubi":
+            raise NotImplementedError("mm_fusion_mode='mean' / s_fusion_mode in {'hm','sum'} are SURVEY.md row f4")
+        self.modality = _cfg(cfg, "modality", "vat")
+        self.kwai = cfg["data.input.dataset"] == "kwai"
+        self.mods = "v" if self.kwai else "vat"
+        dev = _cfg(cfg, "device", None)
+        dev = torch.device(dev) if dev is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise ElimrecError("elimrec_b200 has no CPU path: config.device must be a CUDA device")
+        self.device_ = dev
+
+        self.embedding_user = nn.Embedding(self.num_users, D)
+        self.embedding_item = nn.Embedding(self.num_items, D)
+        nn.init.xavier_uniform_(self.embedding_user.weight)
+        nn.init.xavier_uniform_(self.embedding_item.weight)
+        # item features, L2-row-normalised once (EliMRec.py:366-381); constant afterwards
+        self._feat = {m: F.normalize(getattr(ds, f"{m}_feat").to(dev).float(), dim=1).contiguous() for m in self.mods}
+        for m in self.mods:
+            setattr(self, f"{m}_feat", self._feat[m])
+        for m in self.mods:
+            setattr(self, f"{m}_dense", nn.Linear(self._feat[m].shape[1], D))
+        self.item_feat_dim = D * (1 + len(self.mods))
+        for m in self.mods:
+            nn.init.xavier_uniform_(getattr(self, f"{m}_dense").weight)
+        self.embedding_user_after_GCN = nn.Linear(self.item_feat_dim, D)
+        nn.init.xavier_uniform_(self.embedding_user_after_GCN.weight)
+        self.embedding_item_after_GCN = nn.Linear(self.item_feat_dim, D)
+        nn.init.xavier_uniform_(self.embedding_item_after_GCN.weight)
+        self.all_items = self.all_users = None
+        self.all_s_embs = None
+        self.graph = BipartiteGraph(ds.train_matrix, dev, cfg["adj_type"])
+        self.f = nn.Sigmoid()
+        self.s_dense_v = nn.Linear(D, D)
+        self.s_dense_a = nn.Linear(D, D)
+        self.s_dense_t = nn.Linear(D, D)
+        nn.init.xavier_uniform_(self.s_dense_v.weight)
+        nn.init.xavier_uniform_(self.s_dense_a.weight)
+        nn.init.xavier_uniform_(self.s_dense_t.weight)
+        self._ws = None
+        self._adam = None
+
+    # parameters that take part in the computation, in a fixed order
+    @property
+    def _param_names(self):
+        names = ["embedding_user.weight", "embedding_item.weight"]
+        for m in self.mods:
+            names += [f"{m}_dense.weight", f"{m}_dense.bias"]
+        names += ["embedding_user_after_GCN.weight", "embedding_user_after_GCN.bias",
+                  "embedding_item_after_GCN.weight", "embedding_item_after_GCN.bias"]
+        for m in self.mods:
+            names += [f"s_dense_{m}.weight", f"s_dense_{m}.bias"]
+        return names
+
+    def _params(self):
+        d = dict(self.named_parameters())
+        return {n: d[n] for n in self._param_names}
+
+    # ------------------------------------------------------------------------------------------
+    # workspace: every buffer of a step, allocated once (static addresses => CUDA-graph friendly)
+    # ------------------------------------------------------------------------------------------
+    def _workspace(self, B):
+        ws = self._ws
+        if ws is not None and ws["B"] == B:
+            return ws
+        dev, U, I, L = self.device_, self.num_users, self.num_items, self.n_layers
+        N, G = U + I, 1 + len(self.mods)
+        Fw = D * G
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        ws = dict(B=B, G=G, F=Fw)
+        ws["X0_i"] = e(I, Fw)
+        rows = lambda side: U if side == "u" else I
+        ws["XW"], ws["XN"] = {}, {}
+        for k in range(1, L):  # layer L is consumed by the fused mean epilogue and never stored
+            side = "u" if k % 2 == 1 else "i"
+            ws["XW"][k] = e(rows(side), Fw)
+            ws["XN"][k] = e(rows("i" if side == "u" else "u"), D)
+        ws["O"] = e(N, Fw)
+        ws["F_all"] = e(N, D)
+        ws["S"] = [e(N, D) for _ in self.mods]
+        nt = 1 + len(self.mods)
+        ws["nt"] = nt
+        ws["loss"] = e(1)
+        ws["terms"] = e(nt * B)
+        ws["inst_rows"] = torch.empty(3 * B, dtype=torch.int32, device=dev)
+        ws["inst_grad"] = e(3 * B, D * nt)
+        ws["O_inst"] = e(3 * B, Fw)
+        ws["dO_inst"] = e(3 * B, Fw)
+        R = max(U, I)
+        ws["dW"] = [e(R, Fw), e(R, Fw)]
+        ws["dN"] = [e(R, D), e(R, D)]
+        # gradients of the small parameters
+        ws["g"] = {n: torch.zeros_like(p, device=dev) for n, p in self._params().items()
+                   if not n.startswith("embedding_user.w") and not n.startswith("embedding_item.w")}
+        # split-K plan + workspaces
+        dmax = max(self._feat[m].shape[1] for m in self.mods)
+        ws["split_proj"] = max(1, min(256, (I + 1023) // 1024))
+        ws["split_inst"] = max(1, min(64, (3 * B + 127) // 128))
+        need = max(ws["split_proj"] * dmax * D, ws["split_inst"] * Fw * D)
+        ws["gemm_ws"] = e(need)
+        ws["colsum_ws"] = e(max(ops.colsum_ws_floats(I, D), ops.colsum_ws_floats(3 * B, D)))
+        self._ws = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------
+    # forward  (compute + gcn_cf + bpr losses; EliMRec.py:228-272,144-153,115-142)
+    # ------------------------------------------------------------------------------------------
+    def _forward(self, users, pos, neg):
+        P = self._params()
+        U, I, L = self.num_users, self.num_items, self.n_layers
+        B = int(users.numel())
+        ws = self._workspace(B)
+        G, Fw = ws["G"], ws["F"]
+        g = self.graph
+        Eu = P["embedding_user.weight"].detach()
+        Ei = P["embedding_item.weight"].detach()
+        X0_i = ws["X0_i"]
+        # layer 0, item side: [E_i | P_v | P_a | P_t]   (projections write straight into the slab)
+        ops.copy_2d(Ei, X0_i, I, D)
+        for j, m in enumerate(self.mods):
+            Wm, bm = P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach()
+            Dm = Wm.shape[1]
+            ops.gemm(I, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, c_off=D * (j + 1))
+        # propagation: layer k has a WIDE side (distinct per graph) and a NARROW side (shared, 64 wide)
+        O = ws["O"]
+        Ou, Oi = O[:U], O[U:]
+        prev_u = [(Eu, D)]       # layers seen by user rows, in order
+        prev_i = [(X0_i, Fw)]    # layers seen by item rows
+        wide_in, narrow_in = X0_i, Eu
+        inv = 1.0 / (L + 1)
+        for k in range(1, L + 1):
+            users_wide = (k % 2 == 1)
+            half_w, half_n = (g.ui, g.iu) if users_wide else (g.iu, g.ui)
+            last = (k == L)
+            if not last:
+                Yw, Yn = ws["XW"][k], ws["XN"][k]
+                ops.spmm(half_w, wide_in, Yw, Fw)
+                ops.spmm(half_n, narrow_in, Yn, D)
+                if users_wide:
+                    prev_u.append((Yw, Fw)); prev_i.append((Yn, D))
+                else:
+                    prev_i.append((Yw, Fw)); prev_u.append((Yn, D))
+                wide_in, narrow_in = Yw, Yn
+            else:
+                out_w, out_n = (Ou, Oi) if users_wide else (Oi, Ou)
+                pw, pn = (prev_u, prev_i) if users_wide else (prev_i, prev_u)
+                ops.spmm(half_w, wide_in, None, Fw, ops.mean_epilogue(pw, out_w, Fw, inv))
+                ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv))
+        # fusion Linear (concat) and single-modal heads over all rows
+        F_all = ws["F_all"]
+        Wu, bu = P["embedding_user_after_GCN.weight"].detach(), P["embedding_user_after_GCN.bias"].detach()
+        Wi, bi = P["embedding_item_after_GCN.weight"].detach(), P["embedding_item_after_GCN.bias"].detach()
+        ops.gemm(U, D, Fw, O, Fw, 1, Wu, 1, Fw, F_all, D, 1, bias=bu)
+        ops.gemm(I, D, Fw, O, Fw, 1, Wi, 1, Fw, F_all, D, 1, bias=bi, a_off=U * Fw, c_off=U * D)
+        for j, m in enumerate(self.mods):
+            Ws, bs = P[f"s_dense_{m}.weight"].detach(), P[f"s_dense_{m}.bias"].detach()
+            ops.gemm(U + I, D, D, O, Fw, 1, Ws, 1, D, ws["S"][j], D, 1, bias=bs, a_off=D * (j + 1))
+        # cached tables (what predict() reads later, EliMRec.py:98-99,109)
+        self.all_users, self.all_items = F_all[:U], F_all[U:]
+        self.all_s_embs = {}
+        for j, m in enumerate(self.mods):
+            self.all_s_embs[f"pre_fusion_user_{m}"] = ws["S"][j][:U]
+            self.all_s_embs[f"pre_fusion_item_{m}"] = ws["S"][j][U:]
+        self._tables_version = getattr(self, "_tables_version", 0) + 1
+        # fused BPR forward+backward on the sampled rows
+        if self.kwai:
+            self.modality = "v"  # EliMRec.py:133-134
+        alpha = float(self.config.alpha)
+        if self.predict_type == "normal":
+            weights = [1.0] + [0.0] * len(self.mods)
+        else:
+            weights = [1.0] + [alpha * self.modality.count(m) for m in self.mods]
+        ops.bpr([F_all] + ws["S"], weights, users, pos, neg, U, ws["loss"], ws["inst_rows"], ws["inst_grad"], ws["terms"])
+        return ws["loss"][0]
+
+    # ------------------------------------------------------------------------------------------
+    # backward: instance rows -> fusion/head weights -> 2L SpMMs -> projection weights
+    # ------------------------------------------------------------------------------------------
+    def _backward(self, gscale=None):
+        """Returns {param name: gradient view}.  ``gscale``: 1-element device tensor (upstream grad) or None."""
+        P = self._params()
+        ws = self._ws
+        U, I, L, B = self.num_users, self.num_items, self.n_layers, ws["B"]
+        N, G, Fw, nt = U + I, ws["G"], ws["F"], ws["nt"]
+        g = self.graph
+        O, ig, rows = ws["O"], ws["inst_grad"], ws["inst_rows"]
+        ld = D * nt
+        Oin, dOin = ws["O_inst"], ws["dO_inst"]
+        gws, cws, gr = ws["gemm_ws"], ws["colsum_ws"], ws["g"]
+        sk = ws["split_inst"]
+        if gscale is not None:
+            gscale = gscale.reshape(1)
+        ops.gather_rows(rows, O, Oin, Fw)
+        Wu, Wi = P["embedding_user_after_GCN.weight"].detach(), P["embedding_item_after_GCN.weight"].detach()
+        # d O[inst] = dF[inst] @ W_{u|i} + [0 | dS_v @ Ws_v | ...]
+        ops.gemm(B, Fw, D, ig, ld, 1, Wu, Fw, 1, dOin, Fw, 1, scale=gscale)
+        ops.gemm(2 * B, Fw, D, ig, ld, 1, Wi, Fw, 1, dOin, Fw, 1, scale=gscale, a_off=B * ld, c_off=B * Fw)
+        for j, m in enumerate(self.mods):
+            Ws = P[f"s_dense_{m}.weight"].detach()
+            ops.gemm(3 * B, D, D, ig, ld, 1, Ws, D, 1, dOin, Fw, 1, accumulate=True, scale=gscale,
+                     a_off=D * (j + 1), c_off=D * (j + 1))
+        # weight gradients of the fusion Linear and the heads:  dW[n, c] = sum_r dY[r, n] * O[inst r, c]
+        ops.gemm(Fw, D, B, Oin, 1, Fw, ig, ld, 1, gr["embedding_user_after_GCN.weight"], 1, Fw, split_k=sk, ws=gws,
+                 scale=gscale)
+        ops.gemm(Fw, D, 2 * B, Oin, 1, Fw, ig, ld, 1, gr["embedding_item_after_GCN.weight"], 1, Fw, split_k=sk, ws=gws,
+                 scale=gscale, a_off=B * Fw, b_off=B * ld)
+        ops.colsum(B, D, ig, ld, gr["embedding_user_after_GCN.bias"], cws, scale=gscale)
+        ops.colsum(2 * B, D, ig, ld, gr["embedding_item_after_GCN.bias"], cws, scale=gscale, a_off=B * ld)
+        for j, m in enumerate(self.mods):
+            c0 = D * (j + 1)
+            ops.gemm(D, D, 3 * B, Oin, 1, Fw, ig, ld, 1, gr[f"s_dense_{m}.weight"], 1, D, split_k=sk, ws=gws, scale=gscale,
+                     a_off=c0, b_off=c0)
+            ops.colsum(3 * B, D, ig, ld, gr[f"s_dense_{m}.bias"], cws, scale=gscale, a_off=c0)
+        # layer-mean gradient G = dO / (L+1), row-sparse; it enters every layer of the chain
+        inv = 1.0 / (L + 1)
+        lo = {"u": (0, U, 0), "i": (U, N, U)}
+        nrows = {"u": U, "i": I}
+
+        def add_G(dst, side, wide):
+            a, b, off = lo[side]
+            ops.scatter_add_rows(rows, a, b, off, dOin, Fw, dst, Fw if wide else D, inv)
+
+        s_w = "u" if L % 2 == 1 else "i"      # wide side of the last layer
+        s_n = "i" if s_w == "u" else "u"
+        dWc, dNc = ws["dW"][0][:nrows[s_w]], ws["dN"][0][:nrows[s_n]]
+        dWc.zero_(); dNc.zero_()
+        add_G(dWc, s_w, True)
+        add_G(dNc, s_n, False)
+        flip = 1
+        for k in range(L, 0, -1):
+            s = "u" if k % 2 == 1 else "i"    # wide side of layer k
+            o = "i" if s == "u" else "u"
+            half_o, half_s = (g.iu, g.ui) if s == "u" else (g.ui, g.iu)
+            nW, nN = ws["dW"][flip][:nrows[o]], ws["dN"][flip][:nrows[s]]
+            ops.spmm(half_o, dWc, nW, Fw)     # d x_{k-1}[o, wide]   = A[o,s] @ d x_k[s, wide]
+            ops.spmm(half_s, dNc, nN, D)      # d x_{k-1}[s, narrow] = A[s,o] @ d x_k[o, narrow]
+            add_G(nW, o, True)
+            add_G(nN, s, False)
+            dWc, dNc, flip = nW, nN, flip ^ 1
+        # now dWc = d x_0[item rows, wide] = [dE_i | dP_v | dP_a | dP_t], dNc = d x_0[user rows] = dE_u
+        grads = {"embedding_user.weight": dNc, "embedding_item.weight": dWc[:, :D]}
+        skp = ws["split_proj"]
+        for j, m in enumerate(self.mods):
+            Xm = self._feat[m]
+            Dm = Xm.shape[1]
+            c0 = D * (j + 1)
+            ops.gemm(Dm, D, I, Xm, 1, Dm, dWc, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=skp, ws=gws, b_off=c0)
+            ops.colsum(I, D, dWc, Fw, gr[f"{m}_dense.bias"], cws, a_off=c0)
+        grads.update(gr)
+        return grads
+
+    # ------------------------------------------------------------------------------------------
+    # public training API
+    # ------------------------------------------------------------------------------------------
+    def _triples(self, users, pos, neg):
+        dev = self.device_
+        cv = lambda x: (x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))).to(dev, non_blocking=True).long().contiguous()
+        return cv(users), cv(pos), cv(neg)
+
+    def bpr_loss(self, users, pos_items, neg_items):
+        """models/EliMRec.py:115-142.  Returns a scalar tensor whose backward fills ``.grad``."""
+        users, pos, neg = self._triples(users, pos_items, neg_items)
+        P = self._params()
+        if next(iter(P.values())).device != self.device_:
+            raise ElimrecError("model parameters are not on config.device; call .to(config.device)")
+        return _StepFunction.apply(self, users, pos, neg, *[P[n] for n in self._param_names])
+
+    def getEmbedding(self, users, pos_items, neg_items):
+        raise NotImplementedError("row gathers are fused into bpr_loss (elimrec_bpr_forward_backward)")
+
+    def make_optimizer(self, lr=None, weight_decay=None, betas=(0.9, 0.999), eps=1e-8):
+        from .optim import FusedAdam
+        self._adam = FusedAdam(self, lr if lr is not None else self.config.lr,
+                               weight_decay if weight_decay is not None else self.config.weight_decay, betas, eps)
+        return self._adam
+
+    def train_step(self, users, pos_items, neg_items):
+        """main.py:94-102 in one call: forward, backward, Adam.  Returns the loss (device scalar)."""
+        if self._adam is None:
+            self.make_optimizer()
+        users, pos, neg = self._triples(users, pos_items, neg_items)
+        with torch.no_grad():
+            loss = self._forward(users, pos, neg)
+            grads = self._backward(None)
+            self._adam.apply(grads)
+        return loss
+
+    # ------------------------------------------------------------------------------------------
+    # scoring (predict, EliMRec.py:96-113) - tables cached by the last training forward
+    # ------------------------------------------------------------------------------------------
+    def _active_mods(self):
+        if self.predict_type == "normal":
+            return []
+        return [j for j, m in enumerate(self.mods) if m in self.modality]
+
+    def rank_tables(self):
+        """Descriptor of the cached tables for the rank kernels (normalised single-modal tables are
+        refreshed once per training forward, not per batch)."""
+        if self.all_users is None:
+            raise TypeError("'NoneType' object is not subscriptable (predict before any bpr_loss, as in the reference)")
+        ws = self._ws
+        if ws.get("S_norm_version") != self._tables_version:
+            if "S_norm" not in ws:
+                ws["S_norm"] = [torch.empty_like(s) for s in ws["S"]]
+            for s, sn in zip(ws["S"], ws["S_norm"]):
+                ops.row_normalize(s, sn)
+            ws["S_norm_version"] = self._tables_version
+        act = self._active_mods()
+        U = self.num_users
+        su = [ws["S_norm"][j][:U] for j in act]
+        si = [ws["S_norm"][j][U:] for j in act]
+        return ops.rank_tables(U, self.num_items, PREDICT_MODE[self.predict_type], self.all_users, self.all_items, su, si)
+
+    @torch.no_grad()
+    def predict(self, user_ids, candidate_items=None):
+        users = torch.as_tensor(np.asarray(user_ids)).to(self.device_).int().contiguous()
+        t = self.rank_tables()
+        mean = None
+        if self.predict_type == "TIE":
+            mean = torch.empty(users.numel(), dtype=torch.float32, device=self.device_)
+            ops.rank_rowmean(t, users, mean)
+        out = torch.empty(users.numel(), self.num_items, dtype=torch.float32, device=self.device_)
+        ops.rank_scores(t, users, mean, out)
+        return out.cpu()
+
+    def forward(self, users, items):
+        raise NotImplementedError("EliMRec.forward is not on the path main.py drives")
+
+
+__all__ = ["BasicModel", "EliMRec", "CALLS"]

@@ -1,0 +1,136 @@
+"""Tensor-level wrappers of the C-ABI (one Python function per ``elimrec_*`` entry point).
+
+Every wrapper takes CUDA tensors, passes raw device pointers + the current torch stream, and
+raises on failure.  No wrapper allocates on the hot path; callers pass preallocated outputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MeanEpilogue, RankTables, call, ptr, stream
+
+F32 = torch.float32
+
+
+def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None):
+    """Y[rows of half] = A_half @ X  (+ optional fused layer-mean epilogue)."""
+    call("elimrec_spmm", width, half.n_seg, ptr(half.seg), ptr(half.heavy), ptr(half.counter), ptr(half.col),
+         ptr(half.val), ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0),
+         ptr(half.partial), (C.byref(epi) if epi is not None else None), stream())
+
+
+def mean_epilogue(prev, out: torch.Tensor, width: int, scale: float) -> MeanEpilogue:
+    e = MeanEpilogue()
+    e.n_prev = len(prev)
+    for k, (t, w) in enumerate(prev):
+        e.prev[k] = ptr(t, F32)
+        e.prev_ld[k] = t.stride(0)
+        e.prev_width[k] = w
+    e.mean_out = ptr(out, F32)
+    e.mean_ld = out.stride(0)
+    e.mean_width = width
+    e.mean_scale = scale
+    return e
+
+
+def scatter_add_rows(rows, lo, hi, off, src, src_width, dst, width, scale):
+    call("elimrec_scatter_add_rows", rows.numel(), ptr(rows, torch.int32), lo, hi, off, ptr(src, F32), src.stride(0),
+         src_width, ptr(dst, F32), dst.stride(0), width, scale, stream())
+
+
+def gather_rows(rows, src, dst, width):
+    call("elimrec_gather_rows", rows.numel(), ptr(rows, torch.int32), ptr(src, F32), src.stride(0), ptr(dst, F32),
+         dst.stride(0), width, stream())
+
+
+def copy_2d(src, dst, n_rows, width):
+    call("elimrec_copy_2d", n_rows, width, ptr(src, F32), src.stride(0), ptr(dst, F32), dst.stride(0), stream())
+
+
+def gemm(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, Cm, c_sm, c_sn, bias=None, accumulate=False, split_k=1, ws=None,
+         scale=None, a_off=0, b_off=0, c_off=0):
+    """C(m,n) = [C +] scale * sum_k A(m,k) B(k,n) [+ bias(n)]; *_off are element offsets into the tensors."""
+    if split_k > 1:
+        need = split_k * M * N
+        if ws is None or ws.numel() < need:
+            raise _lib.ElimrecError(f"gemm workspace too small: need {need} floats")
+    call("elimrec_gemm", M, N, K, ptr(A, F32) + 4 * a_off, a_sm, a_sk, ptr(B, F32) + 4 * b_off, b_sk, b_sn,
+         ptr(Cm, F32) + 4 * c_off, c_sm, c_sn, ptr(bias, F32, True), int(accumulate), split_k, ptr(ws, F32, True),
+         ptr(scale, F32, True), stream())
+
+
+def colsum(M, N, A, ld, out, ws, accumulate=False, scale=None, a_off=0):
+    call("elimrec_colsum", M, N, ptr(A, F32) + 4 * a_off, ld, ptr(out, F32), ptr(ws, F32), int(accumulate),
+         ptr(scale, F32, True), stream())
+
+
+def colsum_ws_floats(M, N):
+    return int(_lib.lib().elimrec_colsum_workspace_floats(M, N))
+
+
+def bpr(tables, weights, users, pos, neg, num_users, loss_out, inst_rows, inst_grad, ws):
+    n = len(tables)
+    tp = (C.c_void_p * n)(*[ptr(t, F32) for t in tables])
+    wp = (C.c_float * n)(*weights)
+    call("elimrec_bpr_forward_backward", users.numel(), n, tp, wp, ptr(users, torch.int64), ptr(pos, torch.int64),
+         ptr(neg, torch.int64), num_users, ptr(loss_out, F32), ptr(inst_rows, torch.int32), ptr(inst_grad, F32),
+         ptr(ws, F32), stream())
+
+
+def adam_tick(step_dev, consts_dev, lr, b1, b2):
+    call("elimrec_adam_tick", ptr(step_dev, torch.int64), ptr(consts_dev, torch.float64), lr, b1, b2, stream())
+
+
+def adam_apply(p, g, row_len, g_ld, m, v, consts_dev, b1, b2, eps, wd, g_off=0):
+    call("elimrec_adam_apply", p.numel(), ptr(p, F32), ptr(g, F32) + 4 * g_off, row_len, g_ld, ptr(m, F32), ptr(v, F32),
+         ptr(consts_dev, torch.float64), b1, b2, eps, wd, stream())
+
+
+def row_normalize(src, dst):
+    call("elimrec_row_normalize", src.shape[0], ptr(src, F32), ptr(dst, F32), stream())
+
+
+def rank_tables(num_users, num_items, mode, f_user, f_item, s_user, s_item) -> RankTables:
+    t = RankTables()
+    t.num_users, t.num_items, t.n_mod, t.mode = num_users, num_items, len(s_user), mode
+    t.f_user, t.f_item = ptr(f_user, F32), ptr(f_item, F32)
+    for m, (a, b) in enumerate(zip(s_user, s_item)):
+        t.s_user[m], t.s_item[m] = ptr(a, F32), ptr(b, F32)
+    return t
+
+
+def rank_rowmean(t, eval_users, out):
+    call("elimrec_rank_rowmean", C.byref(t), eval_users.numel(), ptr(eval_users, torch.int32), ptr(out, F32), stream())
+
+
+def rank_scores(t, eval_users, ui_mean, out):
+    call("elimrec_rank_scores", C.byref(t), eval_users.numel(), ptr(eval_users, torch.int32), ptr(ui_mean, F32, True),
+         ptr(out, F32), stream())
+
+
+def rank_topk(t, eval_users, ui_mean, train_ptr, train_items, K, idx, val):
+    call("elimrec_rank_topk", C.byref(t), eval_users.numel(), ptr(eval_users, torch.int32), ptr(ui_mean, F32, True),
+         ptr(train_ptr, torch.int64), ptr(train_items, torch.int32), K, ptr(idx, torch.int32), ptr(val, F32), stream())
+
+
+def topk_matrix(scores, K, idx, val):
+    call("elimrec_topk_matrix", scores.shape[0], scores.shape[1], ptr(scores, F32), K, ptr(idx, torch.int32),
+         ptr(val, F32), stream())
+
+
+def metric_rows(topk_idx, truth_ptr, truth_items, metric_ids, K, rows, sums):
+    ids = np.ascontiguousarray(metric_ids, dtype=np.int32)
+    inv = np.ascontiguousarray(1.0 / np.log2(np.arange(K, dtype=np.float64) + 2.0))
+    call("elimrec_metric_rows", topk_idx.shape[0], K, ptr(topk_idx, torch.int32), ptr(truth_ptr, torch.int64),
+         ptr(truth_items, torch.int32), ids.size, ids.ctypes.data, inv.ctypes.data, ptr(rows, F32),
+         ptr(sums, torch.float64, True), stream())
+
+
+def sample_triples_device(seed, epoch, n, user_ids, row_ptr, items, num_items, ou, op, on):
+    call("elimrec_sample_triples_device", seed, epoch, n, user_ids.numel(), ptr(user_ids, torch.int32),
+         ptr(row_ptr, torch.int64), ptr(items, torch.int32), num_items, ptr(ou, torch.int64), ptr(op, torch.int64),
+         ptr(on, torch.int64), stream())

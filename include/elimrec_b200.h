@@ -1,0 +1,200 @@
+/* elimrec_b200 - C-ABI of the B200-native EliMRec hot path (libelimrec_b200.so).
+ *
+ * Drop-in boundary.  The reference has no FFI for its model math (it calls torch
+ * ops from Python) and three Cython->C++ entry points for evaluation / sampling; every function
+ * below names the reference interface it replaces.  Host side stays Python (the reference's host
+ * language) and binds these with ctypes - see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.  All `const float*`/`float*`/`int*`
+ *     arguments are DEVICE pointers unless the name ends in `_host`.
+ *   - every launch goes to `stream` (a cudaStream_t passed as void*); no host synchronisation, no
+ *     allocation, no ownership transfer: the caller (torch) allocates inputs, outputs, workspaces.
+ *   - return 0 on success, <0 on error; elimrec_last_error() returns a thread-local message.
+ *   - re-entrant; no hidden global state.  Never throws across the boundary.
+ *   - embedding width is fixed at ELIMREC_D = 64 (`recdim=64`, conf/EliMRec.properties:6).
+ */
+#ifndef ELIMREC_B200_H
+#define ELIMREC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELIMREC_D 64
+#define ELIMREC_MAX_LAYERS 8
+#define ELIMREC_MAX_MODS 3
+
+typedef void* elimrec_stream_t; /* cudaStream_t */
+
+const char* elimrec_last_error(void);
+int elimrec_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * spmm - replaces torch.sparse.mm(norm_adj, all_emb) (models/EliMRec.py:244) and its
+ * SparseAddmmBackward (A is symmetric for adj_type='pre', so backward = forward on the gradient).
+ *
+ * The normalised adjacency is kept as two CSR halves (user rows -> item cols, item rows -> user cols)
+ * in "segment" form built once on the host (elimrec_b200/graph.py): seg[s] = {row, edge_begin,
+ * edge_end, heavy_id}.  Rows longer than the segment length are split; their segments come first in
+ * the list, write partial sums to `partial[s]` and the last-arriving segment reduces them in a fixed
+ * order (deterministic).  heavy[h] = {first_segment, n_segments}; `counter[h]` must be zero on
+ * entry and is left zero.
+ *
+ * Y[row, 0:width] = sum_e val[e] * X[col[e], 0:width]           width in {64, 128, 256}
+ *
+ * Optional fused layer-mean epilogue (models/EliMRec.py:246-247, torch.stack + torch.mean):
+ *   if mean_out != NULL this launch is the LAST propagation layer; instead of (or in addition to)
+ *   storing Y it writes   mean_out[row, 0:mean_width] = (sum_k layer_k[row] + Y[row]) * mean_scale
+ *   where layer_k (k < n_prev) are the previous layers' rows, `prev_width[k]` wide (64 -> broadcast to
+ *   every 64-column block), summed in order k = 0..n_prev-1 exactly like the reference.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t n_prev;
+    const float* prev[ELIMREC_MAX_LAYERS];
+    int64_t prev_ld[ELIMREC_MAX_LAYERS];
+    int32_t prev_width[ELIMREC_MAX_LAYERS];
+    float* mean_out;
+    int64_t mean_ld;
+    int32_t mean_width;
+    float mean_scale;
+} elimrec_mean_epilogue_t;
+
+int elimrec_spmm(int width, int n_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
+                 const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y /* may be NULL */,
+                 int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi /* may be NULL */,
+                 elimrec_stream_t stream);
+
+/* rows[r] selects a destination row; dst[rows[r], 0:width] += scale * src[r, 0:src_width] (atomic).
+ * src_width == width: plain; src_width == fold*width: the `fold` 64-column blocks are summed first
+ * (gradient of the 64->wide broadcast).  Used to seed / add the row-sparse layer-mean gradient. */
+int elimrec_scatter_add_rows(int n_rows, const int32_t* rows, int32_t row_lo, int32_t row_hi, int32_t row_offset,
+                             const float* src, int64_t src_ld, int src_width, float* dst, int64_t dst_ld, int width,
+                             float scale, elimrec_stream_t stream);
+/* dst[r, :] = src[rows[r], :] */
+int elimrec_gather_rows(int n_rows, const int32_t* rows, const float* src, int64_t src_ld, float* dst, int64_t dst_ld,
+                        int width, elimrec_stream_t stream);
+/* out[r, g*64 + c] = src[r, c] for g < n_rep   (layer-0 user rows feed every modality graph) */
+int elimrec_broadcast_cols(int64_t n_rows, const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int n_rep,
+                           elimrec_stream_t stream);
+int elimrec_copy_2d(int64_t n_rows, int width, const float* src, int64_t src_ld, float* dst, int64_t dst_ld,
+                    elimrec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * gemm - replaces nn.Linear forward/backward for v_dense/a_dense/t_dense (models/EliMRec.py:233-236),
+ * embedding_{user,item}_after_GCN (:261-270) and s_dense_* (:146-151).
+ *
+ * C(m,n) = [C(m,n) +] sum_k A(m,k) * B(k,n) [+ bias[n]]   with fully general element strides, so that
+ * transposes and column-block views need no copies.  split_k > 1 writes per-slice partials to
+ * `workspace` ([split_k x M x N] floats) and reduces them in slice order (deterministic).
+ * precision: 0 = fp32 FFMA.  (tensor-core paths: see elimrec_linear_tf32_* below.)
+ * ------------------------------------------------------------------------------------------------ */
+int elimrec_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t a_sm, int64_t a_sk, const float* B,
+                 int64_t b_sk, int64_t b_sn, float* C, int64_t c_sm, int64_t c_sn, const float* bias, int accumulate,
+                 int split_k, float* workspace, const float* scale_dev /* may be NULL */, elimrec_stream_t stream);
+int64_t elimrec_gemm_workspace_floats(int64_t M, int64_t N, int split_k);
+/* out[n] = [out[n] +] sum_m A[m*ld + n] * (*scale_dev)  (bias gradients), deterministic */
+int elimrec_colsum(int64_t M, int64_t N, const float* A, int64_t ld, float* out, float* workspace, int accumulate,
+                   const float* scale_dev, elimrec_stream_t stream);
+int64_t elimrec_colsum_workspace_floats(int64_t M, int64_t N);
+
+/* Tensor-core linear layers (tcgen05, TF32 inputs, fp32 accumulate in TMEM):
+ *   fwd : Y[M x 64] (ldy) = X[M x K] * W[64 x K]^T + b          (K % 32 == 0)
+ *   wgrad: dW[64 x K] = dY[M x 64]^T (lddy) * X[M x K]            split over M, deterministic reduce
+ * return -2 if the shape is unsupported (caller falls back to elimrec_gemm). */
+int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, const float* W, const float* b,
+                            float* Y, int64_t ldy, elimrec_stream_t stream);
+int elimrec_linear_tf32_wgrad(int64_t M, int64_t K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
+                              float* dW, float* workspace, elimrec_stream_t stream);
+int64_t elimrec_linear_tf32_wgrad_workspace_floats(int64_t M, int64_t K);
+
+/* ------------------------------------------------------------------------------------------------
+ * bpr - replaces getEmbedding gathers + original_bpr_loss x (1+M) + their autograd
+ * (models/EliMRec.py:115-142, 277-297).
+ *
+ * tables[t] : [N x 64] fp32, users first then items (t = 0 fused table, t >= 1 single-modal heads)
+ * weight[t] : 1 for t = 0, alpha (or 0 if the modality is ablated) for t >= 1
+ * users/pos/neg : int64 [B] (what main.py:94-96 passes)
+ * loss_out  : 1 float.   inst_rows : int32 [3B] node ids (u | U+pos | U+neg)
+ * inst_grad : [3B x 64*n_tables]  d loss / d tables[t][inst_rows[r]]  (t-th 64-column block)
+ * workspace : n_tables * B floats
+ * ------------------------------------------------------------------------------------------------ */
+int elimrec_bpr_forward_backward(int B, int n_tables, const float* const* tables_host, const float* weight_host,
+                                 const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t num_users,
+                                 float* loss_out, int32_t* inst_rows, float* inst_grad, float* workspace,
+                                 elimrec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * adam - replaces torch.optim.Adam(lr, weight_decay) .step() (main.py:49,101): coupled L2,
+ * betas (0.9, 0.999), eps 1e-8, bias correction from the device-resident step counter.
+ * elimrec_adam_tick increments *step_dev and refreshes consts_dev = {lr/bc1, sqrt(bc2)} (2 doubles);
+ * elimrec_adam_apply updates one tensor; grad may be a strided view (row_len, grad_ld).
+ * ------------------------------------------------------------------------------------------------ */
+int elimrec_adam_tick(int64_t* step_dev, double* consts_dev, double lr, double beta1, double beta2,
+                      elimrec_stream_t stream);
+int elimrec_adam_apply(int64_t n, float* param, const float* grad, int64_t row_len, int64_t grad_ld, float* exp_avg,
+                       float* exp_avg_sq, const double* consts_dev, double beta1, double beta2, float eps,
+                       float weight_decay, elimrec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * sampler - replaces _pairwise_sampling_v2 + randint_choice (data/sampler.py:93-126,
+ * util/cython/random_choice.pyx:12-62).
+ *
+ * compat (HOST, sequential by construction): bit-exact replay of the reference's libc rand()
+ * stream.  `rng_state_host` is 40 uint32 words owned by the caller (seed with *_seed; glibc TYPE_3
+ * additive-feedback generator re-implemented so that it is re-entrant and independent of libc).
+ * device: counter-based Philox4x32-10, same distribution, one thread per triple.
+ * ------------------------------------------------------------------------------------------------ */
+void elimrec_compat_rng_seed(uint32_t* rng_state_host, uint32_t seed);
+uint32_t elimrec_compat_rng_next(uint32_t* rng_state_host);
+int elimrec_sample_epoch_compat(uint32_t* rng_state_host, int32_t n_train_users, const int32_t* user_ids_host,
+                                const int64_t* row_ptr_host, const int32_t* items_host, int32_t num_items,
+                                int64_t num_samples, int64_t* out_users_host, int64_t* out_pos_host,
+                                int64_t* out_neg_host);
+int elimrec_sample_triples_device(uint64_t seed, uint64_t epoch, int64_t num_samples, int32_t n_train_users,
+                                  const int32_t* user_ids, const int64_t* row_ptr, const int32_t* items,
+                                  int32_t num_items, int64_t* out_users, int64_t* out_pos, int64_t* out_neg,
+                                  elimrec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * rank - replaces EliMRec.predict + general_cm_fusion (models/EliMRec.py:96-113,155-188), the
+ * train-item masking loop (uni_evaluator.py:149-154) and cpp_evaluate_matrix / metric.h
+ * (evaluator/backend/cpp/include/evaluate.h:45-64, metric.h:17-114).
+ *
+ * mode: 0 = 'normal' sigmoid(sigmoid(u.i)), 1 = 'TE', 2 = 'TIE'.  s_user/s_item: L2-row-normalised
+ * single-modal tables of the ACTIVE modalities (n_mod of them, reference order v,a,t).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t num_users, num_items, n_mod, mode;
+    const float* f_user; /* [U x 64] */
+    const float* f_item; /* [I x 64] */
+    const float* s_user[ELIMREC_MAX_MODS];
+    const float* s_item[ELIMREC_MAX_MODS];
+} elimrec_rank_tables_t;
+
+/* out[r, :] = row / max(||row||, 1e-12)   (F.normalize, EliMRec.py:163-170) */
+int elimrec_row_normalize(int64_t n_rows, const float* src, float* dst, elimrec_stream_t stream);
+/* mean_i sigmoid(u.i) per evaluated user (EliMRec.py:107) */
+int elimrec_rank_rowmean(const elimrec_rank_tables_t* t, int n_eval, const int32_t* eval_users, float* ui_mean,
+                         elimrec_stream_t stream);
+/* full score matrix [n_eval x I] (predict(); parity tests) */
+int elimrec_rank_scores(const elimrec_rank_tables_t* t, int n_eval, const int32_t* eval_users, const float* ui_mean,
+                        float* scores, elimrec_stream_t stream);
+/* fused score + train mask + per-user top-K (ties: lowest index).  train CSR indexed by user id. */
+int elimrec_rank_topk(const elimrec_rank_tables_t* t, int n_eval, const int32_t* eval_users, const float* ui_mean,
+                      const int64_t* train_ptr, const int32_t* train_items, int K, int32_t* topk_idx, float* topk_val,
+                      elimrec_stream_t stream);
+/* top-K of an explicit score matrix (arg_top_k_2d, util/cython/include/arg_topk.h:15-45) */
+int elimrec_topk_matrix(int n_rows, int n_cols, const float* scores, int K, int32_t* topk_idx, float* topk_val,
+                        elimrec_stream_t stream);
+/* metric curves: rows[r, j*K + i] for metric_ids[j] in {1 Precision, 2 Recall, 3 MAP, 4 NDCG, 5 MRR}; truth CSR is
+ * indexed by POSITION r (already gathered for the evaluated users), items sorted ascending.
+ * inv_log2_host: K doubles 1/log2(i+2).  sums: [n_metrics*K] doubles, accumulated (zero it first). */
+int elimrec_metric_rows(int n_eval, int K, const int32_t* topk_idx, const int64_t* truth_ptr,
+                        const int32_t* truth_items, int n_metrics, const int32_t* metric_ids_host,
+                        const double* inv_log2_host, float* rows, double* sums, elimrec_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELIMREC_B200_H */
