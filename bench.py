@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py - BPR train triples/sec (+ full-rank eval users/sec) on synthetic Tiktok-shape data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiktok] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  Contract: see the task statement; in short
+  value        whole-job triples/s of K train steps (fwd + bwd + Adam), inputs resident in HBM
+  e2e          same metric through the public API with HOST triples: per step H2D of the batch from
+               pinned memory and a D2H read of the loss are inside the timed region
+  eval         users/s of one full `evaluate()` (TIE, K=20, Precision/Recall/NDCG), device + e2e
+  roofline     the propagation SpMM (wide launch) against the measured HBM copy bandwidth
+  cpu_baseline the oracle port (torch-CPU restatement of the reference) timed on this host, rank 0
+`--impl reference` times that same CPU port as the reference arm (the reference is Python + Cython
+and cannot travel to the GPU box; the port is pinned to it by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 2048
+TOPK = 20
+METRIC = "bpr_train_triples_per_sec"
+UNIT = "triples/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="tiktok")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--eval-users", type=int, default=0, help="0 = all test users")
+    ap.add_argument("--cuda-graph", type=int, default=1)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.p, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_dataset(workload):
+    from elimrec_b200 import synth
+    from elimrec_b200.data import Dataset
+    t0 = time.time()
+    inter, feats = synth.make_shape(workload)
+    name = "kwai" if workload == "kwai" else workload
+    ds = Dataset(None, interactions=inter, features=feats, name=name)
+    log(f"[bench] dataset {workload}: U={ds.num_users} I={ds.num_items} E_train={ds.train_matrix.nnz} ({time.time() - t0:.1f}s)")
+    return ds, name
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(ds, name, steps, warmup, budget_s, eval_users=256):
+    import torch
+    from oracle.ref_model import OracleEliMRec
+    from oracle import ref_eval
+    torch.manual_seed(2022)
+    U, I = ds.num_users, ds.num_items
+    mods = "v" if name == "kwai" else "vat"
+    dims = {m: getattr(ds, f"{m}_feat").shape[1] for m in mods}
+    G = 1 + len(mods)
+    xav = lambda *s: torch.nn.init.xavier_uniform_(torch.empty(*s))
+    params = {"embedding_user.weight": xav(U, 64), "embedding_item.weight": xav(I, 64)}
+    for m in mods:
+        params[f"{m}_dense.weight"], params[f"{m}_dense.bias"] = xav(64, dims[m]), torch.zeros(64)
+    for s in ("user", "item"):
+        params[f"embedding_{s}_after_GCN.weight"], params[f"embedding_{s}_after_GCN.bias"] = xav(64, 64 * G), torch.zeros(64)
+    for m in mods:
+        params[f"s_dense_{m}.weight"], params[f"s_dense_{m}.bias"] = xav(64, 64), torch.zeros(64)
+    orc = OracleEliMRec(params, {m: getattr(ds, f"{m}_feat") for m in mods}, ds.train_matrix, U, I, kwai=(name == "kwai"),
+                        alpha=0.5)
+    opt = torch.optim.Adam(list(orc.p.values()), lr=1e-3, weight_decay=1e-4)
+    rng = np.random.default_rng(0)
+    tm = ds.train_matrix
+    times = []
+    t_start = time.time()
+    done = 0
+    for s in range(warmup + steps):
+        u = rng.integers(0, U, BATCH)
+        p = tm.indices[tm.indptr[u]]
+        n = rng.integers(0, I, BATCH)
+        t0 = time.time()
+        loss = orc.bpr_loss(u, p, n)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        float(loss)
+        dt = time.time() - t0
+        if s >= warmup:
+            times.append(dt)
+        done += 1
+        if time.time() - t_start + dt > budget_s and len(times) >= 1:
+            break
+    step_s = float(np.mean(times))
+    # eval sample
+    users = list(ds.get_user_test_dict().keys())[:eval_users]
+    truth = ds.get_user_test_dict()
+    t0 = time.time()
+    ref_eval.evaluate(lambda us: orc.predict(us, "TIE").numpy(), ds.get_user_train_dict(), {x: truth[x] for x in users},
+                      top_k=[TOPK], batch_size=128)
+    ev_s = time.time() - t0
+    return dict(step_s=step_s, timed_steps=len(times), eval_users_per_s=len(users) / ev_s, eval_users=len(users),
+                threads=torch.get_num_threads())
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import torch
+        ds, name = build_dataset(args.workload)
+        r = cpu_port_run(ds, name, args.steps, args.warmup, budget_s=200.0)
+        v = BATCH / r["step_s"]
+        sample = (f"{r['timed_steps']} of {args.steps} requested full train steps (fwd+bwd+Adam, batch {BATCH}) of the "
+                  f"{args.workload}-shape graph, {args.warmup} warm-up; eval on the first {r['eval_users']} test users")
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": r["timed_steps"],
+                "warmup": args.warmup, "ms_per_step": 1e3 * r["step_s"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}-shape EliMRec train step, batch {BATCH}, layer_num 3, recdim 64"},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "eval": {"value": r["eval_users_per_s"], "unit": "users/s", "n_users": r["eval_users"]},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from elimrec_b200 import _lib
+    from elimrec_b200.data import Config
+    from elimrec_b200.model import EliMRec
+    from elimrec_b200.sampler import PairwiseSamplerV2
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ds, name = build_dataset(args.workload)
+    conf = Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH})
+    torch.manual_seed(2022)
+    model = EliMRec(conf, ds).to(dev)
+    model.make_optimizer()
+    if world > 1:
+        model.enable_data_parallel()
+    sampler_dev = PairwiseSamplerV2(ds, batch_size=BATCH, mode="device", device=dev, seed=2022 + rank)
+    sampler_host = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat")
+    n_steps = args.warmup + args.steps
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: triples already in HBM ---------------------------------------------
+    u, p, n = sampler_dev.sample_epoch_device(n_steps * BATCH)
+    batches = [(u[i * BATCH:(i + 1) * BATCH], p[i * BATCH:(i + 1) * BATCH], n[i * BATCH:(i + 1) * BATCH]) for i in range(n_steps)]
+    use_graph = bool(args.cuda_graph) and world == 1
+    runner = model.make_graphed_step() if use_graph else None
+
+    def step(b):
+        return runner(*b) if runner is not None else model.train_step(*b)
+
+    for b in batches[:args.warmup]:
+        step(b)
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _lib.CALLS["launches"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for b in batches[args.warmup:]:
+        loss = step(b)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.CALLS["launches"] if runner is None else runner.launches_per_step * args.steps
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms)
+    value = world * BATCH * args.steps / (ms / 1e3)
+    final_loss = float(loss)
+
+    # ---- e2e arm: host triples, H2D + loss D2H every step ----------------------------------------
+    hu, hp, hn = sampler_host.sample_epoch_host()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a[:n_steps * BATCH])).pin_memory()
+    hu, hp, hn = pin(hu), pin(hp), pin(hn)
+    du, dp_, dn = (torch.empty(BATCH, dtype=torch.int64, device=dev) for _ in range(3))
+
+    def e2e_step(i):
+        sl = slice(i * BATCH, (i + 1) * BATCH)
+        du.copy_(hu[sl], non_blocking=True)
+        dp_.copy_(hp[sl], non_blocking=True)
+        dn.copy_(hn[sl], non_blocking=True)
+        return float(step((du, dp_, dn)))  # .item(): the D2H read main.py:102 does
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.warmup, n_steps):
+        e2e_step(i)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * args.steps / float(te)
+
+    # ---- per-kernel CUDA-event profile + roofline of the wide SpMM -------------------------------
+    kernels = {}
+    roofline = None
+    if rank == 0:
+        _lib.PROFILE["on"], _lib.PROFILE["events"] = True, []
+        for b in batches[args.warmup:args.warmup + min(5, args.steps)]:
+            model.train_step(*b)
+        torch.cuda.synchronize()
+        _lib.PROFILE["on"] = False
+        agg = {}
+        for tag, a, b_ in _lib.PROFILE["events"]:
+            agg.setdefault(tag, []).append(a.elapsed_time(b_))
+        nprof = min(5, args.steps)
+        kernels = {k: {"ms_per_step": round(sum(v) / nprof, 4), "launches_per_step": len(v) // nprof,
+                       "avg_us": round(1e3 * sum(v) / len(v), 2)} for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        Fw = 64 * (1 + len(model.mods))
+        tag = f"spmm{Fw}"
+        if tag in agg:
+            g = model.graph
+            # wide launches alternate between the two halves; algorithmic bytes per launch:
+            #   nnz*(4+4) + (rows_out+1)*4 + (rows_in + rows_out)*F*4, averaged over the launches of a step
+            per = [h.nnz * 8 + (h.n_rows + 1) * 4 + (h.n_cols + h.n_rows) * Fw * 4 for h in (g.ui, g.iu)]
+            alg = float(np.mean(per))
+            avg_s = 1e-3 * sum(agg[tag]) / len(agg[tag])
+            ach = alg / avg_s / 1e9
+            roofline = {"kernel": f"spmm_seg_kernel<{Fw}>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": which, "bytes_per_launch": alg,
+                        "avg_launch_us": 1e6 * avg_s, "share_of_step": sum(agg[tag]) / sum(sum(v) for v in agg.values())}
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- evaluation: full-ranking users/s ----------------------------------------------------------
+    ev = None
+    if not args.no_eval:
+        model.eval()
+        model.predict_type = "TIE"
+        evalr = model.test_evaluator.evaluator
+        users = list(ds.get_user_test_dict().keys())
+        if args.eval_users:
+            users = users[:args.eval_users]
+        kw = dict(test_users=users) if args.eval_users else {}
+        evalr.evaluate(model, **kw)  # warm-up (device CSR upload, smem opt-in)
+        sync_all()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        res, buf = evalr.evaluate(model, **kw)   # returns host ndarray: the D2H of the result is inside
+        b_.record()
+        sync_all()
+        wall = time.perf_counter() - t0
+        tm = torch.tensor([a.elapsed_time(b_) / 1e3, wall], device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ev = {"value": len(users) / float(tm[0]), "unit": "users/s", "n_users": len(users), "e2e_value": len(users) / float(tm[1]),
+              "topk": TOPK, "predict_type": "TIE", "result": [float(x) for x in res]}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        r = cpu_port_run(ds, name, steps=2, warmup=1, budget_s=45.0)
+        cpu = {"value": BATCH / r["step_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+               "sample": f"{r['timed_steps']} full train steps (batch {BATCH}) of the same {args.workload}-shape graph after 1 warm-up; "
+                         f"eval {r['eval_users']} users", "eval_users_per_s": r["eval_users_per_s"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}-shape EliMRec train step (sample + fwd + bwd + Adam), batch {BATCH}/GPU, "
+                                       f"layer_num 3, recdim 64, U={ds.num_users} I={ds.num_items} E_train={ds.train_matrix.nnz}",
+                           "parallelism": f"dp{world}" if world > 1 else "single",
+                           "l2_policy": "per-step working set (features + propagation slabs, >0.9 GB) exceeds the 126 MB L2; no flush",
+                           "cuda_graph": bool(runner is not None), "sampler": "device Philox (value) / compat libc stream (e2e)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "eval": ev,
+                "kernels": kernels, "final_loss": final_loss}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -92,13 +92,24 @@ def lib():
     return _lib
 
 
-# count of kernel-launching C-ABI calls (bench.py reports launches per step from this)
-CALLS = {"n": 0}
+# kernels launched through the C-ABI (bench.py reports `gpu_launches` from this) and an optional
+# per-family CUDA-event profile (bench.py --profile-kernels; events sit on the launching stream)
+CALLS = {"n": 0, "launches": 0}
+_LAUNCHES = {"elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2}
+PROFILE = {"on": False, "events": []}
 
 
-def call(name: str, *args):
-    rc = getattr(lib(), name)(*args)
+def call(name: str, *args, launches=None, tag=None):
+    if PROFILE["on"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        PROFILE["events"].append((tag or name, e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args)
     CALLS["n"] += 1
+    CALLS["launches"] += launches if launches is not None else _LAUNCHES.get(name, 1)
     if rc != 0:
         raise ElimrecError(f"{name} failed ({rc}): {lib().elimrec_last_error().decode()}")
 

@@ -234,7 +234,7 @@ class EliMRec(BasicModel):
         for j, m in enumerate(self.mods):
             Wm, bm = P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach()
             Dm = Wm.shape[1]
-            ops.gemm(I, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, c_off=D * (j + 1))
+            ops.gemm(I, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, c_off=D * (j + 1), tag="proj_fwd")
         # propagation: layer k has a WIDE side (distinct per graph) and a NARROW side (shared, 64 wide)
         O = ws["O"]
         Ou, Oi = O[:U], O[U:]
@@ -264,11 +264,11 @@ class EliMRec(BasicModel):
         F_all = ws["F_all"]
         Wu, bu = P["embedding_user_after_GCN.weight"].detach(), P["embedding_user_after_GCN.bias"].detach()
         Wi, bi = P["embedding_item_after_GCN.weight"].detach(), P["embedding_item_after_GCN.bias"].detach()
-        ops.gemm(U, D, Fw, O, Fw, 1, Wu, 1, Fw, F_all, D, 1, bias=bu)
-        ops.gemm(I, D, Fw, O, Fw, 1, Wi, 1, Fw, F_all, D, 1, bias=bi, a_off=U * Fw, c_off=U * D)
+        ops.gemm(U, D, Fw, O, Fw, 1, Wu, 1, Fw, F_all, D, 1, bias=bu, tag="fuse_fwd")
+        ops.gemm(I, D, Fw, O, Fw, 1, Wi, 1, Fw, F_all, D, 1, bias=bi, a_off=U * Fw, c_off=U * D, tag="fuse_fwd")
         for j, m in enumerate(self.mods):
             Ws, bs = P[f"s_dense_{m}.weight"].detach(), P[f"s_dense_{m}.bias"].detach()
-            ops.gemm(U + I, D, D, O, Fw, 1, Ws, 1, D, ws["S"][j], D, 1, bias=bs, a_off=D * (j + 1))
+            ops.gemm(U + I, D, D, O, Fw, 1, Ws, 1, D, ws["S"][j], D, 1, bias=bs, a_off=D * (j + 1), tag="head_fwd")
         # cached tables (what predict() reads later, EliMRec.py:98-99,109)
         self.all_users, self.all_items = F_all[:U], F_all[U:]
         self.all_s_embs = {}
@@ -358,7 +358,7 @@ class EliMRec(BasicModel):
             Xm = self._feat[m]
             Dm = Xm.shape[1]
             c0 = D * (j + 1)
-            ops.gemm(Dm, D, I, Xm, 1, Dm, dWc, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=skp, ws=gws, b_off=c0)
+            ops.gemm(Dm, D, I, Xm, 1, Dm, dWc, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=skp, ws=gws, b_off=c0, tag="proj_wgrad")
             ops.colsum(I, D, dWc, Fw, gr[f"{m}_dense.bias"], cws, a_off=c0)
         grads.update(gr)
         return grads
@@ -396,8 +396,70 @@ class EliMRec(BasicModel):
         with torch.no_grad():
             loss = self._forward(users, pos, neg)
             grads = self._backward(None)
+            if getattr(self, "_dp", False):
+                grads = self._allreduce_grads(grads)
             self._adam.apply(grads)
         return loss
+
+    # -- data-parallel replicas: each rank draws its own triples, gradients are averaged (NCCL) ----
+    def enable_data_parallel(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise ElimrecError("enable_data_parallel needs an initialised torch.distributed process group")
+        self._dp = dist.get_world_size() > 1
+        for p in self.parameters():  # identical starting point on every rank
+            dist.broadcast(p.data, src=0)
+
+    def _allreduce_grads(self, grads):
+        """One flat bucket (embedding tables + every small gradient), one all-reduce(AVG)."""
+        import torch.distributed as dist
+        ws = self._ws
+        if "bucket" not in ws:
+            P = self._params()
+            names = [n for n in self._param_names if n in grads]
+            sizes = [P[n].numel() for n in names]
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.device_)
+            views, o = {}, 0
+            for n, sz in zip(names, sizes):
+                views[n] = flat[o:o + sz].view(P[n].shape)
+                o += sz
+            ws["bucket"], ws["bucket_views"] = flat, views
+        for n, v in ws["bucket_views"].items():
+            v.copy_(grads[n])
+        dist.all_reduce(ws["bucket"], op=dist.ReduceOp.AVG)
+        return ws["bucket_views"]
+
+    # -- whole step as one CUDA graph (launch-bound otherwise: ~60 small launches per step) ------------
+    def make_graphed_step(self, batch_size=None):
+        B = int(batch_size or self.config["batch_size"])
+        if self._adam is None:
+            self.make_optimizer()
+        dev = self.device_
+        su, sp_, sn = (torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3))
+        model = self
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # warm-up outside capture: allocates workspace + Adam state
+            self.train_step(su, sp_, sn)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        # undo the warm-up step so that graphed and eager runs see the same parameter trajectory
+        graph = torch.cuda.CUDAGraph()
+        before = CALLS["launches"]
+        with torch.cuda.graph(graph):
+            loss = self.train_step(su, sp_, sn)
+        n_launch = CALLS["launches"] - before + 2  # + the two memsets of the backward seeds
+
+        class _Runner:
+            launches_per_step = n_launch
+
+            def __call__(self, users, pos, neg):
+                u, p, n = model._triples(users, pos, neg)
+                su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
+                graph.replay()
+                return loss
+
+        return _Runner()
 
     # ------------------------------------------------------------------------------------------
     # scoring (predict, EliMRec.py:96-113) - tables cached by the last training forward

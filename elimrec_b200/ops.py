@@ -20,7 +20,7 @@ def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None):
     """Y[rows of half] = A_half @ X  (+ optional fused layer-mean epilogue)."""
     call("elimrec_spmm", width, half.n_seg, ptr(half.seg), ptr(half.heavy), ptr(half.counter), ptr(half.col),
          ptr(half.val), ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0),
-         ptr(half.partial), (C.byref(epi) if epi is not None else None), stream())
+         ptr(half.partial), (C.byref(epi) if epi is not None else None), stream(), tag=f"spmm{width}")
 
 
 def mean_epilogue(prev, out: torch.Tensor, width: int, scale: float) -> MeanEpilogue:
@@ -34,6 +34,7 @@ def mean_epilogue(prev, out: torch.Tensor, width: int, scale: float) -> MeanEpil
     e.mean_ld = out.stride(0)
     e.mean_width = width
     e.mean_scale = scale
+    e._keepalive = (prev, out)
     return e
 
 
@@ -52,7 +53,7 @@ def copy_2d(src, dst, n_rows, width):
 
 
 def gemm(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, Cm, c_sm, c_sn, bias=None, accumulate=False, split_k=1, ws=None,
-         scale=None, a_off=0, b_off=0, c_off=0):
+         scale=None, a_off=0, b_off=0, c_off=0, tag=None):
     """C(m,n) = [C +] scale * sum_k A(m,k) B(k,n) [+ bias(n)]; *_off are element offsets into the tensors."""
     if split_k > 1:
         need = split_k * M * N
@@ -60,7 +61,7 @@ def gemm(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, Cm, c_sm, c_sn, bias=None, accum
             raise _lib.ElimrecError(f"gemm workspace too small: need {need} floats")
     call("elimrec_gemm", M, N, K, ptr(A, F32) + 4 * a_off, a_sm, a_sk, ptr(B, F32) + 4 * b_off, b_sk, b_sn,
          ptr(Cm, F32) + 4 * c_off, c_sm, c_sn, ptr(bias, F32, True), int(accumulate), split_k, ptr(ws, F32, True),
-         ptr(scale, F32, True), stream())
+         ptr(scale, F32, True), stream(), launches=(2 if split_k > 1 else 1), tag=tag or "gemm")
 
 
 def colsum(M, N, A, ld, out, ws, accumulate=False, scale=None, a_off=0):
@@ -100,6 +101,7 @@ def rank_tables(num_users, num_items, mode, f_user, f_item, s_user, s_item) -> R
     t.f_user, t.f_item = ptr(f_user, F32), ptr(f_item, F32)
     for m, (a, b) in enumerate(zip(s_user, s_item)):
         t.s_user[m], t.s_item[m] = ptr(a, F32), ptr(b, F32)
+    t._keepalive = (f_user, f_item, list(s_user), list(s_item))  # the descriptor only holds raw pointers
     return t
 
 

@@ -1,0 +1,292 @@
+"""-m gpu: every C-ABI kernel family against an independent fp64 / oracle computation."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import FP32_TOL, rel_err
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _rand_graph(U, I, nnz, heavy_rows, seed):
+    rng = np.random.default_rng(seed)
+    u = rng.integers(0, U, size=nnz)
+    i = rng.integers(0, I, size=nnz)
+    for r, d in heavy_rows:  # rows much longer than the segment length, incl. > 32 segments
+        u = np.concatenate([u, np.full(d, r)])
+        i = np.concatenate([i, rng.choice(I, size=d, replace=False)])
+    m = sp.csr_matrix((np.ones(u.size), (u, i)), shape=(U, I))
+    m.sum_duplicates()
+    m.data[:] = 1
+    m[U - 1, :] = 0  # an empty row
+    m.eliminate_zeros()
+    return m
+
+
+@pytest.mark.parametrize("width", [64, 128, 256])
+def test_spmm_matches_fp64(dev, width):
+    from elimrec_b200 import ops
+    from elimrec_b200.graph import BipartiteGraph
+    U, I = 700, 500
+    m = _rand_graph(U, I, 6000, [(3, 480), (10, 130), (11, 65)], seed=width)
+    g = BipartiteGraph(m, dev, seg_len=8 if width == 64 else 64)
+    for half, n_in in ((g.ui, I), (g.iu, U)):
+        X = torch.randn(n_in, width, device=dev)
+        Y = torch.full((half.n_rows, width), float("nan"), device=dev)
+        ops.spmm(half, X, Y, width)
+        A = sp.csr_matrix((half.vals_host.astype(np.float64), half.indices_host, half.indptr_host), shape=(half.n_rows, n_in))
+        ref = A @ X.double().cpu().numpy()
+        assert rel_err(Y, ref) < FP32_TOL
+        Y2 = torch.empty_like(Y)
+        ops.spmm(half, X, Y2, width)
+        assert torch.equal(Y, Y2), "split-row reduction must be deterministic"
+        assert int(half.counter.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("width,G", [(256, 4), (64, 4), (128, 2), (64, 2)])
+def test_spmm_mean_epilogue(dev, width, G):
+    from elimrec_b200 import ops
+    from elimrec_b200.graph import BipartiteGraph
+    U, I, Fw = 300, 400, 64 * G
+    g = BipartiteGraph(_rand_graph(U, I, 3000, [(5, 200)], seed=1), dev)
+    half = g.ui
+    X = torch.randn(I, width, device=dev)
+    prev = [(torch.randn(U, 64, device=dev), 64), (torch.randn(U, Fw, device=dev), Fw), (torch.randn(U, 64, device=dev), 64)]
+    out = torch.empty(U + 3, Fw, device=dev)[3:]  # offset view: row stride only
+    ops.spmm(half, X, None, width, ops.mean_epilogue(prev, out, Fw, 0.25))
+    A = sp.csr_matrix((half.vals_host.astype(np.float64), half.indices_host, half.indptr_host), shape=(U, I))
+    y = torch.from_numpy(A @ X.double().cpu().numpy())
+    if width == 64:
+        y = y.repeat(1, G)
+    acc = torch.zeros(U, Fw, dtype=torch.float64)
+    for t, w in prev:
+        acc += t.double().cpu().repeat(1, G) if w == 64 else t.double().cpu()
+    ref = (acc + y) * 0.25
+    assert rel_err(out, ref) < FP32_TOL
+
+
+def test_row_ops(dev):
+    from elimrec_b200 import ops
+    src = torch.randn(50, 256, device=dev)
+    rows = torch.tensor([3, 7, 3, 49, 20, 3], dtype=torch.int32, device=dev)
+    dst = torch.empty(6, 256, device=dev)
+    ops.gather_rows(rows, src, dst, 256)
+    assert torch.equal(dst, src[rows.long()])
+    acc = torch.zeros(30, 256, device=dev)
+    ops.scatter_add_rows(rows, 0, 30, 0, dst, 256, acc, 256, 0.5)
+    ref = torch.zeros(30, 256, dtype=torch.float64)
+    for r, n in enumerate(rows.tolist()):
+        if n < 30:
+            ref[n] += 0.5 * dst[r].double().cpu()
+    assert rel_err(acc, ref) < 1e-6
+    acc = torch.zeros(40, 64, device=dev)
+    ops.scatter_add_rows(rows, 10, 50, 10, dst, 256, acc, 64, 1.0)  # folded (sum of the 4 blocks), row window
+    ref = torch.zeros(40, 64, dtype=torch.float64)
+    for r, n in enumerate(rows.tolist()):
+        if 10 <= n < 50:
+            ref[n - 10] += dst[r].double().cpu().view(4, 64).sum(0)
+    assert rel_err(acc, ref) < 1e-6
+    a = torch.randn(9, 64, device=dev)
+    slab = torch.zeros(9, 256, device=dev)
+    ops.copy_2d(a, slab[:, 64:], 9, 64)
+    assert torch.equal(slab[:, 64:128], a) and float(slab[:, :64].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("M,N,K,split", [(300, 64, 100, 1), (1000, 64, 24, 1), (128, 256, 64, 1), (768, 64, 5000, 16),
+                                         (100, 64, 2048, 7), (64, 64, 300, 3), (5, 3, 2, 1)])
+def test_gemm_strided(dev, M, N, K, split):
+    from elimrec_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=gen).to(dev)
+    B = torch.randn(K, N, generator=gen).to(dev)
+    bias = torch.randn(N, generator=gen).to(dev)
+    ref = A.double() @ B.double()
+    ws = torch.empty(max(1, split * M * N), device=dev)
+    # NN, row-major everything
+    C = torch.empty(M, N, device=dev)
+    ops.gemm(M, N, K, A, K, 1, B, N, 1, C, N, 1, bias=bias, split_k=split, ws=ws)
+    assert rel_err(C, ref + bias.double()) < FP32_TOL
+    # NT (Linear forward: B given as [N x K]) into a column block of a wider slab, accumulate
+    Bt = B.t().contiguous()
+    slab = torch.ones(M, N + 64, device=dev)
+    ops.gemm(M, N, K, A, K, 1, Bt, 1, K, slab, N + 64, 1, accumulate=True, split_k=split, ws=ws, c_off=64)
+    assert rel_err(slab[:, 64:], ref + 1.0) < FP32_TOL and float((slab[:, :64] - 1).abs().sum()) == 0
+    # TN with transposed output and a device scale (weight-gradient form)
+    At = A.t().contiguous()
+    Ct = torch.empty(N, M, device=dev)
+    scale = torch.tensor([0.5], device=dev)
+    ops.gemm(M, N, K, At, 1, M, B, N, 1, Ct, 1, M, split_k=split, ws=ws, scale=scale)
+    assert rel_err(Ct.t(), 0.5 * ref) < FP32_TOL
+
+
+def test_colsum(dev):
+    from elimrec_b200 import ops
+    A = torch.randn(3000, 256, device=dev)
+    out = torch.ones(64, device=dev)
+    ws = torch.empty(ops.colsum_ws_floats(3000, 64), device=dev)
+    ops.colsum(3000, 64, A, 256, out, ws, accumulate=True, a_off=128)
+    assert rel_err(out, A[:, 128:192].double().sum(0) + 1) < FP32_TOL
+
+
+def test_bpr_forward_backward(dev):
+    from elimrec_b200 import ops
+    from oracle.ref_model import OracleEliMRec
+    U, I, B, nt = 50, 80, 333, 4
+    tabs = [torch.randn(U + I, 64) * (0.1 + t) for t in range(nt)]
+    tabs[1][5] = 0.0  # zero row: the eps clamp of F.normalize
+    w = [1.0, 0.5, 0.0, 0.25]
+    u = torch.randint(0, U, (B,)); p = torch.randint(0, I, (B,)); n = torch.randint(0, I, (B,))
+    u[0] = 5
+    leaf = [t.clone().double().requires_grad_(True) for t in tabs]
+    loss = sum(wt * OracleEliMRec._bpr(t[u], t[U + p], t[U + n]) for wt, t in zip(w, leaf))
+    loss.backward()
+    dt = [t.to(dev) for t in tabs]
+    lo = torch.empty(1, device=dev)
+    rows = torch.empty(3 * B, dtype=torch.int32, device=dev)
+    ig = torch.empty(3 * B, 64 * nt, device=dev)
+    ops.bpr(dt, w, u.to(dev), p.to(dev), n.to(dev), U, lo, rows, ig, torch.empty(nt * B, device=dev))
+    assert abs(float(lo) - float(loss)) < 1e-6 * abs(float(loss))
+    assert torch.equal(rows.cpu().long(), torch.cat([u, U + p, U + n]))
+    for t in range(nt):
+        dense = torch.zeros(U + I, 64, dtype=torch.float64)
+        dense.index_add_(0, rows.cpu().long(), ig[:, 64 * t:64 * (t + 1)].double().cpu())
+        assert rel_err(dense, leaf[t].grad) < FP32_TOL, t
+
+
+def test_adam_matches_torch(dev):
+    from elimrec_b200 import ops
+    p0 = torch.randn(1000, 64)
+    ref = p0.clone().to(dev).requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=1e-4)
+    p = p0.clone().to(dev)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    consts = torch.zeros(2, dtype=torch.float64, device=dev)
+    for s in range(5):
+        gwide = torch.randn(1000, 256, device=dev) * 0.01
+        ref.grad = gwide[:, 64:128].contiguous()
+        opt.step()
+        ops.adam_tick(step, consts, 1e-3, 0.9, 0.999)
+        ops.adam_apply(p, gwide[:, 64:128], 64, 256, m, v, consts, 0.9, 0.999, 1e-8, 1e-4)  # strided gradient view
+    assert int(step) == 5
+    assert rel_err(p, ref) < 1e-6
+    assert rel_err(p - p0.to(dev), ref.detach() - p0.to(dev)) < 1e-4  # the UPDATE itself, not just the weights
+
+
+def _rank_inputs(dev, U, I, n_mod, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    fu, fi = torch.randn(U, 64, generator=g) * 0.3, torch.randn(I, 64, generator=g) * 0.3
+    su = [torch.randn(U, 64, generator=g) for _ in range(n_mod)]
+    si = [torch.randn(I, 64, generator=g) for _ in range(n_mod)]
+    return fu, fi, su, si
+
+
+def _ref_scores(fu, fi, su, si, users, mode):
+    import torch.nn.functional as F
+    ui = torch.sigmoid(fu[users] @ fi.t())
+    if mode == 0:
+        return torch.sigmoid(ui)
+    def cm(x):
+        for a, b in zip(su, si):
+            x = x * torch.sigmoid(F.normalize(a[users], dim=1) @ F.normalize(b, dim=1).t())
+        return x
+    if mode == 1:
+        return torch.sigmoid(cm(ui))
+    return torch.sigmoid(cm(ui) - cm(ui.mean(-1, keepdim=True)))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n_mod", [1, 3])
+def test_rank_scores_topk_metrics(dev, mode, n_mod):
+    from elimrec_b200 import ops
+    from oracle import ref_eval
+    from gpu_util import topk_sets_match
+    U, I, K = 150, 1000 + 37, 20
+    fu, fi, su, si = _rank_inputs(dev, U, I, n_mod)
+    users = torch.randperm(U)[:101]
+    ref = _ref_scores(fu, fi, su, si, users, mode).numpy()
+    sun = [torch.empty_like(a, device=dev) for a in su]
+    sin_ = [torch.empty_like(a, device=dev) for a in si]
+    for a, b in zip(su + si, sun + sin_):
+        ops.row_normalize(a.to(dev), b)
+    t = ops.rank_tables(U, I, mode, fu.to(dev), fi.to(dev), sun if mode else [], sin_ if mode else [])
+    eu = users.to(dev).int()
+    mean = torch.empty(eu.numel(), device=dev)
+    ops.rank_rowmean(t, eu, mean)
+    assert rel_err(mean, torch.sigmoid(fu[users] @ fi.t()).mean(-1)) < FP32_TOL
+    sc = torch.empty(eu.numel(), I, device=dev)
+    ops.rank_scores(t, eu, mean, sc)
+    assert rel_err(sc, ref) < FP32_TOL
+    # train mask: random sorted item lists per USER id
+    rng = np.random.default_rng(1)
+    train = {u: np.sort(rng.choice(I, size=rng.integers(0, 90), replace=False)) for u in range(U)}
+    train[int(users[0])] = np.arange(0, 200)  # a user masking whole tiles
+    ptr = np.zeros(U + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([train[u].size for u in range(U)])
+    flat = np.concatenate([train[u] for u in range(U)]).astype(np.int32)
+    idx = torch.empty(eu.numel(), K, dtype=torch.int32, device=dev)
+    val = torch.empty(eu.numel(), K, device=dev)
+    ops.rank_topk(t, eu, mean, torch.from_numpy(ptr).to(dev), torch.from_numpy(flat).to(dev), K, idx, val)
+    masked = [train[int(u)] for u in users]
+    exact, explained, bad = topk_sets_match(idx.cpu().numpy(), ref, masked, K, tol=2e-6)
+    assert bad == 0 and exact >= 0.9 * len(masked), (exact, explained, bad)
+    # metric curves from the GPU top-K are bit-equal to the oracle's (and to the reference's own C++ when built)
+    truth = [np.sort(rng.choice(I, size=rng.integers(1, 30), replace=False)).tolist() for _ in masked]
+    tp = np.zeros(len(truth) + 1, dtype=np.int64)
+    tp[1:] = np.cumsum([len(x) for x in truth])
+    tf = np.concatenate(truth).astype(np.int32)
+    rows = torch.empty(len(truth), 5 * K, device=dev)
+    sums = torch.zeros(5 * K, dtype=torch.float64, device=dev)
+    ops.metric_rows(idx, torch.from_numpy(tp).to(dev), torch.from_numpy(tf).to(dev), [1, 2, 3, 4, 5], K, rows, sums)
+    want = ref_eval.metric_rows(idx.cpu().numpy(), truth, [1, 2, 3, 4, 5], K)
+    assert np.array_equal(rows.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert np.allclose(sums.cpu().numpy(), want.astype(np.float64).sum(0), rtol=1e-12)
+    if ref_eval.ref_cpp_available():
+        s = sc.cpu().numpy().copy()
+        for r, mi in enumerate(masked):
+            s[r, mi] = -np.inf
+        cpp = ref_eval.ref_cpp_metric_rows(s, truth, [1, 2, 3, 4, 5], K)
+        # the reference C++ ranks the GPU's own scores: identical curves unless a tie group straddles rank K
+        assert (np.abs(cpp - rows.cpu().numpy()).max(axis=1) < 1e-6).mean() > 0.97
+
+
+def test_topk_matrix_ties_lowest_index(dev):
+    from elimrec_b200 import ops
+    from oracle import ref_eval
+    rng = np.random.default_rng(3)
+    s = rng.integers(0, 12, size=(40, 333)).astype(np.float32)  # massive ties
+    s[0, :] = 1.0
+    s[1, 5] = -np.inf
+    idx = torch.empty(40, 20, dtype=torch.int32, device=dev)
+    val = torch.empty(40, 20, device=dev)
+    ops.topk_matrix(torch.from_numpy(s).to(dev), 20, idx, val)
+    assert np.array_equal(idx.cpu().numpy(), ref_eval.topk_lowest_index(s, 20))
+
+
+def test_device_sampler_bit_exact_and_valid(dev):
+    from elimrec_b200 import synth
+    from elimrec_b200.data import Dataset
+    from elimrec_b200.sampler import PairwiseSamplerV2
+    from oracle import philox_sampler
+    inter, feats = synth.make_shape("tiny")
+    ds = Dataset(None, interactions=inter, features=feats, name="tiny")
+    s = PairwiseSamplerV2(ds, batch_size=64, mode="device", device=dev, seed=2022)
+    s.epoch = 3
+    u, p, n = (x.cpu().numpy() for x in s.sample_epoch_device(5000))
+    ru, rp, rn = philox_sampler.sample_triples(2022, 3, 5000, s.users, s.ptr, s.items, ds.num_items)
+    assert np.array_equal(u, ru) and np.array_equal(p, rp) and np.array_equal(n, rn)
+    tm = ds.train_matrix
+    assert np.asarray(tm[u, p]).all() and not np.asarray(tm[u, n]).any()
+    # distribution: users uniform over users with train items (chi-square, very loose)
+    cnt = np.bincount(u, minlength=ds.num_users)[s.users]
+    exp = 5000 / s.users.size
+    assert ((cnt - exp) ** 2 / exp).sum() < 3 * s.users.size
+    batches = list(s)
+    assert sum(b[0].numel() for b in batches) == s.num_trainings and batches[0][0].is_cuda

@@ -1,0 +1,180 @@
+"""-m gpu: the drop-in model / evaluator / sampler against the golden vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import FP32_TOL, build_model, rel_err, topk_sets_match
+from helpers import csr_from_golden, dict_from_csr, golden_dataset, golden_params
+
+
+def _golden_model(g, **cfg):
+    ds = golden_dataset(g)
+    name = "kwai" if g["_name"] == "kwai" else "synthg"
+    return build_model(ds, golden_params(g), dataset_name=name, alpha=0.5, test_batch_size=16, **cfg), ds
+
+
+def _batch(g, i):
+    return g[f"batch{i}_users"], g[f"batch{i}_pos"], g[f"batch{i}_neg"]
+
+
+def _assert_post_adam_close(v, want, name):
+    """Weights after a few Adam steps.  Adam divides by sqrt(v)+eps, so an element whose gradient is
+    within rounding noise of zero can move by a sizeable fraction of lr in EITHER implementation; the
+    gradients themselves are gated at 1e-5 (test_loss_grads_tables_vs_golden) and the Adam kernel at
+    1e-6 given equal gradients (test_adam_matches_torch).  Here: 99.9% of the elements within 1e-5
+    (norm-wise) and every element within 1e-4."""
+    a = v.detach().double().cpu().numpy()
+    b = np.asarray(want, dtype=np.float64)
+    scale = np.abs(b).max()
+    d = np.abs(a - b) / scale
+    assert d.max() < 1e-4, (name, d.max())
+    assert (d > FP32_TOL).mean() < 1e-3, (name, (d > FP32_TOL).mean())
+
+
+def test_state_dict_layout_matches_reference(golden):
+    model, _ = _golden_model(golden)
+    sd = model.state_dict()
+    want = golden_params(golden)
+    assert list(sd.keys()) == list(want.keys())
+    for k, v in want.items():
+        assert tuple(sd[k].shape) == v.shape, k
+
+
+def test_loss_grads_tables_vs_golden(golden):
+    model, _ = _golden_model(golden)
+    loss = model.bpr_loss(*[torch.tensor(x) for x in _batch(golden, 0)])
+    assert loss.requires_grad and loss.dim() == 0
+    loss.backward(retain_graph=True)   # main.py:100
+    assert abs(float(loss) - float(golden["loss0"])) < FP32_TOL * abs(float(golden["loss0"]))
+    n_checked = 0
+    for name, p in model.named_parameters():
+        key = "grad0/" + name
+        if key in golden:
+            assert p.grad is not None, name
+            assert rel_err(p.grad, golden[key]) < FP32_TOL, name
+            n_checked += 1
+        else:
+            assert p.grad is None, name
+    assert n_checked >= 8
+    assert rel_err(model.all_users, golden["all_users"]) < FP32_TOL
+    assert rel_err(model.all_items, golden["all_items"]) < FP32_TOL
+    for m in model.mods:
+        assert rel_err(model.all_s_embs[f"pre_fusion_user_{m}"], golden[f"s_user_{m}"]) < FP32_TOL
+        assert rel_err(model.all_s_embs[f"pre_fusion_item_{m}"], golden[f"s_item_{m}"]) < FP32_TOL
+    # the fused layer-mean slab = cat of the reference's per-graph light_out
+    U = model.num_users
+    O = model._ws["O"]
+    for j, b in enumerate(["i"] + list(model.mods)):
+        assert rel_err(O[:, 64 * j:64 * (j + 1)], golden[f"light_{b}"]) < FP32_TOL, b
+
+
+def test_predict_before_forward_raises(golden):
+    model, _ = _golden_model(golden)
+    with pytest.raises(TypeError):
+        model.predict([0, 1], None)
+
+
+@pytest.mark.parametrize("pt", ["TIE", "TE", "normal"])
+def test_predict_and_evaluate_vs_golden(golden, pt):
+    model, ds = _golden_model(golden)
+    model.bpr_loss(*[torch.tensor(x) for x in _batch(golden, 0)])
+    model.eval()
+    model.predict_type = pt
+    sc = model.predict(golden["predict_users"].tolist(), None)
+    assert sc.device.type == "cpu" and sc.dtype == torch.float32
+    assert rel_err(sc, golden[f"predict_{pt}"]) < FP32_TOL
+    res, buf = model.evaluate()
+    np.testing.assert_allclose(res, golden[f"evaluate_{pt}"], rtol=0, atol=5e-5)  # identical to 4 decimals
+    assert [("%.4f" % a) for a in res] == [("%.4f" % a) for a in golden[f"evaluate_{pt}"]]
+    res, buf = model.test()
+    assert [("%.4f" % a) for a in res] == [("%.4f" % a) for a in golden[f"test_{pt}"]]
+    assert len(buf.split("\t")) == 3
+    if pt == "TIE":  # per-user metric rows of the reference's C++ evaluator, first 16 valid users
+        ev = model.valid_evaluator.evaluator
+        _, _, rows = ev.evaluate(model, test_users=golden["predict_users"].tolist(), return_rows=True)
+        assert np.abs(rows.cpu().numpy() - golden["metric_rows_TIE"]).max() < 1e-6
+
+
+def test_three_steps_fused_adam_vs_golden(golden):
+    model, _ = _golden_model(golden)
+    model.make_optimizer(lr=1e-3, weight_decay=1e-4)
+    losses = [float(model.train_step(*_batch(golden, i))) for i in range(3)]
+    np.testing.assert_allclose(losses, golden["losses"], rtol=2e-5)
+    for k, v in model.state_dict().items():
+        _assert_post_adam_close(v, golden["sd3/" + k], k)
+
+
+def test_three_steps_autograd_torch_adam_vs_golden(golden):
+    """The unmodified main.py loop: torch.optim.Adam over .grad filled by bpr_loss().backward()."""
+    model, _ = _golden_model(golden)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    for i in range(3):
+        loss = model.bpr_loss(*[torch.tensor(x).to("cuda:0") for x in _batch(golden, i)])
+        opt.zero_grad()
+        loss.backward(retain_graph=True)
+        opt.step()
+    for k, v in model.state_dict().items():
+        _assert_post_adam_close(v, golden["sd3/" + k], k)
+
+
+def test_sampler_dropin_drives_training(golden):
+    from elimrec_b200.sampler import PairwiseSamplerV2
+    model, ds = _golden_model(golden)
+    it = PairwiseSamplerV2(ds, neg_num=1, batch_size=128, shuffle=True)
+    np.random.seed(2022)
+    model.make_optimizer()
+    losses = []
+    for i, (u, p, n) in enumerate(it):
+        if i < 3:
+            assert np.array_equal(u, golden[f"batch{i}_users"])
+        losses.append(float(model.train_step(u, p, n)))
+    assert len(losses) == len(it) and losses[2] == pytest.approx(float(golden["losses"][2]), rel=2e-5)
+
+
+@pytest.mark.parametrize("shape,layers", [("small", 3), ("small", 2), ("medium", 3)])
+def test_vs_oracle_fresh_weights(shape, layers):
+    """Bigger graphs, fresh xavier weights, odd batch size; loss / grads / tables / top-K vs the oracle."""
+    from elimrec_b200 import synth
+    from elimrec_b200.data import Dataset
+    from oracle import ref_eval
+    from oracle.ref_model import OracleEliMRec
+    inter, feats = synth.make_shape(shape)
+    ds = Dataset(None, interactions=inter, features=feats, name=shape)
+    torch.manual_seed(5)
+    model = build_model(ds, None, dataset_name=shape, alpha=0.3, layer_num=layers)
+    params = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    orc = OracleEliMRec(params, {m: getattr(ds, f"{m}_feat") for m in "vat"}, ds.train_matrix, ds.num_users,
+                        ds.num_items, alpha=0.3, n_layers=layers)
+    rng = np.random.default_rng(0)
+    B = 1000 + 7
+    u = rng.integers(0, ds.num_users, B)
+    u[:5] = u[0]  # duplicate users inside a batch
+    tm = ds.train_matrix
+    p = np.array([tm.indices[tm.indptr[x]] for x in u])
+    n = rng.integers(0, ds.num_items, B)
+    loss = model.bpr_loss(u, p, n)
+    loss.backward()
+    lo = orc.bpr_loss(u, p, n)
+    assert abs(float(loss) - float(lo)) < FP32_TOL * abs(float(lo))
+    og = orc.grads(lo)
+    for name, prm in model.named_parameters():
+        assert rel_err(prm.grad, og[name]) < 2 * FP32_TOL, name
+    assert rel_err(model.all_users, orc.cache["users"]) < FP32_TOL
+    assert rel_err(model.all_items, orc.cache["items"]) < FP32_TOL
+    # ranking: top-K index sets vs the oracle, ties/near-ties classified
+    model.eval()
+    users = list(ds.get_user_test_dict().keys())[:200]
+    train = ds.get_user_train_dict()
+    for pt in ("TIE", "TE"):
+        model.predict_type = pt
+        ev = model.test_evaluator.evaluator
+        res, _ = ev.evaluate(model, test_users=users)
+        idx = ev.last_topk[0].cpu().numpy()
+        ref = orc.predict(users, pt).numpy()
+        exact, explained, bad = topk_sets_match(idx, ref, [train.get(x, []) for x in users], 20, tol=3e-6)
+        assert bad == 0 and exact > 0.8 * len(users), (pt, exact, explained, bad)
+        want, _ = ref_eval.evaluate(lambda us: orc.predict(us, pt).numpy(), train, {x: ds.get_user_test_dict()[x] for x in users},
+                                    top_k=[20], batch_size=128)
+        assert np.abs(res - want).max() < 5e-5, (pt, res, want)
