@@ -41,6 +41,7 @@ _SIGS = {
     "elimrec_colsum": [i64, i64, vp, i64, vp, vp, i32, vp, vp],
     "elimrec_linear_tf32_fwd": [i64, i64, vp, i64, vp, vp, vp, i64, vp],
     "elimrec_linear_tf32_wgrad": [i64, i64, vp, i64, vp, i64, vp, vp, vp],
+    "elimrec_round_tf32": [i64, vp, vp, vp],
     "elimrec_bpr_forward_backward": [i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "elimrec_adam_tick": [vp, vp, f64, f64, f64, vp],
     "elimrec_adam_apply": [i64, vp, vp, i64, i64, vp, vp, vp, f64, f64, f32, f32, vp],

@@ -1,16 +1,469 @@
-// Tensor-core (tcgen05 / TMEM) linear layers - placeholder translation unit.
-// Until the UMMA kernels land, both entry points report "unsupported shape" (-2) and the host
-// routes the projection layers through the exact-fp32 elimrec_gemm path.
+// Tensor-core linear layers for sm_100a: tcgen05.mma (kind::tf32) with TMA-fed shared-memory operands
+// and the fp32 accumulator in TMEM.  Replaces cuBLAS SGEMM behind nn.Linear for the modal-feature
+// projections v_dense / a_dense / t_dense (reference models/EliMRec.py:233-236), which stream the
+// constant [I x D_m] feature matrices every step and are HBM-bound (32 flop per feature byte).
+//
+//   fwd  : Y[M x 64] (ldy) = X[M x K] (ldx) * W[64 x K]^T + b
+//          CTA = one 128-row tile of X; per k-block of 32 floats (one 128-byte swizzle atom) TMA brings
+//          a [128 x 32] tile of X and a [64 x 32] tile of W (both K-major, SWIZZLE_128B), one elected
+//          thread issues 4 x tcgen05.mma 128x64x8; a 4-stage mbarrier ring overlaps TMA with MMA; four
+//          epilogue warps read the accumulator with tcgen05.ld, add the bias and write coalesced rows.
+//   wgrad: dW[64 x K] = dY[M x 64]^T * X[M x K]   (reduction over the M rows)
+//          computed transposed, D^T[c, n] = sum_m X[m, c] dY[m, n], so that both operands are
+//          MN-major tiles straight from row-major memory: A' = X^T (128 columns of X per MMA tile),
+//          B' = dY.  A CTA owns up to 256 columns of X and a contiguous range of rows, keeps its
+//          [256 x 64] partial in TMEM for the whole range and writes it once; a second kernel
+//          reduces the row-range partials in a fixed order (deterministic).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (warp_id % 4 selects the TMEM lane quadrant a warp may read).
+#include <cuda.h>
 #include "common.cuh"
 
-ELIMREC_API int elimrec_linear_tf32_fwd(int64_t, int64_t, const float*, int64_t, const float*, const float*, float*,
-                                        int64_t, elimrec_stream_t) {
-    elimrec_set_error("elimrec_linear_tf32_fwd: not built in this revision");
-    return -2;
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-ELIMREC_API int elimrec_linear_tf32_wgrad(int64_t, int64_t, const float*, int64_t, const float*, int64_t, float*, float*,
-                                          elimrec_stream_t) {
-    elimrec_set_error("elimrec_linear_tf32_wgrad: not built in this revision");
-    return -2;
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-ELIMREC_API int64_t elimrec_linear_tf32_wgrad_workspace_floats(int64_t, int64_t) { return 0; }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (32*(warp%4) + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor, version 1):
+//   [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 | [46,48) version=1 | [61,64) layout=2
+//   layout: 2 = SWIZZLE_128B (16-byte swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only layout the
+//   hardware accepts for MN-major 32-bit (tf32) operands - cutlass sm100_common.inl "for mn-major tf32 operands,
+//   SW128_32B is the only available smem layout"; TMA counterpart CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return umma_desc(saddr, lbo_bytes, sbo_bytes, 2);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
+// a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+constexpr int F_BM = 128, F_BN = 64, F_BK = 32, F_STAGES = 4;
+constexpr int F_A_BYTES = F_BM * F_BK * 4, F_B_BYTES = F_BN * F_BK * 4, F_STAGE = F_A_BYTES + F_B_BYTES;
+constexpr int F_SMEM = F_STAGES * F_STAGE + 1024;  // + slack for the 1024-byte alignment swizzle-128B needs
+constexpr int F_TMEM_COLS = 64;
+
+__global__ void __launch_bounds__(192)
+linear_tf32_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const float* __restrict__ bias, float* __restrict__ Y, long long ldy, int M, int num_kb) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[F_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[F_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * F_BM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < F_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, F_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % F_STAGES;
+                const uint32_t ph = (kb / F_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], F_STAGE);
+                uint8_t* a = smem + s * F_STAGE;
+                tma_load_2d(&tmA, &full_bar[s], a, kb * F_BK, m0);
+                tma_load_2d(&tmB, &full_bar[s], a + F_A_BYTES, kb * F_BK, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % F_STAGES;
+                const uint32_t ph = (kb / F_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a = smem_u32(smem + s * F_STAGE);
+                const uint32_t b = a + F_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < F_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte atom
+                    const uint64_t da = umma_desc_sw128(a + k * 32, 16, 1024);
+                    const uint64_t db = umma_desc_sw128(b + k * 32, 16, 1024);
+                    umma_tf32(tmem_d, da, db, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);     // accumulator complete
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        float v[64];
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_32x32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        // transpose through shared memory (the pipeline stages are idle now) for coalesced row stores
+        float* st = reinterpret_cast<float*>(smem) + q * (32 * 65);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) st[lane * 65 + j] = v[j] + (bias != nullptr ? __ldg(bias + j) : 0.f);
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+            const int row = m0 + q * 32 + r;
+            if (row < M) {
+                float* y = Y + (long long)row * ldy;
+                y[lane] = st[r * 65 + lane];
+                y[32 + lane] = st[r * 65 + 32 + lane];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, F_TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// row-major fp32 [rows x cols] with row stride ld (floats); box = [box_rows x 32 floats], 128-byte swizzle,
+// out-of-bounds elements read as zero (handles the M and K tails)
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient:  dW[n, c] = sum_m dY[m, n] * X[m, c]      (computed as D^T[c, n], both operands MN-major)
+// ---------------------------------------------------------------------------------------------
+constexpr int G_BR = 32;                 // rows of X / dY per pipeline stage (4 MMA k-steps of 8 rows)
+constexpr int G_KC = 256;                // columns of X owned by one CTA (two 128-wide MMA tiles)
+constexpr int G_STAGES = 4;
+constexpr int G_BOX = G_BR * 128;        // one TMA box: [32 rows x 32 floats] = 4 KB
+constexpr int G_XB = G_KC / 32;          // X boxes per stage
+constexpr int G_STAGE = (G_XB + 2) * G_BOX;
+constexpr int G_SMEM = G_STAGES * G_STAGE + 1024;
+constexpr int G_TMEM_COLS = 128;
+
+__global__ void __launch_bounds__(192)
+linear_tf32_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                         float* __restrict__ part, int M, int K, int rb_per_cta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[G_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[G_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * G_KC;                     // first X column of this CTA
+    const int n_tiles = (min(K - c0, G_KC) + 127) / 128;  // 1 or 2 MMA tiles
+    const int n_boxes = (min(K - c0, G_KC) + 31) / 32;    // X boxes that contain any valid column
+    const int nrb = (M + G_BR - 1) / G_BR;
+    const int rb0 = blockIdx.y * rb_per_cta;
+    const int rb1 = min(nrb, rb0 + rb_per_cta);
+    const int n_it = max(0, rb1 - rb0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmG);
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, G_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % G_STAGES;
+                const uint32_t ph = (it / G_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], (uint32_t)(n_boxes + 2) * G_BOX);
+                uint8_t* base = smem + s * G_STAGE;
+                const int row = (rb0 + it) * G_BR;
+                for (int b = 0; b < n_boxes; ++b) tma_load_2d(&tmX, &full_bar[s], base + b * G_BOX, c0 + b * 32, row);
+                tma_load_2d(&tmG, &full_bar[s], base + G_XB * G_BOX, 0, row);
+                tma_load_2d(&tmG, &full_bar[s], base + (G_XB + 1) * G_BOX, 32, row);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(128, 64, 1, 1);  // A = X^T and B = dY are both MN-major
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % G_STAGES;
+                const uint32_t ph = (it / G_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t xb = smem_u32(smem + s * G_STAGE);
+                const uint32_t gb = xb + G_XB * G_BOX;
+                for (int t = 0; t < n_tiles; ++t) {
+#pragma unroll
+                    for (int j = 0; j < G_BR / 8; ++j) {  // one MMA = 8 rows = two 4-row (512-byte) swizzle atoms per 32-column group
+                        const uint64_t da = umma_desc(xb + t * 4 * G_BOX + j * 1024, G_BOX, 512, 1);
+                        const uint64_t db = umma_desc(gb + j * 1024, G_BOX, 512, 1);
+                        umma_tf32(tmem_d + t * 64, da, db, idesc, (it | j) != 0);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        float* out = part + (long long)blockIdx.y * 64 * K;   // this row-range's partial, laid out like dW [64 x K]
+        for (int t = 0; t < n_tiles; ++t) {
+            float v[64];
+            const int c = c0 + t * 128 + q * 32 + lane;
+            if (n_it > 0) {
+                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + t * 64;
+                tmem_ld_32x32(taddr, v);
+                tmem_ld_32x32(taddr + 32, v + 32);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int n = 0; n < 64; ++n) v[n] = 0.f;
+            }
+            if (c < K) {
+#pragma unroll
+                for (int n = 0; n < 64; ++n) out[(long long)n * K + c] = v[n];  // 32 consecutive c per warp store
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, G_TMEM_COLS);
+}
+
+__global__ void wgrad_reduce_kernel(long long n, int n_part, const float* __restrict__ part, float* __restrict__ dW) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int p = 0; p < n_part; ++p) s += part[(long long)p * n + i];  // fixed order: deterministic
+    dW[i] = s;
+}
+
+void wgrad_plan(int64_t M, int64_t K, int* nk, int* rs, int* rb_per_cta) {
+    *nk = (int)((K + G_KC - 1) / G_KC);
+    const int nrb = (int)((M + G_BR - 1) / G_BR);
+    int r = 148 / *nk;
+    if (r < 1) r = 1;
+    if (r > nrb) r = nrb;
+    *rb_per_cta = (nrb + r - 1) / r;
+    *rs = (nrb + *rb_per_cta - 1) / *rb_per_cta;
+}
+
+}  // namespace
+
+ELIMREC_API int64_t elimrec_linear_tf32_wgrad_workspace_floats(int64_t M, int64_t K) {
+    int nk, rs, rbp;
+    wgrad_plan(M, K, &nk, &rs, &rbp);
+    return (int64_t)rs * 64 * K;
+}
+
+ELIMREC_API int elimrec_linear_tf32_wgrad(int64_t M, int64_t K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
+                                          float* dW, float* workspace, elimrec_stream_t stream) {
+    if (M <= 0 || K <= 0) return 0;
+    if (K % 4 != 0 || ldx % 4 != 0 || lddy % 4 != 0 || !aligned16(X) || !aligned16(dY) || M > 0x7fffffff || workspace == nullptr) {
+        elimrec_set_error("elimrec_linear_tf32_wgrad: unsupported shape/alignment (K=%lld ldx=%lld lddy=%lld)", (long long)K,
+                          (long long)ldx, (long long)lddy);
+        return -2;
+    }
+    CUtensorMap tmX, tmG;
+    if (make_map(&tmX, X, M, K, ldx, G_BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) != 0 ||
+        make_map(&tmG, dY, M, 64, lddy, G_BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) != 0) {
+        elimrec_set_error("elimrec_linear_tf32_wgrad: cuTensorMapEncodeTiled failed");
+        return -3;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+        if (e != cudaSuccess) {
+            elimrec_set_error("elimrec_linear_tf32_wgrad: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            return -3;
+        }
+        configured = true;
+    }
+    int nk, rs, rbp;
+    wgrad_plan(M, K, &nk, &rs, &rbp);
+    cudaStream_t st = er_stream(stream);
+    linear_tf32_wgrad_kernel<<<dim3(nk, rs), 192, G_SMEM, st>>>(tmX, tmG, workspace, (int)M, (int)K, rbp);
+    ER_LAUNCH_CHECK();
+    const long long n = 64LL * K;
+    wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, rs, workspace, dW);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+namespace {
+__global__ void round_tf32_kernel(long long n, const float* __restrict__ src, float* __restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));  // round-to-nearest (the MMA itself truncates)
+    dst[i] = __uint_as_float(r);
+}
+}  // namespace
+
+ELIMREC_API int elimrec_round_tf32(int64_t n, const float* src, float* dst, elimrec_stream_t stream) {
+    if (n <= 0) return 0;
+    round_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, er_stream(stream)>>>(n, src, dst);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, const float* W, const float* b,
+                                        float* Y, int64_t ldy, elimrec_stream_t stream) {
+    if (M <= 0) return 0;
+    if (K < 4 || K % 4 != 0 || ldx % 4 != 0 || !aligned16(X) || !aligned16(W) || M > 0x7fffffff) {
+        elimrec_set_error("elimrec_linear_tf32_fwd: unsupported shape/alignment (K=%lld ldx=%lld)", (long long)K, (long long)ldx);
+        return -2;
+    }
+    CUtensorMap tmA, tmB;
+    if (make_map(&tmA, X, M, K, ldx, F_BM) != 0 || make_map(&tmB, W, 64, K, K, F_BN) != 0) {
+        elimrec_set_error("elimrec_linear_tf32_fwd: cuTensorMapEncodeTiled failed");
+        return -3;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+        if (e != cudaSuccess) {
+            elimrec_set_error("elimrec_linear_tf32_fwd: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            return -3;
+        }
+        configured = true;
+    }
+    const int num_kb = (int)((K + F_BK - 1) / F_BK);
+    const unsigned grid = (unsigned)((M + F_BM - 1) / F_BM);
+    linear_tf32_fwd_kernel<<<grid, 192, F_SMEM, er_stream(stream)>>>(tmA, tmB, b, Y, ldy, (int)M, num_kb);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+

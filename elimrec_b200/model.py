@@ -116,6 +116,10 @@ class EliMRec(BasicModel):
         if self.mm_fusion_mode != "concat" or self.fusion_mode != "rubi":
             raise NotImplementedError("mm_fusion_mode='mean' / s_fusion_mode in {'hm','sum'} are SURVEY.md row f4")
         self.modality = _cfg(cfg, "modality", "vat")
+        # 'tf32': modal projections on the tcgen05 tensor cores (1e-3 parity class); 'fp32': exact FFMA path (1e-5)
+        self.proj_precision = _cfg(cfg, "proj_precision", "tf32")
+        if self.proj_precision not in ("tf32", "fp32"):
+            raise ElimrecError("proj_precision must be 'tf32' or 'fp32'")
         self.kwai = cfg["data.input.dataset"] == "kwai"
         self.mods = "v" if self.kwai else "vat"
         dev = _cfg(cfg, "device", None)
@@ -153,6 +157,14 @@ class EliMRec(BasicModel):
         nn.init.xavier_uniform_(self.s_dense_t.weight)
         self._ws = None
         self._adam = None
+
+    def _feat_tc(self, m):
+        """Features pre-rounded (to nearest) to TF32 once; what the tensor-core projections stream."""
+        cache = self.__dict__.setdefault("_feat_tf32", {})
+        if m not in cache:
+            cache[m] = torch.empty_like(self._feat[m])
+            ops.round_tf32(self._feat[m], cache[m])
+        return cache[m]
 
     # parameters that take part in the computation, in a fixed order
     @property
@@ -212,6 +224,8 @@ class EliMRec(BasicModel):
         ws["split_inst"] = max(1, min(64, (3 * B + 127) // 128))
         need = max(ws["split_proj"] * dmax * D, ws["split_inst"] * Fw * D)
         ws["gemm_ws"] = e(need)
+        ws["W_tf32"] = {m: e(D, self._feat[m].shape[1]) for m in self.mods}
+        ws["wgrad_ws"] = e(max(1, max(ops.linear_tf32_wgrad_ws_floats(I, self._feat[m].shape[1]) for m in self.mods)))
         ws["colsum_ws"] = e(max(ops.colsum_ws_floats(I, D), ops.colsum_ws_floats(3 * B, D)))
         self._ws = ws
         return ws
@@ -234,7 +248,12 @@ class EliMRec(BasicModel):
         for j, m in enumerate(self.mods):
             Wm, bm = P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach()
             Dm = Wm.shape[1]
-            ops.gemm(I, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, c_off=D * (j + 1), tag="proj_fwd")
+            if self.proj_precision == "tf32" and Dm % 4 == 0:
+                Wr = ws["W_tf32"][m]
+                ops.round_tf32(Wm, Wr)
+                ops.linear_tf32_fwd(self._feat_tc(m), Wr, bm, X0_i, col=D * (j + 1))
+            else:
+                ops.gemm(I, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, c_off=D * (j + 1), tag="proj_fwd")
         # propagation: layer k has a WIDE side (distinct per graph) and a NARROW side (shared, 64 wide)
         O = ws["O"]
         Ou, Oi = O[:U], O[U:]
@@ -358,7 +377,11 @@ class EliMRec(BasicModel):
             Xm = self._feat[m]
             Dm = Xm.shape[1]
             c0 = D * (j + 1)
-            ops.gemm(Dm, D, I, Xm, 1, Dm, dWc, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=skp, ws=gws, b_off=c0, tag="proj_wgrad")
+            if self.proj_precision == "tf32" and Dm % 4 == 0:
+                ops.linear_tf32_wgrad(dWc, self._feat_tc(m), gr[f"{m}_dense.weight"], ws["wgrad_ws"], col=c0)
+            else:
+                ops.gemm(Dm, D, I, Xm, 1, Dm, dWc, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=skp, ws=gws, b_off=c0,
+                         tag="proj_wgrad")
             ops.colsum(I, D, dWc, Fw, gr[f"{m}_dense.bias"], cws, a_off=c0)
         grads.update(gr)
         return grads

@@ -64,6 +64,29 @@ def gemm(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, Cm, c_sm, c_sn, bias=None, accum
          ptr(scale, F32, True), stream(), launches=(2 if split_k > 1 else 1), tag=tag or "gemm")
 
 
+def linear_tf32_fwd(X, W, b, Y, col=0, tag="proj_fwd_tc"):
+    """Y[:, col:col+64] = X @ W^T + b on the tcgen05 tensor cores (TF32 inputs, fp32 accumulate).
+    X may be a column-block view (row stride != K)."""
+    M, K = X.shape
+    call("elimrec_linear_tf32_fwd", M, K, ptr(X, F32), X.stride(0), ptr(W, F32), ptr(b, F32, True),
+         ptr(Y, F32) + 4 * col, Y.stride(0), stream(), tag=tag)
+
+
+def round_tf32(src, dst):
+    call("elimrec_round_tf32", src.numel(), ptr(src, F32), ptr(dst, F32), stream())
+
+
+def linear_tf32_wgrad(dY, X, dW, ws, col=0, tag="proj_wgrad_tc"):
+    """dW[64 x K] = dY[:, col:col+64]^T @ X on the tcgen05 tensor cores; deterministic row-range reduction."""
+    M, K = X.shape
+    call("elimrec_linear_tf32_wgrad", M, K, ptr(dY, F32) + 4 * col, dY.stride(0), ptr(X, F32), X.stride(0), ptr(dW, F32),
+         ptr(ws, F32), stream(), launches=2, tag=tag)
+
+
+def linear_tf32_wgrad_ws_floats(M, K):
+    return int(_lib.lib().elimrec_linear_tf32_wgrad_workspace_floats(M, K))
+
+
 def colsum(M, N, A, ld, out, ws, accumulate=False, scale=None, a_off=0):
     call("elimrec_colsum", M, N, ptr(A, F32) + 4 * a_off, ld, ptr(out, F32), ptr(ws, F32), int(accumulate),
          ptr(scale, F32, True), stream())

@@ -107,6 +107,9 @@ int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, c
 int elimrec_linear_tf32_wgrad(int64_t M, int64_t K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
                               float* dW, float* workspace, elimrec_stream_t stream);
 int64_t elimrec_linear_tf32_wgrad_workspace_floats(int64_t M, int64_t K);
+/* dst[i] = round-to-nearest TF32 of src[i] (tcgen05.mma kind::tf32 truncates its inputs; pre-rounding the constant
+ * features once and the weights per step removes the truncation bias).  src == dst allowed. */
+int elimrec_round_tf32(int64_t n, const float* src, float* dst, elimrec_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * bpr - replaces getEmbedding gathers + original_bpr_loss x (1+M) + their autograd

@@ -17,6 +17,7 @@ TC_TOL = 1e-3     # TF32 / bf16 tensor-core GEMMs within 1e-3 relative
 def build_model(ds, params=None, dataset_name="synthg", **cfg):
     from elimrec_b200.data import Config
     from elimrec_b200.model import EliMRec
+    cfg.setdefault("proj_precision", "fp32")   # exact path unless a test asks for the tensor-core projections
     conf = Config(**{"data.input.dataset": dataset_name, "topks": [20], "device": torch.device("cuda:0"), **cfg})
     model = EliMRec(conf, ds).to(conf.device)
     if params is not None:

@@ -279,7 +279,7 @@ def test_device_sampler_bit_exact_and_valid(dev):
     ds = Dataset(None, interactions=inter, features=feats, name="tiny")
     s = PairwiseSamplerV2(ds, batch_size=64, mode="device", device=dev, seed=2022)
     s.epoch = 3
-    u, p, n = (x.cpu().numpy() for x in s.sample_epoch_device(5000))
+    u, p, n = (x.cpu().numpy().copy() for x in s.sample_epoch_device(5000))
     ru, rp, rn = philox_sampler.sample_triples(2022, 3, 5000, s.users, s.ptr, s.items, ds.num_items)
     assert np.array_equal(u, ru) and np.array_equal(p, rp) and np.array_equal(n, rn)
     tm = ds.train_matrix
@@ -290,3 +290,40 @@ def test_device_sampler_bit_exact_and_valid(dev):
     assert ((cnt - exp) ** 2 / exp).sum() < 3 * s.users.size
     batches = list(s)
     assert sum(b[0].numel() for b in batches) == s.num_trainings and batches[0][0].is_cuda
+
+
+@pytest.mark.parametrize("M,K,ldx_extra,ldy", [(1000, 128, 0, 64), (76085 // 8, 768, 0, 256), (333, 100, 0, 64), (4096, 64, 192, 64),
+                                               (130, 2048, 0, 64), (128, 32, 0, 64)])
+def test_linear_tf32_fwd_tcgen05(dev, M, K, ldx_extra, ldy):
+    """tcgen05 TF32 projection GEMM vs fp64; tolerance = the north star's 1e-3 for TF32 GEMMs."""
+    from elimrec_b200 import ops
+    from gpu_util import TC_TOL
+    g = torch.Generator().manual_seed(M + K)
+    Xfull = torch.randn(M, K + ldx_extra, generator=g).to(dev)
+    X = Xfull[:, ldx_extra:] if ldx_extra else Xfull           # column-block view of a wider slab
+    W = (torch.randn(64, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(64, generator=g).to(dev)
+    Y = torch.full((M + 1, ldy), 7.0, device=dev)
+    ops.linear_tf32_fwd(X, W, b, Y[:M], col=ldy - 64)
+    ref = X.double() @ W.double().t() + b.double()
+    assert rel_err(Y[:M, ldy - 64:], ref) < TC_TOL
+    assert float((Y[M] - 7).abs().max()) == 0 and (ldy == 64 or float((Y[:M, :ldy - 64] - 7).abs().max()) == 0)
+
+
+@pytest.mark.parametrize("M,K,lddy", [(5000, 128, 256), (76085 // 4, 768, 256), (777, 100, 64), (300, 2048, 64), (33, 160, 128)])
+def test_linear_tf32_wgrad_tcgen05(dev, M, K, lddy):
+    """tcgen05 TF32 weight gradient (MN-major operands, TMEM-resident partials) vs fp64."""
+    from elimrec_b200 import ops
+    from gpu_util import TC_TOL
+    g = torch.Generator().manual_seed(M * 7 + K)
+    X = torch.randn(M, K, generator=g).to(dev)
+    dYfull = torch.randn(M, lddy, generator=g).to(dev)
+    col = lddy - 64
+    dW = torch.full((64, K), 3.0, device=dev)
+    ws = torch.empty(ops.linear_tf32_wgrad_ws_floats(M, K), device=dev)
+    ops.linear_tf32_wgrad(dYfull, X, dW, ws, col=col)
+    ref = dYfull[:, col:].double().t() @ X.double()
+    assert rel_err(dW, ref) < TC_TOL
+    dW2 = torch.empty_like(dW)
+    ops.linear_tf32_wgrad(dYfull, X, dW2, ws, col=col)
+    assert torch.equal(dW, dW2)

@@ -178,3 +178,17 @@ def test_vs_oracle_fresh_weights(shape, layers):
         want, _ = ref_eval.evaluate(lambda us: orc.predict(us, pt).numpy(), train, {x: ds.get_user_test_dict()[x] for x in users},
                                     top_k=[20], batch_size=128)
         assert np.abs(res - want).max() < 5e-5, (pt, res, want)
+
+
+def test_tf32_projection_mode_within_1e3(golden):
+    """proj_precision='tf32' (tcgen05 projections + wgrad): loss / grads / tables within the TF32 class tolerance."""
+    from gpu_util import TC_TOL
+    model, _ = _golden_model(golden, proj_precision="tf32")
+    loss = model.bpr_loss(*[torch.tensor(x) for x in _batch(golden, 0)])
+    loss.backward()
+    assert abs(float(loss) - float(golden["loss0"])) < TC_TOL * abs(float(golden["loss0"]))
+    for name, p in model.named_parameters():
+        if ("grad0/" + name) in golden:
+            assert rel_err(p.grad, golden["grad0/" + name]) < 2 * TC_TOL, name
+    assert rel_err(model.all_items, golden["all_items"]) < TC_TOL
+    assert rel_err(model.all_users, golden["all_users"]) < TC_TOL
