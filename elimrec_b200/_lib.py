@@ -26,6 +26,11 @@ class MeanEpilogue(C.Structure):
                 ("mean_scale", f32)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("numel", i64), ("row_len", i64),
+                ("grad_ld", i64)]
+
+
 class RankTables(C.Structure):
     _fields_ = [("num_users", i32), ("num_items", i32), ("n_mod", i32), ("mode", i32), ("f_user", vp),
                 ("f_item", vp), ("s_user", vp * MAX_MODS), ("s_item", vp * MAX_MODS)]
@@ -43,6 +48,9 @@ _SIGS = {
     "elimrec_linear_tf32_wgrad": [i64, i64, vp, i64, vp, i64, vp, vp, vp],
     "elimrec_round_tf32": [i64, vp, vp, vp],
     "elimrec_bpr_forward_backward": [i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],
+    "elimrec_inst_backward": [i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, vp, C.POINTER(vp),
+                              C.POINTER(vp), vp, vp],
+    "elimrec_adam_apply_multi": [i32, C.POINTER(AdamTensor), vp, f64, f64, f32, f32, vp],
     "elimrec_adam_tick": [vp, vp, f64, f64, f64, vp],
     "elimrec_adam_apply": [i64, vp, vp, i64, i64, vp, vp, vp, f64, f64, f32, f32, vp],
     "elimrec_sample_epoch_compat": [vp, i32, vp, vp, vp, i32, i64, vp, vp, vp],
@@ -58,6 +66,7 @@ _I64_RET = {
     "elimrec_gemm_workspace_floats": [i64, i64, i32],
     "elimrec_colsum_workspace_floats": [i64, i64],
     "elimrec_linear_tf32_wgrad_workspace_floats": [i64, i64],
+    "elimrec_inst_backward_workspace_floats": [i32, i32, i32],
 }
 # every symbol include/elimrec_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = sorted(list(_SIGS) + list(_I64_RET) + ["elimrec_last_error", "elimrec_abi_version",
@@ -96,7 +105,7 @@ def lib():
 # kernels launched through the C-ABI (bench.py reports `gpu_launches` from this) and an optional
 # per-family CUDA-event profile (bench.py --profile-kernels; events sit on the launching stream)
 CALLS = {"n": 0, "launches": 0}
-_LAUNCHES = {"elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2}
+_LAUNCHES = {"elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2, "elimrec_inst_backward": 3}
 PROFILE = {"on": False, "events": []}
 
 

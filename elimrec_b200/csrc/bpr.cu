@@ -120,6 +120,191 @@ __global__ void adam_apply_kernel(long long n, float* __restrict__ p, const floa
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the fusion Linear (embedding_{user,item}_after_GCN) and the single-modal heads (s_dense_*) on the
+// 3B instance rows only (their gradient is zero on every other row).  Three launches replace the ~18 tiny
+// GEMM / column-sum launches a generic implementation needs.
+//   inst_dO   : dO[r, :] = g * ( dF[r] @ W_{u|i}  +  [0 | dS_v[r] @ Ws_v | dS_a[r] @ Ws_a | dS_t[r] @ Ws_t] )
+//   inst_dW   : per 64-row chunk, partial outer products  dY^T O  for every weight (and column sums for the biases)
+//   inst_dWred: fixed-order sum of the chunk partials (deterministic), scaled by the upstream gradient g
+// ---------------------------------------------------------------------------------------------
+struct InstW {
+    const float* Wu;   // [64 x F]
+    const float* Wi;   // [64 x F]
+    const float* Ws[ELIMREC_MAX_MODS];  // [64 x 64]
+};
+
+constexpr int IRB = 16;  // rows per CTA in inst_dO
+
+__global__ void __launch_bounds__(256)
+inst_dO_kernel(int B, int nt, int F, InstW w, const float* __restrict__ ig, const float* __restrict__ gscale,
+               float* __restrict__ dO) {
+    __shared__ float gs[IRB][64 * (1 + ELIMREC_MAX_MODS)];
+    const int nbu = (B + IRB - 1) / IRB;
+    const bool user = (int)blockIdx.x < nbu;
+    const int r0 = user ? blockIdx.x * IRB : B + (blockIdx.x - nbu) * IRB;
+    const int r1 = min(user ? B : 3 * B, r0 + IRB);
+    const int ld = 64 * nt;
+    for (int i = threadIdx.x; i < IRB * ld; i += blockDim.x) {
+        const int r = i / ld, c = i % ld;
+        gs[r][c] = (r0 + r < r1) ? ig[(long long)(r0 + r) * ld + c] : 0.f;
+    }
+    __syncthreads();
+    const float g = (gscale != nullptr) ? __ldg(gscale) : 1.f;
+    const float* W = user ? w.Wu : w.Wi;
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+        float acc[IRB];
+#pragma unroll
+        for (int r = 0; r < IRB; ++r) acc[r] = 0.f;
+        for (int n = 0; n < 64; ++n) {
+            const float wv = __ldg(W + n * F + c);
+#pragma unroll
+            for (int r = 0; r < IRB; ++r) acc[r] = fmaf(gs[r][n], wv, acc[r]);
+        }
+        const int blk = c >> 6;
+        if (blk >= 1) {
+            const float* Ws = w.Ws[blk - 1];
+            const int cc = c & 63;
+            for (int n = 0; n < 64; ++n) {
+                const float wv = __ldg(Ws + n * 64 + cc);
+#pragma unroll
+                for (int r = 0; r < IRB; ++r) acc[r] = fmaf(gs[r][blk * 64 + n], wv, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < IRB; ++r)
+            if (r0 + r < r1) dO[(long long)(r0 + r) * F + c] = g * acc[r];
+    }
+}
+
+constexpr int IRC = 32;  // rows per chunk in inst_dW (32 KB of instance gradients in shared memory)
+
+// partial layout per chunk: [64 x F] fusion weight | [M][64 x 64] heads | [64*nt] bias column sums
+__global__ void __launch_bounds__(256)
+inst_dW_kernel(int B, int nt, int F, const float* __restrict__ ig, const float* __restrict__ Oin, float* __restrict__ part) {
+    __shared__ float gs[IRC][64 * (1 + ELIMREC_MAX_MODS)];
+    const int ncu = (B + IRC - 1) / IRC;
+    const bool user = (int)blockIdx.x < ncu;
+    const int r0 = user ? blockIdx.x * IRC : B + (blockIdx.x - ncu) * IRC;
+    const int r1 = min(user ? B : 3 * B, r0 + IRC);
+    const int nr = r1 - r0;
+    const int ld = 64 * nt;
+    for (int i = threadIdx.x; i < IRC * ld; i += blockDim.x) {
+        const int r = i / ld, c = i % ld;
+        gs[r][c] = (r < nr) ? ig[(long long)(r0 + r) * ld + c] : 0.f;
+    }
+    __syncthreads();
+    const long long psz = 64LL * F + (long long)(nt - 1) * 4096 + ld;
+    float* out = part + (long long)blockIdx.x * psz;
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+        float acc[64];
+#pragma unroll
+        for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+        for (int r = 0; r < nr; ++r) {
+            const float o = __ldg(Oin + (long long)(r0 + r) * F + c);
+#pragma unroll
+            for (int n = 0; n < 64; ++n) acc[n] = fmaf(gs[r][n], o, acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < 64; ++n) out[(long long)n * F + c] = acc[n];
+        const int blk = c >> 6;
+        if (blk >= 1) {
+#pragma unroll
+            for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+            for (int r = 0; r < nr; ++r) {
+                const float o = __ldg(Oin + (long long)(r0 + r) * F + c);
+#pragma unroll
+                for (int n = 0; n < 64; ++n) acc[n] = fmaf(gs[r][blk * 64 + n], o, acc[n]);
+            }
+            float* hw = out + 64LL * F + (long long)(blk - 1) * 4096;
+#pragma unroll
+            for (int n = 0; n < 64; ++n) hw[n * 64 + (c & 63)] = acc[n];
+        }
+    }
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        float sacc = 0.f;
+        for (int r = 0; r < nr; ++r) sacc += gs[r][c];
+        out[64LL * F + (long long)(nt - 1) * 4096 + c] = sacc;
+    }
+}
+
+struct InstOut {
+    float* dWu; float* dWi; float* dbu; float* dbi;
+    float* dWs[ELIMREC_MAX_MODS]; float* dbs[ELIMREC_MAX_MODS];
+};
+
+__global__ void inst_dWred_kernel(int B, int nt, int F, const float* __restrict__ part, const float* __restrict__ gscale,
+                                  InstOut o) {
+    const int ncu = (B + IRC - 1) / IRC, nci = (2 * B + IRC - 1) / IRC;
+    const int ld = 64 * nt;
+    const long long psz = 64LL * F + (long long)(nt - 1) * 4096 + ld;
+    const long long nWf = 64LL * F, nWs = (long long)(nt - 1) * 4096;
+    const long long total = 2 * nWf + nWs + 64 * 2 + 64 * (nt - 1);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float g = (gscale != nullptr) ? __ldg(gscale) : 1.f;
+    int c0, c1;          // chunk range
+    long long off;       // offset inside a chunk partial
+    float* dst;
+    if (i < nWf) { c0 = 0; c1 = ncu; off = i; dst = o.dWu + i; }
+    else if (i < 2 * nWf) { c0 = ncu; c1 = ncu + nci; off = i - nWf; dst = o.dWi + (i - nWf); }
+    else if (i < 2 * nWf + nWs) {
+        const long long j = i - 2 * nWf;
+        c0 = 0; c1 = ncu + nci; off = nWf + j; dst = o.dWs[j / 4096] + (j % 4096);
+    } else {
+        const long long j = i - 2 * nWf - nWs;   // biases: [bu 64 | bi 64 | bs_m 64 each]
+        if (j < 64) { c0 = 0; c1 = ncu; off = nWf + nWs + j; dst = o.dbu + j; }
+        else if (j < 128) { c0 = ncu; c1 = ncu + nci; off = nWf + nWs + (j - 64); dst = o.dbi + (j - 64); }
+        else { const long long q = j - 128; c0 = 0; c1 = ncu + nci; off = nWf + nWs + 64 + q; dst = o.dbs[q / 64] + (q % 64); }
+    }
+    float sacc = 0.f;
+    for (int c = c0; c < c1; ++c) sacc += part[(long long)c * psz + off];
+    *dst = g * sacc;
+}
+
+struct AdamMulti {
+    int n;
+    float* p[ELIMREC_ADAM_MAX_TENSORS];
+    const float* g[ELIMREC_ADAM_MAX_TENSORS];
+    float* m[ELIMREC_ADAM_MAX_TENSORS];
+    float* v[ELIMREC_ADAM_MAX_TENSORS];
+    long long numel[ELIMREC_ADAM_MAX_TENSORS];
+    long long row_len[ELIMREC_ADAM_MAX_TENSORS];
+    long long g_ld[ELIMREC_ADAM_MAX_TENSORS];
+    int block_start[ELIMREC_ADAM_MAX_TENSORS + 1];
+};
+constexpr int ADAM_CHUNK = 2048;  // elements per CTA
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamMulti a, const double* __restrict__ consts, double b1d, double b2d, float eps,
+                  float wd) {
+    int t = 0;
+    while (t + 1 < a.n && (int)blockIdx.x >= a.block_start[t + 1]) ++t;
+    const long long base = (long long)(blockIdx.x - a.block_start[t]) * ADAM_CHUNK;
+    const long long end = min(a.numel[t], base + ADAM_CHUNK);
+    const float step_size = (float)consts[0];
+    const float bc2s = (float)consts[1];
+    const float b2 = (float)b2d;
+    const float omb1 = (float)(1.0 - b1d), omb2 = (float)(1.0 - b2d);
+    float* __restrict__ p = a.p[t];
+    const float* __restrict__ g = a.g[t];
+    float* __restrict__ m = a.m[t];
+    float* __restrict__ v = a.v[t];
+    const long long rl = a.row_len[t], gl = a.g_ld[t];
+    for (long long i = base + threadIdx.x; i < end; i += 256) {
+        const long long gi = (gl == rl) ? i : (i / rl) * gl + (i % rl);
+        const float pi = p[i];
+        float gr = fmaf(wd, pi, g[gi]);
+        float mi = m[i];
+        mi = mi + (gr - mi) * omb1;
+        float vi = fmaf(omb2 * gr, gr, v[i] * b2);
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2s + eps));
+    }
+}
+
 }  // namespace
 
 ELIMREC_API int elimrec_bpr_forward_backward(int B, int n_tables, const float* const* tables_host,
@@ -162,6 +347,63 @@ ELIMREC_API int elimrec_adam_apply(int64_t n, float* param, const float* grad, i
     adam_apply_kernel<<<(unsigned)blocks, 256, 0, er_stream(stream)>>>(n, param, grad, row_len, grad_ld, exp_avg,
                                                                        exp_avg_sq, consts_dev, beta1, beta2, eps,
                                                                        weight_decay);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+
+ELIMREC_API int64_t elimrec_inst_backward_workspace_floats(int B, int n_tables, int F) {
+    const int64_t chunks = (B + IRC - 1) / IRC + (2 * B + IRC - 1) / IRC;
+    return chunks * (64LL * F + (int64_t)(n_tables - 1) * 4096 + 64 * n_tables);
+}
+
+ELIMREC_API int elimrec_inst_backward(int B, int n_tables, int F, const float* inst_grad, const float* O_inst,
+                                      const float* gscale_dev, const float* Wu, const float* Wi,
+                                      const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu,
+                                      float* dbi, float* const* dWs_host, float* const* dbs_host, float* workspace,
+                                      elimrec_stream_t stream) {
+    ER_CHECK_ARG(B > 0 && n_tables >= 1 && n_tables <= 1 + ELIMREC_MAX_MODS, "bad batch / table count");
+    ER_CHECK_ARG(F == 64 * n_tables, "F must be 64 * n_tables (concat fusion)");
+    InstW w{};
+    w.Wu = Wu; w.Wi = Wi;
+    InstOut o{};
+    o.dWu = dWu; o.dWi = dWi; o.dbu = dbu; o.dbi = dbi;
+    for (int m = 0; m < n_tables - 1; ++m) {
+        w.Ws[m] = Ws_host[m];
+        o.dWs[m] = dWs_host[m];
+        o.dbs[m] = dbs_host[m];
+    }
+    cudaStream_t st = er_stream(stream);
+    const int nb = (B + IRB - 1) / IRB + (2 * B + IRB - 1) / IRB;
+    inst_dO_kernel<<<nb, 256, 0, st>>>(B, n_tables, F, w, inst_grad, gscale_dev, dO_inst);
+    ER_LAUNCH_CHECK();
+    const int nc = (B + IRC - 1) / IRC + (2 * B + IRC - 1) / IRC;
+    inst_dW_kernel<<<nc, 256, 0, st>>>(B, n_tables, F, inst_grad, O_inst, workspace);
+    ER_LAUNCH_CHECK();
+    const long long total = 2 * 64LL * F + (long long)(n_tables - 1) * 4096 + 128 + 64 * (n_tables - 1);
+    inst_dWred_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, n_tables, F, workspace, gscale_dev, o);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_adam_apply_multi(int n_tensors, const elimrec_adam_tensor_t* t, const double* consts_dev,
+                                         double beta1, double beta2, float eps, float weight_decay,
+                                         elimrec_stream_t stream) {
+    ER_CHECK_ARG(n_tensors >= 0 && n_tensors <= ELIMREC_ADAM_MAX_TENSORS, "too many tensors");
+    if (n_tensors == 0) return 0;
+    AdamMulti a{};
+    a.n = n_tensors;
+    int blocks = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        ER_CHECK_ARG(t[i].row_len > 0 && t[i].grad_ld >= t[i].row_len && t[i].numel >= 0, "bad tensor descriptor");
+        a.p[i] = t[i].param; a.g[i] = t[i].grad; a.m[i] = t[i].exp_avg; a.v[i] = t[i].exp_avg_sq;
+        a.numel[i] = t[i].numel; a.row_len[i] = t[i].row_len; a.g_ld[i] = t[i].grad_ld;
+        a.block_start[i] = blocks;
+        blocks += (int)((t[i].numel + ADAM_CHUNK - 1) / ADAM_CHUNK);
+    }
+    a.block_start[n_tensors] = blocks;
+    if (blocks == 0) return 0;
+    adam_multi_kernel<<<blocks, 256, 0, er_stream(stream)>>>(a, consts_dev, beta1, beta2, eps, weight_decay);
     ER_LAUNCH_CHECK();
     return 0;
 }

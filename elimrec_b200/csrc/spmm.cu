@@ -6,8 +6,9 @@
 // output columns, so every neighbour row is fetched as fully coalesced 16-byte vector loads
 // (256 B / 512 B / 1 KB per row).  UNR independent row fetches are kept in flight per lane to cover
 // L2 latency - the operand slab (48-115 MB at the single-GPU shapes) is L2 resident.
-// Rows longer than seg_len are split; the last-arriving segment reduces the partial sums in a FIXED
-// order, so results are bit-reproducible run to run (no float atomics).
+// Rows longer than seg_len are split over whole CTAs (8 segments each, reduced in shared memory); the
+// last-arriving CTA of a row adds the per-CTA partial sums in a FIXED order, so results are
+// bit-reproducible run to run (no float atomics).
 #include "common.cuh"
 
 namespace {
@@ -79,37 +80,57 @@ spmm_seg_kernel(int n_seg, const int4* __restrict__ seg, const int2* __restrict_
         acc[0].w += __shfl_xor_sync(full, acc[0].w, 16);
     }
 
-    if (sg.w >= 0) {  // split row: publish partial, last arriver reduces in segment order
-        float4* pp = reinterpret_cast<float4*>(partial + (long long)warp * F);
+    if (sg.w >= 0) {
+        // Split row.  Its segment count is padded to a multiple of 8 on the host, so all 8 warps of this CTA work on
+        // the SAME row: reduce them in shared memory first (fixed order), then one partial per CTA goes to scratch and
+        // the last-arriving CTA of the row (atomic counter) adds the CTA partials in CTA order.  Deterministic.
+        __shared__ float4 red[8][F / 4];
+        const int wib = threadIdx.x >> 5;
         if (F != 64 || lane < 16) {
 #pragma unroll
-            for (int i = 0; i < NV; ++i) pp[l + i * 32] = acc[i];
+            for (int i = 0; i < NV; ++i) red[wib][l + i * 32] = acc[i];
         }
-        __threadfence();
-        const int2 hv = __ldg(heavy + sg.w);
-        int old = 0;
-        if (lane == 0) old = atomicAdd(counter + sg.w, 1);
-        old = __shfl_sync(full, old, 0);
-        if (old != hv.y - 1) return;
-        __threadfence();
+        __syncthreads();
+        if (wib != 0) return;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* ps = reinterpret_cast<const float4*>(partial + (long long)hv.x * F) + l;
-        constexpr int RU = 8;
-        for (int s = 0; s < hv.y; s += RU) {
-            float4 t[RU][NV];
+        for (int i = 0; i < NV; ++i) {
+            float4 t = red[0][l + i * 32];
 #pragma unroll
-            for (int u = 0; u < RU; ++u)
-#pragma unroll
-                for (int i = 0; i < NV; ++i)
-                    t[u][i] = (s + u < hv.y) ? __ldcg(ps + (long long)(s + u) * (F / 4) + i * 32)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < RU; ++u)
-#pragma unroll
-                for (int i = 0; i < NV; ++i) add4(acc[i], t[u][i]);
+            for (int w2 = 1; w2 < 8; ++w2) add4(t, red[w2][l + i * 32]);
+            acc[i] = t;
         }
-        if (lane == 0) counter[sg.w] = 0;  // leave the counter ready for the next launch
+        const int2 hv = __ldg(heavy + sg.w);  // {first CTA of the row, number of CTAs}
+        if (hv.y > 1) {
+            float4* pp = reinterpret_cast<float4*>(partial + (long long)blockIdx.x * F);
+            if (F != 64 || lane < 16) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) pp[l + i * 32] = acc[i];
+            }
+            __threadfence();
+            int old = 0;
+            if (lane == 0) old = atomicAdd(counter + sg.w, 1);
+            old = __shfl_sync(full, old, 0);
+            if (old != hv.y - 1) return;
+            __threadfence();
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* ps = reinterpret_cast<const float4*>(partial + (long long)hv.x * F) + l;
+            constexpr int RU = 8;
+            for (int s2 = 0; s2 < hv.y; s2 += RU) {
+                float4 t[RU][NV];
+#pragma unroll
+                for (int u = 0; u < RU; ++u)
+#pragma unroll
+                    for (int i = 0; i < NV; ++i)
+                        t[u][i] = (s2 + u < hv.y) ? __ldcg(ps + (long long)(s2 + u) * (F / 4) + i * 32)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < RU; ++u)
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) add4(acc[i], t[u][i]);
+            }
+            if (lane == 0) counter[sg.w] = 0;  // leave the counter ready for the next launch
+        }
     }
 
     const int row = sg.x;

@@ -39,14 +39,15 @@ class CsrHalf:
         self.seg = torch.from_numpy(seg).to(device)
         self.heavy = torch.from_numpy(heavy if heavy.size else np.zeros((1, 2), np.int32)).to(device)
         self.counter = torch.zeros(max(1, heavy.shape[0]), dtype=torch.int32, device=device)
-        self.partial = torch.empty(max(1, n_hseg) * 256, dtype=torch.float32, device=device)
+        self.partial = torch.empty(max(1, n_hseg // 8) * 256, dtype=torch.float32, device=device)
         self.col = torch.from_numpy(self.indices_host).to(device)
         self.val = torch.from_numpy(self.vals_host).to(device)
         self.indptr = torch.from_numpy(self.indptr_host).to(device)
 
 
 def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: int | None = None):
-    """seg[s] = (row, edge_begin, edge_end, heavy_id or -1); split rows first, longest first."""
+    """seg[s] = (row, edge_begin, edge_end, heavy_id or -1); split rows first (longest first), each padded to a
+    multiple of 8 segments so that a CTA of 8 warps never mixes rows; heavy[h] = (first CTA, number of CTAs)."""
     n_rows = indptr.size - 1
     row_hi = n_rows if row_hi is None else row_hi
     rows = np.arange(row_lo, row_hi, dtype=np.int64)
@@ -61,18 +62,20 @@ def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: in
     h_beg = beg[heavy_mask][order]
     h_deg = deg[heavy_mask][order]
     h_nseg = nseg[heavy_mask][order]
-    n_hseg = int(h_nseg.sum())
+    h_nseg_pad = -(-h_nseg // 8) * 8            # one CTA (8 warps) = 8 segments of ONE row; pad with empty segments
+    n_hseg = int(h_nseg_pad.sum())
     segs = []
     heavy = np.zeros((h_rows.size, 2), dtype=np.int32)
     if h_rows.size:
-        first = np.concatenate([[0], np.cumsum(h_nseg)[:-1]])
-        heavy[:, 0] = first
-        heavy[:, 1] = h_nseg
-        hid = np.repeat(np.arange(h_rows.size), h_nseg)
-        k = np.arange(n_hseg) - np.repeat(first, h_nseg)
-        sb = np.repeat(h_beg, h_nseg) + k * seg_len
-        se = np.minimum(sb + seg_len, np.repeat(h_beg + h_deg, h_nseg))
-        segs.append(np.stack([np.repeat(h_rows, h_nseg), sb, se, hid], axis=1))
+        first = np.concatenate([[0], np.cumsum(h_nseg_pad)[:-1]])
+        heavy[:, 0] = first // 8                 # first CTA (= partial slot) of the row
+        heavy[:, 1] = h_nseg_pad // 8            # CTAs of the row
+        hid = np.repeat(np.arange(h_rows.size), h_nseg_pad)
+        k = np.arange(n_hseg) - np.repeat(first, h_nseg_pad)
+        row_end = np.repeat(h_beg + h_deg, h_nseg_pad)
+        sb = np.minimum(np.repeat(h_beg, h_nseg_pad) + k * seg_len, row_end)
+        se = np.minimum(sb + seg_len, row_end)
+        segs.append(np.stack([np.repeat(h_rows, h_nseg_pad), sb, se, hid], axis=1))
     l_rows = rows[~heavy_mask]
     l_beg = beg[~heavy_mask]
     segs.append(np.stack([l_rows, l_beg, l_beg + deg[~heavy_mask], np.full(l_rows.size, -1)], axis=1))

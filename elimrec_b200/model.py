@@ -225,6 +225,7 @@ class EliMRec(BasicModel):
         need = max(ws["split_proj"] * dmax * D, ws["split_inst"] * Fw * D)
         ws["gemm_ws"] = e(need)
         ws["W_tf32"] = {m: e(D, self._feat[m].shape[1]) for m in self.mods}
+        ws["inst_ws"] = e(ops.inst_backward_ws_floats(B, nt, Fw))
         ws["wgrad_ws"] = e(max(1, max(ops.linear_tf32_wgrad_ws_floats(I, self._feat[m].shape[1]) for m in self.mods)))
         ws["colsum_ws"] = e(max(ops.colsum_ws_floats(I, D), ops.colsum_ws_floats(3 * B, D)))
         self._ws = ws
@@ -243,6 +244,14 @@ class EliMRec(BasicModel):
         Eu = P["embedding_user.weight"].detach()
         Ei = P["embedding_item.weight"].detach()
         X0_i = ws["X0_i"]
+        # propagation: layer k has a WIDE side (distinct per graph) and a NARROW side (shared, 64 wide); the two
+        # launches of a layer are independent and run on two streams
+        O = ws["O"]
+        Ou, Oi = O[:U], O[U:]
+        prev_u = [(Eu, D)]       # layers seen by user rows, in order
+        prev_i = [(X0_i, Fw)]    # layers seen by item rows
+        inv = 1.0 / (L + 1)
+        side = ops.fork_side()   # narrow layer 1 (A_iu @ E_u) does not depend on the projections
         # layer 0, item side: [E_i | P_v | P_a | P_t]   (projections write straight into the slab)
         ops.copy_2d(Ei, X0_i, I, D)
         for j, m in enumerate(self.mods):
@@ -254,21 +263,18 @@ class EliMRec(BasicModel):
                 ops.linear_tf32_fwd(self._feat_tc(m), Wr, bm, X0_i, col=D * (j + 1))
             else:
                 ops.gemm(I, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, c_off=D * (j + 1), tag="proj_fwd")
-        # propagation: layer k has a WIDE side (distinct per graph) and a NARROW side (shared, 64 wide)
-        O = ws["O"]
-        Ou, Oi = O[:U], O[U:]
-        prev_u = [(Eu, D)]       # layers seen by user rows, in order
-        prev_i = [(X0_i, Fw)]    # layers seen by item rows
         wide_in, narrow_in = X0_i, Eu
-        inv = 1.0 / (L + 1)
         for k in range(1, L + 1):
             users_wide = (k % 2 == 1)
             half_w, half_n = (g.ui, g.iu) if users_wide else (g.iu, g.ui)
             last = (k == L)
+            if k > 1:
+                side = ops.fork_side()
             if not last:
                 Yw, Yn = ws["XW"][k], ws["XN"][k]
+                with torch.cuda.stream(side):
+                    ops.spmm(half_n, narrow_in, Yn, D)
                 ops.spmm(half_w, wide_in, Yw, Fw)
-                ops.spmm(half_n, narrow_in, Yn, D)
                 if users_wide:
                     prev_u.append((Yw, Fw)); prev_i.append((Yn, D))
                 else:
@@ -277,8 +283,13 @@ class EliMRec(BasicModel):
             else:
                 out_w, out_n = (Ou, Oi) if users_wide else (Oi, Ou)
                 pw, pn = (prev_u, prev_i) if users_wide else (prev_i, prev_u)
+                if L == 1:
+                    ops.join_side(side)      # the narrow epilogue reads layer 0 of its side (X0_i when L is odd)
+                    side = ops.fork_side()
+                with torch.cuda.stream(side):
+                    ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv))
                 ops.spmm(half_w, wide_in, None, Fw, ops.mean_epilogue(pw, out_w, Fw, inv))
-                ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv))
+            ops.join_side(side)
         # fusion Linear (concat) and single-modal heads over all rows
         F_all = ws["F_all"]
         Wu, bu = P["embedding_user_after_GCN.weight"].detach(), P["embedding_user_after_GCN.bias"].detach()
@@ -325,25 +336,12 @@ class EliMRec(BasicModel):
             gscale = gscale.reshape(1)
         ops.gather_rows(rows, O, Oin, Fw)
         Wu, Wi = P["embedding_user_after_GCN.weight"].detach(), P["embedding_item_after_GCN.weight"].detach()
-        # d O[inst] = dF[inst] @ W_{u|i} + [0 | dS_v @ Ws_v | ...]
-        ops.gemm(B, Fw, D, ig, ld, 1, Wu, Fw, 1, dOin, Fw, 1, scale=gscale)
-        ops.gemm(2 * B, Fw, D, ig, ld, 1, Wi, Fw, 1, dOin, Fw, 1, scale=gscale, a_off=B * ld, c_off=B * Fw)
-        for j, m in enumerate(self.mods):
-            Ws = P[f"s_dense_{m}.weight"].detach()
-            ops.gemm(3 * B, D, D, ig, ld, 1, Ws, D, 1, dOin, Fw, 1, accumulate=True, scale=gscale,
-                     a_off=D * (j + 1), c_off=D * (j + 1))
-        # weight gradients of the fusion Linear and the heads:  dW[n, c] = sum_r dY[r, n] * O[inst r, c]
-        ops.gemm(Fw, D, B, Oin, 1, Fw, ig, ld, 1, gr["embedding_user_after_GCN.weight"], 1, Fw, split_k=sk, ws=gws,
-                 scale=gscale)
-        ops.gemm(Fw, D, 2 * B, Oin, 1, Fw, ig, ld, 1, gr["embedding_item_after_GCN.weight"], 1, Fw, split_k=sk, ws=gws,
-                 scale=gscale, a_off=B * Fw, b_off=B * ld)
-        ops.colsum(B, D, ig, ld, gr["embedding_user_after_GCN.bias"], cws, scale=gscale)
-        ops.colsum(2 * B, D, ig, ld, gr["embedding_item_after_GCN.bias"], cws, scale=gscale, a_off=B * ld)
-        for j, m in enumerate(self.mods):
-            c0 = D * (j + 1)
-            ops.gemm(D, D, 3 * B, Oin, 1, Fw, ig, ld, 1, gr[f"s_dense_{m}.weight"], 1, D, split_k=sk, ws=gws, scale=gscale,
-                     a_off=c0, b_off=c0)
-            ops.colsum(3 * B, D, ig, ld, gr[f"s_dense_{m}.bias"], cws, scale=gscale, a_off=c0)
+        # fusion Linear + heads, backward on the instance rows: dO[inst], all weight and bias gradients (3 launches)
+        ops.inst_backward(B, nt, Fw, ig, Oin, gscale, Wu, Wi, [P[f"s_dense_{m}.weight"].detach() for m in self.mods], dOin,
+                          gr["embedding_user_after_GCN.weight"], gr["embedding_item_after_GCN.weight"],
+                          gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
+                          [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods],
+                          ws["inst_ws"])
         # layer-mean gradient G = dO / (L+1), row-sparse; it enters every layer of the chain
         inv = 1.0 / (L + 1)
         lo = {"u": (0, U, 0), "i": (U, N, U)}
@@ -365,10 +363,13 @@ class EliMRec(BasicModel):
             o = "i" if s == "u" else "u"
             half_o, half_s = (g.iu, g.ui) if s == "u" else (g.ui, g.iu)
             nW, nN = ws["dW"][flip][:nrows[o]], ws["dN"][flip][:nrows[s]]
+            side = ops.fork_side()
+            with torch.cuda.stream(side):
+                ops.spmm(half_s, dNc, nN, D)  # d x_{k-1}[s, narrow] = A[s,o] @ d x_k[o, narrow]
+                add_G(nN, s, False)
             ops.spmm(half_o, dWc, nW, Fw)     # d x_{k-1}[o, wide]   = A[o,s] @ d x_k[s, wide]
-            ops.spmm(half_s, dNc, nN, D)      # d x_{k-1}[s, narrow] = A[s,o] @ d x_k[o, narrow]
             add_G(nW, o, True)
-            add_G(nN, s, False)
+            ops.join_side(side)
             dWc, dNc, flip = nW, nN, flip ^ 1
         # now dWc = d x_0[item rows, wide] = [dE_i | dP_v | dP_a | dP_t], dNc = d x_0[user rows] = dE_u
         grads = {"embedding_user.weight": dNc, "embedding_item.weight": dWc[:, :D]}

@@ -15,6 +15,33 @@ from ._lib import MeanEpilogue, RankTables, call, ptr, stream
 
 F32 = torch.float32
 
+# ---- two-stream fork/join: a layer's WIDE and NARROW SpMM are independent and run concurrently (the narrow one is
+# latency-bound and hides under the bandwidth-bound wide one); under CUDA-graph capture these become parallel branches.
+_SIDE = {}
+
+
+def fork_side():
+    cur = torch.cuda.current_stream()
+    if _lib.PROFILE["on"]:      # per-kernel event timing needs the launches serialised
+        return cur
+    key = (cur.device.index, cur.cuda_stream)
+    side = _SIDE.get(key)
+    if side is None:
+        side = _SIDE[key] = torch.cuda.Stream(device=cur.device)
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    side.wait_event(ev)
+    return side
+
+
+def join_side(side):
+    if side == torch.cuda.current_stream():
+        return
+    ev = torch.cuda.Event()
+    ev.record(side)
+    torch.cuda.current_stream().wait_event(ev)
+
+
 
 def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None):
     """Y[rows of half] = A_half @ X  (+ optional fused layer-mean epilogue)."""
@@ -103,6 +130,32 @@ def bpr(tables, weights, users, pos, neg, num_users, loss_out, inst_rows, inst_g
     call("elimrec_bpr_forward_backward", users.numel(), n, tp, wp, ptr(users, torch.int64), ptr(pos, torch.int64),
          ptr(neg, torch.int64), num_users, ptr(loss_out, F32), ptr(inst_rows, torch.int32), ptr(inst_grad, F32),
          ptr(ws, F32), stream())
+
+
+def inst_backward_ws_floats(B, nt, F):
+    return int(_lib.lib().elimrec_inst_backward_workspace_floats(B, nt, F))
+
+
+def inst_backward(B, nt, F, inst_grad, O_inst, gscale, Wu, Wi, Ws, dO_inst, dWu, dWi, dbu, dbi, dWs, dbs, ws):
+    """Backward of the fusion Linear + heads on the 3B instance rows (3 launches)."""
+    n = nt - 1
+    wsp = (C.c_void_p * max(n, 1))(*[ptr(t, F32) for t in Ws])
+    dwp = (C.c_void_p * max(n, 1))(*[ptr(t, F32) for t in dWs])
+    dbp = (C.c_void_p * max(n, 1))(*[ptr(t, F32) for t in dbs])
+    call("elimrec_inst_backward", B, nt, F, ptr(inst_grad, F32), ptr(O_inst, F32), ptr(gscale, F32, True), ptr(Wu, F32),
+         ptr(Wi, F32), wsp, ptr(dO_inst, F32), ptr(dWu, F32), ptr(dWi, F32), ptr(dbu, F32), ptr(dbi, F32), dwp, dbp,
+         ptr(ws, F32), stream())
+
+
+def adam_apply_multi(items, consts_dev, b1, b2, eps, wd):
+    """items: list of (param, grad_view, exp_avg, exp_avg_sq); one launch for all of them."""
+    arr = (_lib.AdamTensor * len(items))()
+    for k, (p, g, m, v) in enumerate(items):
+        row_len = p.shape[-1]
+        arr[k].param, arr[k].grad, arr[k].exp_avg, arr[k].exp_avg_sq = ptr(p, F32), ptr(g, F32), ptr(m, F32), ptr(v, F32)
+        arr[k].numel, arr[k].row_len = p.numel(), row_len
+        arr[k].grad_ld = g.stride(0) if g.dim() == 2 else row_len
+    call("elimrec_adam_apply_multi", len(items), arr, ptr(consts_dev, torch.float64), b1, b2, eps, wd, stream())
 
 
 def adam_tick(step_dev, consts_dev, lr, b1, b2):

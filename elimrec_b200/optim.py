@@ -34,12 +34,12 @@ class FusedAdam:
         """One Adam step from a {name: gradient view} dict (EliMRec._backward output)."""
         P = self.model._params()
         ops.adam_tick(self.step_dev, self.consts, self.lr, self.betas[0], self.betas[1])
+        items = []
         for name, g in grads.items():
             p = P[name]
             m, v = self._st(name, p)
-            row_len = p.shape[-1]
-            g_ld = g.stride(0) if g.dim() == 2 else row_len
-            ops.adam_apply(p.data, g, row_len, g_ld, m, v, self.consts, self.betas[0], self.betas[1], self.eps, self.wd)
+            items.append((p.data, g, m, v))
+        ops.adam_apply_multi(items, self.consts, self.betas[0], self.betas[1], self.eps, self.wd)
 
     # torch.optim-like surface for the autograd path
     def zero_grad(self, set_to_none=True):

@@ -37,9 +37,10 @@ int elimrec_abi_version(void);
  * The normalised adjacency is kept as two CSR halves (user rows -> item cols, item rows -> user cols)
  * in "segment" form built once on the host (elimrec_b200/graph.py): seg[s] = {row, edge_begin,
  * edge_end, heavy_id}.  Rows longer than the segment length are split; their segments come first in
- * the list, write partial sums to `partial[s]` and the last-arriving segment reduces them in a fixed
- * order (deterministic).  heavy[h] = {first_segment, n_segments}; `counter[h]` must be zero on
- * entry and is left zero.
+ * the list, padded per row to a multiple of 8 (one CTA = 8 segments of ONE row), each CTA reduces its 8
+ * warps in shared memory and writes one partial to `partial[cta]`; the last-arriving CTA of the row adds
+ * them in a fixed order (deterministic).  heavy[h] = {first_cta, n_ctas}; `counter[h]` must be zero
+ * on entry and is left zero.  `partial` holds (n_heavy_segments / 8) * width floats.
  *
  * Y[row, 0:width] = sum_e val[e] * X[col[e], 0:width]           width in {64, 128, 256}
  *
@@ -127,6 +128,17 @@ int elimrec_bpr_forward_backward(int B, int n_tables, const float* const* tables
                                  float* loss_out, int32_t* inst_rows, float* inst_grad, float* workspace,
                                  elimrec_stream_t stream);
 
+/* Backward of embedding_{user,item}_after_GCN and s_dense_* (models/EliMRec.py:261-270,146-151) restricted to
+ * the 3B instance rows, where alone their gradient is non-zero:
+ *   dO_inst [3B x F]   = g * (dF @ W_{u|i} + per-block dS_m @ Ws_m)        (rows < B use Wu, the rest Wi)
+ *   dWu/dWi [64 x F], dbu/dbi [64], dWs[m] [64 x 64], dbs[m] [64]             (deterministic chunked reduction)
+ * O_inst [3B x F] = rows of the layer-mean slab gathered at inst_rows; F = 64 * n_tables. */
+int64_t elimrec_inst_backward_workspace_floats(int B, int n_tables, int F);
+int elimrec_inst_backward(int B, int n_tables, int F, const float* inst_grad, const float* O_inst,
+                          const float* gscale_dev /* may be NULL */, const float* Wu, const float* Wi,
+                          const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu, float* dbi,
+                          float* const* dWs_host, float* const* dbs_host, float* workspace, elimrec_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * adam - replaces torch.optim.Adam(lr, weight_decay) .step() (main.py:49,101): coupled L2,
  * betas (0.9, 0.999), eps 1e-8, bias correction from the device-resident step counter.
@@ -135,6 +147,17 @@ int elimrec_bpr_forward_backward(int B, int n_tables, const float* const* tables
  * ------------------------------------------------------------------------------------------------ */
 int elimrec_adam_tick(int64_t* step_dev, double* consts_dev, double lr, double beta1, double beta2,
                       elimrec_stream_t stream);
+#define ELIMREC_ADAM_MAX_TENSORS 24
+typedef struct {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t numel, row_len, grad_ld;
+} elimrec_adam_tensor_t;
+/* all parameter tensors in ONE launch (torch's _multi_tensor_adam); descriptors are host memory, copied by value */
+int elimrec_adam_apply_multi(int n_tensors, const elimrec_adam_tensor_t* tensors_host, const double* consts_dev,
+                             double beta1, double beta2, float eps, float weight_decay, elimrec_stream_t stream);
 int elimrec_adam_apply(int64_t n, float* param, const float* grad, int64_t row_len, int64_t grad_ld, float* exp_avg,
                        float* exp_avg_sq, const double* consts_dev, double beta1, double beta2, float eps,
                        float weight_decay, elimrec_stream_t stream);

@@ -327,3 +327,62 @@ def test_linear_tf32_wgrad_tcgen05(dev, M, K, lddy):
     dW2 = torch.empty_like(dW)
     ops.linear_tf32_wgrad(dYfull, X, dW2, ws, col=col)
     assert torch.equal(dW, dW2)
+
+
+@pytest.mark.parametrize("B,nt", [(100, 4), (2048, 4), (333, 2)])
+def test_inst_backward_fused(dev, B, nt):
+    """Fused backward of the fusion Linear + heads on the 3B instance rows vs torch autograd (fp64)."""
+    from elimrec_b200 import ops
+    F = 64 * nt
+    g = torch.Generator().manual_seed(B + nt)
+    ig = torch.randn(3 * B, F, generator=g, dtype=torch.float64) * 0.01
+    Oin = torch.randn(3 * B, F, generator=g, dtype=torch.float64)
+    Wu = torch.randn(64, F, generator=g, dtype=torch.float64)
+    Wi = torch.randn(64, F, generator=g, dtype=torch.float64)
+    Ws = [torch.randn(64, 64, generator=g, dtype=torch.float64) for _ in range(nt - 1)]
+    gs = torch.tensor([0.7], dtype=torch.float64)
+    # reference: Y_f = O W^T + b, Y_m = O[:, blk] Ws^T + b; given dY, dO = dY W etc.
+    dF, dS = ig[:, :64], [ig[:, 64 * (m + 1):64 * (m + 2)] for m in range(nt - 1)]
+    dO = torch.cat([dF[:B] @ Wu, dF[B:] @ Wi])
+    for m in range(nt - 1):
+        dO[:, 64 * (m + 1):64 * (m + 2)] += dS[m] @ Ws[m]
+    dO *= gs
+    want = dict(dWu=gs * dF[:B].t() @ Oin[:B], dWi=gs * dF[B:].t() @ Oin[B:], dbu=gs * dF[:B].sum(0), dbi=gs * dF[B:].sum(0))
+    f = lambda t: t.float().to(dev).contiguous()
+    out = dict(dO=torch.empty(3 * B, F, device=dev), dWu=torch.empty(64, F, device=dev), dWi=torch.empty(64, F, device=dev),
+               dbu=torch.empty(64, device=dev), dbi=torch.empty(64, device=dev))
+    dWs = [torch.empty(64, 64, device=dev) for _ in range(nt - 1)]
+    dbs = [torch.empty(64, device=dev) for _ in range(nt - 1)]
+    ws = torch.empty(ops.inst_backward_ws_floats(B, nt, F), device=dev)
+    ops.inst_backward(B, nt, F, f(ig), f(Oin), f(gs), f(Wu), f(Wi), [f(w) for w in Ws], out["dO"], out["dWu"], out["dWi"],
+                      out["dbu"], out["dbi"], dWs, dbs, ws)
+    assert rel_err(out["dO"], dO) < FP32_TOL
+    for k, v in want.items():
+        assert rel_err(out[k], v) < FP32_TOL, k
+    for m in range(nt - 1):
+        blk = slice(64 * (m + 1), 64 * (m + 2))
+        assert rel_err(dWs[m], gs * dS[m].t() @ Oin[:, blk]) < FP32_TOL
+        assert rel_err(dbs[m], gs * dS[m].sum(0)) < FP32_TOL
+
+
+def test_adam_multi_matches_torch(dev):
+    from elimrec_b200 import ops
+    shapes = [(1000, 64), (64, 768), (64,), (3000, 64), (64, 64)]
+    ps = [torch.randn(*s) for s in shapes]
+    refs = [p.clone().to(dev).requires_grad_(True) for p in ps]
+    opt = torch.optim.Adam(refs, lr=1e-3, weight_decay=1e-4)
+    mine = [p.clone().to(dev) for p in ps]
+    st = [(torch.zeros_like(p), torch.zeros_like(p)) for p in mine]
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    consts = torch.zeros(2, dtype=torch.float64, device=dev)
+    for it in range(4):
+        gwide = torch.randn(3000, 256, device=dev) * 0.01
+        grads = [torch.randn(*s, device=dev) * 0.01 for s in shapes]
+        grads[3] = gwide[:, 128:192]                      # strided view
+        for r, g in zip(refs, grads):
+            r.grad = g.contiguous()
+        opt.step()
+        ops.adam_tick(step, consts, 1e-3, 0.9, 0.999)
+        ops.adam_apply_multi([(p, g, m, v) for p, g, (m, v) in zip(mine, grads, st)], consts, 0.9, 0.999, 1e-8, 1e-4)
+    for p, r in zip(mine, refs):
+        assert rel_err(p, r) < 1e-6

@@ -50,11 +50,12 @@ def test_segments_partition_edges(seg_len):
     assert (covered == 1).all()
     assert set(seg[:, 0].tolist()) == set(range(200))           # empty rows still get a (zero) segment
     hs = seg[:n_hseg]
-    assert (hs[:, 3] >= 0).all() and (seg[n_hseg:, 3] == -1).all()
-    for h, (first, n) in enumerate(heavy):
-        assert (seg[first:first + n, 3] == h).all() and len(set(seg[first:first + n, 0])) == 1
+    assert n_hseg % 8 == 0 and (hs[:, 3] >= 0).all() and (seg[n_hseg:, 3] == -1).all()
+    for h, (first_cta, n_cta) in enumerate(heavy):
+        blk = seg[8 * first_cta:8 * (first_cta + n_cta)]
+        assert (blk[:, 3] == h).all() and len(set(blk[:, 0])) == 1   # a CTA of 8 warps never mixes rows
     if heavy.shape[0] > 1:
-        d = [indptr[seg[f, 0] + 1] - indptr[seg[f, 0]] for f, _ in heavy]
+        d = [indptr[seg[8 * f, 0] + 1] - indptr[seg[8 * f, 0]] for f, _ in heavy]
         assert d == sorted(d, reverse=True)
     # row-range restricted lists (multi-GPU shards)
     seg2, _, _ = G.build_segments(indptr, seg_len, 50, 120)
