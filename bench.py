@@ -206,6 +206,7 @@ def main():
     model.make_optimizer()
     if world > 1:
         model.enable_data_parallel()
+    log(f"[bench] rank {rank}/{world}: model ready")
     sampler_dev = PairwiseSamplerV2(ds, batch_size=BATCH, mode="device", device=dev, seed=2022 + rank)
     sampler_host = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat")
     n_steps = args.warmup + args.steps
@@ -238,6 +239,7 @@ def main():
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+    log(f"[bench] rank {rank}: device-resident arm {ms / args.steps:.3f} ms/step")
     launches = _lib.CALLS["launches"] if runner is None else runner.launches_per_step * args.steps
     tms = torch.tensor([ms], device=dev)
     if world > 1:
@@ -271,16 +273,20 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * args.steps / float(te)
+    log(f"[bench] rank {rank}: e2e arm done")
 
     # ---- per-kernel CUDA-event profile + roofline of the wide SpMM -------------------------------
     kernels = {}
     roofline = None
     if rank == 0:
+        # rank-local, serialised launches, NO collective (the other ranks do not take part in this pass)
+        dp_saved, model._dp = getattr(model, "_dp", False), False
         _lib.PROFILE["on"], _lib.PROFILE["events"] = True, []
         for b in batches[args.warmup:args.warmup + min(5, args.steps)]:
             model.train_step(*b)
         torch.cuda.synchronize()
         _lib.PROFILE["on"] = False
+        model._dp = dp_saved
         agg = {}
         for tag, a, b_ in _lib.PROFILE["events"]:
             agg.setdefault(tag, []).append(a.elapsed_time(b_))
@@ -307,6 +313,10 @@ def main():
                         "frac": ach / peak, "traffic": None, "peak_source": which, "bytes_per_launch": alg,
                         "avg_launch_us": 1e6 * avg_s, "share_of_step": sum(agg[tag]) / sum(sum(v) for v in agg.values())}
     clk = clocks.stop() if rank == 0 else None
+    sync_all()
+    if world > 1:   # the profile pass above stepped rank 0 only: put every replica back on the same weights
+        for prm in model.parameters():
+            dist.broadcast(prm.data, src=0)
 
     # ---- evaluation: full-ranking users/s ----------------------------------------------------------
     ev = None

@@ -103,10 +103,8 @@ class UniEvaluator(AbstractEvaluator):
         n_all = users.numel()
         if world_size is None and torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world_size = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        lo, hi = 0, n_all
-        if world_size and world_size > 1:
-            per = (n_all + world_size - 1) // world_size
-            lo, hi = min(n_all, rank * per), min(n_all, (rank + 1) * per)
+        from .dist import shard_range
+        lo, hi = shard_range(n_all, rank or 0, world_size or 1)
         n = hi - lo
         ncol = self.metrics_num * K
         sums = torch.zeros(ncol, dtype=torch.float64, device=dev)

@@ -436,22 +436,13 @@ class EliMRec(BasicModel):
 
     def _allreduce_grads(self, grads):
         """One flat bucket (embedding tables + every small gradient), one all-reduce(AVG)."""
-        import torch.distributed as dist
+        from .dist import GradBucket
         ws = self._ws
         if "bucket" not in ws:
             P = self._params()
-            names = [n for n in self._param_names if n in grads]
-            sizes = [P[n].numel() for n in names]
-            flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.device_)
-            views, o = {}, 0
-            for n, sz in zip(names, sizes):
-                views[n] = flat[o:o + sz].view(P[n].shape)
-                o += sz
-            ws["bucket"], ws["bucket_views"] = flat, views
-        for n, v in ws["bucket_views"].items():
-            v.copy_(grads[n])
-        dist.all_reduce(ws["bucket"], op=dist.ReduceOp.AVG)
-        return ws["bucket_views"]
+            ws["bucket"] = GradBucket({n: tuple(P[n].shape) for n in self._param_names if n in grads}, self.device_)
+        ws["bucket"].pack(grads)
+        return ws["bucket"].all_reduce_mean()
 
     # -- whole step as one CUDA graph (launch-bound otherwise: ~60 small launches per step) ------------
     def make_graphed_step(self, batch_size=None):

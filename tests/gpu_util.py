@@ -18,7 +18,8 @@ def build_model(ds, params=None, dataset_name="synthg", **cfg):
     from elimrec_b200.data import Config
     from elimrec_b200.model import EliMRec
     cfg.setdefault("proj_precision", "fp32")   # exact path unless a test asks for the tensor-core projections
-    conf = Config(**{"data.input.dataset": dataset_name, "topks": [20], "device": torch.device("cuda:0"), **cfg})
+    cfg.setdefault("device", torch.device("cuda:0"))
+    conf = Config(**{"data.input.dataset": dataset_name, "topks": [20], **cfg})
     model = EliMRec(conf, ds).to(conf.device)
     if params is not None:
         sd = {k: torch.as_tensor(v) for k, v in params.items()}
