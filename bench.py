@@ -164,6 +164,15 @@ def cpu_port_run(ds, name, steps, warmup, budget_s, eval_users=256):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: route everything else a library may print there (e.g. NCCL's version
+    # banner) to stderr by pointing fd 1 at stderr and keeping a private handle on the real stdout
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(line):
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,7 +194,7 @@ def main():
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "eval": {"value": r["eval_users_per_s"], "unit": "users/s", "n_users": r["eval_users"]},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     import torch
@@ -362,7 +371,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "eval": ev,
                 "kernels": kernels, "final_loss": final_loss}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
