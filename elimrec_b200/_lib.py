@@ -37,7 +37,7 @@ class RankTables(C.Structure):
 
 
 _SIGS = {
-    "elimrec_spmm": [i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
+    "elimrec_spmm": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
     "elimrec_scatter_add_rows": [i32, vp, i32, i32, i32, vp, i64, i32, vp, i64, i32, f32, vp],
     "elimrec_gather_rows": [i32, vp, vp, i64, vp, i64, i32, vp],
     "elimrec_broadcast_cols": [i64, vp, i64, vp, i64, i32, vp],

@@ -24,16 +24,19 @@ struct MeanEpi {
     float scale;
 };
 
-template <int F>
-__global__ void __launch_bounds__(256)
-spmm_seg_kernel(int n_seg, const int4* __restrict__ seg, const int2* __restrict__ heavy, int* __restrict__ counter,
+// HEAVY = false: segments [seg_base, n_seg) are whole rows (lean path, tuned for FULL occupancy: 32 registers, 64 warps/SM -
+// the gather is latency-bound until ~11 TB/s of L2->SM traffic, measured: 2 fetches in flight x 64 warps beats 8 x 16).
+// HEAVY = true : segments [0, n_heavy_seg) belong to split rows, one CTA = 8 segments of one row.
+template <int F, bool MEAN, bool HEAVY, int UNR_, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int2* __restrict__ heavy, int* __restrict__ counter,
                 const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
                 long long ldx, float* __restrict__ Y, long long ldy, float* __restrict__ partial, MeanEpi epi) {
     constexpr int EPW = (F == 64) ? 2 : 1;          // edges per warp-iteration
     constexpr int NV = (F >= 128) ? F / 128 : 1;    // float4 per lane
-    constexpr int UNR = (F == 256) ? 4 : 8;         // row fetches in flight per lane
+    constexpr int UNR = UNR_;                       // row fetches in flight per lane
     const unsigned full = 0xffffffffu;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = seg_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (warp >= n_seg) return;
     const int4 sg = __ldg(seg + warp);
@@ -80,7 +83,7 @@ spmm_seg_kernel(int n_seg, const int4* __restrict__ seg, const int2* __restrict_
         acc[0].w += __shfl_xor_sync(full, acc[0].w, 16);
     }
 
-    if (sg.w >= 0) {
+    if (HEAVY) {
         // Split row.  Its segment count is padded to a multiple of 8 on the host, so all 8 warps of this CTA work on
         // the SAME row: reduce them in shared memory first (fixed order), then one partial per CTA goes to scratch and
         // the last-arriving CTA of the row (atomic counter) adds the CTA partials in CTA order.  Deterministic.
@@ -139,7 +142,7 @@ spmm_seg_kernel(int n_seg, const int4* __restrict__ seg, const int2* __restrict_
 #pragma unroll
         for (int i = 0; i < NV; ++i) yp[i * 32] = acc[i];
     }
-    if (epi.out != nullptr) {
+    if (MEAN) {
         // fused torch.mean(torch.stack(layers, 1), 1): ((x0 + x1) + ...) + x_L, then * 1/(L+1)
         if (F == 64) {
             const int c = l * 4;
@@ -222,7 +225,7 @@ __global__ void copy_2d_kernel(long long n_rows, int width4, const float* __rest
 
 }  // namespace
 
-ELIMREC_API int elimrec_spmm(int width, int n_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
+ELIMREC_API int elimrec_spmm(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
                              const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy,
                              float* partial, const elimrec_mean_epilogue_t* epi, elimrec_stream_t stream) {
     ER_CHECK_ARG(width == 64 || width == 128 || width == 256, "width must be 64, 128 or 256");
@@ -246,17 +249,26 @@ ELIMREC_API int elimrec_spmm(int width, int n_seg, const int32_t* seg, const int
         me.width = epi->mean_width;
         me.scale = epi->mean_scale;
     }
-    const int threads = 256;
-    const int blocks = (n_seg + 7) / 8;
     const int4* sg = reinterpret_cast<const int4*>(seg);
     const int2* hv = reinterpret_cast<const int2*>(heavy);
     cudaStream_t st = er_stream(stream);
-    if (width == 64)
-        spmm_seg_kernel<64><<<blocks, threads, 0, st>>>(n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me);
-    else if (width == 128)
-        spmm_seg_kernel<128><<<blocks, threads, 0, st>>>(n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me);
-    else
-        spmm_seg_kernel<256><<<blocks, threads, 0, st>>>(n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me);
+    const bool mean = me.out != nullptr;
+    ER_CHECK_ARG(n_heavy_seg >= 0 && n_heavy_seg % 8 == 0 && n_heavy_seg <= n_seg, "n_heavy_seg must be a multiple of 8");
+    const int hb = n_heavy_seg / 8;                      // CTAs of split rows
+    const int lb = (n_seg - n_heavy_seg + 7) / 8;        // CTAs of whole rows
+#define LAUNCH(F, MEAN)                                                                                                   \
+    do {                                                                                                                  \
+        if (hb > 0 && part != 2)                                                                                          \
+            spmm_seg_kernel<F, MEAN, true, (F == 256 ? 4 : 8), 1><<<hb, 256, 0, st>>>(0, n_heavy_seg, sg, hv, counter, col, \
+                                                                                      val, X, ldx, Y, ldy, partial, me);   \
+        if (lb > 0 && part != 1)                                                                                          \
+            spmm_seg_kernel<F, MEAN, false, 2, (MEAN ? 6 : 8)><<<lb, 256, 0, st>>>(n_heavy_seg, n_seg, sg, hv, counter, col, \
+                                                                                   val, X, ldx, Y, ldy, partial, me);      \
+    } while (0)
+    if (width == 64) { if (mean) LAUNCH(64, true); else LAUNCH(64, false); }
+    else if (width == 128) { if (mean) LAUNCH(128, true); else LAUNCH(128, false); }
+    else { if (mean) LAUNCH(256, true); else LAUNCH(256, false); }
+#undef LAUNCH
     ER_LAUNCH_CHECK();
     return 0;
 }
@@ -303,3 +315,4 @@ ELIMREC_API int elimrec_copy_2d(int64_t n_rows, int width, const float* src, int
     ER_LAUNCH_CHECK();
     return 0;
 }
+

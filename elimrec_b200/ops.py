@@ -20,11 +20,11 @@ F32 = torch.float32
 _SIDE = {}
 
 
-def fork_side():
+def fork_side(slot=0):
     cur = torch.cuda.current_stream()
     if _lib.PROFILE["on"]:      # per-kernel event timing needs the launches serialised
         return cur
-    key = (cur.device.index, cur.cuda_stream)
+    key = (cur.device.index, cur.cuda_stream, slot)
     side = _SIDE.get(key)
     if side is None:
         side = _SIDE[key] = torch.cuda.Stream(device=cur.device)
@@ -44,10 +44,20 @@ def join_side(side):
 
 
 def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None):
-    """Y[rows of half] = A_half @ X  (+ optional fused layer-mean epilogue)."""
-    call("elimrec_spmm", width, half.n_seg, ptr(half.seg), ptr(half.heavy), ptr(half.counter), ptr(half.col),
-         ptr(half.val), ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0),
-         ptr(half.partial), (C.byref(epi) if epi is not None else None), stream(), tag=f"spmm{width}")
+    """Y[rows of half] = A_half @ X  (+ optional fused layer-mean epilogue).  The split (Zipf-head) rows run as their
+    own launch on a side stream, concurrently with the whole rows."""
+    def go(part, launches):
+        call("elimrec_spmm", width, part, half.n_seg, half.n_heavy_seg, ptr(half.seg), ptr(half.heavy), ptr(half.counter),
+             ptr(half.col), ptr(half.val), ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0),
+             ptr(half.partial), (C.byref(epi) if epi is not None else None), stream(), launches=launches, tag=f"spmm{width}")
+    if half.n_heavy_seg == 0 or _lib.PROFILE["on"]:
+        go(0, 2 if half.n_heavy_seg else 1)
+        return
+    side = fork_side(1)
+    with torch.cuda.stream(side):
+        go(1, 1)
+    go(2, 1)
+    join_side(side)
 
 
 def mean_epilogue(prev, out: torch.Tensor, width: int, scale: float) -> MeanEpilogue:

@@ -43,6 +43,8 @@ int elimrec_abi_version(void);
  * on entry and is left zero.  `partial` holds (n_heavy_segments / 8) * width floats.
  *
  * Y[row, 0:width] = sum_e val[e] * X[col[e], 0:width]           width in {64, 128, 256}
+ * Split rows and whole rows are two launches (different register budgets); `part` lets the caller put them on
+ * two streams - they write disjoint rows.
  *
  * Optional fused layer-mean epilogue (models/EliMRec.py:246-247, torch.stack + torch.mean):
  *   if mean_out != NULL this launch is the LAST propagation layer; instead of (or in addition to)
@@ -61,7 +63,8 @@ typedef struct {
     float mean_scale;
 } elimrec_mean_epilogue_t;
 
-int elimrec_spmm(int width, int n_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
+int elimrec_spmm(int width, int part /* 0 = all rows, 1 = split rows only, 2 = whole rows only */, int n_seg,
+                 int n_heavy_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
                  const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y /* may be NULL */,
                  int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi /* may be NULL */,
                  elimrec_stream_t stream);
