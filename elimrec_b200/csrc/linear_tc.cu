@@ -215,6 +215,157 @@ linear_tf32_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward, 3xTF32 ("x3"): fp32-class accuracy on the tensor cores.
+//   A = A_hi + A_lo, W = W_hi + W_lo (each part exactly representable in TF32),  A W^T ~= A_hi W_hi + A_hi W_lo + A_lo W_hi
+// W_hi / W_lo are pre-split in global memory (tiny); the A tile arrives raw by TMA and is split IN SHARED MEMORY by
+// the four epilogue warps (element-wise, so the 128-byte swizzle is untouched: hi overwrites the raw tile, lo goes to a
+// twin buffer at the same offset), fenced to the async proxy, then three MMAs per k-step read it.  Still HBM-bound:
+// per 16 KB A tile the split costs ~300 SM cycles and the 12 MMAs ~200, the TMA stream ~700.
+// ---------------------------------------------------------------------------------------------
+constexpr int X_STAGES = 4;
+constexpr int X_STAGE = 2 * F_A_BYTES + 2 * F_B_BYTES;   // A_hi | A_lo | W_hi | W_lo
+constexpr int X_SMEM = X_STAGES * X_STAGE + 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(192)
+linear_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                     const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ bias, float* __restrict__ Y,
+                     long long ldy, int M, int num_kb) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[X_STAGES];
+    __shared__ __align__(8) uint64_t split_bar[X_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[X_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * F_BM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmBh);
+        tma_prefetch_desc(&tmBl);
+        for (int s = 0; s < X_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&split_bar[s], 128);   // every thread of the 4 split/epilogue warps arrives
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, F_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % X_STAGES;
+                const uint32_t ph = (kb / X_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], F_A_BYTES + 2 * F_B_BYTES);
+                uint8_t* a = smem + s * X_STAGE;
+                tma_load_2d(&tmA, &full_bar[s], a, kb * F_BK, m0);
+                tma_load_2d(&tmBh, &full_bar[s], a + 2 * F_A_BYTES, kb * F_BK, 0);
+                tma_load_2d(&tmBl, &full_bar[s], a + 2 * F_A_BYTES + F_B_BYTES, kb * F_BK, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % X_STAGES;
+                const uint32_t ph = (kb / X_STAGES) & 1;
+                mbar_wait(&split_bar[s], ph);
+                tc_fence_after();
+                const uint32_t ah = smem_u32(smem + s * X_STAGE);
+                const uint32_t al = ah + F_A_BYTES;
+                const uint32_t bh = ah + 2 * F_A_BYTES;
+                const uint32_t bl = bh + F_B_BYTES;
+#pragma unroll
+                for (int k = 0; k < F_BK / 8; ++k) {
+                    const uint64_t dah = umma_desc_sw128(ah + k * 32, 16, 1024);
+                    const uint64_t dal = umma_desc_sw128(al + k * 32, 16, 1024);
+                    const uint64_t dbh = umma_desc_sw128(bh + k * 32, 16, 1024);
+                    const uint64_t dbl = umma_desc_sw128(bl + k * 32, 16, 1024);
+                    umma_tf32(tmem_d, dal, dbh, idesc, (kb | k) != 0);   // small terms first
+                    umma_tf32(tmem_d, dah, dbl, idesc, 1);
+                    umma_tf32(tmem_d, dah, dbh, idesc, 1);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // ---- split phase: raw fp32 tile -> (hi, lo) TF32 pair, in place / twin buffer --------------------------------
+        const int t = threadIdx.x - 64;   // 0..127
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % X_STAGES;
+            const uint32_t ph = (kb / X_STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            float4* hi = reinterpret_cast<float4*>(smem + s * X_STAGE);
+            float4* lo = reinterpret_cast<float4*>(smem + s * X_STAGE + F_A_BYTES);
+#pragma unroll
+            for (int i = 0; i < F_A_BYTES / 16 / 128; ++i) {
+                const int idx = i * 128 + t;
+                const float4 x = hi[idx];
+                float4 h, l;
+                h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+                l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+                hi[idx] = h;
+                lo[idx] = l;
+            }
+            fence_proxy_async();           // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&split_bar[s]);
+        }
+        // ---- epilogue ---------------------------------------------------------------------------------------------
+        const int q = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        float v[64];
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_32x32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        float* st = reinterpret_cast<float*>(smem) + q * (32 * 65);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) st[lane * 65 + j] = v[j] + (bias != nullptr ? __ldg(bias + j) : 0.f);
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+            const int row = m0 + q * 32 + r;
+            if (row < M) {
+                float* y = Y + (long long)row * ldy;
+                y[lane] = st[r * 65 + lane];
+                y[32 + lane] = st[r * 65 + 32 + lane];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, F_TMEM_COLS);
+}
+
+__global__ void split_tf32_kernel(long long n, const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = src[i];
+    const float h = tf32_rna(x);
+    hi[i] = h;
+    lo[i] = tf32_rna(x - h);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -467,3 +618,40 @@ ELIMREC_API int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, in
     return 0;
 }
 
+
+
+ELIMREC_API int elimrec_split_tf32(int64_t n, const float* src, float* hi, float* lo, elimrec_stream_t stream) {
+    if (n <= 0) return 0;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, er_stream(stream)>>>(n, src, hi, lo);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_linear_x3_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, const float* W_hi, const float* W_lo,
+                                      const float* b, float* Y, int64_t ldy, elimrec_stream_t stream) {
+    if (M <= 0) return 0;
+    if (K < 4 || K % 4 != 0 || ldx % 4 != 0 || !aligned16(X) || !aligned16(W_hi) || !aligned16(W_lo) || M > 0x7fffffff) {
+        elimrec_set_error("elimrec_linear_x3_fwd: unsupported shape/alignment (K=%lld ldx=%lld)", (long long)K, (long long)ldx);
+        return -2;
+    }
+    CUtensorMap tmA, tmBh, tmBl;
+    if (make_map(&tmA, X, M, K, ldx, F_BM) != 0 || make_map(&tmBh, W_hi, 64, K, K, F_BN) != 0 ||
+        make_map(&tmBl, W_lo, 64, K, K, F_BN) != 0) {
+        elimrec_set_error("elimrec_linear_x3_fwd: cuTensorMapEncodeTiled failed");
+        return -3;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(linear_x3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM);
+        if (e != cudaSuccess) {
+            elimrec_set_error("elimrec_linear_x3_fwd: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            return -3;
+        }
+        configured = true;
+    }
+    const int num_kb = (int)((K + F_BK - 1) / F_BK);
+    const unsigned grid = (unsigned)((M + F_BM - 1) / F_BM);
+    linear_x3_fwd_kernel<<<grid, 192, X_SMEM, er_stream(stream)>>>(tmA, tmBh, tmBl, b, Y, ldy, (int)M, num_kb);
+    ER_LAUNCH_CHECK();
+    return 0;
+}

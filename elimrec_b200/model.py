@@ -120,6 +120,10 @@ class EliMRec(BasicModel):
         self.proj_precision = _cfg(cfg, "proj_precision", "tf32")
         if self.proj_precision not in ("tf32", "fp32"):
             raise ElimrecError("proj_precision must be 'tf32' or 'fp32'")
+        # fusion Linear + single-modal heads: 'x3' = 3xTF32 on the tensor cores (fp32-class accuracy), 'fp32' = FFMA
+        self.fuse_precision = _cfg(cfg, "fuse_precision", "x3")
+        if self.fuse_precision not in ("x3", "fp32"):
+            raise ElimrecError("fuse_precision must be 'x3' or 'fp32'")
         self.kwai = cfg["data.input.dataset"] == "kwai"
         self.mods = "v" if self.kwai else "vat"
         dev = _cfg(cfg, "device", None)
@@ -226,6 +230,9 @@ class EliMRec(BasicModel):
         ws["gemm_ws"] = e(need)
         ws["W_tf32"] = {m: e(D, self._feat[m].shape[1]) for m in self.mods}
         ws["inst_ws"] = e(ops.inst_backward_ws_floats(B, nt, Fw))
+        ws["W_split"] = {"u": (e(D, Fw), e(D, Fw)), "i": (e(D, Fw), e(D, Fw))}
+        for m in self.mods:
+            ws["W_split"][m] = (e(D, D), e(D, D))
         ws["wgrad_ws"] = e(max(1, max(ops.linear_tf32_wgrad_ws_floats(I, self._feat[m].shape[1]) for m in self.mods)))
         ws["colsum_ws"] = e(max(ops.colsum_ws_floats(I, D), ops.colsum_ws_floats(3 * B, D)))
         self._ws = ws
@@ -294,11 +301,22 @@ class EliMRec(BasicModel):
         F_all = ws["F_all"]
         Wu, bu = P["embedding_user_after_GCN.weight"].detach(), P["embedding_user_after_GCN.bias"].detach()
         Wi, bi = P["embedding_item_after_GCN.weight"].detach(), P["embedding_item_after_GCN.bias"].detach()
-        ops.gemm(U, D, Fw, O, Fw, 1, Wu, 1, Fw, F_all, D, 1, bias=bu, tag="fuse_fwd")
-        ops.gemm(I, D, Fw, O, Fw, 1, Wi, 1, Fw, F_all, D, 1, bias=bi, a_off=U * Fw, c_off=U * D, tag="fuse_fwd")
-        for j, m in enumerate(self.mods):
-            Ws, bs = P[f"s_dense_{m}.weight"].detach(), P[f"s_dense_{m}.bias"].detach()
-            ops.gemm(U + I, D, D, O, Fw, 1, Ws, 1, D, ws["S"][j], D, 1, bias=bs, a_off=D * (j + 1), tag="head_fwd")
+        if self.fuse_precision == "x3":
+            sp = ws["W_split"]
+            ops.split_tf32(Wu, *sp["u"])
+            ops.split_tf32(Wi, *sp["i"])
+            ops.linear_x3_fwd(O[:U], sp["u"][0], sp["u"][1], bu, F_all[:U], tag="fuse_fwd_x3")
+            ops.linear_x3_fwd(O[U:], sp["i"][0], sp["i"][1], bi, F_all[U:], tag="fuse_fwd_x3")
+            for j, m in enumerate(self.mods):
+                Ws, bs = P[f"s_dense_{m}.weight"].detach(), P[f"s_dense_{m}.bias"].detach()
+                ops.split_tf32(Ws, *sp[m])
+                ops.linear_x3_fwd(O[:, D * (j + 1):D * (j + 2)], sp[m][0], sp[m][1], bs, ws["S"][j], tag="head_fwd_x3")
+        else:
+            ops.gemm(U, D, Fw, O, Fw, 1, Wu, 1, Fw, F_all, D, 1, bias=bu, tag="fuse_fwd")
+            ops.gemm(I, D, Fw, O, Fw, 1, Wi, 1, Fw, F_all, D, 1, bias=bi, a_off=U * Fw, c_off=U * D, tag="fuse_fwd")
+            for j, m in enumerate(self.mods):
+                Ws, bs = P[f"s_dense_{m}.weight"].detach(), P[f"s_dense_{m}.bias"].detach()
+                ops.gemm(U + I, D, D, O, Fw, 1, Ws, 1, D, ws["S"][j], D, 1, bias=bs, a_off=D * (j + 1), tag="head_fwd")
         # cached tables (what predict() reads later, EliMRec.py:98-99,109)
         self.all_users, self.all_items = F_all[:U], F_all[U:]
         self.all_s_embs = {}

@@ -109,6 +109,17 @@ def linear_tf32_fwd(X, W, b, Y, col=0, tag="proj_fwd_tc"):
          ptr(Y, F32) + 4 * col, Y.stride(0), stream(), tag=tag)
 
 
+def split_tf32(src, hi, lo):
+    call("elimrec_split_tf32", src.numel(), ptr(src, F32), ptr(hi, F32), ptr(lo, F32), stream())
+
+
+def linear_x3_fwd(X, W_hi, W_lo, b, Y, col=0, tag="linear_x3"):
+    """Y[:, col:col+64] = X @ W^T + b with 3xTF32 on tcgen05 (fp32-class accuracy); X may be a strided column block."""
+    M, K = X.shape
+    call("elimrec_linear_x3_fwd", M, K, ptr(X, F32), X.stride(0), ptr(W_hi, F32), ptr(W_lo, F32), ptr(b, F32, True),
+         ptr(Y, F32) + 4 * col, Y.stride(0), stream(), tag=tag)
+
+
 def round_tf32(src, dst):
     call("elimrec_round_tf32", src.numel(), ptr(src, F32), ptr(dst, F32), stream())
 

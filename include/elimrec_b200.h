@@ -111,6 +111,12 @@ int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, c
 int elimrec_linear_tf32_wgrad(int64_t M, int64_t K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
                               float* dW, float* workspace, elimrec_stream_t stream);
 int64_t elimrec_linear_tf32_wgrad_workspace_floats(int64_t M, int64_t K);
+/* 3xTF32 forward: same contract as elimrec_linear_tf32_fwd but fp32-class accuracy (error ~1e-6 relative):
+ * X is split into TF32 hi/lo parts inside the kernel, W_hi / W_lo come pre-split from elimrec_split_tf32, and
+ * X W^T = X_hi W_hi + X_hi W_lo + X_lo W_hi is accumulated in TMEM.  Used for the fusion Linear and the heads. */
+int elimrec_linear_x3_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, const float* W_hi, const float* W_lo,
+                          const float* b, float* Y, int64_t ldy, elimrec_stream_t stream);
+int elimrec_split_tf32(int64_t n, const float* src, float* hi, float* lo, elimrec_stream_t stream);
 /* dst[i] = round-to-nearest TF32 of src[i] (tcgen05.mma kind::tf32 truncates its inputs; pre-rounding the constant
  * features once and the weights per step removes the truncation bias).  src == dst allowed. */
 int elimrec_round_tf32(int64_t n, const float* src, float* dst, elimrec_stream_t stream);

@@ -386,3 +386,22 @@ def test_adam_multi_matches_torch(dev):
         ops.adam_apply_multi([(p, g, m, v) for p, g, (m, v) in zip(mine, grads, st)], consts, 0.9, 0.999, 1e-8, 1e-4)
     for p, r in zip(mine, refs):
         assert rel_err(p, r) < 1e-6
+
+
+@pytest.mark.parametrize("M,K,ldx_extra", [(1000, 256, 0), (112741 // 4, 64, 192), (333, 100, 0), (130, 768, 0), (128, 32, 0)])
+def test_linear_x3_fwd_fp32_class(dev, M, K, ldx_extra):
+    """3xTF32 tcgen05 linear: must sit in the fp32 tolerance class (1e-5), not the TF32 one."""
+    from elimrec_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    Xfull = torch.randn(M, K + ldx_extra, generator=g).to(dev)
+    X = Xfull[:, ldx_extra:] if ldx_extra else Xfull
+    W = (torch.randn(64, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(64, generator=g).to(dev)
+    Wh, Wl = torch.empty_like(W), torch.empty_like(W)
+    ops.split_tf32(W, Wh, Wl)
+    assert float((W - (Wh + Wl)).abs().max()) < 1e-6 * float(W.abs().max())
+    Y = torch.full((M + 1, 64), 7.0, device=dev)
+    ops.linear_x3_fwd(X, Wh, Wl, b, Y[:M])
+    ref = X.double() @ W.double().t() + b.double()
+    assert rel_err(Y[:M], ref) < FP32_TOL
+    assert float((Y[M] - 7).abs().max()) == 0
