@@ -31,6 +31,10 @@ class AdamTensor(C.Structure):
                 ("grad_ld", i64)]
 
 
+class PrepTensor(C.Structure):
+    _fields_ = [("src", vp), ("hi", vp), ("lo", vp), ("numel", i64)]
+
+
 class RankTables(C.Structure):
     _fields_ = [("num_users", i32), ("num_items", i32), ("n_mod", i32), ("mode", i32), ("f_user", vp),
                 ("f_item", vp), ("s_user", vp * MAX_MODS), ("s_item", vp * MAX_MODS)]
@@ -48,6 +52,8 @@ _SIGS = {
     "elimrec_linear_tf32_wgrad": [i64, i64, vp, i64, vp, i64, vp, vp, vp],
     "elimrec_round_tf32": [i64, vp, vp, vp],
     "elimrec_split_tf32": [i64, vp, vp, vp, vp],
+    "elimrec_prep_weights_tf32": [i32, C.POINTER(PrepTensor), vp],
+    "elimrec_fuse_heads_x3": [i64, i32, vp, i64, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(vp), vp],
     "elimrec_linear_x3_fwd": [i64, i64, vp, i64, vp, vp, vp, vp, i64, vp],
     "elimrec_bpr_forward_backward": [i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "elimrec_inst_backward": [i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, vp, C.POINTER(vp),

@@ -356,6 +356,167 @@ linear_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 1) tmem_dealloc(tmem_d, F_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused consumer of the layer-mean slab O [rows x 64(1+M)]  (3xTF32, one pass over O):
+//   F[r]   = O[r, :]            @ Wf^T   + bf          (embedding_{user|item}_after_GCN, models/EliMRec.py:261-270)
+//   S_m[r] = O[r, 64(m+1)..+64] @ Ws_m^T + bs_m        (s_dense_m, models/EliMRec.py:146-151)
+// k-block kb covers O columns [32 kb, 32 kb + 32): it always feeds the fusion accumulator and, for kb >= 2, the head of
+// graph block kb/2.  (1+M) accumulators of 64 columns live in TMEM; each A tile is split hi/lo in shared memory once and
+// used by up to 6 MMAs per k-step.
+// ---------------------------------------------------------------------------------------------
+constexpr int H_STAGES = 3;
+constexpr int H_STAGE = 2 * F_A_BYTES + 4 * F_B_BYTES;   // A_hi | A_lo | Wf_hi | Wf_lo | Ws_hi | Ws_lo
+constexpr int H_SMEM = H_STAGES * H_STAGE + 1024;
+
+struct HeadMaps {
+    CUtensorMap hi[ELIMREC_MAX_MODS];
+    CUtensorMap lo[ELIMREC_MAX_MODS];
+};
+struct HeadOut {
+    const float* bias[1 + ELIMREC_MAX_MODS];
+    float* out[1 + ELIMREC_MAX_MODS];      // each [rows x 64], row stride 64
+};
+
+__global__ void __launch_bounds__(192)
+fuse_heads_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmFh,
+                     const __grid_constant__ CUtensorMap tmFl, const __grid_constant__ HeadMaps hm, HeadOut ho, int M_rows,
+                     int n_heads) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[H_STAGES];
+    __shared__ __align__(8) uint64_t split_bar[H_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[H_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * F_BM;
+    const int num_kb = 2 * (1 + n_heads);
+    const uint32_t tmem_cols = (n_heads >= 2) ? 256u : 128u;   // power of two >= 64 (1 + n_heads)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmFh);
+        tma_prefetch_desc(&tmFl);
+        for (int s = 0; s < H_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&split_bar[s], 128);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % H_STAGES;
+                const uint32_t ph = (kb / H_STAGES) & 1;
+                const int head = kb / 2 - 1;   // -1: identity block, no head
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], F_A_BYTES + 2 * F_B_BYTES + (head >= 0 ? 2 * F_B_BYTES : 0));
+                uint8_t* a = smem + s * H_STAGE;
+                uint8_t* b = a + 2 * F_A_BYTES;
+                tma_load_2d(&tmA, &full_bar[s], a, kb * F_BK, m0);
+                tma_load_2d(&tmFh, &full_bar[s], b, kb * F_BK, 0);
+                tma_load_2d(&tmFl, &full_bar[s], b + F_B_BYTES, kb * F_BK, 0);
+                if (head >= 0) {
+                    tma_load_2d(&hm.hi[head], &full_bar[s], b + 2 * F_B_BYTES, (kb & 1) * F_BK, 0);
+                    tma_load_2d(&hm.lo[head], &full_bar[s], b + 3 * F_B_BYTES, (kb & 1) * F_BK, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % H_STAGES;
+                const uint32_t ph = (kb / H_STAGES) & 1;
+                const int head = kb / 2 - 1;
+                mbar_wait(&split_bar[s], ph);
+                tc_fence_after();
+                const uint32_t ah = smem_u32(smem + s * H_STAGE);
+                const uint32_t al = ah + F_A_BYTES;
+                const uint32_t fh = ah + 2 * F_A_BYTES, fl = fh + F_B_BYTES, sh = fl + F_B_BYTES, sl = sh + F_B_BYTES;
+#pragma unroll
+                for (int k = 0; k < F_BK / 8; ++k) {
+                    const uint64_t dah = umma_desc_sw128(ah + k * 32, 16, 1024);
+                    const uint64_t dal = umma_desc_sw128(al + k * 32, 16, 1024);
+                    const uint64_t dfh = umma_desc_sw128(fh + k * 32, 16, 1024);
+                    const uint64_t dfl = umma_desc_sw128(fl + k * 32, 16, 1024);
+                    umma_tf32(tmem_d, dal, dfh, idesc, (kb | k) != 0);
+                    umma_tf32(tmem_d, dah, dfl, idesc, 1);
+                    umma_tf32(tmem_d, dah, dfh, idesc, 1);
+                    if (head >= 0) {
+                        const uint64_t dsh = umma_desc_sw128(sh + k * 32, 16, 1024);
+                        const uint64_t dsl = umma_desc_sw128(sl + k * 32, 16, 1024);
+                        const uint32_t dcol = tmem_d + 64 * (head + 1);
+                        umma_tf32(dcol, dal, dsh, idesc, ((kb & 1) | k) != 0);
+                        umma_tf32(dcol, dah, dsl, idesc, 1);
+                        umma_tf32(dcol, dah, dsh, idesc, 1);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        const int t = threadIdx.x - 64;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % H_STAGES;
+            const uint32_t ph = (kb / H_STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            float4* hi = reinterpret_cast<float4*>(smem + s * H_STAGE);
+            float4* lo = reinterpret_cast<float4*>(smem + s * H_STAGE + F_A_BYTES);
+#pragma unroll
+            for (int i = 0; i < F_A_BYTES / 16 / 128; ++i) {
+                const int idx = i * 128 + t;
+                const float4 x = hi[idx];
+                float4 h, l;
+                h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+                l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+                hi[idx] = h;
+                lo[idx] = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(&split_bar[s]);
+        }
+        const int q = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        float* st = reinterpret_cast<float*>(smem) + q * (32 * 65);
+        for (int o = 0; o <= n_heads; ++o) {
+            float v[64];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + 64 * o;
+            tmem_ld_32x32(taddr, v);
+            tmem_ld_32x32(taddr + 32, v + 32);
+            tmem_ld_wait();
+            const float* bias = ho.bias[o];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 64; ++j) st[lane * 65 + j] = v[j] + (bias != nullptr ? __ldg(bias + j) : 0.f);
+            __syncwarp();
+            float* outp = ho.out[o];
+            for (int r = 0; r < 32; ++r) {
+                const int row = m0 + q * 32 + r;
+                if (row < M_rows) {
+                    float* y = outp + (long long)row * 64;
+                    y[lane] = st[r * 65 + lane];
+                    y[32 + lane] = st[r * 65 + 32 + lane];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+}
+
 __global__ void split_tf32_kernel(long long n, const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -620,6 +781,45 @@ ELIMREC_API int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, in
 
 
 
+namespace {
+struct PrepMulti {
+    int n;
+    const float* src[ELIMREC_PREP_MAX];
+    float* hi[ELIMREC_PREP_MAX];
+    float* lo[ELIMREC_PREP_MAX];   // NULL: round only
+    long long numel[ELIMREC_PREP_MAX];
+    int block_start[ELIMREC_PREP_MAX + 1];
+};
+__global__ void prep_multi_kernel(const __grid_constant__ PrepMulti a) {
+    int t = 0;
+    while (t + 1 < a.n && (int)blockIdx.x >= a.block_start[t + 1]) ++t;
+    const long long i = (long long)(blockIdx.x - a.block_start[t]) * 256 + threadIdx.x;
+    if (i >= a.numel[t]) return;
+    const float x = a.src[t][i];
+    const float h = tf32_rna(x);
+    a.hi[t][i] = h;
+    if (a.lo[t] != nullptr) a.lo[t][i] = tf32_rna(x - h);
+}
+}  // namespace
+
+ELIMREC_API int elimrec_prep_weights_tf32(int n, const elimrec_prep_tensor_t* t, elimrec_stream_t stream) {
+    ER_CHECK_ARG(n >= 0 && n <= ELIMREC_PREP_MAX, "too many tensors");
+    if (n == 0) return 0;
+    PrepMulti a{};
+    a.n = n;
+    int blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        a.src[i] = t[i].src; a.hi[i] = t[i].hi; a.lo[i] = t[i].lo; a.numel[i] = t[i].numel;
+        a.block_start[i] = blocks;
+        blocks += (int)((t[i].numel + 255) / 256);
+    }
+    a.block_start[n] = blocks;
+    if (blocks == 0) return 0;
+    prep_multi_kernel<<<blocks, 256, 0, er_stream(stream)>>>(a);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
 ELIMREC_API int elimrec_split_tf32(int64_t n, const float* src, float* hi, float* lo, elimrec_stream_t stream) {
     if (n <= 0) return 0;
     split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, er_stream(stream)>>>(n, src, hi, lo);
@@ -652,6 +852,51 @@ ELIMREC_API int elimrec_linear_x3_fwd(int64_t M, int64_t K, const float* X, int6
     const int num_kb = (int)((K + F_BK - 1) / F_BK);
     const unsigned grid = (unsigned)((M + F_BM - 1) / F_BM);
     linear_x3_fwd_kernel<<<grid, 192, X_SMEM, er_stream(stream)>>>(tmA, tmBh, tmBl, b, Y, ldy, (int)M, num_kb);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+
+ELIMREC_API int elimrec_fuse_heads_x3(int64_t rows, int n_heads, const float* O, int64_t ldo, const float* Wf_hi,
+                                      const float* Wf_lo, const float* bf, const float* const* Ws_hi_host,
+                                      const float* const* Ws_lo_host, const float* const* bs_host, float* F_out,
+                                      float* const* S_out_host, elimrec_stream_t stream) {
+    if (rows <= 0) return 0;
+    ER_CHECK_ARG(n_heads >= 1 && n_heads <= ELIMREC_MAX_MODS, "n_heads out of range");
+    const int64_t K = 64 * (1 + n_heads);
+    if (ldo % 4 != 0 || ldo < K || !aligned16(O) || !aligned16(Wf_hi) || !aligned16(Wf_lo) || rows > 0x7fffffff) {
+        elimrec_set_error("elimrec_fuse_heads_x3: unsupported shape/alignment");
+        return -2;
+    }
+    CUtensorMap tmA, tmFh, tmFl;
+    HeadMaps hm;
+    HeadOut ho{};
+    int bad = make_map(&tmA, O, rows, K, ldo, F_BM) | make_map(&tmFh, Wf_hi, 64, K, K, F_BN) | make_map(&tmFl, Wf_lo, 64, K, K, F_BN);
+    ho.bias[0] = bf;
+    ho.out[0] = F_out;
+    for (int m = 0; m < ELIMREC_MAX_MODS; ++m) {
+        const int mm = m < n_heads ? m : 0;   // unused maps still have to be valid descriptors
+        bad |= make_map(&hm.hi[m], Ws_hi_host[mm], 64, 64, 64, F_BN) | make_map(&hm.lo[m], Ws_lo_host[mm], 64, 64, 64, F_BN);
+        if (m < n_heads) {
+            ho.bias[m + 1] = bs_host[m];
+            ho.out[m + 1] = S_out_host[m];
+        }
+    }
+    if (bad) {
+        elimrec_set_error("elimrec_fuse_heads_x3: cuTensorMapEncodeTiled failed");
+        return -3;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fuse_heads_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+        if (e != cudaSuccess) {
+            elimrec_set_error("elimrec_fuse_heads_x3: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            return -3;
+        }
+        configured = true;
+    }
+    const unsigned grid = (unsigned)((rows + F_BM - 1) / F_BM);
+    fuse_heads_x3_kernel<<<grid, 192, H_SMEM, er_stream(stream)>>>(tmA, tmFh, tmFl, hm, ho, (int)rows, n_heads);
     ER_LAUNCH_CHECK();
     return 0;
 }

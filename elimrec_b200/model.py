@@ -222,6 +222,9 @@ class EliMRec(BasicModel):
         # gradients of the small parameters
         ws["g"] = {n: torch.zeros_like(p, device=dev) for n, p in self._params().items()
                    if not n.startswith("embedding_user.w") and not n.startswith("embedding_item.w")}
+        ws["g_proj_bias"] = torch.zeros(D * len(self.mods), dtype=torch.float32, device=dev)
+        for j, m in enumerate(self.mods):   # the projection bias gradients are views of one buffer (one column-sum pass)
+            ws["g"][f"{m}_dense.bias"] = ws["g_proj_bias"][D * j:D * (j + 1)]
         # split-K plan + workspaces
         dmax = max(self._feat[m].shape[1] for m in self.mods)
         ws["split_proj"] = max(1, min(256, (I + 1023) // 1024))
@@ -234,7 +237,7 @@ class EliMRec(BasicModel):
         for m in self.mods:
             ws["W_split"][m] = (e(D, D), e(D, D))
         ws["wgrad_ws"] = e(max(1, max(ops.linear_tf32_wgrad_ws_floats(I, self._feat[m].shape[1]) for m in self.mods)))
-        ws["colsum_ws"] = e(max(ops.colsum_ws_floats(I, D), ops.colsum_ws_floats(3 * B, D)))
+        ws["colsum_ws"] = e(ops.colsum_ws_floats(I, D * len(self.mods)))
         self._ws = ws
         return ws
 
@@ -258,6 +261,18 @@ class EliMRec(BasicModel):
         prev_u = [(Eu, D)]       # layers seen by user rows, in order
         prev_i = [(X0_i, Fw)]    # layers seen by item rows
         inv = 1.0 / (L + 1)
+        # weights for the tensor-core layers: TF32 rounding (projections) and hi/lo split (fusion, heads) in one launch
+        prep = []
+        if self.proj_precision == "tf32":
+            prep += [(P[f"{m}_dense.weight"].detach(), ws["W_tf32"][m], None) for m in self.mods
+                     if self._feat[m].shape[1] % 4 == 0]
+        if self.fuse_precision == "x3":
+            sp = ws["W_split"]
+            prep += [(P["embedding_user_after_GCN.weight"].detach(), *sp["u"]),
+                     (P["embedding_item_after_GCN.weight"].detach(), *sp["i"])]
+            prep += [(P[f"s_dense_{m}.weight"].detach(), *sp[m]) for m in self.mods]
+        if prep:
+            ops.prep_weights_tf32(prep)
         side = ops.fork_side()   # narrow layer 1 (A_iu @ E_u) does not depend on the projections
         # layer 0, item side: [E_i | P_v | P_a | P_t]   (projections write straight into the slab)
         ops.copy_2d(Ei, X0_i, I, D)
@@ -265,9 +280,7 @@ class EliMRec(BasicModel):
             Wm, bm = P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach()
             Dm = Wm.shape[1]
             if self.proj_precision == "tf32" and Dm % 4 == 0:
-                Wr = ws["W_tf32"][m]
-                ops.round_tf32(Wm, Wr)
-                ops.linear_tf32_fwd(self._feat_tc(m), Wr, bm, X0_i, col=D * (j + 1))
+                ops.linear_tf32_fwd(self._feat_tc(m), ws["W_tf32"][m], bm, X0_i, col=D * (j + 1))
             else:
                 ops.gemm(I, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, c_off=D * (j + 1), tag="proj_fwd")
         wide_in, narrow_in = X0_i, Eu
@@ -303,14 +316,11 @@ class EliMRec(BasicModel):
         Wi, bi = P["embedding_item_after_GCN.weight"].detach(), P["embedding_item_after_GCN.bias"].detach()
         if self.fuse_precision == "x3":
             sp = ws["W_split"]
-            ops.split_tf32(Wu, *sp["u"])
-            ops.split_tf32(Wi, *sp["i"])
-            ops.linear_x3_fwd(O[:U], sp["u"][0], sp["u"][1], bu, F_all[:U], tag="fuse_fwd_x3")
-            ops.linear_x3_fwd(O[U:], sp["i"][0], sp["i"][1], bi, F_all[U:], tag="fuse_fwd_x3")
-            for j, m in enumerate(self.mods):
-                Ws, bs = P[f"s_dense_{m}.weight"].detach(), P[f"s_dense_{m}.bias"].detach()
-                ops.split_tf32(Ws, *sp[m])
-                ops.linear_x3_fwd(O[:, D * (j + 1):D * (j + 2)], sp[m][0], sp[m][1], bs, ws["S"][j], tag="head_fwd_x3")
+            bs = [P[f"s_dense_{m}.bias"].detach() for m in self.mods]
+            hh, hl = [sp[m][0] for m in self.mods], [sp[m][1] for m in self.mods]
+            # one pass over the user rows of O and one over the item rows (different fusion weights)
+            ops.fuse_heads_x3(O[:U], sp["u"][0], sp["u"][1], bu, hh, hl, bs, F_all[:U], [s_[:U] for s_ in ws["S"]])
+            ops.fuse_heads_x3(O[U:], sp["i"][0], sp["i"][1], bi, hh, hl, bs, F_all[U:], [s_[U:] for s_ in ws["S"]])
         else:
             ops.gemm(U, D, Fw, O, Fw, 1, Wu, 1, Fw, F_all, D, 1, bias=bu, tag="fuse_fwd")
             ops.gemm(I, D, Fw, O, Fw, 1, Wi, 1, Fw, F_all, D, 1, bias=bi, a_off=U * Fw, c_off=U * D, tag="fuse_fwd")
@@ -401,7 +411,7 @@ class EliMRec(BasicModel):
             else:
                 ops.gemm(Dm, D, I, Xm, 1, Dm, dWc, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=skp, ws=gws, b_off=c0,
                          tag="proj_wgrad")
-            ops.colsum(I, D, dWc, Fw, gr[f"{m}_dense.bias"], cws, a_off=c0)
+        ops.colsum(I, D * len(self.mods), dWc, Fw, ws["g_proj_bias"], cws, a_off=D)   # all db_m in one pass
         grads.update(gr)
         return grads
 

@@ -109,6 +109,22 @@ def linear_tf32_fwd(X, W, b, Y, col=0, tag="proj_fwd_tc"):
          ptr(Y, F32) + 4 * col, Y.stride(0), stream(), tag=tag)
 
 
+def prep_weights_tf32(items):
+    """items: list of (src, hi, lo_or_None) - all rounded / split in one launch."""
+    arr = (_lib.PrepTensor * len(items))()
+    for k, (src, hi, lo) in enumerate(items):
+        arr[k].src, arr[k].hi, arr[k].lo, arr[k].numel = ptr(src, F32), ptr(hi, F32), ptr(lo, F32, True), src.numel()
+    call("elimrec_prep_weights_tf32", len(items), arr, stream())
+
+
+def fuse_heads_x3(O_rows, Wf_hi, Wf_lo, bf, Ws_hi, Ws_lo, bs, F_out, S_out, tag="fuse_heads_x3"):
+    """F_out = O_rows @ Wf^T + bf and S_out[m] = O_rows[:, 64(m+1):64(m+2)] @ Ws[m]^T + bs[m] in ONE pass over O_rows."""
+    n = len(Ws_hi)
+    arr = lambda ts: (C.c_void_p * 3)(*([ptr(t, F32) for t in ts] + [None] * (3 - n)))
+    call("elimrec_fuse_heads_x3", O_rows.shape[0], n, ptr(O_rows, F32), O_rows.stride(0), ptr(Wf_hi, F32), ptr(Wf_lo, F32),
+         ptr(bf, F32), arr(Ws_hi), arr(Ws_lo), arr(bs), ptr(F_out, F32), arr(S_out), stream(), tag=tag)
+
+
 def split_tf32(src, hi, lo):
     call("elimrec_split_tf32", src.numel(), ptr(src, F32), ptr(hi, F32), ptr(lo, F32), stream())
 

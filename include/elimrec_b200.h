@@ -117,6 +117,23 @@ int64_t elimrec_linear_tf32_wgrad_workspace_floats(int64_t M, int64_t K);
 int elimrec_linear_x3_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, const float* W_hi, const float* W_lo,
                           const float* b, float* Y, int64_t ldy, elimrec_stream_t stream);
 int elimrec_split_tf32(int64_t n, const float* src, float* hi, float* lo, elimrec_stream_t stream);
+/* One pass over `rows` rows of the layer-mean slab O [rows x 64(1+n_heads)] (row stride ldo) producing, with 3xTF32:
+ *   F_out[r]    = O[r, :] @ Wf^T + bf                          (fusion Linear, models/EliMRec.py:261-270)
+ *   S_out[m][r] = O[r, 64(m+1) .. 64(m+2)) @ Ws[m]^T + bs[m]    (single-modal heads, models/EliMRec.py:146-151)
+ * Wf_* are [64 x 64(1+n_heads)], Ws_* [64 x 64] hi/lo parts from elimrec_prep_weights_tf32; outputs have row stride 64. */
+int elimrec_fuse_heads_x3(int64_t rows, int n_heads, const float* O, int64_t ldo, const float* Wf_hi, const float* Wf_lo,
+                          const float* bf, const float* const* Ws_hi_host, const float* const* Ws_lo_host,
+                          const float* const* bs_host, float* F_out, float* const* S_out_host, elimrec_stream_t stream);
+/* several small weight tensors prepared for the tensor cores in ONE launch: hi = rna_tf32(src); if lo != NULL,
+ * lo = rna_tf32(src - hi) (3xTF32 split), else round only */
+#define ELIMREC_PREP_MAX 16
+typedef struct {
+    const float* src;
+    float* hi;
+    float* lo;
+    int64_t numel;
+} elimrec_prep_tensor_t;
+int elimrec_prep_weights_tf32(int n, const elimrec_prep_tensor_t* tensors_host, elimrec_stream_t stream);
 /* dst[i] = round-to-nearest TF32 of src[i] (tcgen05.mma kind::tf32 truncates its inputs; pre-rounding the constant
  * features once and the weights per step removes the truncation bias).  src == dst allowed. */
 int elimrec_round_tf32(int64_t n, const float* src, float* dst, elimrec_stream_t stream);

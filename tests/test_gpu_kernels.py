@@ -405,3 +405,29 @@ def test_linear_x3_fwd_fp32_class(dev, M, K, ldx_extra):
     ref = X.double() @ W.double().t() + b.double()
     assert rel_err(Y[:M], ref) < FP32_TOL
     assert float((Y[M] - 7).abs().max()) == 0
+
+
+@pytest.mark.parametrize("rows,n_heads", [(1000, 3), (36656 // 3, 3), (130, 1), (128, 2)])
+def test_fuse_heads_x3_one_pass(dev, rows, n_heads):
+    """Fused fusion-Linear + heads over the layer-mean slab (3xTF32, fp32 tolerance class)."""
+    from elimrec_b200 import ops
+    F = 64 * (1 + n_heads)
+    g = torch.Generator().manual_seed(rows + n_heads)
+    Oall = torch.randn(rows + 5, F, generator=g).to(dev)
+    O = Oall[5:]                                     # row-offset view (like O[U:])
+    Wf = (torch.randn(64, F, generator=g) / F ** 0.5).to(dev)
+    bf = torch.randn(64, generator=g).to(dev)
+    Ws = [(torch.randn(64, 64, generator=g) / 8).to(dev) for _ in range(n_heads)]
+    bs = [torch.randn(64, generator=g).to(dev) for _ in range(n_heads)]
+    mk = lambda w: (torch.empty_like(w), torch.empty_like(w))
+    (Fh, Fl), sp = mk(Wf), [mk(w) for w in Ws]
+    ops.prep_weights_tf32([(Wf, Fh, Fl)] + [(w, h, l) for w, (h, l) in zip(Ws, sp)])
+    Fo = torch.full((rows + 1, 64), 7.0, device=dev)
+    So = [torch.full((rows + 1, 64), 7.0, device=dev) for _ in range(n_heads)]
+    ops.fuse_heads_x3(O, Fh, Fl, bf, [h for h, _ in sp], [l for _, l in sp], bs, Fo[:rows], [s_[:rows] for s_ in So])
+    assert rel_err(Fo[:rows], O.double() @ Wf.double().t() + bf.double()) < FP32_TOL
+    for m in range(n_heads):
+        ref = O[:, 64 * (m + 1):64 * (m + 2)].double() @ Ws[m].double().t() + bs[m].double()
+        assert rel_err(So[m][:rows], ref) < FP32_TOL, m
+        assert float((So[m][rows] - 7).abs().max()) == 0
+    assert float((Fo[rows] - 7).abs().max()) == 0
