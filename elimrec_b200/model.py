@@ -261,28 +261,11 @@ class EliMRec(BasicModel):
         prev_u = [(Eu, D)]       # layers seen by user rows, in order
         prev_i = [(X0_i, Fw)]    # layers seen by item rows
         inv = 1.0 / (L + 1)
-        # weights for the tensor-core layers: TF32 rounding (projections) and hi/lo split (fusion, heads) in one launch
-        prep = []
-        if self.proj_precision == "tf32":
-            prep += [(P[f"{m}_dense.weight"].detach(), ws["W_tf32"][m], None) for m in self.mods
-                     if self._feat[m].shape[1] % 4 == 0]
-        if self.fuse_precision == "x3":
-            sp = ws["W_split"]
-            prep += [(P["embedding_user_after_GCN.weight"].detach(), *sp["u"]),
-                     (P["embedding_item_after_GCN.weight"].detach(), *sp["i"])]
-            prep += [(P[f"s_dense_{m}.weight"].detach(), *sp[m]) for m in self.mods]
-        if prep:
-            ops.prep_weights_tf32(prep)
+        self._prep_weights(P, ws)
         side = ops.fork_side()   # narrow layer 1 (A_iu @ E_u) does not depend on the projections
         # layer 0, item side: [E_i | P_v | P_a | P_t]   (projections write straight into the slab)
         ops.copy_2d(Ei, X0_i, I, D)
-        for j, m in enumerate(self.mods):
-            Wm, bm = P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach()
-            Dm = Wm.shape[1]
-            if self.proj_precision == "tf32" and Dm % 4 == 0:
-                ops.linear_tf32_fwd(self._feat_tc(m), ws["W_tf32"][m], bm, X0_i, col=D * (j + 1))
-            else:
-                ops.gemm(I, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, c_off=D * (j + 1), tag="proj_fwd")
+        self._proj_forward(P, ws, X0_i, 0, I)
         wide_in, narrow_in = X0_i, Eu
         for k in range(1, L + 1):
             users_wide = (k % 2 == 1)
@@ -401,19 +384,49 @@ class EliMRec(BasicModel):
             dWc, dNc, flip = nW, nN, flip ^ 1
         # now dWc = d x_0[item rows, wide] = [dE_i | dP_v | dP_a | dP_t], dNc = d x_0[user rows] = dE_u
         grads = {"embedding_user.weight": dNc, "embedding_item.weight": dWc[:, :D]}
-        skp = ws["split_proj"]
+        self._proj_wgrad(ws, dWc, 0, I)
+        grads.update(gr)
+        return grads
+
+    # projections over item rows [r0, r1) - the whole table on one GPU, the owned block when row-sharded
+    def _prep_weights(self, P, ws):
+        """TF32 rounding (projections) and hi/lo split (fusion, heads) of the small weights, one launch."""
+        prep = []
+        if self.proj_precision == "tf32":
+            prep += [(P[f"{m}_dense.weight"].detach(), ws["W_tf32"][m], None) for m in self.mods
+                     if self._feat[m].shape[1] % 4 == 0]
+        if self.fuse_precision == "x3":
+            sp = ws["W_split"]
+            prep += [(P["embedding_user_after_GCN.weight"].detach(), *sp["u"]),
+                     (P["embedding_item_after_GCN.weight"].detach(), *sp["i"])]
+            prep += [(P[f"s_dense_{m}.weight"].detach(), *sp[m]) for m in self.mods]
+        if prep:
+            ops.prep_weights_tf32(prep)
+
+    def _proj_forward(self, P, ws, X0_i, r0, r1):
+        Fw = ws["F"]
+        for j, m in enumerate(self.mods):
+            Wm, bm = P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach()
+            Dm = Wm.shape[1]
+            if self.proj_precision == "tf32" and Dm % 4 == 0:
+                ops.linear_tf32_fwd(self._feat_tc(m)[r0:r1], ws["W_tf32"][m], bm, X0_i[r0:r1], col=D * (j + 1))
+            else:
+                ops.gemm(r1 - r0, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, a_off=r0 * Dm,
+                         c_off=r0 * Fw + D * (j + 1), tag="proj_fwd")
+
+    def _proj_wgrad(self, ws, dX0_i, r0, r1):
+        """dW_m, db_m from rows [r0, r1) of d x_0[item rows] = [dE_i | dP_v | dP_a | dP_t]."""
+        Fw, gr = ws["F"], ws["g"]
         for j, m in enumerate(self.mods):
             Xm = self._feat[m]
             Dm = Xm.shape[1]
             c0 = D * (j + 1)
             if self.proj_precision == "tf32" and Dm % 4 == 0:
-                ops.linear_tf32_wgrad(dWc, self._feat_tc(m), gr[f"{m}_dense.weight"], ws["wgrad_ws"], col=c0)
+                ops.linear_tf32_wgrad(dX0_i[r0:r1], self._feat_tc(m)[r0:r1], gr[f"{m}_dense.weight"], ws["wgrad_ws"], col=c0)
             else:
-                ops.gemm(Dm, D, I, Xm, 1, Dm, dWc, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=skp, ws=gws, b_off=c0,
-                         tag="proj_wgrad")
-        ops.colsum(I, D * len(self.mods), dWc, Fw, ws["g_proj_bias"], cws, a_off=D)   # all db_m in one pass
-        grads.update(gr)
-        return grads
+                ops.gemm(Dm, D, r1 - r0, Xm, 1, Dm, dX0_i, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=ws["split_proj"],
+                         ws=ws["gemm_ws"], a_off=r0 * Dm, b_off=r0 * Fw + c0, tag="proj_wgrad")
+        ops.colsum(r1 - r0, D * len(self.mods), dX0_i, Fw, ws["g_proj_bias"], ws["colsum_ws"], a_off=r0 * Fw + D)
 
     # ------------------------------------------------------------------------------------------
     # public training API
@@ -519,16 +532,25 @@ class EliMRec(BasicModel):
             raise TypeError("'NoneType' object is not subscriptable (predict before any bpr_loss, as in the reference)")
         ws = self._ws
         if ws.get("S_norm_version") != self._tables_version:
-            if "S_norm" not in ws:
-                ws["S_norm"] = [torch.empty_like(s) for s in ws["S"]]
-            for s, sn in zip(ws["S"], ws["S_norm"]):
-                ops.row_normalize(s, sn)
+            fu, fi, su, si = self._tables()
+            ws["S_norm"] = [(torch.empty_like(a), torch.empty_like(b)) for a, b in zip(su, si)]
+            for (a, b), (an, bn) in zip(zip(su, si), ws["S_norm"]):
+                ops.row_normalize(a, an)
+                ops.row_normalize(b, bn)
+            ws["rank_f"] = (fu, fi)
             ws["S_norm_version"] = self._tables_version
         act = self._active_mods()
+        fu, fi = ws["rank_f"]
+        su = [ws["S_norm"][j][0] for j in act]
+        si = [ws["S_norm"][j][1] for j in act]
+        return ops.rank_tables(self.num_users, self.num_items, PREDICT_MODE[self.predict_type], fu, fi, su, si)
+
+    def _tables(self):
+        """(fused users, fused items, [single-modal users], [single-modal items]) cached by the last training forward."""
         U = self.num_users
-        su = [ws["S_norm"][j][:U] for j in act]
-        si = [ws["S_norm"][j][U:] for j in act]
-        return ops.rank_tables(U, self.num_items, PREDICT_MODE[self.predict_type], self.all_users, self.all_items, su, si)
+        S = self._ws["S"]
+        return (self.all_users.contiguous(), self.all_items.contiguous(), [s_[:U].contiguous() for s_ in S],
+                [s_[U:].contiguous() for s_ in S])
 
     @torch.no_grad()
     def predict(self, user_ids, candidate_items=None):
