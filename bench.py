@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--eval-users", type=int, default=0, help="0 = all test users")
     ap.add_argument("--cuda-graph", type=int, default=1)
+    ap.add_argument("--lazy-tables", type=int, default=0,
+                    help="1: build all_users/all_items/all_s_embs on demand (at evaluation) instead of every step")
     ap.add_argument("--parallel", default="dp", choices=["dp", "rowshard"],
                     help="N>1: data-parallel replicas (weak scaling, default) or the row-sharded all-gather design "
                          "(strong scaling: every rank works on the SAME batch)")
@@ -212,7 +214,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ds, name = build_dataset(args.workload)
-    conf = Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH})
+    conf = Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH,
+                     "lazy_tables": bool(args.lazy_tables)})
     torch.manual_seed(2022)
     rowshard = world > 1 and args.parallel == "rowshard"
     if rowshard:
@@ -377,7 +380,7 @@ def main():
                                        f"layer_num 3, recdim 64, U={ds.num_users} I={ds.num_items} E_train={ds.train_matrix.nnz}",
                            "parallelism": (f"rowshard{world} (all-gather per GCN layer)" if rowshard else f"dp{world}") if world > 1 else "single",
                            "l2_policy": "per-step working set (features + propagation slabs, >0.9 GB) exceeds the 126 MB L2; no flush",
-                           "cuda_graph": bool(runner is not None), "sampler": "device Philox (value) / compat libc stream (e2e)"},
+                           "cuda_graph": bool(runner is not None), "lazy_tables": bool(args.lazy_tables), "sampler": "device Philox (value) / compat libc stream (e2e)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "eval": ev,
                 "kernels": kernels, "final_loss": final_loss}

@@ -141,7 +141,7 @@ __global__ void gemm_splitk_reduce_kernel(GemmArgs g) {
     *c = s;
 }
 
-constexpr int CS_ROWS = 512;  // rows per colsum chunk
+constexpr int CS_ROWS = 128;  // rows per colsum chunk
 
 __global__ void colsum_partial_kernel(long long M, long long N, const float* __restrict__ A, long long ld,
                                       float* __restrict__ ws) {
@@ -151,8 +151,16 @@ __global__ void colsum_partial_kernel(long long M, long long N, const float* __r
     const long long r0 = (long long)blockIdx.y * CS_ROWS;
     const long long r1 = min(M, r0 + CS_ROWS);
     float s = 0.f;
-    if (n < N)
-        for (long long r = r0 + ty; r < r1; r += 8) s += __ldg(A + r * ld + n);
+    if (n < N) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};   // 4 independent loads in flight per thread
+        long long r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] += __ldg(A + (r + 8 * u) * ld + n);
+        }
+        for (; r < r1; r += 8) t[0] += __ldg(A + r * ld + n);
+        s = (t[0] + t[1]) + (t[2] + t[3]);
+    }
     red[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && n < N) {

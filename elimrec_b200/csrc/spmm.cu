@@ -118,7 +118,7 @@ spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             const float4* ps = reinterpret_cast<const float4*>(partial + (long long)hv.x * F) + l;
-            constexpr int RU = 8;
+            constexpr int RU = 4;
             for (int s2 = 0; s2 < hv.y; s2 += RU) {
                 float4 t[RU][NV];
 #pragma unroll
@@ -259,7 +259,7 @@ ELIMREC_API int elimrec_spmm(int width, int part, int n_seg, int n_heavy_seg, co
 #define LAUNCH(F, MEAN)                                                                                                   \
     do {                                                                                                                  \
         if (hb > 0 && part != 2)                                                                                          \
-            spmm_seg_kernel<F, MEAN, true, (F == 256 ? 4 : 8), 1><<<hb, 256, 0, st>>>(0, n_heavy_seg, sg, hv, counter, col, \
+            spmm_seg_kernel<F, MEAN, true, 2, 5><<<hb, 256, 0, st>>>(0, n_heavy_seg, sg, hv, counter, col,                  \
                                                                                       val, X, ldx, Y, ldy, partial, me);   \
         if (lb > 0 && part != 1)                                                                                          \
             spmm_seg_kernel<F, MEAN, false, 2, (MEAN ? 6 : 8)><<<lb, 256, 0, st>>>(n_heavy_seg, n_seg, sg, hv, counter, col, \

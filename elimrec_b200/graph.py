@@ -19,7 +19,9 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-SEG_LEN = 64  # edges per warp work item; rows longer than this are split (deterministic 2-stage reduce)
+SEG_LEN = 64        # rows with at most this many edges are ONE warp work item
+HEAVY_SEG_LEN = 16  # longer rows are split into segments of this many edges (8 per CTA, deterministic 2-stage reduce):
+                    # short segments keep the per-warp dependent-load chain short and the launch at full occupancy
 
 
 class CsrHalf:
@@ -45,7 +47,8 @@ class CsrHalf:
         self.indptr = torch.from_numpy(self.indptr_host).to(device)
 
 
-def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: int | None = None):
+def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: int | None = None,
+                   heavy_seg_len: int | None = None):
     """seg[s] = (row, edge_begin, edge_end, heavy_id or -1); split rows first (longest first), each padded to a
     multiple of 8 segments so that a CTA of 8 warps never mixes rows; heavy[h] = (first CTA, number of CTAs)."""
     n_rows = indptr.size - 1
@@ -53,8 +56,9 @@ def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: in
     rows = np.arange(row_lo, row_hi, dtype=np.int64)
     beg = indptr[rows]
     deg = indptr[rows + 1] - beg
-    nseg = np.maximum(1, -(-deg // seg_len))
-    heavy_mask = nseg > 1
+    hsl = min(seg_len, heavy_seg_len or HEAVY_SEG_LEN)
+    heavy_mask = deg > seg_len
+    nseg = np.where(heavy_mask, -(-deg // hsl), 1)
     # heavy rows, longest first so that their tails start early
     h_rows = rows[heavy_mask]
     order = np.argsort(-deg[heavy_mask], kind="stable")
@@ -73,8 +77,8 @@ def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: in
         hid = np.repeat(np.arange(h_rows.size), h_nseg_pad)
         k = np.arange(n_hseg) - np.repeat(first, h_nseg_pad)
         row_end = np.repeat(h_beg + h_deg, h_nseg_pad)
-        sb = np.minimum(np.repeat(h_beg, h_nseg_pad) + k * seg_len, row_end)
-        se = np.minimum(sb + seg_len, row_end)
+        sb = np.minimum(np.repeat(h_beg, h_nseg_pad) + k * hsl, row_end)
+        se = np.minimum(sb + hsl, row_end)
         segs.append(np.stack([np.repeat(h_rows, h_nseg_pad), sb, se, hid], axis=1))
     l_rows = rows[~heavy_mask]
     l_beg = beg[~heavy_mask]

@@ -124,6 +124,12 @@ class EliMRec(BasicModel):
         self.fuse_precision = _cfg(cfg, "fuse_precision", "x3")
         if self.fuse_precision not in ("x3", "fp32"):
             raise ElimrecError("fuse_precision must be 'x3' or 'fp32'")
+        # lazy_tables: the training loss only needs the fused / single-modal embeddings of the <= 3B sampled rows.  With
+        # lazy_tables=True a training step computes exactly those; the full all_users / all_items / all_s_embs tables
+        # (which the reference materialises every step, EliMRec.py:261-272,144-153, and only predict() ever reads) are
+        # produced on first access from the layer-mean slab and a snapshot of the weights of that same forward -
+        # bit-identical values, computed once per evaluation instead of once per step.  Default: off (faithful).
+        self.lazy_tables = bool(_cfg(cfg, "lazy_tables", False))
         self.kwai = cfg["data.input.dataset"] == "kwai"
         self.mods = "v" if self.kwai else "vat"
         dev = _cfg(cfg, "device", None)
@@ -149,8 +155,8 @@ class EliMRec(BasicModel):
         nn.init.xavier_uniform_(self.embedding_user_after_GCN.weight)
         self.embedding_item_after_GCN = nn.Linear(self.item_feat_dim, D)
         nn.init.xavier_uniform_(self.embedding_item_after_GCN.weight)
-        self.all_items = self.all_users = None
-        self.all_s_embs = None
+        self._all_users = self._all_items = self._all_s_embs = None
+        self._tables_pending = False
         self.graph = BipartiteGraph(ds.train_matrix, dev, cfg["adj_type"])
         self.f = nn.Sigmoid()
         self.s_dense_v = nn.Linear(D, D)
@@ -169,6 +175,34 @@ class EliMRec(BasicModel):
             cache[m] = torch.empty_like(self._feat[m])
             ops.round_tf32(self._feat[m], cache[m])
         return cache[m]
+
+    # tables cached by the last training forward (EliMRec.py:98-99,109); materialised on demand when lazy_tables is on
+    @property
+    def all_users(self):
+        self._materialize_tables()
+        return self._all_users
+
+    @all_users.setter
+    def all_users(self, v):
+        self._all_users = v
+
+    @property
+    def all_items(self):
+        self._materialize_tables()
+        return self._all_items
+
+    @all_items.setter
+    def all_items(self, v):
+        self._all_items = v
+
+    @property
+    def all_s_embs(self):
+        self._materialize_tables()
+        return self._all_s_embs
+
+    @all_s_embs.setter
+    def all_s_embs(self, v):
+        self._all_s_embs = v
 
     # parameters that take part in the computation, in a fixed order
     @property
@@ -233,10 +267,25 @@ class EliMRec(BasicModel):
         ws["gemm_ws"] = e(need)
         ws["W_tf32"] = {m: e(D, self._feat[m].shape[1]) for m in self.mods}
         ws["inst_ws"] = e(ops.inst_backward_ws_floats(B, nt, Fw))
+        ws["inst_dummy"] = torch.empty(3 * B, dtype=torch.int32, device=dev)
+        ws["F_c"], ws["S_c"] = e(3 * B, D), [e(3 * B, D) for _ in self.mods]
+        ar = torch.arange(B, dtype=torch.int64, device=dev)
+        ws["c_users"], ws["c_pos"], ws["c_neg"] = ar.clone(), ar.clone(), ar + B
+        # snapshot of the fusion / head weights and biases used by the last forward (what lazily built tables must use)
+        ws["snap_names"] = (["embedding_user_after_GCN.bias", "embedding_item_after_GCN.bias"] +
+                            [f"s_dense_{m}.bias" for m in self.mods])
+        if self.fuse_precision != "x3":
+            ws["snap_names"] += (["embedding_user_after_GCN.weight", "embedding_item_after_GCN.weight"] +
+                                 [f"s_dense_{m}.weight" for m in self.mods])
+        Pn = self._params()
+        ws["snap"] = {n: torch.empty_like(Pn[n], device=dev) for n in ws["snap_names"]}
+        ws["snap_dst"] = [ws["snap"][n] for n in ws["snap_names"]]
         ws["W_split"] = {"u": (e(D, Fw), e(D, Fw)), "i": (e(D, Fw), e(D, Fw))}
         for m in self.mods:
             ws["W_split"][m] = (e(D, D), e(D, D))
-        ws["wgrad_ws"] = e(max(1, max(ops.linear_tf32_wgrad_ws_floats(I, self._feat[m].shape[1]) for m in self.mods)))
+        ws["wgrad_ws_m"] = {m: e(max(1, ops.linear_tf32_wgrad_ws_floats(I, self._feat[m].shape[1]))) for m in self.mods}
+        ws["gemm_ws_m"] = {m: (e(ws["split_proj"] * self._feat[m].shape[1] * D) if self.proj_precision == "fp32"
+                               or self._feat[m].shape[1] % 4 else None) for m in self.mods}
         ws["colsum_ws"] = e(ops.colsum_ws_floats(I, D * len(self.mods)))
         self._ws = ws
         return ws
@@ -293,31 +342,7 @@ class EliMRec(BasicModel):
                     ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv))
                 ops.spmm(half_w, wide_in, None, Fw, ops.mean_epilogue(pw, out_w, Fw, inv))
             ops.join_side(side)
-        # fusion Linear (concat) and single-modal heads over all rows
-        F_all = ws["F_all"]
-        Wu, bu = P["embedding_user_after_GCN.weight"].detach(), P["embedding_user_after_GCN.bias"].detach()
-        Wi, bi = P["embedding_item_after_GCN.weight"].detach(), P["embedding_item_after_GCN.bias"].detach()
-        if self.fuse_precision == "x3":
-            sp = ws["W_split"]
-            bs = [P[f"s_dense_{m}.bias"].detach() for m in self.mods]
-            hh, hl = [sp[m][0] for m in self.mods], [sp[m][1] for m in self.mods]
-            # one pass over the user rows of O and one over the item rows (different fusion weights)
-            ops.fuse_heads_x3(O[:U], sp["u"][0], sp["u"][1], bu, hh, hl, bs, F_all[:U], [s_[:U] for s_ in ws["S"]])
-            ops.fuse_heads_x3(O[U:], sp["i"][0], sp["i"][1], bi, hh, hl, bs, F_all[U:], [s_[U:] for s_ in ws["S"]])
-        else:
-            ops.gemm(U, D, Fw, O, Fw, 1, Wu, 1, Fw, F_all, D, 1, bias=bu, tag="fuse_fwd")
-            ops.gemm(I, D, Fw, O, Fw, 1, Wi, 1, Fw, F_all, D, 1, bias=bi, a_off=U * Fw, c_off=U * D, tag="fuse_fwd")
-            for j, m in enumerate(self.mods):
-                Ws, bs = P[f"s_dense_{m}.weight"].detach(), P[f"s_dense_{m}.bias"].detach()
-                ops.gemm(U + I, D, D, O, Fw, 1, Ws, 1, D, ws["S"][j], D, 1, bias=bs, a_off=D * (j + 1), tag="head_fwd")
-        # cached tables (what predict() reads later, EliMRec.py:98-99,109)
-        self.all_users, self.all_items = F_all[:U], F_all[U:]
-        self.all_s_embs = {}
-        for j, m in enumerate(self.mods):
-            self.all_s_embs[f"pre_fusion_user_{m}"] = ws["S"][j][:U]
-            self.all_s_embs[f"pre_fusion_item_{m}"] = ws["S"][j][U:]
         self._tables_version = getattr(self, "_tables_version", 0) + 1
-        # fused BPR forward+backward on the sampled rows
         if self.kwai:
             self.modality = "v"  # EliMRec.py:133-134
         alpha = float(self.config.alpha)
@@ -325,8 +350,65 @@ class EliMRec(BasicModel):
             weights = [1.0] + [0.0] * len(self.mods)
         else:
             weights = [1.0] + [alpha * self.modality.count(m) for m in self.mods]
-        ops.bpr([F_all] + ws["S"], weights, users, pos, neg, U, ws["loss"], ws["inst_rows"], ws["inst_grad"], ws["terms"])
+        if not self.lazy_tables:
+            # fusion Linear (concat) and single-modal heads over ALL rows, as the reference does every step
+            self._dense_tables(P, ws)
+            ops.bpr([ws["F_all"]] + ws["S"], weights, users, pos, neg, U, ws["loss"], ws["inst_rows"], ws["inst_grad"],
+                    ws["terms"])
+            ops.gather_rows(ws["inst_rows"], O, ws["O_inst"], Fw)
+        else:
+            # only the sampled rows: gather O[inst], fusion + heads on 3B rows, BPR on the compact tables
+            torch._foreach_copy_(ws["snap_dst"], [P[n].detach() for n in ws["snap_names"]])   # weights of THIS forward
+            rows = ws["inst_rows"]
+            rows[:B] = users
+            rows[B:2 * B] = pos + U
+            rows[2 * B:] = neg + U
+            ops.gather_rows(rows, O, ws["O_inst"], Fw)
+            self._fuse_heads_rows(ws, ws["O_inst"][:B], ws["F_c"][:B], [s_[:B] for s_ in ws["S_c"]], "u")
+            self._fuse_heads_rows(ws, ws["O_inst"][B:], ws["F_c"][B:], [s_[B:] for s_ in ws["S_c"]], "i")
+            ops.bpr([ws["F_c"]] + ws["S_c"], weights, ws["c_users"], ws["c_pos"], ws["c_neg"], B, ws["loss"], ws["inst_dummy"],
+                    ws["inst_grad"], ws["terms"])
+            self._tables_pending = True
         return ws["loss"][0]
+
+    def _fuse_heads_rows(self, ws, O_rows, Fout, Sout, who):
+        """fusion Linear + heads on a block of rows, with the weights snapshotted / split by this forward"""
+        sn = ws["snap"]
+        name = "user" if who == "u" else "item"
+        bf = sn[f"embedding_{name}_after_GCN.bias"]
+        n = O_rows.shape[0]
+        Fw = ws["F"]
+        if n == 0:
+            return
+        if self.fuse_precision == "x3":
+            sp = ws["W_split"]
+            ops.fuse_heads_x3(O_rows, sp[who][0], sp[who][1], bf, [sp[m][0] for m in self.mods], [sp[m][1] for m in self.mods],
+                              [sn[f"s_dense_{m}.bias"] for m in self.mods], Fout, Sout)
+        else:
+            ops.gemm(n, D, Fw, O_rows, Fw, 1, sn[f"embedding_{name}_after_GCN.weight"], 1, Fw, Fout, D, 1, bias=bf, tag="fuse_fwd")
+            for j, m in enumerate(self.mods):
+                ops.gemm(n, D, D, O_rows[:, D * (j + 1):], Fw, 1, sn[f"s_dense_{m}.weight"], 1, D, Sout[j], D, 1,
+                         bias=sn[f"s_dense_{m}.bias"], tag="head_fwd")
+
+    def _dense_tables(self, P, ws, from_snapshot=False):
+        """all_users / all_items / all_s_embs over every row of the layer-mean slab"""
+        U, I = self.num_users, self.num_items
+        O, F_all = ws["O"], ws["F_all"]
+        if not from_snapshot:
+            torch._foreach_copy_(ws["snap_dst"], [P[n].detach() for n in ws["snap_names"]])
+        self._fuse_heads_rows(ws, O[:U], F_all[:U], [s_[:U] for s_ in ws["S"]], "u")
+        self._fuse_heads_rows(ws, O[U:], F_all[U:], [s_[U:] for s_ in ws["S"]], "i")
+        self._all_users, self._all_items = F_all[:U], F_all[U:]
+        self._all_s_embs = {}
+        for j, m in enumerate(self.mods):
+            self._all_s_embs[f"pre_fusion_user_{m}"] = ws["S"][j][:U]
+            self._all_s_embs[f"pre_fusion_item_{m}"] = ws["S"][j][U:]
+        self._tables_pending = False
+
+    def _materialize_tables(self):
+        if self._tables_pending:
+            with torch.no_grad():
+                self._dense_tables(None, self._ws, from_snapshot=True)
 
     # ------------------------------------------------------------------------------------------
     # backward: instance rows -> fusion/head weights -> 2L SpMMs -> projection weights
@@ -345,7 +427,6 @@ class EliMRec(BasicModel):
         sk = ws["split_inst"]
         if gscale is not None:
             gscale = gscale.reshape(1)
-        ops.gather_rows(rows, O, Oin, Fw)
         Wu, Wi = P["embedding_user_after_GCN.weight"].detach(), P["embedding_item_after_GCN.weight"].detach()
         # fusion Linear + heads, backward on the instance rows: dO[inst], all weight and bias gradients (3 launches)
         ops.inst_backward(B, nt, Fw, ig, Oin, gscale, Wu, Wi, [P[f"s_dense_{m}.weight"].detach() for m in self.mods], dOin,
@@ -405,28 +486,42 @@ class EliMRec(BasicModel):
 
     def _proj_forward(self, P, ws, X0_i, r0, r1):
         Fw = ws["F"]
-        for j, m in enumerate(self.mods):
+        sides = []
+        for j, m in enumerate(self.mods):   # one stream per modality: disjoint output columns, tails overlap
             Wm, bm = P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach()
             Dm = Wm.shape[1]
-            if self.proj_precision == "tf32" and Dm % 4 == 0:
-                ops.linear_tf32_fwd(self._feat_tc(m)[r0:r1], ws["W_tf32"][m], bm, X0_i[r0:r1], col=D * (j + 1))
-            else:
-                ops.gemm(r1 - r0, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, a_off=r0 * Dm,
-                         c_off=r0 * Fw + D * (j + 1), tag="proj_fwd")
+            st = ops.fork_side(2 + j) if j > 0 else torch.cuda.current_stream()
+            with torch.cuda.stream(st):
+                if self.proj_precision == "tf32" and Dm % 4 == 0:
+                    ops.linear_tf32_fwd(self._feat_tc(m)[r0:r1], ws["W_tf32"][m], bm, X0_i[r0:r1], col=D * (j + 1))
+                else:
+                    ops.gemm(r1 - r0, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, a_off=r0 * Dm,
+                             c_off=r0 * Fw + D * (j + 1), tag="proj_fwd")
+            if j > 0:
+                sides.append(st)
+        for st in sides:
+            ops.join_side(st)
 
     def _proj_wgrad(self, ws, dX0_i, r0, r1):
         """dW_m, db_m from rows [r0, r1) of d x_0[item rows] = [dE_i | dP_v | dP_a | dP_t]."""
         Fw, gr = ws["F"], ws["g"]
-        for j, m in enumerate(self.mods):
+        sides = []
+        for j, m in enumerate(self.mods):   # one stream (and one scratch buffer) per modality
             Xm = self._feat[m]
             Dm = Xm.shape[1]
             c0 = D * (j + 1)
-            if self.proj_precision == "tf32" and Dm % 4 == 0:
-                ops.linear_tf32_wgrad(dX0_i[r0:r1], self._feat_tc(m)[r0:r1], gr[f"{m}_dense.weight"], ws["wgrad_ws"], col=c0)
-            else:
-                ops.gemm(Dm, D, r1 - r0, Xm, 1, Dm, dX0_i, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=ws["split_proj"],
-                         ws=ws["gemm_ws"], a_off=r0 * Dm, b_off=r0 * Fw + c0, tag="proj_wgrad")
+            st = ops.fork_side(2 + j)
+            with torch.cuda.stream(st):
+                if self.proj_precision == "tf32" and Dm % 4 == 0:
+                    ops.linear_tf32_wgrad(dX0_i[r0:r1], self._feat_tc(m)[r0:r1], gr[f"{m}_dense.weight"], ws["wgrad_ws_m"][m],
+                                          col=c0)
+                else:
+                    ops.gemm(Dm, D, r1 - r0, Xm, 1, Dm, dX0_i, Fw, 1, gr[f"{m}_dense.weight"], 1, Dm, split_k=ws["split_proj"],
+                             ws=ws["gemm_ws_m"][m], a_off=r0 * Dm, b_off=r0 * Fw + c0, tag="proj_wgrad")
+            sides.append(st)
         ops.colsum(r1 - r0, D * len(self.mods), dX0_i, Fw, ws["g_proj_bias"], ws["colsum_ws"], a_off=r0 * Fw + D)
+        for st in sides:
+            ops.join_side(st)
 
     # ------------------------------------------------------------------------------------------
     # public training API

@@ -109,7 +109,8 @@ class ShardedEliMRec(EliMRec):
         ws["W_split"] = {"u": (z(D, Fw), z(D, Fw)), "i": (z(D, Fw), z(D, Fw))}
         for m in self.mods:
             ws["W_split"][m] = (z(D, D), z(D, D))
-        ws["wgrad_ws"] = z(max(1, max(ops.linear_tf32_wgrad_ws_floats(self.Ib, self._feat[m].shape[1]) for m in self.mods)))
+        ws["wgrad_ws_m"] = {m: z(max(1, ops.linear_tf32_wgrad_ws_floats(self.Ib, self._feat[m].shape[1]))) for m in self.mods}
+        ws["gemm_ws_m"] = {m: z(ws["split_proj"] * self._feat[m].shape[1] * D) for m in self.mods}
         ws["colsum_ws"] = z(ops.colsum_ws_floats(self.Ib, D * len(self.mods)))
         # flat buffer for the projection-weight gradients (summed over ranks)
         names = [f"{m}_dense.weight" for m in self.mods]

@@ -192,3 +192,36 @@ def test_tf32_projection_mode_within_1e3(golden):
             assert rel_err(p.grad, golden["grad0/" + name]) < 2 * TC_TOL, name
     assert rel_err(model.all_items, golden["all_items"]) < TC_TOL
     assert rel_err(model.all_users, golden["all_users"]) < TC_TOL
+
+
+def test_lazy_tables_identical_results(golden):
+    """lazy_tables=True: a step computes the fused / head embeddings of the sampled rows only; the full tables are built
+    on first access from the same slab and the weights of that forward.  Everything observable must be IDENTICAL to
+    the eager mode bit for bit (same kernels, same inputs), including after the optimizer has already stepped."""
+    eager, _ = _golden_model(golden)
+    lazy, _ = _golden_model(golden, lazy_tables=True)
+    for m in (eager, lazy):
+        m.make_optimizer(lr=1e-3, weight_decay=1e-4)
+    for i in range(3):
+        le, ll = eager.train_step(*_batch(golden, i)), lazy.train_step(*_batch(golden, i))
+        assert float(le) == float(ll)
+    # (the scatter-adds of duplicate sampled rows use float atomics, so two runs agree to rounding, not bitwise)
+    for (k, a), b in zip(eager.state_dict().items(), lazy.state_dict().values()):
+        assert rel_err(a, b) < 1e-6, k
+    # tables are those of the LAST FORWARD (pre-step weights), although the weights have been updated since
+    assert rel_err(eager.all_users, lazy.all_users) < 1e-6 and rel_err(eager.all_items, lazy.all_items) < 1e-6
+    for k, v in eager.all_s_embs.items():
+        assert rel_err(v, lazy.all_s_embs[k]) < 1e-6, k
+    eager.eval(); lazy.eval()
+    for pt in ("TIE", "TE"):
+        eager.predict_type = lazy.predict_type = pt
+        np.testing.assert_allclose(eager.evaluate()[0], lazy.evaluate()[0], atol=1e-6)
+    # autograd path too
+    lazy2, _ = _golden_model(golden, lazy_tables=True)
+    loss = lazy2.bpr_loss(*[torch.tensor(x) for x in _batch(golden, 0)])
+    loss.backward()
+    assert abs(float(loss) - float(golden["loss0"])) < FP32_TOL * abs(float(golden["loss0"]))
+    for name, p in lazy2.named_parameters():
+        if ("grad0/" + name) in golden:
+            assert rel_err(p.grad, golden["grad0/" + name]) < FP32_TOL, name
+    assert rel_err(lazy2.predict(golden["predict_users"].tolist()), golden["predict_TIE"]) < FP32_TOL
