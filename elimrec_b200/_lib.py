@@ -53,6 +53,8 @@ _SIGS = {
     "elimrec_round_tf32": [i64, vp, vp, vp],
     "elimrec_split_tf32": [i64, vp, vp, vp, vp],
     "elimrec_prep_weights_tf32": [i32, C.POINTER(PrepTensor), vp],
+    "elimrec_fuse_heads_x3_all": [i64, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp,
+                                  C.POINTER(vp), vp],
     "elimrec_fuse_heads_x3": [i64, i32, vp, i64, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(vp), vp],
     "elimrec_linear_x3_fwd": [i64, i64, vp, i64, vp, vp, vp, vp, i64, vp],
     "elimrec_bpr_forward_backward": [i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],

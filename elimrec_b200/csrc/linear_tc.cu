@@ -517,6 +517,187 @@ fuse_heads_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant over the WHOLE slab O [N x 64(1+M)] (users first, then items): one CTA per SM walks 128-row tiles
+// (user tiles use the user fusion weights, item tiles the item ones), the accumulators are double-buffered in TMEM
+// (2 x 256 columns) and separate warps split (4), issue MMAs (1), load (1) and drain (4), so the epilogue of tile i
+// overlaps the main loop of tile i+1 and the prologue is paid once per SM instead of once per tile.
+// ---------------------------------------------------------------------------------------------
+struct FuseAllMaps {
+    CUtensorMap A;            // O, all N rows
+    CUtensorMap Fh[2], Fl[2]; // fusion weights hi/lo: [0] users, [1] items
+    CUtensorMap Sh[ELIMREC_MAX_MODS], Sl[ELIMREC_MAX_MODS];
+};
+struct FuseAllOut {
+    const float* bias_f[2];
+    const float* bias_s[ELIMREC_MAX_MODS];
+    float* out[1 + ELIMREC_MAX_MODS];   // [N x 64] each: fused table, then the heads
+};
+
+__global__ void __launch_bounds__(320, 1)
+fuse_heads_x3_all_kernel(const __grid_constant__ FuseAllMaps mp, FuseAllOut ho, int U, int N, int n_heads, int n_user_tiles,
+                         int n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[H_STAGES];
+    __shared__ __align__(8) uint64_t split_bar[H_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[H_STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = 2 * (1 + n_heads);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mp.A);
+        for (int s = 0; s < H_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&split_bar[s], 128);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 4);   // one arrival per drain warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int who = tile < n_user_tiles ? 0 : 1;
+                const int row0 = who == 0 ? tile * F_BM : U + (tile - n_user_tiles) * F_BM;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % H_STAGES;
+                    const uint32_t ph = (it / H_STAGES) & 1;
+                    const int head = kb / 2 - 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], F_A_BYTES + 2 * F_B_BYTES + (head >= 0 ? 2 * F_B_BYTES : 0));
+                    uint8_t* a = smem + s * H_STAGE;
+                    uint8_t* b = a + 2 * F_A_BYTES;
+                    tma_load_2d(&mp.A, &full_bar[s], a, kb * F_BK, row0);
+                    tma_load_2d(&mp.Fh[who], &full_bar[s], b, kb * F_BK, 0);
+                    tma_load_2d(&mp.Fl[who], &full_bar[s], b + F_B_BYTES, kb * F_BK, 0);
+                    if (head >= 0) {
+                        tma_load_2d(&mp.Sh[head], &full_bar[s], b + 2 * F_B_BYTES, (kb & 1) * F_BK, 0);
+                        tma_load_2d(&mp.Sl[head], &full_bar[s], b + 3 * F_B_BYTES, (kb & 1) * F_BK, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
+            int it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc) {
+                const int buf = tc & 1;
+                mbar_wait(&tempty_bar[buf], ((tc >> 1) & 1) ^ 1);   // drained by the epilogue two tiles ago
+                tc_fence_after();
+                const uint32_t dbase = tmem_d + buf * 256;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % H_STAGES;
+                    const uint32_t ph = (it / H_STAGES) & 1;
+                    const int head = kb / 2 - 1;
+                    mbar_wait(&split_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t ah = smem_u32(smem + s * H_STAGE);
+                    const uint32_t al = ah + F_A_BYTES;
+                    const uint32_t fh = ah + 2 * F_A_BYTES, fl = fh + F_B_BYTES, sh = fl + F_B_BYTES, sl = sh + F_B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < F_BK / 8; ++k) {
+                        const uint64_t dah = umma_desc_sw128(ah + k * 32, 16, 1024);
+                        const uint64_t dal = umma_desc_sw128(al + k * 32, 16, 1024);
+                        const uint64_t dfh = umma_desc_sw128(fh + k * 32, 16, 1024);
+                        const uint64_t dfl = umma_desc_sw128(fl + k * 32, 16, 1024);
+                        umma_tf32(dbase, dal, dfh, idesc, (kb | k) != 0);
+                        umma_tf32(dbase, dah, dfl, idesc, 1);
+                        umma_tf32(dbase, dah, dfh, idesc, 1);
+                        if (head >= 0) {
+                            const uint64_t dsh = umma_desc_sw128(sh + k * 32, 16, 1024);
+                            const uint64_t dsl = umma_desc_sw128(sl + k * 32, 16, 1024);
+                            const uint32_t dcol = dbase + 64 * (head + 1);
+                            umma_tf32(dcol, dal, dsh, idesc, ((kb & 1) | k) != 0);
+                            umma_tf32(dcol, dah, dsl, idesc, 1);
+                            umma_tf32(dcol, dah, dsh, idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull_bar[buf]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---- split warps: raw fp32 A tile -> TF32 hi (in place) + lo (twin buffer) --------------------------------------
+        const int t = threadIdx.x - 64;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % H_STAGES;
+                const uint32_t ph = (it / H_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                float4* hi = reinterpret_cast<float4*>(smem + s * H_STAGE);
+                float4* lo = reinterpret_cast<float4*>(smem + s * H_STAGE + F_A_BYTES);
+#pragma unroll
+                for (int i = 0; i < F_A_BYTES / 16 / 128; ++i) {
+                    const int idx = i * 128 + t;
+                    const float4 x = hi[idx];
+                    float4 h, l;
+                    h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+                    l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+                    hi[idx] = h;
+                    lo[idx] = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(&split_bar[s]);
+            }
+        }
+    } else {
+        // ---- drain warps: TMEM -> registers -> global (each thread owns one row: 64 consecutive floats per output) -----
+        const int q = warp & 3;
+        int tc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc) {
+            const int buf = tc & 1;
+            const int who = tile < n_user_tiles ? 0 : 1;
+            const int row0 = who == 0 ? tile * F_BM : U + (tile - n_user_tiles) * F_BM;
+            const int row_end = who == 0 ? U : N;
+            const int row = row0 + q * 32 + lane;
+            mbar_wait(&tfull_bar[buf], (tc >> 1) & 1);
+            tc_fence_after();
+            for (int o = 0; o <= n_heads; ++o) {
+                float v[64];
+                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + buf * 256 + 64 * o;
+                tmem_ld_32x32(taddr, v);
+                tmem_ld_32x32(taddr + 32, v + 32);
+                tmem_ld_wait();
+                if (o == n_heads) {   // last read of this buffer: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                }
+                const float* bias = (o == 0) ? ho.bias_f[who] : ho.bias_s[o - 1];
+                if (row < row_end) {
+                    float4* y = reinterpret_cast<float4*>(ho.out[o] + (long long)row * 64);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + j);
+                        y[j] = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, 512);
+}
+
 __global__ void split_tf32_kernel(long long n, const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -897,6 +1078,58 @@ ELIMREC_API int elimrec_fuse_heads_x3(int64_t rows, int n_heads, const float* O,
     }
     const unsigned grid = (unsigned)((rows + F_BM - 1) / F_BM);
     fuse_heads_x3_kernel<<<grid, 192, H_SMEM, er_stream(stream)>>>(tmA, tmFh, tmFl, hm, ho, (int)rows, n_heads);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+
+ELIMREC_API int elimrec_fuse_heads_x3_all(int64_t num_users, int64_t num_items, int n_heads, const float* O, int64_t ldo,
+                                          const float* Wu_hi, const float* Wu_lo, const float* bu, const float* Wi_hi,
+                                          const float* Wi_lo, const float* bi, const float* const* Ws_hi_host,
+                                          const float* const* Ws_lo_host, const float* const* bs_host, float* F_out,
+                                          float* const* S_out_host, elimrec_stream_t stream) {
+    const int64_t N = num_users + num_items;
+    if (N <= 0) return 0;
+    ER_CHECK_ARG(n_heads >= 1 && n_heads <= ELIMREC_MAX_MODS, "n_heads out of range");
+    const int64_t K = 64 * (1 + n_heads);
+    if (ldo % 4 != 0 || ldo < K || !aligned16(O) || N > 0x7fffffff) {
+        elimrec_set_error("elimrec_fuse_heads_x3_all: unsupported shape/alignment");
+        return -2;
+    }
+    FuseAllMaps mp;
+    FuseAllOut ho{};
+    int bad = make_map(&mp.A, O, N, K, ldo, F_BM);
+    bad |= make_map(&mp.Fh[0], Wu_hi, 64, K, K, F_BN) | make_map(&mp.Fl[0], Wu_lo, 64, K, K, F_BN);
+    bad |= make_map(&mp.Fh[1], Wi_hi, 64, K, K, F_BN) | make_map(&mp.Fl[1], Wi_lo, 64, K, K, F_BN);
+    ho.bias_f[0] = bu; ho.bias_f[1] = bi;
+    ho.out[0] = F_out;
+    for (int m = 0; m < ELIMREC_MAX_MODS; ++m) {
+        const int mm = m < n_heads ? m : 0;
+        bad |= make_map(&mp.Sh[m], Ws_hi_host[mm], 64, 64, 64, F_BN) | make_map(&mp.Sl[m], Ws_lo_host[mm], 64, 64, 64, F_BN);
+        ho.bias_s[m] = bs_host[mm];
+        if (m < n_heads) ho.out[m + 1] = S_out_host[m];
+    }
+    if (bad) {
+        elimrec_set_error("elimrec_fuse_heads_x3_all: cuTensorMapEncodeTiled failed");
+        return -3;
+    }
+    static bool configured = false;
+    static int n_sm = 148;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fuse_heads_x3_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+        if (e != cudaSuccess) {
+            elimrec_set_error("elimrec_fuse_heads_x3_all: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            return -3;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    const int n_ut = (int)((num_users + F_BM - 1) / F_BM), n_it = (int)((num_items + F_BM - 1) / F_BM);
+    const int n_tiles = n_ut + n_it;
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    fuse_heads_x3_all_kernel<<<grid, 320, H_SMEM, er_stream(stream)>>>(mp, ho, (int)num_users, (int)N, n_heads, n_ut, n_tiles);
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -396,8 +396,14 @@ class EliMRec(BasicModel):
         O, F_all = ws["O"], ws["F_all"]
         if not from_snapshot:
             torch._foreach_copy_(ws["snap_dst"], [P[n].detach() for n in ws["snap_names"]])
-        self._fuse_heads_rows(ws, O[:U], F_all[:U], [s_[:U] for s_ in ws["S"]], "u")
-        self._fuse_heads_rows(ws, O[U:], F_all[U:], [s_[U:] for s_ in ws["S"]], "i")
+        if self.fuse_precision == "x3":
+            sp, sn = ws["W_split"], ws["snap"]
+            ops.fuse_heads_x3_all(U, I, O, sp["u"], sn["embedding_user_after_GCN.bias"], sp["i"],
+                                  sn["embedding_item_after_GCN.bias"], [sp[m][0] for m in self.mods],
+                                  [sp[m][1] for m in self.mods], [sn[f"s_dense_{m}.bias"] for m in self.mods], F_all, ws["S"])
+        else:
+            self._fuse_heads_rows(ws, O[:U], F_all[:U], [s_[:U] for s_ in ws["S"]], "u")
+            self._fuse_heads_rows(ws, O[U:], F_all[U:], [s_[U:] for s_ in ws["S"]], "i")
         self._all_users, self._all_items = F_all[:U], F_all[U:]
         self._all_s_embs = {}
         for j, m in enumerate(self.mods):

@@ -125,6 +125,15 @@ def fuse_heads_x3(O_rows, Wf_hi, Wf_lo, bf, Ws_hi, Ws_lo, bs, F_out, S_out, tag=
          ptr(bf, F32), arr(Ws_hi), arr(Ws_lo), arr(bs), ptr(F_out, F32), arr(S_out), stream(), tag=tag)
 
 
+def fuse_heads_x3_all(U, I, O, Wu, bu, Wi, bi, Ws_hi, Ws_lo, bs, F_out, S_out, tag="fuse_heads_x3_all"):
+    """Persistent one-pass fusion Linear + heads over the whole slab O [(U+I) x F]; Wu/Wi are (hi, lo) pairs."""
+    n = len(Ws_hi)
+    arr = lambda ts: (C.c_void_p * 3)(*([ptr(t, F32) for t in ts] + [None] * (3 - n)))
+    call("elimrec_fuse_heads_x3_all", U, I, n, ptr(O, F32), O.stride(0), ptr(Wu[0], F32), ptr(Wu[1], F32), ptr(bu, F32),
+         ptr(Wi[0], F32), ptr(Wi[1], F32), ptr(bi, F32), arr(Ws_hi), arr(Ws_lo), arr(bs), ptr(F_out, F32), arr(S_out), stream(),
+         tag=tag)
+
+
 def split_tf32(src, hi, lo):
     call("elimrec_split_tf32", src.numel(), ptr(src, F32), ptr(hi, F32), ptr(lo, F32), stream())
 

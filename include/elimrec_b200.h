@@ -124,6 +124,13 @@ int elimrec_split_tf32(int64_t n, const float* src, float* hi, float* lo, elimre
 int elimrec_fuse_heads_x3(int64_t rows, int n_heads, const float* O, int64_t ldo, const float* Wf_hi, const float* Wf_lo,
                           const float* bf, const float* const* Ws_hi_host, const float* const* Ws_lo_host,
                           const float* const* bs_host, float* F_out, float* const* S_out_host, elimrec_stream_t stream);
+/* Same, persistent, over the WHOLE slab O [(U+I) x 64(1+n_heads)] (users first): user rows use Wu/bu, item rows Wi/bi;
+ * F_out and S_out[m] are [(U+I) x 64].  One CTA per SM, TMEM double-buffered accumulators, epilogue overlapped. */
+int elimrec_fuse_heads_x3_all(int64_t num_users, int64_t num_items, int n_heads, const float* O, int64_t ldo,
+                              const float* Wu_hi, const float* Wu_lo, const float* bu, const float* Wi_hi,
+                              const float* Wi_lo, const float* bi, const float* const* Ws_hi_host,
+                              const float* const* Ws_lo_host, const float* const* bs_host, float* F_out,
+                              float* const* S_out_host, elimrec_stream_t stream);
 /* several small weight tensors prepared for the tensor cores in ONE launch: hi = rna_tf32(src); if lo != NULL,
  * lo = rna_tf32(src - hi) (3xTF32 split), else round only */
 #define ELIMREC_PREP_MAX 16

@@ -431,3 +431,29 @@ def test_fuse_heads_x3_one_pass(dev, rows, n_heads):
         assert rel_err(So[m][:rows], ref) < FP32_TOL, m
         assert float((So[m][rows] - 7).abs().max()) == 0
     assert float((Fo[rows] - 7).abs().max()) == 0
+
+
+@pytest.mark.parametrize("U,I,n_heads", [(300, 500, 3), (36656 // 4, 76085 // 4, 3), (128, 1, 1), (50, 70, 2)])
+def test_fuse_heads_x3_all_persistent(dev, U, I, n_heads):
+    """Persistent whole-slab variant (TMEM double buffering): user rows with Wu, item rows with Wi, fp32 class."""
+    from elimrec_b200 import ops
+    F = 64 * (1 + n_heads)
+    g = torch.Generator().manual_seed(U + I)
+    O = torch.randn(U + I, F, generator=g).to(dev)
+    mk = lambda *s: (torch.randn(*s, generator=g) / s[-1] ** 0.5).to(dev)
+    Wu, Wi, bu, bi = mk(64, F), mk(64, F), mk(64), mk(64)
+    Ws, bs = [mk(64, 64) for _ in range(n_heads)], [mk(64) for _ in range(n_heads)]
+    pair = lambda w: (torch.empty_like(w), torch.empty_like(w))
+    Wus, Wis, Wss = pair(Wu), pair(Wi), [pair(w) for w in Ws]
+    ops.prep_weights_tf32([(Wu, *Wus), (Wi, *Wis)] + [(w, h, l) for w, (h, l) in zip(Ws, Wss)])
+    Fo = torch.full((U + I + 1, 64), 7.0, device=dev)
+    So = [torch.full((U + I + 1, 64), 7.0, device=dev) for _ in range(n_heads)]
+    ops.fuse_heads_x3_all(U, I, O, Wus, bu, Wis, bi, [h for h, _ in Wss], [l for _, l in Wss], bs, Fo, So)
+    Od = O.double()
+    assert rel_err(Fo[:U], Od[:U] @ Wu.double().t() + bu.double()) < FP32_TOL
+    assert rel_err(Fo[U:U + I], Od[U:] @ Wi.double().t() + bi.double()) < FP32_TOL
+    for m in range(n_heads):
+        ref = Od[:, 64 * (m + 1):64 * (m + 2)] @ Ws[m].double().t() + bs[m].double()
+        assert rel_err(So[m][:U + I], ref) < FP32_TOL, m
+        assert float((So[m][U + I] - 7).abs().max()) == 0
+    assert float((Fo[U + I] - 7).abs().max()) == 0
