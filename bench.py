@@ -240,7 +240,7 @@ def main():
     # ---- device-resident arm: triples already in HBM ---------------------------------------------
     u, p, n = sampler_dev.sample_epoch_device(n_steps * BATCH)
     batches = [(u[i * BATCH:(i + 1) * BATCH], p[i * BATCH:(i + 1) * BATCH], n[i * BATCH:(i + 1) * BATCH]) for i in range(n_steps)]
-    use_graph = bool(args.cuda_graph) and world == 1
+    use_graph = bool(args.cuda_graph) and not rowshard
     runner = model.make_graphed_step() if use_graph else None
 
     def step(b):

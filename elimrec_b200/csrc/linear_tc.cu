@@ -367,6 +367,7 @@ linear_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 constexpr int H_STAGES = 3;
 constexpr int H_STAGE = 2 * F_A_BYTES + 4 * F_B_BYTES;   // A_hi | A_lo | Wf_hi | Wf_lo | Ws_hi | Ws_lo
 constexpr int H_SMEM = H_STAGES * H_STAGE + 1024;
+constexpr int HA_SMEM = H_SMEM + 4 * 32 * 65 * 4;        // + one 32x64 transpose tile per drain warp (persistent variant)
 
 struct HeadMaps {
     CUtensorMap hi[ELIMREC_MAX_MODS];
@@ -681,13 +682,22 @@ fuse_heads_x3_all_kernel(const __grid_constant__ FuseAllMaps mp, FuseAllOut ho, 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[buf]);
                 }
+                // transpose through a private shared-memory tile so that every store instruction writes whole rows
+                // (a thread-per-row float4 store touches 32 different 128-byte lines per instruction: LSU-throttled)
                 const float* bias = (o == 0) ? ho.bias_f[who] : ho.bias_s[o - 1];
-                if (row < row_end) {
-                    float4* y = reinterpret_cast<float4*>(ho.out[o] + (long long)row * 64);
+                float* st = reinterpret_cast<float*>(smem + H_STAGES * H_STAGE) + q * (32 * 65);
+                __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + j);
-                        y[j] = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+                for (int j = 0; j < 64; ++j) st[lane * 65 + j] = v[j];
+                __syncwarp();
+                const float b0 = __ldg(bias + lane), b1 = __ldg(bias + 32 + lane);
+                float* outp = ho.out[o];
+                const int rbase = row0 + q * 32;
+                for (int r = 0; r < 32; ++r) {
+                    if (rbase + r < row_end) {
+                        float* y = outp + (long long)(rbase + r) * 64;
+                        y[lane] = st[r * 65 + lane] + b0;
+                        y[32 + lane] = st[r * 65 + 32 + lane] + b1;
                     }
                 }
             }
@@ -1116,7 +1126,7 @@ ELIMREC_API int elimrec_fuse_heads_x3_all(int64_t num_users, int64_t num_items, 
     static bool configured = false;
     static int n_sm = 148;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fuse_heads_x3_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(fuse_heads_x3_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HA_SMEM);
         if (e != cudaSuccess) {
             elimrec_set_error("elimrec_fuse_heads_x3_all: shared-memory opt-in failed: %s", cudaGetErrorString(e));
             return -3;
@@ -1129,7 +1139,7 @@ ELIMREC_API int elimrec_fuse_heads_x3_all(int64_t num_users, int64_t num_items, 
     const int n_ut = (int)((num_users + F_BM - 1) / F_BM), n_it = (int)((num_items + F_BM - 1) / F_BM);
     const int n_tiles = n_ut + n_it;
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    fuse_heads_x3_all_kernel<<<grid, 320, H_SMEM, er_stream(stream)>>>(mp, ho, (int)num_users, (int)N, n_heads, n_ut, n_tiles);
+    fuse_heads_x3_all_kernel<<<grid, 320, HA_SMEM, er_stream(stream)>>>(mp, ho, (int)num_users, (int)N, n_heads, n_ut, n_tiles);
     ER_LAUNCH_CHECK();
     return 0;
 }

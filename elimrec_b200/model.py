@@ -600,11 +600,26 @@ class EliMRec(BasicModel):
             self.train_step(su, sp_, sn)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        # undo the warm-up step so that graphed and eager runs see the same parameter trajectory
-        graph = torch.cuda.CUDAGraph()
+        dp = getattr(self, "_dp", False)
         before = CALLS["launches"]
-        with torch.cuda.graph(graph):
-            loss = self.train_step(su, sp_, sn)
+        if not dp:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self.train_step(su, sp_, sn)
+            graphs = (graph,)
+        else:
+            # data-parallel replicas: graph 1 = forward + backward + gradient packing, then ONE eager NCCL all-reduce of
+            # the flat bucket, then graph 2 = Adam on the averaged bucket (collectives stay outside the captures)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                with torch.no_grad():
+                    loss = self._forward(su, sp_, sn)
+                    grads = self._backward(None)
+                    self._ws["bucket"].pack(grads)
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                with torch.no_grad():
+                    self._adam.apply(self._ws["bucket"].views)
+            graphs = (g1, g2)
         n_launch = CALLS["launches"] - before + 2  # + the two memsets of the backward seeds
 
         class _Runner:
@@ -613,7 +628,10 @@ class EliMRec(BasicModel):
             def __call__(self, users, pos, neg):
                 u, p, n = model._triples(users, pos, neg)
                 su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
-                graph.replay()
+                graphs[0].replay()
+                if dp:
+                    model._ws["bucket"].all_reduce_mean()
+                    graphs[1].replay()
                 return loss
 
         return _Runner()
