@@ -138,7 +138,8 @@ def test_eval_fullsize_properties(tiktok):
     # metric means equal the mean of the per-user rows; recall/precision consistency: P@K * K = hits = R@K * |truth|
     r = rows.cpu().numpy()
     np.testing.assert_allclose(r.astype(np.float64).mean(0).reshape(3, 20)[:, 19], res1, rtol=1e-6)   # device mean is fp64
-    tl = np.array([len(ds.get_user_test_dict()[x]) for x in users])
+    td = ds.get_user_test_dict()
+    tl = np.array([len(td[x]) for x in users])
     np.testing.assert_allclose(r[:, 19] * 20, r[:, 39] * tl, rtol=1e-5, atol=1e-5)
 
 
