@@ -194,7 +194,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": r["timed_steps"],
                 "warmup": args.warmup, "ms_per_step": 1e3 * r["step_s"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}-shape EliMRec train step, batch {BATCH}, layer_num 3, recdim 64"},
+                "config": {"workload": f"{args.workload}-shape EliMRec train step (sample + fwd + bwd + Adam), batch {BATCH}/GPU, "
+                                       f"layer_num 3, recdim 64, U={ds.num_users} I={ds.num_items} E_train={ds.train_matrix.nnz}"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "eval": {"value": r["eval_users_per_s"], "unit": "users/s", "n_users": r["eval_users"]},
@@ -331,8 +332,14 @@ def main():
             alg = float(np.mean(per))
             avg_s = 1e-3 * sum(agg[tag]) / len(agg[tag])
             ach = alg / avg_s / 1e9
+            traffic = None
+            try:   # DRAM bytes per wide launch from the committed ncu --set full capture (Tiktok shape only)
+                if args.workload == "tiktok":
+                    traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json")))["avg_wide_launch_bytes"]
+            except Exception:
+                pass
             roofline = {"kernel": f"spmm_seg_kernel<{Fw}>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": which, "bytes_per_launch": alg,
+                        "frac": ach / peak, "traffic": traffic, "peak_source": which, "bytes_per_launch": alg,
                         "avg_launch_us": 1e6 * avg_s, "share_of_step": sum(agg[tag]) / sum(sum(v) for v in agg.values())}
     clk = clocks.stop() if rank == 0 else None
     sync_all()
