@@ -40,6 +40,12 @@ class RankTables(C.Structure):
                 ("f_item", vp), ("s_user", vp * MAX_MODS), ("s_item", vp * MAX_MODS)]
 
 
+class RankTcTables(C.Structure):
+    _fields_ = [("num_users", i32), ("num_items", i32), ("n_mod", i32), ("mode", i32), ("user_hi", vp * (1 + MAX_MODS)),
+                ("user_lo", vp * (1 + MAX_MODS)), ("item_hi", vp * (1 + MAX_MODS)), ("item_lo", vp * (1 + MAX_MODS)),
+                ("inv_scale", f32 * (1 + MAX_MODS))]
+
+
 _SIGS = {
     "elimrec_spmm": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
     "elimrec_scatter_add_rows": [i32, vp, i32, i32, i32, vp, i64, i32, vp, i64, i32, f32, vp],
@@ -70,6 +76,8 @@ _SIGS = {
     "elimrec_rank_scores": [C.POINTER(RankTables), i32, vp, vp, vp, vp],
     "elimrec_rank_topk": [C.POINTER(RankTables), i32, vp, vp, vp, vp, i32, vp, vp, vp],
     "elimrec_topk_matrix": [i32, i32, vp, i32, vp, vp, vp],
+    "elimrec_split_fp16": [i64, vp, f32, vp, vp, vp],
+    "elimrec_rank_tc": [C.POINTER(RankTcTables), i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "elimrec_metric_rows": [i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp],
 }
 _I64_RET = {
@@ -77,6 +85,7 @@ _I64_RET = {
     "elimrec_colsum_workspace_floats": [i64, i64],
     "elimrec_linear_tf32_wgrad_workspace_floats": [i64, i64],
     "elimrec_inst_backward_workspace_floats": [i32, i32, i32],
+    "elimrec_rank_tc_workspace_bytes": [i32],
 }
 # every symbol include/elimrec_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = sorted(list(_SIGS) + list(_I64_RET) + ["elimrec_last_error", "elimrec_abi_version",
@@ -115,7 +124,7 @@ def lib():
 # kernels launched through the C-ABI (bench.py reports `gpu_launches` from this) and an optional
 # per-family CUDA-event profile (bench.py --profile-kernels; events sit on the launching stream)
 CALLS = {"n": 0, "launches": 0}
-_LAUNCHES = {"elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2, "elimrec_inst_backward": 3}
+_LAUNCHES = {"elimrec_rank_tc": 2, "elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2, "elimrec_inst_backward": 3}
 PROFILE = {"on": False, "events": []}
 
 

@@ -111,14 +111,20 @@ class UniEvaluator(AbstractEvaluator):
         rows = torch.empty(max(n, 1), ncol, dtype=torch.float32, device=dev)
         if n > 0:
             u = users[lo:hi]
-            tables = model.rank_tables()
-            mean = None
-            if model.predict_type == "TIE":
-                mean = torch.empty(n, dtype=torch.float32, device=dev)
-                ops.rank_rowmean(tables, u, mean)
             idx = torch.empty(n, K, dtype=torch.int32, device=dev)
             val = torch.empty(n, K, dtype=torch.float32, device=dev)
-            ops.rank_topk(tables, u, mean, st["train_ptr"], st["train_items"], K, idx, val)
+            mean = torch.empty(n, dtype=torch.float32, device=dev) if model.predict_type == "TIE" else None
+            backend = model.config["rank_backend"] if "rank_backend" in model.config else "tc"
+            if backend == "tc":      # tensor cores, fp16 hi/lo operand pairs (fp32-class accuracy)
+                tables = model.rank_tc_tables()
+                if mean is not None:
+                    ops.rank_tc(tables, 0, u, None, None, None, K, None, None, mean)
+                ops.rank_tc(tables, 1, u, mean, st["train_ptr"], st["train_items"], K, idx, val, None)
+            else:                    # exact fp32 FFMA path
+                tables = model.rank_tables()
+                if mean is not None:
+                    ops.rank_rowmean(tables, u, mean)
+                ops.rank_topk(tables, u, mean, st["train_ptr"], st["train_items"], K, idx, val)
             # truth CSR re-based to the shard
             tp = (truth_ptr[lo:hi + 1] - truth_ptr[lo]).contiguous()
             ti = truth_items[int(truth_ptr[lo]):int(truth_ptr[hi])] if n_all else truth_items

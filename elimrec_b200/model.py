@@ -664,6 +664,32 @@ class EliMRec(BasicModel):
         si = [ws["S_norm"][j][1] for j in act]
         return ops.rank_tables(self.num_users, self.num_items, PREDICT_MODE[self.predict_type], fu, fi, su, si)
 
+    def rank_tc_tables(self):
+        """fp16 hi/lo split of the cached tables for the tensor-core evaluator (rebuilt once per training forward)."""
+        self.rank_tables()                      # refreshes the normalised single-modal tables
+        ws = self._ws
+        key = (self._tables_version, self.predict_type, self.modality)
+        if ws.get("rank_tc_key") != key:
+            fu, fi = ws["rank_f"]
+            act = self._active_mods()
+            srcs = [(fu, fi)] + [ws["S_norm"][j] for j in act]
+            out = []
+            for k, (a, b) in enumerate(srcs):
+                parts = []
+                scales = []
+                for x in (a, b):
+                    amax = float(x.abs().max()) if k == 0 else 1.0      # heads are L2-normalised: |x| <= 1
+                    sc = 2.0 ** np.floor(np.log2(4096.0 / max(amax, 1e-30)))
+                    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+                    lo = torch.empty_like(hi)
+                    ops.split_fp16(x.contiguous(), float(sc), hi, lo)
+                    parts += [hi, lo]
+                    scales.append(sc)
+                out.append((parts[0], parts[1], parts[2], parts[3], float(1.0 / (scales[0] * scales[1]))))
+            ws["rank_tc"] = ops.rank_tc_tables(self.num_users, self.num_items, PREDICT_MODE[self.predict_type], out)
+            ws["rank_tc_key"] = key
+        return ws["rank_tc"]
+
     def _tables(self):
         """(fused users, fused items, [single-modal users], [single-modal items]) cached by the last training forward."""
         U = self.num_users

@@ -241,6 +241,37 @@ def rank_topk(t, eval_users, ui_mean, train_ptr, train_items, K, idx, val):
          ptr(train_ptr, torch.int64), ptr(train_items, torch.int32), K, ptr(idx, torch.int32), ptr(val, F32), stream())
 
 
+def split_fp16(src, scale, hi, lo):
+    call("elimrec_split_fp16", src.numel(), ptr(src, F32), scale, ptr(hi, torch.float16), ptr(lo, torch.float16), stream())
+
+
+def rank_tc_tables(num_users, num_items, mode, tables):
+    """tables: list over t of (user_hi, user_lo, item_hi, item_lo, inv_scale); t = 0 fused, then the active heads."""
+    t = _lib.RankTcTables()
+    t.num_users, t.num_items, t.n_mod, t.mode = num_users, num_items, len(tables) - 1, mode
+    for k, (uh, ul, ih, il, inv) in enumerate(tables):
+        t.user_hi[k], t.user_lo[k] = ptr(uh, torch.float16), ptr(ul, torch.float16)
+        t.item_hi[k], t.item_lo[k] = ptr(ih, torch.float16), ptr(il, torch.float16)
+        t.inv_scale[k] = inv
+    t._keepalive = tables
+    return t
+
+
+_RANK_TC_WS = {}
+
+
+def rank_tc(t, what, eval_users, ui_mean, train_ptr, train_items, K, idx, val, mean_out):
+    n = eval_users.numel()
+    need = int(_lib.lib().elimrec_rank_tc_workspace_bytes(n))
+    key = eval_users.device.index
+    ws = _RANK_TC_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _RANK_TC_WS[key] = torch.empty(need, dtype=torch.uint8, device=eval_users.device)
+    call("elimrec_rank_tc", C.byref(t), what, n, ptr(eval_users, torch.int32), ptr(ui_mean, F32, True),
+         ptr(train_ptr, torch.int64, True), ptr(train_items, torch.int32, True), K, ptr(idx, torch.int32, True),
+         ptr(val, F32, True), ptr(mean_out, F32, True), ptr(ws), stream(), tag="rank_tc")
+
+
 def topk_matrix(scores, K, idx, val):
     call("elimrec_topk_matrix", scores.shape[0], scores.shape[1], ptr(scores, F32), K, ptr(idx, torch.int32),
          ptr(val, F32), stream())

@@ -243,6 +243,23 @@ int elimrec_rank_scores(const elimrec_rank_tables_t* t, int n_eval, const int32_
 int elimrec_rank_topk(const elimrec_rank_tables_t* t, int n_eval, const int32_t* eval_users, const float* ui_mean,
                       const int64_t* train_ptr, const int32_t* train_items, int K, int32_t* topk_idx, float* topk_val,
                       elimrec_stream_t stream);
+/* Tensor-core evaluator (tcgen05 kind::f16, fp32-class accuracy through fp16 hi/lo operand pairs; csrc/rank_tc.cu).
+ * Tables are pre-split with elimrec_split_fp16: value * scale = hi + lo (scale a power of two), [rows x 64] fp16.
+ * table 0 = fused table, 1..n_mod = L2-normalised single-modal heads; inv_scale[t] = 1 / (user scale * item scale).
+ * what = 0: mean_out[r] = mean_i sigmoid(u.i) (row mean for TIE); what = 1: fused score + train mask + top-K. */
+typedef struct {
+    int32_t num_users, num_items, n_mod, mode;
+    const void* user_hi[1 + ELIMREC_MAX_MODS];
+    const void* user_lo[1 + ELIMREC_MAX_MODS];
+    const void* item_hi[1 + ELIMREC_MAX_MODS];
+    const void* item_lo[1 + ELIMREC_MAX_MODS];
+    float inv_scale[1 + ELIMREC_MAX_MODS];
+} elimrec_rank_tc_tables_t;
+int elimrec_split_fp16(int64_t n, const float* src, float scale, void* hi, void* lo, elimrec_stream_t stream);
+int elimrec_rank_tc(const elimrec_rank_tc_tables_t* t, int what, int n_eval, const int32_t* eval_users, const float* ui_mean,
+                    const int64_t* train_ptr, const int32_t* train_items, int K, int32_t* topk_idx, float* topk_val,
+                    float* mean_out, void* workspace, elimrec_stream_t stream);
+int64_t elimrec_rank_tc_workspace_bytes(int n_eval);
 /* top-K of an explicit score matrix (arg_top_k_2d, util/cython/include/arg_topk.h:15-45) */
 int elimrec_topk_matrix(int n_rows, int n_cols, const float* scores, int K, int32_t* topk_idx, float* topk_val,
                         elimrec_stream_t stream);

@@ -457,3 +457,52 @@ def test_fuse_heads_x3_all_persistent(dev, U, I, n_heads):
         assert rel_err(So[m][:U + I], ref) < FP32_TOL, m
         assert float((So[m][U + I] - 7).abs().max()) == 0
     assert float((Fo[U + I] - 7).abs().max()) == 0
+
+
+@pytest.mark.parametrize("mode,n_mod", [(2, 3), (1, 3), (0, 1), (2, 1)])
+def test_rank_tc_matches_exact_path(dev, mode, n_mod):
+    """Tensor-core evaluator (fp16 hi/lo pairs, tcgen05) vs the exact fp32 FFMA rank kernel and the fp64 scores."""
+    from elimrec_b200 import ops
+    from gpu_util import topk_sets_match
+    U, I, K = 700, 5000 + 13, 20
+    fu, fi, su, si = _rank_inputs(dev, U, I, n_mod, seed=5)
+    fu, fi = fu * 0.5, fi * 0.5
+    users = torch.randperm(U)[:300 + 7]
+    eu = users.to(dev).int()
+    norm = lambda t: torch.nn.functional.normalize(t, dim=1)
+    sun, sin_ = [norm(a).to(dev) for a in su], [norm(a).to(dev) for a in si]
+    fud, fid = fu.to(dev), fi.to(dev)
+    rng = np.random.default_rng(2)
+    train = {u: np.sort(rng.choice(I, size=rng.integers(0, 60), replace=False)) for u in range(U)}
+    train[int(users[1])] = np.arange(100, 400)
+    ptr_ = np.zeros(U + 1, dtype=np.int64); ptr_[1:] = np.cumsum([train[u].size for u in range(U)])
+    flat = np.concatenate([train[u] for u in range(U)]).astype(np.int32)
+    tp, tf = torch.from_numpy(ptr_).to(dev), torch.from_numpy(flat).to(dev)
+    # exact path
+    t = ops.rank_tables(U, I, mode, fud, fid, sun if mode else [], sin_ if mode else [])
+    mean_x = torch.empty(eu.numel(), device=dev)
+    ops.rank_rowmean(t, eu, mean_x)
+    idx_x = torch.empty(eu.numel(), K, dtype=torch.int32, device=dev); val_x = torch.empty(eu.numel(), K, device=dev)
+    ops.rank_topk(t, eu, mean_x, tp, tf, K, idx_x, val_x)
+    # tensor-core path
+    def split(x, amax):
+        sc = 2.0 ** np.floor(np.log2(4096.0 / amax))
+        hi = torch.empty(x.shape, dtype=torch.float16, device=dev); lo = torch.empty_like(hi)
+        ops.split_fp16(x.contiguous(), float(sc), hi, lo)
+        return hi, lo, sc
+    tabs = []
+    for a, b in [(fud, fid)] + (list(zip(sun, sin_)) if mode else []):
+        ah, al, sa = split(a, float(a.abs().max()))
+        bh, bl, sb = split(b, float(b.abs().max()))
+        tabs.append((ah, al, bh, bl, float(1.0 / (sa * sb))))
+    tt = ops.rank_tc_tables(U, I, mode, tabs)
+    mean_t = torch.empty(eu.numel(), device=dev)
+    ops.rank_tc(tt, 0, eu, None, None, None, K, None, None, mean_t)
+    assert rel_err(mean_t, mean_x) < 2e-6
+    idx_t = torch.empty(eu.numel(), K, dtype=torch.int32, device=dev); val_t = torch.empty(eu.numel(), K, device=dev)
+    ops.rank_tc(tt, 1, eu, mean_t, tp, tf, K, idx_t, val_t, None)
+    assert rel_err(val_t, val_x) < 2e-6
+    same = (idx_t == idx_x).all(dim=1).float().mean()
+    ref = _ref_scores(fu, fi, su, si, users, mode).numpy()
+    exact, explained, bad = topk_sets_match(idx_t.cpu().numpy(), ref, [train[int(u)] for u in users], K, tol=2e-6)
+    assert bad == 0 and float(same) > 0.97, (float(same), exact, explained, bad)
