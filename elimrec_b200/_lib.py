@@ -35,6 +35,10 @@ class PrepTensor(C.Structure):
     _fields_ = [("src", vp), ("hi", vp), ("lo", vp), ("numel", i64)]
 
 
+class LinearDesc(C.Structure):
+    _fields_ = [("M", i64), ("K", i64), ("X", vp), ("ldx", i64), ("W", vp), ("b", vp), ("Y", vp), ("ldy", i64)]
+
+
 class RankTables(C.Structure):
     _fields_ = [("num_users", i32), ("num_items", i32), ("n_mod", i32), ("mode", i32), ("f_user", vp),
                 ("f_item", vp), ("s_user", vp * MAX_MODS), ("s_item", vp * MAX_MODS)]
@@ -48,6 +52,10 @@ class RankTcTables(C.Structure):
 
 _SIGS = {
     "elimrec_spmm": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
+    "elimrec_spmm_masked": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp, vp, vp],
+    "elimrec_mark_rows": [i32, vp, i64, vp, vp],
+    "elimrec_inst_rows": [i32, vp, vp, vp, i32, vp, i64, vp, vp],
+    "elimrec_zero_rows": [i32, vp, i32, i32, i32, vp, i64, i32, vp],
     "elimrec_scatter_add_rows": [i32, vp, i32, i32, i32, vp, i64, i32, vp, i64, i32, f32, vp],
     "elimrec_gather_rows": [i32, vp, vp, i64, vp, i64, i32, vp],
     "elimrec_broadcast_cols": [i64, vp, i64, vp, i64, i32, vp],
@@ -55,6 +63,7 @@ _SIGS = {
     "elimrec_gemm": [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, vp, vp, vp],
     "elimrec_colsum": [i64, i64, vp, i64, vp, vp, i32, vp, vp],
     "elimrec_linear_tf32_fwd": [i64, i64, vp, i64, vp, vp, vp, i64, vp],
+    "elimrec_linear_tf32_fwd_multi": [i32, C.POINTER(LinearDesc), vp],
     "elimrec_linear_tf32_wgrad": [i64, i64, vp, i64, vp, i64, vp, vp, vp],
     "elimrec_round_tf32": [i64, vp, vp, vp],
     "elimrec_split_tf32": [i64, vp, vp, vp, vp],
@@ -65,6 +74,8 @@ _SIGS = {
     "elimrec_linear_x3_fwd": [i64, i64, vp, i64, vp, vp, vp, vp, i64, vp],
     "elimrec_bpr_forward_backward": [i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "elimrec_inst_backward": [i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, vp, C.POINTER(vp),
+                              C.POINTER(vp), vp, vp],
+    "elimrec_inst_backward_part": [i32, i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, vp, C.POINTER(vp),
                               C.POINTER(vp), vp, vp],
     "elimrec_adam_apply_multi": [i32, C.POINTER(AdamTensor), vp, f64, f64, f32, f32, vp],
     "elimrec_adam_tick": [vp, vp, f64, f64, f64, vp],
@@ -124,7 +135,7 @@ def lib():
 # kernels launched through the C-ABI (bench.py reports `gpu_launches` from this) and an optional
 # per-family CUDA-event profile (bench.py --profile-kernels; events sit on the launching stream)
 CALLS = {"n": 0, "launches": 0}
-_LAUNCHES = {"elimrec_rank_tc": 2, "elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2, "elimrec_inst_backward": 3}
+_LAUNCHES = {"elimrec_rank_tc": 2, "elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2, "elimrec_inst_backward": 3, "elimrec_inst_backward_part": 0}
 PROFILE = {"on": False, "events": []}
 
 

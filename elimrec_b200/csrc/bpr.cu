@@ -362,6 +362,16 @@ ELIMREC_API int elimrec_inst_backward(int B, int n_tables, int F, const float* i
                                       const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu,
                                       float* dbi, float* const* dWs_host, float* const* dbs_host, float* workspace,
                                       elimrec_stream_t stream) {
+    return elimrec_inst_backward_part(3, B, n_tables, F, inst_grad, O_inst, gscale_dev, Wu, Wi, Ws_host, dO_inst, dWu, dWi, dbu,
+                                      dbi, dWs_host, dbs_host, workspace, stream);
+}
+
+ELIMREC_API int elimrec_inst_backward_part(int part, int B, int n_tables, int F, const float* inst_grad, const float* O_inst,
+                                           const float* gscale_dev, const float* Wu, const float* Wi,
+                                           const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu,
+                                           float* dbi, float* const* dWs_host, float* const* dbs_host, float* workspace,
+                                           elimrec_stream_t stream) {
+    ER_CHECK_ARG(part >= 1 && part <= 3, "part must be 1 (dO), 2 (weight gradients) or 3 (both)");
     ER_CHECK_ARG(B > 0 && n_tables >= 1 && n_tables <= 1 + ELIMREC_MAX_MODS, "bad batch / table count");
     ER_CHECK_ARG(F == 64 * n_tables, "F must be 64 * n_tables (concat fusion)");
     InstW w{};
@@ -374,9 +384,12 @@ ELIMREC_API int elimrec_inst_backward(int B, int n_tables, int F, const float* i
         o.dbs[m] = dbs_host[m];
     }
     cudaStream_t st = er_stream(stream);
-    const int nb = (B + IRB - 1) / IRB + (2 * B + IRB - 1) / IRB;
-    inst_dO_kernel<<<nb, 256, 0, st>>>(B, n_tables, F, w, inst_grad, gscale_dev, dO_inst);
-    ER_LAUNCH_CHECK();
+    if (part & 1) {
+        const int nb = (B + IRB - 1) / IRB + (2 * B + IRB - 1) / IRB;
+        inst_dO_kernel<<<nb, 256, 0, st>>>(B, n_tables, F, w, inst_grad, gscale_dev, dO_inst);
+        ER_LAUNCH_CHECK();
+    }
+    if (!(part & 2)) return 0;
     const int nc = (B + IRC - 1) / IRC + (2 * B + IRC - 1) / IRC;
     inst_dW_kernel<<<nc, 256, 0, st>>>(B, n_tables, F, inst_grad, O_inst, workspace);
     ER_LAUNCH_CHECK();

@@ -171,15 +171,34 @@ __global__ void colsum_partial_kernel(long long M, long long N, const float* __r
     }
 }
 
-__global__ void colsum_final_kernel(long long n_chunks, long long N, const float* __restrict__ ws, float* out,
-                                    int accumulate, const float* scale_dev) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// 32 columns x 32 chunk-lanes per CTA: lane (ty) adds chunks ty, ty+32, ... (4 loads in flight), then the 32 partial
+// sums of a column are added in a fixed order - deterministic, and ~20 dependent steps instead of n_chunks
+__global__ void __launch_bounds__(1024) colsum_final_kernel(long long n_chunks, long long N, const float* __restrict__ ws,
+                                                            float* out, int accumulate, const float* scale_dev) {
+    __shared__ float red[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long n = (long long)blockIdx.x * 32 + tx;
     float s = 0.f;
-    for (long long c = 0; c < n_chunks; ++c) s += ws[c * N + n];
-    if (scale_dev != nullptr) s *= __ldg(scale_dev);
-    if (accumulate) s += out[n];
-    out[n] = s;
+    if (n < N) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        long long c = ty;
+        for (; c + 96 < n_chunks; c += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] += __ldg(ws + (c + 32 * u) * N + n);
+        }
+        for (; c < n_chunks; c += 32) t[0] += __ldg(ws + c * N + n);
+        s = (t[0] + t[1]) + (t[2] + t[3]);
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t += red[i][tx];
+        if (scale_dev != nullptr) t *= __ldg(scale_dev);
+        if (accumulate) t += out[n];
+        out[n] = t;
+    }
 }
 
 }  // namespace
@@ -238,7 +257,7 @@ ELIMREC_API int elimrec_colsum(int64_t M, int64_t N, const float* A, int64_t ld,
         colsum_partial_kernel<<<grid, 256, 0, st>>>(M, N, A, ld, workspace);
         ER_LAUNCH_CHECK();
     }
-    colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(chunks, N, workspace, out, accumulate, scale_dev);
+    colsum_final_kernel<<<(unsigned)((N + 31) / 32), 1024, 0, st>>>(chunks, N, workspace, out, accumulate, scale_dev);
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -120,32 +120,64 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-constexpr int F_BM = 128, F_BN = 64, F_BK = 32, F_STAGES = 4;
-constexpr int F_A_BYTES = F_BM * F_BK * 4, F_B_BYTES = F_BN * F_BK * 4, F_STAGE = F_A_BYTES + F_B_BYTES;
-constexpr int F_SMEM = F_STAGES * F_STAGE + 1024;  // + slack for the 1024-byte alignment swizzle-128B needs
-constexpr int F_TMEM_COLS = 64;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-__global__ void __launch_bounds__(192)
-linear_tf32_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const float* __restrict__ bias, float* __restrict__ Y, long long ldy, int M, int num_kb) {
+// Persistent: one CTA per SM walks row tiles  tile = blockIdx.x, + gridDim.x, ...  with ONE TMA ring running across tiles
+// (6 stages x 24 KB in flight per SM covers HBM latency at the SM's share of the bandwidth) and two TMEM accumulators,
+// so the store epilogue of tile j overlaps the loads + MMAs of tile j+1.  The grid never exceeds the SM count: an
+// L2-bound kernel launched next to it (the narrow layer-1 SpMM, models/EliMRec.py:244) finds free warp slots on every SM
+// instead of queueing behind a many-wave grid, and there is no wave-quantisation tail.
+constexpr int F_BM = 128, F_BN = 64, F_BK = 32, F_STAGES = 6;
+constexpr int F_A_BYTES = F_BM * F_BK * 4, F_B_BYTES = F_BN * F_BK * 4, F_STAGE = F_A_BYTES + F_B_BYTES;
+constexpr int F_STG = 4 * 32 * 65 * 4;                       // one 32x64 (+pad) transpose tile per epilogue warp
+constexpr int F_SMEM = F_STAGES * F_STAGE + F_STG + 1024;    // + slack for the 1024-byte alignment swizzle-128B needs
+constexpr int F_TMEM_COLS = 128;                             // 2 accumulators x 64 columns
+
+constexpr int F_MAX_PROB = 4;       // problems (modalities) per launch
+struct FwdMulti {
+    CUtensorMap A[F_MAX_PROB], B[F_MAX_PROB];
+    const float* bias[F_MAX_PROB];
+    float* Y[F_MAX_PROB];
+    long long ldy[F_MAX_PROB];
+    int M[F_MAX_PROB], num_kb[F_MAX_PROB];
+    int tile_start[F_MAX_PROB + 1];  // problem p owns tiles [tile_start[p], tile_start[p+1])
+    int n;
+};
+__device__ __forceinline__ int fwd_problem_of(const FwdMulti& mp, int tile) {
+    int p = 0;
+    while (p + 1 < mp.n && tile >= mp.tile_start[p + 1]) ++p;
+    return p;
+}
+
+// Several projections (one per modality: same 64 output columns each, different K) share ONE launch: the tile list is the
+// concatenation of the problems' row tiles, largest K first, dealt round-robin to the CTAs.
+__global__ void __launch_bounds__(192, 1)
+linear_tf32_fwd_kernel(const __grid_constant__ FwdMulti mp) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[F_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[F_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
 
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * F_BM;
 
+    const int n_tiles = mp.tile_start[mp.n];
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
+        for (int p = 0; p < mp.n; ++p) {
+            tma_prefetch_desc(&mp.A[p]);
+            tma_prefetch_desc(&mp.B[p]);
+        }
         for (int s = 0; s < F_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(&tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 4);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, F_TMEM_COLS);
@@ -156,57 +188,84 @@ linear_tf32_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % F_STAGES;
-                const uint32_t ph = (kb / F_STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], F_STAGE);
-                uint8_t* a = smem + s * F_STAGE;
-                tma_load_2d(&tmA, &full_bar[s], a, kb * F_BK, m0);
-                tma_load_2d(&tmB, &full_bar[s], a + F_A_BYTES, kb * F_BK, 0);
+            int it = 0;                          // k-blocks issued so far (ring position), across tiles
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int p = fwd_problem_of(mp, tile);
+                const int m0 = (tile - mp.tile_start[p]) * F_BM, num_kb = mp.num_kb[p];
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % F_STAGES;
+                    mbar_wait(&empty_bar[s], ((it / F_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full_bar[s], F_STAGE);
+                    uint8_t* a = smem + s * F_STAGE;
+                    tma_load_2d(&mp.A[p], &full_bar[s], a, kb * F_BK, m0);
+                    tma_load_2d(&mp.B[p], &full_bar[s], a + F_A_BYTES, kb * F_BK, 0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % F_STAGES;
-                const uint32_t ph = (kb / F_STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            int it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                const int buf = j & 1;
+                mbar_wait(&tempty_bar[buf], ((j >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a = smem_u32(smem + s * F_STAGE);
-                const uint32_t b = a + F_A_BYTES;
+                const uint32_t d = tmem_d + buf * F_BN;
+                const int num_kb = mp.num_kb[fwd_problem_of(mp, tile)];
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % F_STAGES;
+                    mbar_wait(&full_bar[s], (it / F_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(smem + s * F_STAGE);
+                    const uint32_t b = a + F_A_BYTES;
 #pragma unroll
-                for (int k = 0; k < F_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte atom
-                    const uint64_t da = umma_desc_sw128(a + k * 32, 16, 1024);
-                    const uint64_t db = umma_desc_sw128(b + k * 32, 16, 1024);
-                    umma_tf32(tmem_d, da, db, idesc, (kb | k) != 0);
+                    for (int k = 0; k < F_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte atom
+                        const uint64_t da = umma_desc_sw128(a + k * 32, 16, 1024);
+                        const uint64_t db = umma_desc_sw128(b + k * 32, 16, 1024);
+                        umma_tf32(d, da, db, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
                 }
-                umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+                umma_commit(&tfull_bar[buf]);    // accumulator of this tile complete
             }
-            umma_commit(&tmem_full_bar);     // accumulator complete
         }
     } else {
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        float v[64];
-        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_32x32(taddr + 32, v + 32);
-        tmem_ld_wait();
-        // transpose through shared memory (the pipeline stages are idle now) for coalesced row stores
-        float* st = reinterpret_cast<float*>(smem) + q * (32 * 65);
+        float* st = reinterpret_cast<float*>(smem + F_STAGES * F_STAGE) + q * (32 * 65);
+        int j = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            const int buf = j & 1;
+            const int p = fwd_problem_of(mp, tile);
+            const float* bias = mp.bias[p];
+            float* Y = mp.Y[p];
+            const long long ldy = mp.ldy[p];
+            const int M = mp.M[p];
+            float bj[2] = {0.f, 0.f};
+            if (bias != nullptr) { bj[0] = __ldg(bias + lane); bj[1] = __ldg(bias + 32 + lane); }
+            mbar_wait(&tfull_bar[buf], (j >> 1) & 1);
+            tc_fence_after();
+            float v[64];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + buf * F_BN;
+            tmem_ld_32x32(taddr, v);
+            tmem_ld_32x32(taddr + 32, v + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            // transpose through shared memory for coalesced row stores
 #pragma unroll
-        for (int j = 0; j < 64; ++j) st[lane * 65 + j] = v[j] + (bias != nullptr ? __ldg(bias + j) : 0.f);
-        __syncwarp();
-        for (int r = 0; r < 32; ++r) {
-            const int row = m0 + q * 32 + r;
-            if (row < M) {
-                float* y = Y + (long long)row * ldy;
-                y[lane] = st[r * 65 + lane];
-                y[32 + lane] = st[r * 65 + 32 + lane];
+            for (int c = 0; c < 64; ++c) st[lane * 65 + c] = v[c];
+            __syncwarp();
+            const int m0 = (tile - mp.tile_start[p]) * F_BM + q * 32;
+            for (int r = 0; r < 32; ++r) {
+                const int row = m0 + r;
+                if (row < M) {
+                    float* y = Y + (long long)row * ldy;
+                    y[lane] = st[r * 65 + lane] + bj[0];
+                    y[32 + lane] = st[r * 65 + 32 + lane] + bj[1];
+                }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -226,9 +285,6 @@ constexpr int X_STAGES = 4;
 constexpr int X_STAGE = 2 * F_A_BYTES + 2 * F_B_BYTES;   // A_hi | A_lo | W_hi | W_lo
 constexpr int X_SMEM = X_STAGES * X_STAGE + 1024;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -942,32 +998,54 @@ ELIMREC_API int elimrec_round_tf32(int64_t n, const float* src, float* dst, elim
     return 0;
 }
 
-ELIMREC_API int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, const float* W, const float* b,
-                                        float* Y, int64_t ldy, elimrec_stream_t stream) {
-    if (M <= 0) return 0;
-    if (K < 4 || K % 4 != 0 || ldx % 4 != 0 || !aligned16(X) || !aligned16(W) || M > 0x7fffffff) {
-        elimrec_set_error("elimrec_linear_tf32_fwd: unsupported shape/alignment (K=%lld ldx=%lld)", (long long)K, (long long)ldx);
-        return -2;
+ELIMREC_API int elimrec_linear_tf32_fwd_multi(int n, const elimrec_linear_desc_t* d, elimrec_stream_t stream) {
+    ER_CHECK_ARG(n >= 0 && n <= F_MAX_PROB && (n == 0 || d != nullptr), "at most 4 problems per launch");
+    FwdMulti mp{};
+    int order[F_MAX_PROB], cnt = 0;
+    for (int i = 0; i < n; ++i)
+        if (d[i].M > 0) order[cnt++] = i;
+    for (int i = 1; i < cnt; ++i)            // largest K first: the long tiles are dealt before the short ones
+        for (int j = i; j > 0 && d[order[j]].K > d[order[j - 1]].K; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    if (cnt == 0) return 0;
+    for (int i = 0; i < cnt; ++i) {
+        const elimrec_linear_desc_t& q = d[order[i]];
+        if (q.K < 4 || q.K % 4 != 0 || q.ldx % 4 != 0 || !aligned16(q.X) || !aligned16(q.W) || q.M > 0x7fffffff) {
+            elimrec_set_error("elimrec_linear_tf32_fwd: unsupported shape/alignment (K=%lld ldx=%lld)", (long long)q.K, (long long)q.ldx);
+            return -2;
+        }
+        if (make_map(&mp.A[i], q.X, q.M, q.K, q.ldx, F_BM) != 0 || make_map(&mp.B[i], q.W, 64, q.K, q.K, F_BN) != 0) {
+            elimrec_set_error("elimrec_linear_tf32_fwd: cuTensorMapEncodeTiled failed");
+            return -3;
+        }
+        mp.bias[i] = q.b; mp.Y[i] = q.Y; mp.ldy[i] = q.ldy; mp.M[i] = (int)q.M;
+        mp.num_kb[i] = (int)((q.K + F_BK - 1) / F_BK);
+        mp.tile_start[i + 1] = mp.tile_start[i] + (int)((q.M + F_BM - 1) / F_BM);
     }
-    CUtensorMap tmA, tmB;
-    if (make_map(&tmA, X, M, K, ldx, F_BM) != 0 || make_map(&tmB, W, 64, K, K, F_BN) != 0) {
-        elimrec_set_error("elimrec_linear_tf32_fwd: cuTensorMapEncodeTiled failed");
-        return -3;
-    }
+    mp.n = cnt;
     static bool configured = false;
+    static int n_sm = 148;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(linear_tf32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
         if (e != cudaSuccess) {
             elimrec_set_error("elimrec_linear_tf32_fwd: shared-memory opt-in failed: %s", cudaGetErrorString(e));
             return -3;
         }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
-    const int num_kb = (int)((K + F_BK - 1) / F_BK);
-    const unsigned grid = (unsigned)((M + F_BM - 1) / F_BM);
-    linear_tf32_fwd_kernel<<<grid, 192, F_SMEM, er_stream(stream)>>>(tmA, tmB, b, Y, ldy, (int)M, num_kb);
+    const int n_tiles = mp.tile_start[cnt];
+    const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
+    linear_tf32_fwd_kernel<<<grid, 192, F_SMEM, er_stream(stream)>>>(mp);
     ER_LAUNCH_CHECK();
     return 0;
+}
+
+ELIMREC_API int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, const float* W, const float* b,
+                                        float* Y, int64_t ldy, elimrec_stream_t stream) {
+    elimrec_linear_desc_t d{M, K, X, ldx, W, b, Y, ldy};
+    return elimrec_linear_tf32_fwd_multi(1, &d, stream);
 }
 
 

@@ -27,11 +27,17 @@ struct MeanEpi {
 // HEAVY = false: segments [seg_base, n_seg) are whole rows (lean path, tuned for FULL occupancy: 32 registers, 64 warps/SM -
 // the gather is latency-bound until ~11 TB/s of L2->SM traffic, measured: 2 fetches in flight x 64 warps beats 8 x 16).
 // HEAVY = true : segments [0, n_heavy_seg) belong to split rows, one CTA = 8 segments of one row.
-template <int F, bool MEAN, bool HEAVY, int UNR_, int MINB>
+// MASK = true (row-sparse last layer of a training step, see elimrec_spmm_masked):
+//   row_mask != NULL : segments of rows with row_mask[row] == 0 are skipped, their output is left untouched
+//   col_mask != NULL : edges whose column has col_mask[col] == 0 are dropped BEFORE the gather (their X rows are
+//                      never read); the surviving edges keep their order, so the sums equal the unmasked ones
+//                      whenever the dropped rows of X are zero.
+template <int F, bool MEAN, bool HEAVY, int UNR_, int MINB, bool MASK = false>
 __global__ void __launch_bounds__(256, MINB)
 spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int2* __restrict__ heavy, int* __restrict__ counter,
                 const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
-                long long ldx, float* __restrict__ Y, long long ldy, float* __restrict__ partial, MeanEpi epi) {
+                long long ldx, float* __restrict__ Y, long long ldy, float* __restrict__ partial, MeanEpi epi,
+                const unsigned char* __restrict__ row_mask = nullptr, const unsigned char* __restrict__ col_mask = nullptr) {
     constexpr int EPW = (F == 64) ? 2 : 1;          // edges per warp-iteration
     constexpr int NV = (F >= 128) ? F / 128 : 1;    // float4 per lane
     constexpr int UNR = UNR_;                       // row fetches in flight per lane
@@ -40,6 +46,7 @@ spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int
     const int lane = threadIdx.x & 31;
     if (warp >= n_seg) return;
     const int4 sg = __ldg(seg + warp);
+    if (MASK && row_mask != nullptr && __ldg(row_mask + sg.x) == 0) return;   // HEAVY: the 8 warps of a CTA share the row
     const int sub = (F == 64) ? (lane >> 4) : 0;
     const int l = (F == 64) ? (lane & 15) : lane;
 
@@ -55,7 +62,15 @@ spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int
             c = __ldg(col + e);
             w = __ldg(val + e);
         }
-        const int cnt = min(32, sg.z - base);
+        int cnt = min(32, sg.z - base);
+        if (MASK && col_mask != nullptr) {      // order-preserving compaction of the surviving edges onto lanes 0..cnt-1
+            const unsigned alive = __ballot_sync(full, e < sg.z && __ldg(col_mask + c) != 0);
+            cnt = __popc(alive);
+            if (cnt == 0) continue;
+            const int src = __fns(alive, 0, lane + 1) & 31;
+            c = __shfl_sync(full, c, src);
+            w = __shfl_sync(full, w, src);
+        }
         for (int j = 0; j < cnt; j += UNR * EPW) {
             float4 v[UNR][NV];
             float ww[UNR];
@@ -193,6 +208,34 @@ __global__ void scatter_add_rows_kernel(int n_rows, const int* __restrict__ rows
     }
 }
 
+__global__ void mark_rows_kernel(int n_rows, const int* __restrict__ rows, unsigned char* __restrict__ mask) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows) mask[__ldg(rows + r)] = 1;
+}
+
+// rows = [users | U + pos | U + neg] (the instance rows of a BPR batch) and mask[rows] = 1, one launch
+__global__ void inst_rows_kernel(int B, const long long* __restrict__ users, const long long* __restrict__ pos,
+                                 const long long* __restrict__ neg, int num_users, int* __restrict__ rows,
+                                 unsigned char* __restrict__ mask) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= 3 * B) return;
+    const int k = r / B, b = r - k * B;
+    const int node = (k == 0) ? (int)__ldg(users + b) : num_users + (int)__ldg((k == 1 ? pos : neg) + b);
+    rows[r] = node;
+    if (mask != nullptr) mask[node] = 1;
+}
+
+__global__ void zero_rows_kernel(int n_rows, const int* __restrict__ rows, int row_lo, int row_hi, int row_off,
+                                 float* __restrict__ dst, long long dst_ld, int width4) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const int node = __ldg(rows + r);
+    if (node < row_lo || node >= row_hi) return;
+    float4* d = reinterpret_cast<float4*>(dst + (long long)(node - row_off) * dst_ld);
+    for (int c = lane; c < width4; c += 32) d[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 __global__ void gather_rows_kernel(int n_rows, const int* __restrict__ rows, const float* __restrict__ src,
                                    long long src_ld, float* __restrict__ dst, long long dst_ld, int width4) {
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -225,9 +268,11 @@ __global__ void copy_2d_kernel(long long n_rows, int width4, const float* __rest
 
 }  // namespace
 
-ELIMREC_API int elimrec_spmm(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
-                             const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy,
-                             float* partial, const elimrec_mean_epilogue_t* epi, elimrec_stream_t stream) {
+namespace {
+int spmm_launch(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
+                const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                float* partial, const elimrec_mean_epilogue_t* epi, const unsigned char* row_mask,
+                const unsigned char* col_mask, elimrec_stream_t stream) {
     ER_CHECK_ARG(width == 64 || width == 128 || width == 256, "width must be 64, 128 or 256");
     ER_CHECK_ARG(ldx % 4 == 0 && (Y == nullptr || ldy % 4 == 0), "row strides must be multiples of 4 floats");
     ER_CHECK_ARG(Y != nullptr || (epi != nullptr && epi->mean_out != nullptr), "no output requested");
@@ -253,22 +298,83 @@ ELIMREC_API int elimrec_spmm(int width, int part, int n_seg, int n_heavy_seg, co
     const int2* hv = reinterpret_cast<const int2*>(heavy);
     cudaStream_t st = er_stream(stream);
     const bool mean = me.out != nullptr;
+    const bool masked = row_mask != nullptr || col_mask != nullptr;
     ER_CHECK_ARG(n_heavy_seg >= 0 && n_heavy_seg % 8 == 0 && n_heavy_seg <= n_seg, "n_heavy_seg must be a multiple of 8");
     const int hb = n_heavy_seg / 8;                      // CTAs of split rows
     const int lb = (n_seg - n_heavy_seg + 7) / 8;        // CTAs of whole rows
-#define LAUNCH(F, MEAN)                                                                                                   \
+#define LAUNCH(F, MEAN, MASK)                                                                                             \
     do {                                                                                                                  \
         if (hb > 0 && part != 2)                                                                                          \
-            spmm_seg_kernel<F, MEAN, true, 2, 5><<<hb, 256, 0, st>>>(0, n_heavy_seg, sg, hv, counter, col,                  \
-                                                                                      val, X, ldx, Y, ldy, partial, me);   \
+            spmm_seg_kernel<F, MEAN, true, 2, 5, MASK><<<hb, 256, 0, st>>>(0, n_heavy_seg, sg, hv, counter, col, val, X,  \
+                                                                           ldx, Y, ldy, partial, me, row_mask, col_mask); \
         if (lb > 0 && part != 1)                                                                                          \
-            spmm_seg_kernel<F, MEAN, false, 2, (MEAN ? 6 : 8)><<<lb, 256, 0, st>>>(n_heavy_seg, n_seg, sg, hv, counter, col, \
-                                                                                   val, X, ldx, Y, ldy, partial, me);      \
+            spmm_seg_kernel<F, MEAN, false, 2, (MEAN ? 6 : 8), MASK><<<lb, 256, 0, st>>>(                                 \
+                n_heavy_seg, n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me, row_mask, col_mask);          \
     } while (0)
-    if (width == 64) { if (mean) LAUNCH(64, true); else LAUNCH(64, false); }
-    else if (width == 128) { if (mean) LAUNCH(128, true); else LAUNCH(128, false); }
-    else { if (mean) LAUNCH(256, true); else LAUNCH(256, false); }
+#define LAUNCH_W(F)                                                                  \
+    do {                                                                             \
+        if (masked) { if (mean) LAUNCH(F, true, true); else LAUNCH(F, false, true); } \
+        else { if (mean) LAUNCH(F, true, false); else LAUNCH(F, false, false); }      \
+    } while (0)
+    if (width == 64) LAUNCH_W(64);
+    else if (width == 128) LAUNCH_W(128);
+    else LAUNCH_W(256);
+#undef LAUNCH_W
 #undef LAUNCH
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+}  // namespace
+
+ELIMREC_API int elimrec_spmm(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
+                             const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                             float* partial, const elimrec_mean_epilogue_t* epi, elimrec_stream_t stream) {
+    return spmm_launch(width, part, n_seg, n_heavy_seg, seg, heavy, counter, col, val, X, ldx, Y, ldy, partial, epi, nullptr,
+                       nullptr, stream);
+}
+
+ELIMREC_API int elimrec_spmm_masked(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy,
+                                    int32_t* counter, const int32_t* col, const float* val, const float* X, int64_t ldx,
+                                    float* Y, int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi,
+                                    const uint8_t* row_mask, const uint8_t* col_mask, elimrec_stream_t stream) {
+    return spmm_launch(width, part, n_seg, n_heavy_seg, seg, heavy, counter, col, val, X, ldx, Y, ldy, partial, epi, row_mask,
+                       col_mask, stream);
+}
+
+ELIMREC_API int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream) {
+    ER_CHECK_ARG(n_nodes >= 0 && mask != nullptr, "mask required");
+    cudaStream_t st = er_stream(stream);
+    if (n_nodes > 0 && cudaMemsetAsync(mask, 0, (size_t)n_nodes, st) != cudaSuccess) {
+        elimrec_set_error("elimrec_mark_rows: memset failed");
+        return -3;
+    }
+    if (n_rows <= 0) return 0;
+    mark_rows_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(n_rows, rows, mask);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_inst_rows(int B, const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t num_users,
+                                  int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream) {
+    ER_CHECK_ARG(B >= 0 && rows != nullptr, "rows required");
+    cudaStream_t st = er_stream(stream);
+    if (mask != nullptr && n_nodes > 0 && cudaMemsetAsync(mask, 0, (size_t)n_nodes, st) != cudaSuccess) {
+        elimrec_set_error("elimrec_inst_rows: memset failed");
+        return -3;
+    }
+    if (B == 0) return 0;
+    inst_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(B, (const long long*)users, (const long long*)pos,
+                                                         (const long long*)neg, num_users, rows, mask);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_zero_rows(int n_rows, const int32_t* rows, int32_t row_lo, int32_t row_hi, int32_t row_offset,
+                                  float* dst, int64_t dst_ld, int width, elimrec_stream_t stream) {
+    ER_CHECK_ARG(width % 4 == 0 && dst_ld % 4 == 0, "width/stride must be multiples of 4");
+    if (n_rows <= 0) return 0;
+    zero_rows_kernel<<<(n_rows + 7) / 8, 256, 0, er_stream(stream)>>>(n_rows, rows, row_lo, row_hi, row_offset, dst, dst_ld,
+                                                                     width / 4);
     ER_LAUNCH_CHECK();
     return 0;
 }

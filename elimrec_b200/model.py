@@ -233,6 +233,8 @@ class EliMRec(BasicModel):
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         ws = dict(B=B, G=G, F=Fw)
         ws["X0_i"] = e(I, Fw)
+        ws["X0_u"] = e(U, D)                                              # E_u as of the last forward (lazy tables)
+        ws["mask"] = torch.zeros(N, dtype=torch.uint8, device=dev)        # 1 on the <= 3B instance rows of the step
         rows = lambda side: U if side == "u" else I
         ws["XW"], ws["XN"] = {}, {}
         for k in range(1, L):  # layer L is consumed by the fused mean epilogue and never stored
@@ -307,15 +309,29 @@ class EliMRec(BasicModel):
         # launches of a layer are independent and run on two streams
         O = ws["O"]
         Ou, Oi = O[:U], O[U:]
-        prev_u = [(Eu, D)]       # layers seen by user rows, in order
+        prev_u = [(ws["X0_u"], D)]       # layers seen by user rows, in order (E_u as copied by this forward)
         prev_i = [(X0_i, Fw)]    # layers seen by item rows
         inv = 1.0 / (L + 1)
+        lazy = self.lazy_tables
+        mask = ws["mask"]
+        mask_of = {"u": mask[:U], "i": mask[U:]}
         self._prep_weights(P, ws)
-        side = ops.fork_side()   # narrow layer 1 (A_iu @ E_u) does not depend on the projections
-        # layer 0, item side: [E_i | P_v | P_a | P_t]   (projections write straight into the slab)
-        ops.copy_2d(Ei, X0_i, I, D)
-        self._proj_forward(P, ws, X0_i, 0, I)
-        wide_in, narrow_in = X0_i, Eu
+        # The projections (HBM-bound, ~300 MB of features) must reach the SMs BEFORE the narrow layer-1 SpMM (L2-bound, fills
+        # every register file if it arrives first): they start right after the weight prep, while the side stream first does
+        # the small copies and only then the SpMM - the two then overlap instead of queueing.
+        side = ops.fork_side()
+        with torch.cuda.stream(side):
+            if lazy:
+                # the loss reads the layer-mean output at the instance rows only: mark them, and keep E_u of THIS forward
+                # (Adam overwrites the parameter) for tables materialised later
+                ops.inst_rows(users, pos, neg, U, ws["inst_rows"], mask)
+            ops.copy_2d(Eu, ws["X0_u"], U, D)
+            ops.copy_2d(Ei, X0_i, I, D)          # layer 0, item side: [E_i | P_v | P_a | P_t]
+            ev_copy = torch.cuda.Event()
+            ev_copy.record(side)
+        self._proj_forward(P, ws, X0_i, 0, I)    # projections write straight into the slab
+        torch.cuda.current_stream().wait_event(ev_copy)
+        wide_in, narrow_in = X0_i, ws["X0_u"]
         for k in range(1, L + 1):
             users_wide = (k % 2 == 1)
             half_w, half_n = (g.ui, g.iu) if users_wide else (g.iu, g.ui)
@@ -338,9 +354,14 @@ class EliMRec(BasicModel):
                 if L == 1:
                     ops.join_side(side)      # the narrow epilogue reads layer 0 of its side (X0_i when L is odd)
                     side = ops.fork_side()
+                s_w, s_n = ("u", "i") if users_wide else ("i", "u")
                 with torch.cuda.stream(side):
-                    ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv))
-                ops.spmm(half_w, wide_in, None, Fw, ops.mean_epilogue(pw, out_w, Fw, inv))
+                    ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv),
+                             row_mask=mask_of[s_n] if lazy else None)
+                ops.spmm(half_w, wide_in, None, Fw, ops.mean_epilogue(pw, out_w, Fw, inv),
+                         row_mask=mask_of[s_w] if lazy else None)
+                if lazy:   # what completes the last layer on demand (every row, same inputs)
+                    ws["last_layer"] = (half_n, narrow_in, pn, out_n, half_w, wide_in, pw, out_w, inv)
             ops.join_side(side)
         self._tables_version = getattr(self, "_tables_version", 0) + 1
         if self.kwai:
@@ -360,12 +381,12 @@ class EliMRec(BasicModel):
             # only the sampled rows: gather O[inst], fusion + heads on 3B rows, BPR on the compact tables
             torch._foreach_copy_(ws["snap_dst"], [P[n].detach() for n in ws["snap_names"]])   # weights of THIS forward
             rows = ws["inst_rows"]
-            rows[:B] = users
-            rows[B:2 * B] = pos + U
-            rows[2 * B:] = neg + U
             ops.gather_rows(rows, O, ws["O_inst"], Fw)
-            self._fuse_heads_rows(ws, ws["O_inst"][:B], ws["F_c"][:B], [s_[:B] for s_ in ws["S_c"]], "u")
+            su_ = ops.fork_side(6)
+            with torch.cuda.stream(su_):
+                self._fuse_heads_rows(ws, ws["O_inst"][:B], ws["F_c"][:B], [s_[:B] for s_ in ws["S_c"]], "u")
             self._fuse_heads_rows(ws, ws["O_inst"][B:], ws["F_c"][B:], [s_[B:] for s_ in ws["S_c"]], "i")
+            ops.join_side(su_)
             ops.bpr([ws["F_c"]] + ws["S_c"], weights, ws["c_users"], ws["c_pos"], ws["c_neg"], B, ws["loss"], ws["inst_dummy"],
                     ws["inst_grad"], ws["terms"])
             self._tables_pending = True
@@ -414,7 +435,14 @@ class EliMRec(BasicModel):
     def _materialize_tables(self):
         if self._tables_pending:
             with torch.no_grad():
-                self._dense_tables(None, self._ws, from_snapshot=True)
+                ws = self._ws
+                Fw = ws["F"]
+                # the training step produced the last layer at its instance rows only: complete it (every row, from the
+                # layer inputs of that same forward), then the fusion Linear + heads with that forward's weights
+                half_n, narrow_in, pn, out_n, half_w, wide_in, pw, out_w, inv = ws["last_layer"]
+                ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv))
+                ops.spmm(half_w, wide_in, None, Fw, ops.mean_epilogue(pw, out_w, Fw, inv))
+                self._dense_tables(None, ws, from_snapshot=True)
 
     # ------------------------------------------------------------------------------------------
     # backward: instance rows -> fusion/head weights -> 2L SpMMs -> projection weights
@@ -435,11 +463,16 @@ class EliMRec(BasicModel):
             gscale = gscale.reshape(1)
         Wu, Wi = P["embedding_user_after_GCN.weight"].detach(), P["embedding_item_after_GCN.weight"].detach()
         # fusion Linear + heads, backward on the instance rows: dO[inst], all weight and bias gradients (3 launches)
-        ops.inst_backward(B, nt, Fw, ig, Oin, gscale, Wu, Wi, [P[f"s_dense_{m}.weight"].detach() for m in self.mods], dOin,
-                          gr["embedding_user_after_GCN.weight"], gr["embedding_item_after_GCN.weight"],
-                          gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
-                          [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods],
-                          ws["inst_ws"])
+        # part 1 (d O[inst]) seeds the propagation backward; part 2 (weight / bias gradients) only feeds Adam -> side stream
+        ib = lambda part: ops.inst_backward(
+            B, nt, Fw, ig, Oin, gscale, Wu, Wi, [P[f"s_dense_{m}.weight"].detach() for m in self.mods], dOin,
+            gr["embedding_user_after_GCN.weight"], gr["embedding_item_after_GCN.weight"],
+            gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
+            [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods], ws["inst_ws"], part=part)
+        side_w = ops.fork_side(5)
+        with torch.cuda.stream(side_w):
+            ib(2)
+        ib(1)
         # layer-mean gradient G = dO / (L+1), row-sparse; it enters every layer of the chain
         inv = 1.0 / (L + 1)
         lo = {"u": (0, U, 0), "i": (U, N, U)}
@@ -452,7 +485,14 @@ class EliMRec(BasicModel):
         s_w = "u" if L % 2 == 1 else "i"      # wide side of the last layer
         s_n = "i" if s_w == "u" else "u"
         dWc, dNc = ws["dW"][0][:nrows[s_w]], ws["dN"][0][:nrows[s_n]]
-        dWc.zero_(); dNc.zero_()
+        lazy = self.lazy_tables
+        mask_of = {"u": ws["mask"][:U], "i": ws["mask"][U:]}
+        if lazy:     # d x_L is non-zero at the instance rows only: zero just those, the first SpMMs skip all other columns
+            for dst, sd, w in ((dWc, s_w, Fw), (dNc, s_n, D)):
+                a, b, off = lo[sd]
+                ops.zero_rows(rows, a, b, off, dst, w)
+        else:
+            dWc.zero_(); dNc.zero_()
         add_G(dWc, s_w, True)
         add_G(dNc, s_n, False)
         flip = 1
@@ -462,16 +502,20 @@ class EliMRec(BasicModel):
             half_o, half_s = (g.iu, g.ui) if s == "u" else (g.ui, g.iu)
             nW, nN = ws["dW"][flip][:nrows[o]], ws["dN"][flip][:nrows[s]]
             side = ops.fork_side()
+            sparse_in = lazy and k == L
             with torch.cuda.stream(side):
-                ops.spmm(half_s, dNc, nN, D)  # d x_{k-1}[s, narrow] = A[s,o] @ d x_k[o, narrow]
+                # d x_{k-1}[s, narrow] = A[s,o] @ d x_k[o, narrow]
+                ops.spmm(half_s, dNc, nN, D, col_mask=mask_of[o] if sparse_in else None)
                 add_G(nN, s, False)
-            ops.spmm(half_o, dWc, nW, Fw)     # d x_{k-1}[o, wide]   = A[o,s] @ d x_k[s, wide]
+            # d x_{k-1}[o, wide]   = A[o,s] @ d x_k[s, wide]
+            ops.spmm(half_o, dWc, nW, Fw, col_mask=mask_of[s] if sparse_in else None)
             add_G(nW, o, True)
             ops.join_side(side)
             dWc, dNc, flip = nW, nN, flip ^ 1
         # now dWc = d x_0[item rows, wide] = [dE_i | dP_v | dP_a | dP_t], dNc = d x_0[user rows] = dE_u
         grads = {"embedding_user.weight": dNc, "embedding_item.weight": dWc[:, :D]}
         self._proj_wgrad(ws, dWc, 0, I)
+        ops.join_side(side_w)
         grads.update(gr)
         return grads
 
@@ -492,19 +536,20 @@ class EliMRec(BasicModel):
 
     def _proj_forward(self, P, ws, X0_i, r0, r1):
         Fw = ws["F"]
-        sides = []
-        for j, m in enumerate(self.mods):   # one stream per modality: disjoint output columns, tails overlap
+        tc, sides = [], []
+        for j, m in enumerate(self.mods):
             Wm, bm = P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach()
             Dm = Wm.shape[1]
-            st = ops.fork_side(2 + j) if j > 0 else torch.cuda.current_stream()
-            with torch.cuda.stream(st):
-                if self.proj_precision == "tf32" and Dm % 4 == 0:
-                    ops.linear_tf32_fwd(self._feat_tc(m)[r0:r1], ws["W_tf32"][m], bm, X0_i[r0:r1], col=D * (j + 1))
-                else:
+            if self.proj_precision == "tf32" and Dm % 4 == 0:
+                tc.append((self._feat_tc(m)[r0:r1], ws["W_tf32"][m], bm, X0_i[r0:r1], D * (j + 1)))
+            else:   # exact-fp32 FFMA path, one stream per modality (disjoint output columns)
+                st = ops.fork_side(2 + j)
+                with torch.cuda.stream(st):
                     ops.gemm(r1 - r0, D, Dm, self._feat[m], Dm, 1, Wm, 1, Dm, X0_i, Fw, 1, bias=bm, a_off=r0 * Dm,
                              c_off=r0 * Fw + D * (j + 1), tag="proj_fwd")
-            if j > 0:
                 sides.append(st)
+        if tc:      # every tensor-core projection of the step in ONE persistent launch (one CTA per SM)
+            ops.linear_tf32_fwd_multi(tc)
         for st in sides:
             ops.join_side(st)
 

@@ -43,21 +43,53 @@ def join_side(side):
 
 
 
-def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None):
+def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, row_mask=None, col_mask=None):
     """Y[rows of half] = A_half @ X  (+ optional fused layer-mean epilogue).  The split (Zipf-head) rows run as their
-    own launch on a side stream, concurrently with the whole rows."""
+    own launch on a side stream, concurrently with the whole rows.  ``row_mask`` / ``col_mask`` (uint8 per row / column
+    of this half): the row-sparse last-layer variant, elimrec_spmm_masked."""
+    masked = row_mask is not None or col_mask is not None
+
     def go(part, launches):
-        call("elimrec_spmm", width, part, half.n_seg, half.n_heavy_seg, ptr(half.seg), ptr(half.heavy), ptr(half.counter),
-             ptr(half.col), ptr(half.val), ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0),
-             ptr(half.partial), (C.byref(epi) if epi is not None else None), stream(), launches=launches, tag=f"spmm{width}")
-    if half.n_heavy_seg == 0 or _lib.PROFILE["on"]:
-        go(0, 2 if half.n_heavy_seg else 1)
+        args = [width, part, half.n_seg, half.n_heavy_seg, ptr(half.seg), ptr(half.heavy), ptr(half.counter),
+                ptr(half.col), ptr(half.val), ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0),
+                ptr(half.partial), (C.byref(epi) if epi is not None else None)]
+        if masked:
+            call("elimrec_spmm_masked", *args, ptr(row_mask, torch.uint8, True), ptr(col_mask, torch.uint8, True), stream(),
+                 launches=launches, tag=f"spmm{width}m")
+        else:
+            call("elimrec_spmm", *args, stream(), launches=launches, tag=f"spmm{width}")
+
+    if half.n_heavy_seg == 0:
+        go(0, 1)
         return
+    prof = _lib.PROFILE["on"]
+    if prof:      # one event pair around the whole op (both launches, concurrent as in the step)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.PROFILE["on"] = False
     side = fork_side(1)
     with torch.cuda.stream(side):
         go(1, 1)
     go(2, 1)
     join_side(side)
+    if prof:
+        e1.record()
+        _lib.PROFILE["on"] = True
+        _lib.PROFILE["events"].append((f"spmm{width}m" if masked else f"spmm{width}", e0, e1))
+
+
+def mark_rows(rows, mask):
+    call("elimrec_mark_rows", rows.numel(), ptr(rows, torch.int32), mask.numel(), ptr(mask, torch.uint8), stream(), launches=2)
+
+
+def inst_rows(users, pos, neg, num_users, rows, mask=None):
+    call("elimrec_inst_rows", users.numel(), ptr(users, torch.int64), ptr(pos, torch.int64), ptr(neg, torch.int64), num_users,
+         ptr(rows, torch.int32), (mask.numel() if mask is not None else 0), ptr(mask, torch.uint8, True), stream(),
+         launches=2 if mask is not None else 1)
+
+
+def zero_rows(rows, lo, hi, off, dst, width):
+    call("elimrec_zero_rows", rows.numel(), ptr(rows, torch.int32), lo, hi, off, ptr(dst, F32), dst.stride(0), width, stream())
 
 
 def mean_epilogue(prev, out: torch.Tensor, width: int, scale: float) -> MeanEpilogue:
@@ -107,6 +139,16 @@ def linear_tf32_fwd(X, W, b, Y, col=0, tag="proj_fwd_tc"):
     M, K = X.shape
     call("elimrec_linear_tf32_fwd", M, K, ptr(X, F32), X.stride(0), ptr(W, F32), ptr(b, F32, True),
          ptr(Y, F32) + 4 * col, Y.stride(0), stream(), tag=tag)
+
+
+def linear_tf32_fwd_multi(problems, tag="proj_fwd_tc"):
+    """problems: list of (X, W, b, Y, col) - all in ONE persistent launch (grid <= SM count)."""
+    arr = (_lib.LinearDesc * len(problems))()
+    for k, (X, W, b, Y, col) in enumerate(problems):
+        arr[k].M, arr[k].K = X.shape
+        arr[k].X, arr[k].ldx, arr[k].W, arr[k].b = ptr(X, F32), X.stride(0), ptr(W, F32), ptr(b, F32, True)
+        arr[k].Y, arr[k].ldy = ptr(Y, F32) + 4 * col, Y.stride(0)
+    call("elimrec_linear_tf32_fwd_multi", len(problems), arr, stream(), tag=tag)
 
 
 def prep_weights_tf32(items):
@@ -182,15 +224,16 @@ def inst_backward_ws_floats(B, nt, F):
     return int(_lib.lib().elimrec_inst_backward_workspace_floats(B, nt, F))
 
 
-def inst_backward(B, nt, F, inst_grad, O_inst, gscale, Wu, Wi, Ws, dO_inst, dWu, dWi, dbu, dbi, dWs, dbs, ws):
-    """Backward of the fusion Linear + heads on the 3B instance rows (3 launches)."""
+def inst_backward(B, nt, F, inst_grad, O_inst, gscale, Wu, Wi, Ws, dO_inst, dWu, dWi, dbu, dbi, dWs, dbs, ws, part=3):
+    """Backward of the fusion Linear + heads on the 3B instance rows (3 launches).  part 1 = d O[inst] only (1 launch),
+    part 2 = weight / bias gradients only (2 launches)."""
     n = nt - 1
     wsp = (C.c_void_p * max(n, 1))(*[ptr(t, F32) for t in Ws])
     dwp = (C.c_void_p * max(n, 1))(*[ptr(t, F32) for t in dWs])
     dbp = (C.c_void_p * max(n, 1))(*[ptr(t, F32) for t in dbs])
-    call("elimrec_inst_backward", B, nt, F, ptr(inst_grad, F32), ptr(O_inst, F32), ptr(gscale, F32, True), ptr(Wu, F32),
-         ptr(Wi, F32), wsp, ptr(dO_inst, F32), ptr(dWu, F32), ptr(dWi, F32), ptr(dbu, F32), ptr(dbi, F32), dwp, dbp,
-         ptr(ws, F32), stream())
+    call("elimrec_inst_backward_part", part, B, nt, F, ptr(inst_grad, F32), ptr(O_inst, F32), ptr(gscale, F32, True),
+         ptr(Wu, F32), ptr(Wi, F32), wsp, ptr(dO_inst, F32), ptr(dWu, F32), ptr(dWi, F32), ptr(dbu, F32), ptr(dbi, F32), dwp,
+         dbp, ptr(ws, F32), stream(), launches={1: 1, 2: 2, 3: 3}[part], tag=f"inst_backward{part}")
 
 
 def adam_apply_multi(items, consts_dev, b1, b2, eps, wd):

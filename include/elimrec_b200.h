@@ -69,6 +69,27 @@ int elimrec_spmm(int width, int part /* 0 = all rows, 1 = split rows only, 2 = w
                  int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi /* may be NULL */,
                  elimrec_stream_t stream);
 
+/* Row-sparse variant for the LAST propagation layer of a training step.  The BPR loss reads the layer-mean output
+ * only at the <= 3B sampled rows (models/EliMRec.py:115-142 indexes all_users / all_items with the batch), so
+ *   forward : row_mask[row] == 0  -> the row is skipped, its output left untouched (only sampled rows are produced)
+ *   backward: col_mask[col] == 0  -> the edge is dropped before the gather (d x_L is zero outside the sampled rows)
+ * Masks are byte arrays over the rows / columns of this CSR half; either may be NULL.  Surviving edges keep their
+ * order: rows are bit-identical to elimrec_spmm on the same inputs (width 64 + col_mask: the two half-warps of a warp
+ * split the surviving edges differently, so those sums agree to fp32 rounding instead). */
+int elimrec_spmm_masked(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy,
+                        int32_t* counter, const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y,
+                        int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi, const uint8_t* row_mask,
+                        const uint8_t* col_mask, elimrec_stream_t stream);
+/* mask[0:n_nodes] = 0; mask[rows[r]] = 1 */
+int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream);
+/* rows[0:3B] = [users | num_users + pos | num_users + neg]  (node ids of the batch, models/EliMRec.py:120-122 gathers
+ * exactly these rows); mask (may be NULL): mask[0:n_nodes] = 0 then mask[rows] = 1 */
+int elimrec_inst_rows(int B, const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t num_users,
+                      int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream);
+/* dst[rows[r] - row_offset, 0:width] = 0 for row_lo <= rows[r] < row_hi */
+int elimrec_zero_rows(int n_rows, const int32_t* rows, int32_t row_lo, int32_t row_hi, int32_t row_offset, float* dst,
+                      int64_t dst_ld, int width, elimrec_stream_t stream);
+
 /* rows[r] selects a destination row; dst[rows[r], 0:width] += scale * src[r, 0:src_width] (atomic).
  * src_width == width: plain; src_width == fold*width: the `fold` 64-column blocks are summed first
  * (gradient of the 64->wide broadcast).  Used to seed / add the row-sparse layer-mean gradient. */
@@ -108,6 +129,18 @@ int64_t elimrec_colsum_workspace_floats(int64_t M, int64_t N);
  * return -2 if the shape is unsupported (caller falls back to elimrec_gemm). */
 int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, int64_t ldx, const float* W, const float* b,
                             float* Y, int64_t ldy, elimrec_stream_t stream);
+/* Several such layers in ONE persistent launch (grid <= SM count; the three modal projections of a step,
+ * models/EliMRec.py:233-236): problem i computes Y_i[M_i, 0:64] = X_i[M_i, K_i] W_i[64, K_i]^T + b_i. */
+typedef struct {
+    int64_t M, K;
+    const float* X;
+    int64_t ldx;
+    const float* W;
+    const float* b; /* may be NULL */
+    float* Y;
+    int64_t ldy;
+} elimrec_linear_desc_t;
+int elimrec_linear_tf32_fwd_multi(int n /* <= 4 */, const elimrec_linear_desc_t* problems, elimrec_stream_t stream);
 int elimrec_linear_tf32_wgrad(int64_t M, int64_t K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
                               float* dW, float* workspace, elimrec_stream_t stream);
 int64_t elimrec_linear_tf32_wgrad_workspace_floats(int64_t M, int64_t K);
@@ -168,6 +201,12 @@ int elimrec_bpr_forward_backward(int B, int n_tables, const float* const* tables
  * O_inst [3B x F] = rows of the layer-mean slab gathered at inst_rows; F = 64 * n_tables. */
 int64_t elimrec_inst_backward_workspace_floats(int B, int n_tables, int F);
 int elimrec_inst_backward(int B, int n_tables, int F, const float* inst_grad, const float* O_inst,
+                          const float* gscale_dev /* may be NULL */, const float* Wu, const float* Wi,
+                          const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu, float* dbi,
+                          float* const* dWs_host, float* const* dbs_host, float* workspace, elimrec_stream_t stream);
+/* The same in two independent parts, so that the weight gradients (part 2: they only feed Adam) can run on another
+ * stream while d O[inst] (part 1) seeds the backward propagation.  part 3 = both, in this order. */
+int elimrec_inst_backward_part(int part, int B, int n_tables, int F, const float* inst_grad, const float* O_inst,
                           const float* gscale_dev /* may be NULL */, const float* Wu, const float* Wi,
                           const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu, float* dbi,
                           float* const* dWs_host, float* const* dbs_host, float* workspace, elimrec_stream_t stream);

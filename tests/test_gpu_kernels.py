@@ -50,6 +50,56 @@ def test_spmm_matches_fp64(dev, width):
         assert int(half.counter.abs().sum()) == 0
 
 
+@pytest.mark.parametrize("width", [64, 128, 256])
+def test_spmm_masked_bit_identical(dev, width):
+    """Row-sparse last layer: masked rows / columns give the bits of the dense launch (whole and split rows); width 64 with
+    a column mask regroups the two half-warp partial sums, i.e. agrees to rounding."""
+    from elimrec_b200 import ops
+    from elimrec_b200.graph import BipartiteGraph
+    U, I = 700, 500
+    g = BipartiteGraph(_rand_graph(U, I, 6000, [(3, 480), (10, 130), (11, 65)], seed=width), dev, seg_len=8 if width == 64 else 64)
+    gen = torch.Generator().manual_seed(width)
+    for half, n_in in ((g.ui, I), (g.iu, U)):
+        X = torch.randn(n_in, width, generator=gen).to(dev)
+        Y = torch.empty(half.n_rows, width, device=dev)
+        ops.spmm(half, X, Y, width)
+        # (a) row mask: marked rows equal the dense result, unmarked rows are untouched
+        rm = (torch.rand(half.n_rows, generator=gen) < 0.1).to(torch.uint8)
+        rm[[3, 10]] = 1
+        rm[11] = 0
+        rmd = rm.to(dev)
+        Yr = torch.full_like(Y, 7.0)
+        ops.spmm(half, X, Yr, width, row_mask=rmd)
+        assert torch.equal(Yr[rmd.bool()], Y[rmd.bool()])
+        assert float((Yr[~rmd.bool()] - 7.0).abs().max()) == 0
+        # (b) column mask: equals the dense launch on X with the unmarked rows zeroed; NaNs in dropped rows are never read
+        cm = (torch.rand(n_in, generator=gen) < 0.15).to(torch.uint8).to(dev)
+        Xz = X * cm.float()[:, None]
+        ops.spmm(half, Xz, Y, width)
+        Xn = torch.where(cm.bool()[:, None], X, torch.full_like(X, float("nan")))
+        Yc = torch.full_like(Y, 7.0)
+        ops.spmm(half, Xn, Yc, width, col_mask=cm)
+        if width == 64:   # two edges per warp-iteration: compaction changes which half-warp sums which edge
+            assert rel_err(Yc, Y) < 1e-6 and not bool(torch.isnan(Yc).any())
+        else:
+            assert torch.equal(Yc, Y)
+        assert int(half.counter.abs().sum()) == 0
+    # instance rows + mask in one launch
+    B = 37
+    users = torch.randint(0, U, (B,), generator=gen).to(dev); pos = torch.randint(0, I, (B,), generator=gen).to(dev)
+    neg = torch.randint(0, I, (B,), generator=gen).to(dev)
+    rows = torch.empty(3 * B, dtype=torch.int32, device=dev); mask = torch.full((U + I,), 9, dtype=torch.uint8, device=dev)
+    ops.inst_rows(users, pos, neg, U, rows, mask)
+    ref_rows = torch.cat([users, pos + U, neg + U]).int()
+    assert torch.equal(rows, ref_rows)
+    ref_mask = torch.zeros(U + I, dtype=torch.uint8, device=dev); ref_mask[ref_rows.long()] = 1
+    assert torch.equal(mask, ref_mask)
+    dst = torch.ones(I, 64, device=dev)
+    ops.zero_rows(rows, U, U + I, U, dst, 64)
+    ref = torch.ones(I, 64, device=dev); ref[torch.cat([pos, neg])] = 0
+    assert torch.equal(dst, ref)
+
+
 @pytest.mark.parametrize("width,G", [(256, 4), (64, 4), (128, 2), (64, 2)])
 def test_spmm_mean_epilogue(dev, width, G):
     from elimrec_b200 import ops

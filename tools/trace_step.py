@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel timeline of ONE CUDA-graph-replayed training step (torch.profiler / CUPTI): start, duration, kernel.
-Usage (GPU box): python tools/trace_step.py [workload] > profiles/<name>.txt"""
+Usage (GPU box): python tools/trace_step.py [workload] [lazy] > profiles/<name>.txt"""
 import os
 import sys
 
@@ -15,9 +15,10 @@ from elimrec_b200.sampler import PairwiseSamplerV2  # noqa: E402
 
 def main():
     workload = sys.argv[1] if len(sys.argv) > 1 else "tiktok"
+    lazy = len(sys.argv) > 2 and sys.argv[2] == "lazy"
     dev = torch.device("cuda:0")
     ds, name = bench.build_dataset(workload)
-    conf = Config(**{"data.input.dataset": name, "topks": [20], "device": dev, "alpha": 0.5, "batch_size": 2048})
+    conf = Config(**{"data.input.dataset": name, "topks": [20], "device": dev, "alpha": 0.5, "batch_size": 2048, "lazy_tables": lazy})
     torch.manual_seed(2022)
     model = EliMRec(conf, ds).to(dev)
     model.make_optimizer()
