@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--eval-users", type=int, default=0, help="0 = all test users")
     ap.add_argument("--cuda-graph", type=int, default=1)
-    ap.add_argument("--lazy-tables", type=int, default=0,
+    ap.add_argument("--lazy-tables", type=int, default=1,
                     help="1: build all_users/all_items/all_s_embs on demand (at evaluation) instead of every step")
     ap.add_argument("--parallel", default="dp", choices=["dp", "rowshard"],
                     help="N>1: data-parallel replicas (weak scaling, default) or the row-sharded all-gather design "
@@ -323,13 +323,14 @@ def main():
             pass
         peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         Fw = 64 * (1 + len(model.mods))
-        tag = f"spmm{Fw}"
-        if tag in agg:
-            g = model.graph
-            # wide launches alternate between the two halves; algorithmic bytes per launch:
-            #   nnz*(4+4) + (rows_out+1)*4 + (rows_in + rows_out)*F*4, averaged over the launches of a step
-            per = [h.nnz * 8 + (h.n_rows + 1) * 4 + (h.n_cols + h.n_rows) * Fw * 4 for h in (g.ui, g.iu)]
-            alg = float(np.mean(per))
+        g = model.graph
+        # dominant kernel: spmm_seg_kernel<Fw> (whole rows).  Timed on the launches that are exactly ONE such kernel - the
+        # user-row half has no split rows, so its event pair brackets a single launch on the launching stream.
+        half = g.ui if g.ui.n_heavy_seg == 0 else (g.iu if g.iu.n_heavy_seg == 0 else None)
+        tag = f"spmm{Fw}w"
+        if tag in agg and half is not None:
+            # algorithmic bytes per launch: nnz*(4+4) + (rows_out+1)*4 + (rows_in + rows_out)*F*4
+            alg = float(half.nnz * 8 + (half.n_rows + 1) * 4 + (half.n_cols + half.n_rows) * Fw * 4)
             avg_s = 1e-3 * sum(agg[tag]) / len(agg[tag])
             ach = alg / avg_s / 1e9
             traffic = None
@@ -338,9 +339,14 @@ def main():
                     traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json")))["avg_wide_launch_bytes"]
             except Exception:
                 pass
-            roofline = {"kernel": f"spmm_seg_kernel<{Fw}>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": traffic, "peak_source": which, "bytes_per_launch": alg,
-                        "avg_launch_us": 1e6 * avg_s, "share_of_step": sum(agg[tag]) / sum(sum(v) for v in agg.values())}
+            fam = sum(sum(v) for k, v in agg.items() if k.startswith("spmm"))
+            tot = sum(sum(v) for v in agg.values())
+            roofline = {"kernel": f"spmm_seg_kernel<{Fw}> (whole rows, user-row half)", "bound": "hbm", "achieved": ach, "peak": peak,
+                        "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": which, "bytes_per_launch": alg,
+                        "avg_launch_us": 1e6 * avg_s, "launches_timed": len(agg[tag]),
+                        "share_of_step": sum(sum(v) for k, v in agg.items() if k.startswith(f"spmm{Fw}")) / tot,
+                        "spmm_family_share_of_step": fam / tot,
+                        "note": "operand slab is L2-resident: the kernel is bound by L2->SM gather bandwidth (~11 TB/s), see DESIGN.md 3.1"}
     clk = clocks.stop() if rank == 0 else None
     sync_all()
     if world > 1:   # the profile pass above stepped rank 0 only: put every replica back on the same weights
@@ -379,6 +385,29 @@ def main():
                "sample": f"{r['timed_steps']} full train steps (batch {BATCH}) of the same {args.workload}-shape graph after 1 warm-up; "
                          f"eval {r['eval_users']} users", "eval_users_per_s": r["eval_users_per_s"]}
 
+    # ---- the reference's schedule (every row of every layer + the full tables, every step) next to the default ----------
+    dense = None
+    if rank == 0 and world == 1 and args.lazy_tables and not rowshard:
+        conf_d = Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH,
+                           "lazy_tables": False})
+        torch.manual_seed(2022)
+        md = EliMRec(conf_d, ds).to(dev)
+        md.make_optimizer()
+        rd = md.make_graphed_step() if use_graph else md.train_step
+        for b in batches[:args.warmup]:
+            rd(*b)
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for b in batches[args.warmup:]:
+            ld = rd(*b)
+        d1.record()
+        torch.cuda.synchronize()
+        dms = d0.elapsed_time(d1) / args.steps
+        dense = {"ms_per_step": dms, "value": BATCH / (dms / 1e3), "unit": UNIT, "final_loss": float(ld),
+                 "note": "lazy_tables=False: all rows of the last layer, fusion + heads over all U+I rows each step"}
+        del md, rd
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": ("strong" if rowshard else "weak"), "vs_baseline": None,
@@ -387,10 +416,13 @@ def main():
                                        f"layer_num 3, recdim 64, U={ds.num_users} I={ds.num_items} E_train={ds.train_matrix.nnz}",
                            "parallelism": (f"rowshard{world} (all-gather per GCN layer)" if rowshard else f"dp{world}") if world > 1 else "single",
                            "l2_policy": "per-step working set (features + propagation slabs, >0.9 GB) exceeds the 126 MB L2; no flush",
-                           "cuda_graph": bool(runner is not None), "lazy_tables": bool(args.lazy_tables), "sampler": "device Philox (value) / compat libc stream (e2e)"},
+                           "cuda_graph": bool(runner is not None), "lazy_tables": bool(args.lazy_tables),
+                           "row_sparse_step": ("loss-dead rows of the last two layers and of the fusion/head tables are not computed "
+                                               "in the step (identical loss / gradients / parameters); full tables are completed "
+                                               "at evaluation" if args.lazy_tables else "off"), "sampler": "device Philox (value) / compat libc stream (e2e)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "eval": ev,
-                "kernels": kernels, "final_loss": final_loss}
+                "kernels": kernels, "final_loss": final_loss, "dense_schedule": dense}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -27,33 +27,18 @@ struct MeanEpi {
 // HEAVY = false: segments [seg_base, n_seg) are whole rows (lean path, tuned for FULL occupancy: 32 registers, 64 warps/SM -
 // the gather is latency-bound until ~11 TB/s of L2->SM traffic, measured: 2 fetches in flight x 64 warps beats 8 x 16).
 // HEAVY = true : segments [0, n_heavy_seg) belong to split rows, one CTA = 8 segments of one row.
-// MASK = true (row-sparse last layer of a training step, see elimrec_spmm_masked):
-//   row_mask != NULL : segments of rows with row_mask[row] == 0 are skipped, their output is left untouched
-//   col_mask != NULL : edges whose column has col_mask[col] == 0 are dropped BEFORE the gather (their X rows are
-//                      never read); the surviving edges keep their order, so the sums equal the unmasked ones
-//                      whenever the dropped rows of X are zero.
-template <int F, bool MEAN, bool HEAVY, int UNR_, int MINB, bool MASK = false>
-__global__ void __launch_bounds__(256, MINB)
-spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int2* __restrict__ heavy, int* __restrict__ counter,
-                const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
-                long long ldx, float* __restrict__ Y, long long ldy, float* __restrict__ partial, MeanEpi epi,
-                const unsigned char* __restrict__ row_mask = nullptr, const unsigned char* __restrict__ col_mask = nullptr) {
+// accumulate one segment: acc += sum_e val[e] * X[col[e], :]   (col_mask != NULL: edges to unmarked columns are dropped
+// BEFORE the gather by an order-preserving compaction onto lanes 0..cnt-1)
+template <int F, int UNR, bool MASK>
+__device__ __forceinline__ void seg_accumulate(const int4 sg, const int* __restrict__ col, const float* __restrict__ val,
+                                               const float* __restrict__ X, long long ldx,
+                                               const unsigned char* __restrict__ col_mask, int lane,
+                                               float4 (&acc)[(F >= 128) ? F / 128 : 1]) {
     constexpr int EPW = (F == 64) ? 2 : 1;          // edges per warp-iteration
     constexpr int NV = (F >= 128) ? F / 128 : 1;    // float4 per lane
-    constexpr int UNR = UNR_;                       // row fetches in flight per lane
     const unsigned full = 0xffffffffu;
-    const int warp = seg_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_seg) return;
-    const int4 sg = __ldg(seg + warp);
-    if (MASK && row_mask != nullptr && __ldg(row_mask + sg.x) == 0) return;   // HEAVY: the 8 warps of a CTA share the row
     const int sub = (F == 64) ? (lane >> 4) : 0;
     const int l = (F == 64) ? (lane & 15) : lane;
-
-    float4 acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
     for (int base = sg.y; base < sg.z; base += 32) {
         const int e = base + lane;
         int c = 0;
@@ -63,7 +48,7 @@ spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int
             w = __ldg(val + e);
         }
         int cnt = min(32, sg.z - base);
-        if (MASK && col_mask != nullptr) {      // order-preserving compaction of the surviving edges onto lanes 0..cnt-1
+        if (MASK && col_mask != nullptr) {
             const unsigned alive = __ballot_sync(full, e < sg.z && __ldg(col_mask + c) != 0);
             cnt = __popc(alive);
             if (cnt == 0) continue;
@@ -97,6 +82,78 @@ spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int
         acc[0].z += __shfl_xor_sync(full, acc[0].z, 16);
         acc[0].w += __shfl_xor_sync(full, acc[0].w, 16);
     }
+}
+
+// write one finished row: Y[row] = acc and / or the fused layer-mean epilogue
+template <int F, bool MEAN>
+__device__ __forceinline__ void seg_store(int row, const float4 (&acc)[(F >= 128) ? F / 128 : 1], float* __restrict__ Y,
+                                          long long ldy, const MeanEpi& epi, int lane) {
+    constexpr int NV = (F >= 128) ? F / 128 : 1;
+    const int sub = (F == 64) ? (lane >> 4) : 0;
+    const int l = (F == 64) ? (lane & 15) : lane;
+    if (Y != nullptr && (F != 64 || lane < 16)) {
+        float4* yp = reinterpret_cast<float4*>(Y + (long long)row * ldy) + l;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) yp[i * 32] = acc[i];
+    }
+    if (MEAN) {
+        // fused torch.mean(torch.stack(layers, 1), 1): ((x0 + x1) + ...) + x_L, then * 1/(L+1)
+        if (F == 64) {
+            const int c = l * 4;
+            for (int g = sub; g * 64 < epi.width; g += 2) {
+                const int oc = g * 64 + c;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < epi.n_prev; ++k) {
+                    const int pc = (epi.prev_width[k] == 64) ? c : oc;
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(epi.prev[k] + (long long)row * epi.prev_ld[k] + pc));
+                    if (k == 0) s = t; else add4(s, t);
+                }
+                add4(s, acc[0]);
+                s.x *= epi.scale; s.y *= epi.scale; s.z *= epi.scale; s.w *= epi.scale;
+                *reinterpret_cast<float4*>(epi.out + (long long)row * epi.ld + oc) = s;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int oc = (l + i * 32) * 4;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < epi.n_prev; ++k) {
+                    const int pc = (epi.prev_width[k] == 64) ? (oc & 63) : oc;
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(epi.prev[k] + (long long)row * epi.prev_ld[k] + pc));
+                    if (k == 0) s = t; else add4(s, t);
+                }
+                add4(s, acc[i]);
+                s.x *= epi.scale; s.y *= epi.scale; s.z *= epi.scale; s.w *= epi.scale;
+                *reinterpret_cast<float4*>(epi.out + (long long)row * epi.ld + oc) = s;
+            }
+        }
+    }
+}
+
+// MASK = true (row-sparse last layers of a training step, see elimrec_spmm_masked):
+//   row_mask != NULL : segments of rows with row_mask[row] == 0 are skipped, their output is left untouched
+//   col_mask != NULL : edges whose column has col_mask[col] == 0 are dropped BEFORE the gather (their X rows are
+//                      never read); the surviving edges keep their order, so the sums equal the unmasked ones
+//                      whenever the dropped rows of X are zero.
+template <int F, bool MEAN, bool HEAVY, int UNR_, int MINB, bool MASK = false>
+__global__ void __launch_bounds__(256, MINB)
+spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int2* __restrict__ heavy, int* __restrict__ counter,
+                const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
+                long long ldx, float* __restrict__ Y, long long ldy, float* __restrict__ partial, MeanEpi epi,
+                const unsigned char* __restrict__ row_mask = nullptr, const unsigned char* __restrict__ col_mask = nullptr) {
+    constexpr int NV = (F >= 128) ? F / 128 : 1;    // float4 per lane
+    const unsigned full = 0xffffffffu;
+    const int warp = seg_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_seg) return;
+    const int4 sg = __ldg(seg + warp);
+    if (MASK && row_mask != nullptr && __ldg(row_mask + sg.x) == 0) return;   // HEAVY: the 8 warps of a CTA share the row
+    const int l = (F == 64) ? (lane & 15) : lane;
+
+    float4 acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    seg_accumulate<F, UNR_, MASK>(sg, col, val, X, ldx, col_mask, lane, acc);
 
     if (HEAVY) {
         // Split row.  Its segment count is padded to a multiple of 8 on the host, so all 8 warps of this CTA work on
@@ -151,43 +208,41 @@ spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int
         }
     }
 
-    const int row = sg.x;
-    if (Y != nullptr && (F != 64 || lane < 16)) {
-        float4* yp = reinterpret_cast<float4*>(Y + (long long)row * ldy) + l;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) yp[i * 32] = acc[i];
+    seg_store<F, MEAN>(sg.x, acc, Y, ldy, epi, lane);
+}
+
+// Whole rows under a SPARSE mask (5-50 % of the rows marked): a CTA owns SEGS consecutive segments; its threads fetch the
+// segment descriptors and mask bytes together (two dependent loads per SEGS segments instead of per segment), the marked
+// ones are compacted into shared memory and dealt round-robin to the 8 warps.  The grid is SEGS/8 times smaller than
+// one-warp-per-segment, fits in one or two waves, and so really overlaps with the other launches of the layer; 4 row
+// fetches in flight per lane because few warps are active (8 cost occupancy: measured slower).  (The list order varies run to run, the results do not: every
+// row is still produced by exactly one warp, edges in CSR order.)
+template <int F, bool MEAN, int SEGS>
+__global__ void __launch_bounds__(256, 2)
+spmm_light_sparse_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int* __restrict__ col,
+                         const float* __restrict__ val, const float* __restrict__ X, long long ldx, float* __restrict__ Y,
+                         long long ldy, MeanEpi epi, const unsigned char* __restrict__ row_mask,
+                         const unsigned char* __restrict__ col_mask) {
+    constexpr int NV = (F >= 128) ? F / 128 : 1;
+    __shared__ int4 list[SEGS];
+    __shared__ int n_list;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int first = seg_base + blockIdx.x * SEGS;
+    if (threadIdx.x == 0) n_list = 0;
+    __syncthreads();
+    if (threadIdx.x < SEGS && first + threadIdx.x < n_seg) {
+        const int4 mine = __ldg(seg + first + threadIdx.x);
+        if (row_mask == nullptr || __ldg(row_mask + mine.x) != 0) list[atomicAdd(&n_list, 1)] = mine;
     }
-    if (MEAN) {
-        // fused torch.mean(torch.stack(layers, 1), 1): ((x0 + x1) + ...) + x_L, then * 1/(L+1)
-        if (F == 64) {
-            const int c = l * 4;
-            for (int g = sub; g * 64 < epi.width; g += 2) {
-                const int oc = g * 64 + c;
-                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int k = 0; k < epi.n_prev; ++k) {
-                    const int pc = (epi.prev_width[k] == 64) ? c : oc;
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(epi.prev[k] + (long long)row * epi.prev_ld[k] + pc));
-                    if (k == 0) s = t; else add4(s, t);
-                }
-                add4(s, acc[0]);
-                s.x *= epi.scale; s.y *= epi.scale; s.z *= epi.scale; s.w *= epi.scale;
-                *reinterpret_cast<float4*>(epi.out + (long long)row * epi.ld + oc) = s;
-            }
-        } else {
+    __syncthreads();
+    const int n = n_list;
+    for (int i = wib; i < n; i += 8) {
+        const int4 sg = list[i];
+        float4 acc[NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int oc = (l + i * 32) * 4;
-                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int k = 0; k < epi.n_prev; ++k) {
-                    const int pc = (epi.prev_width[k] == 64) ? (oc & 63) : oc;
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(epi.prev[k] + (long long)row * epi.prev_ld[k] + pc));
-                    if (k == 0) s = t; else add4(s, t);
-                }
-                add4(s, acc[i]);
-                s.x *= epi.scale; s.y *= epi.scale; s.z *= epi.scale; s.w *= epi.scale;
-                *reinterpret_cast<float4*>(epi.out + (long long)row * epi.ld + oc) = s;
-            }
-        }
+        for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        seg_accumulate<F, 4, true>(sg, col, val, X, ldx, col_mask, lane, acc);
+        seg_store<F, MEAN>(sg.x, acc, Y, ldy, epi, lane);
     }
 }
 
@@ -216,13 +271,25 @@ __global__ void mark_rows_kernel(int n_rows, const int* __restrict__ rows, unsig
 // rows = [users | U + pos | U + neg] (the instance rows of a BPR batch) and mask[rows] = 1, one launch
 __global__ void inst_rows_kernel(int B, const long long* __restrict__ users, const long long* __restrict__ pos,
                                  const long long* __restrict__ neg, int num_users, int* __restrict__ rows,
-                                 unsigned char* __restrict__ mask) {
+                                 unsigned char* __restrict__ mask, unsigned char* __restrict__ mask2) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= 3 * B) return;
     const int k = r / B, b = r - k * B;
     const int node = (k == 0) ? (int)__ldg(users + b) : num_users + (int)__ldg((k == 1 ? pos : neg) + b);
     rows[r] = node;
     if (mask != nullptr) mask[node] = 1;
+    if (mask2 != nullptr) mask2[node] = 1;
+}
+
+// out_mask[col] = 1 for every edge (row, col) of a marked row: the rows of the other side that the marked rows read
+__global__ void mark_neighbors_kernel(int n_seg, const int4* __restrict__ seg, const int* __restrict__ col,
+                                      const unsigned char* __restrict__ row_mask, unsigned char* __restrict__ out_mask) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_seg) return;
+    const int4 sg = __ldg(seg + w);
+    if (__ldg(row_mask + sg.x) == 0) return;
+    for (int e = sg.y + lane; e < sg.z; e += 32) out_mask[__ldg(col + e)] = 1;
 }
 
 __global__ void zero_rows_kernel(int n_rows, const int* __restrict__ rows, int row_lo, int row_hi, int row_off,
@@ -272,7 +339,9 @@ namespace {
 int spmm_launch(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
                 const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy,
                 float* partial, const elimrec_mean_epilogue_t* epi, const unsigned char* row_mask,
-                const unsigned char* col_mask, elimrec_stream_t stream) {
+                const unsigned char* col_mask, int density_hint, elimrec_stream_t stream) {
+    // whole rows under a mask: segments per CTA - 256 when only a few % of the rows are marked, else 32
+    const int chunk = (row_mask != nullptr && density_hint <= 10) ? 256 : 32;
     ER_CHECK_ARG(width == 64 || width == 128 || width == 256, "width must be 64, 128 or 256");
     ER_CHECK_ARG(ldx % 4 == 0 && (Y == nullptr || ldy % 4 == 0), "row strides must be multiples of 4 floats");
     ER_CHECK_ARG(Y != nullptr || (epi != nullptr && epi->mean_out != nullptr), "no output requested");
@@ -307,9 +376,17 @@ int spmm_launch(int width, int part, int n_seg, int n_heavy_seg, const int32_t* 
         if (hb > 0 && part != 2)                                                                                          \
             spmm_seg_kernel<F, MEAN, true, 2, 5, MASK><<<hb, 256, 0, st>>>(0, n_heavy_seg, sg, hv, counter, col, val, X,  \
                                                                            ldx, Y, ldy, partial, me, row_mask, col_mask); \
-        if (lb > 0 && part != 1)                                                                                          \
-            spmm_seg_kernel<F, MEAN, false, 2, (MEAN ? 6 : 8), MASK><<<lb, 256, 0, st>>>(                                 \
-                n_heavy_seg, n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me, row_mask, col_mask);          \
+        if (lb > 0 && part != 1) {                                                                                        \
+            if (!MASK || (row_mask == nullptr && F == 64)) /* measured: narrow col-mask-only is faster one warp per segment */ \
+                spmm_seg_kernel<F, MEAN, false, 2, (MEAN ? 6 : 8), MASK><<<lb, 256, 0, st>>>(                             \
+                    n_heavy_seg, n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me, nullptr, col_mask);       \
+            else if (chunk == 256)                                                                                        \
+                spmm_light_sparse_kernel<F, MEAN, 256><<<(n_seg - n_heavy_seg + 255) / 256, 256, 0, st>>>(                \
+                    n_heavy_seg, n_seg, sg, col, val, X, ldx, Y, ldy, me, row_mask, col_mask);                            \
+            else                                                                                                          \
+                spmm_light_sparse_kernel<F, MEAN, 32><<<(n_seg - n_heavy_seg + 31) / 32, 256, 0, st>>>(                   \
+                    n_heavy_seg, n_seg, sg, col, val, X, ldx, Y, ldy, me, row_mask, col_mask);                            \
+        }                                                                                                                 \
     } while (0)
 #define LAUNCH_W(F)                                                                  \
     do {                                                                             \
@@ -330,15 +407,16 @@ ELIMREC_API int elimrec_spmm(int width, int part, int n_seg, int n_heavy_seg, co
                              const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy,
                              float* partial, const elimrec_mean_epilogue_t* epi, elimrec_stream_t stream) {
     return spmm_launch(width, part, n_seg, n_heavy_seg, seg, heavy, counter, col, val, X, ldx, Y, ldy, partial, epi, nullptr,
-                       nullptr, stream);
+                       nullptr, 100, stream);
 }
 
 ELIMREC_API int elimrec_spmm_masked(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy,
                                     int32_t* counter, const int32_t* col, const float* val, const float* X, int64_t ldx,
                                     float* Y, int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi,
-                                    const uint8_t* row_mask, const uint8_t* col_mask, elimrec_stream_t stream) {
+                                    const uint8_t* row_mask, const uint8_t* col_mask, int row_density_pct,
+                                    elimrec_stream_t stream) {
     return spmm_launch(width, part, n_seg, n_heavy_seg, seg, heavy, counter, col, val, X, ldx, Y, ldy, partial, epi, row_mask,
-                       col_mask, stream);
+                       col_mask, row_density_pct, stream);
 }
 
 ELIMREC_API int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream) {
@@ -355,16 +433,28 @@ ELIMREC_API int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nod
 }
 
 ELIMREC_API int elimrec_inst_rows(int B, const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t num_users,
-                                  int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream) {
+                                  int32_t* rows, int64_t n_nodes, uint8_t* mask, uint8_t* mask2, elimrec_stream_t stream) {
     ER_CHECK_ARG(B >= 0 && rows != nullptr, "rows required");
     cudaStream_t st = er_stream(stream);
-    if (mask != nullptr && n_nodes > 0 && cudaMemsetAsync(mask, 0, (size_t)n_nodes, st) != cudaSuccess) {
-        elimrec_set_error("elimrec_inst_rows: memset failed");
-        return -3;
+    for (uint8_t* m : {mask, mask2}) {
+        if (m != nullptr && n_nodes > 0 && cudaMemsetAsync(m, 0, (size_t)n_nodes, st) != cudaSuccess) {
+            elimrec_set_error("elimrec_inst_rows: memset failed");
+            return -3;
+        }
     }
     if (B == 0) return 0;
     inst_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(B, (const long long*)users, (const long long*)pos,
-                                                         (const long long*)neg, num_users, rows, mask);
+                                                         (const long long*)neg, num_users, rows, mask, mask2);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_mark_neighbors(int n_seg, const int32_t* seg, const int32_t* col, const uint8_t* row_mask,
+                                       uint8_t* out_mask, elimrec_stream_t stream) {
+    ER_CHECK_ARG(row_mask != nullptr && out_mask != nullptr, "masks required");
+    if (n_seg <= 0) return 0;
+    mark_neighbors_kernel<<<(n_seg + 7) / 8, 256, 0, er_stream(stream)>>>(n_seg, reinterpret_cast<const int4*>(seg), col,
+                                                                         row_mask, out_mask);
     ER_LAUNCH_CHECK();
     return 0;
 }

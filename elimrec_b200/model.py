@@ -124,12 +124,17 @@ class EliMRec(BasicModel):
         self.fuse_precision = _cfg(cfg, "fuse_precision", "x3")
         if self.fuse_precision not in ("x3", "fp32"):
             raise ElimrecError("fuse_precision must be 'x3' or 'fp32'")
-        # lazy_tables: the training loss only needs the fused / single-modal embeddings of the <= 3B sampled rows.  With
-        # lazy_tables=True a training step computes exactly those; the full all_users / all_items / all_s_embs tables
-        # (which the reference materialises every step, EliMRec.py:261-272,144-153, and only predict() ever reads) are
-        # produced on first access from the layer-mean slab and a snapshot of the weights of that same forward -
-        # bit-identical values, computed once per evaluation instead of once per step.  Default: off (faithful).
-        self.lazy_tables = bool(_cfg(cfg, "lazy_tables", False))
+        # lazy_tables (default on): a training step computes exactly what its loss and gradients read.  The BPR loss
+        # indexes the fused / single-modal tables with the <= 3B sampled rows (EliMRec.py:120-128), so the step produces
+        #   * the last propagation layer and its layer mean at those rows only (row-masked SpMM),
+        #   * layer L-1's wide side at the rows those read (their graph neighbours),
+        #   * fusion Linear + heads on the 3B gathered rows,
+        # and the backward skips the columns where d x_L / d x_{L-1} are structurally zero.  Loss, gradients and updated
+        # parameters are the reference's (same sums, same order).  The full all_users / all_items / all_s_embs tables -
+        # which the reference materialises every step (EliMRec.py:261-272,144-153) and only predict() reads - are completed
+        # on first access from the layer inputs and weights THAT forward saw: same values, once per evaluation instead of
+        # once per step.  lazy_tables=False runs the reference's schedule (every row, every step).
+        self.lazy_tables = bool(_cfg(cfg, "lazy_tables", True))
         self.kwai = cfg["data.input.dataset"] == "kwai"
         self.mods = "v" if self.kwai else "vat"
         dev = _cfg(cfg, "device", None)
@@ -235,6 +240,8 @@ class EliMRec(BasicModel):
         ws["X0_i"] = e(I, Fw)
         ws["X0_u"] = e(U, D)                                              # E_u as of the last forward (lazy tables)
         ws["mask"] = torch.zeros(N, dtype=torch.uint8, device=dev)        # 1 on the <= 3B instance rows of the step
+        ws["need2"] = torch.zeros(N, dtype=torch.uint8, device=dev)       # instance rows + the rows they gather (2 hops)
+        ws["density"] = {"u": min(100, 100 * B // max(U, 1) + 1), "i": min(100, 200 * B // max(I, 1) + 1)}   # % rows marked
         rows = lambda side: U if side == "u" else I
         ws["XW"], ws["XN"] = {}, {}
         for k in range(1, L):  # layer L is consumed by the fused mean epilogue and never stored
@@ -313,8 +320,11 @@ class EliMRec(BasicModel):
         prev_i = [(X0_i, Fw)]    # layers seen by item rows
         inv = 1.0 / (L + 1)
         lazy = self.lazy_tables
-        mask = ws["mask"]
+        mask, need2 = ws["mask"], ws["need2"]
         mask_of = {"u": mask[:U], "i": mask[U:]}
+        need2_of = {"u": need2[:U], "i": need2[U:]}
+        sL_w = "u" if L % 2 == 1 else "i"          # wide side of the last layer; layer L-1 is wide on the other side
+        sL_o = "i" if sL_w == "u" else "u"
         self._prep_weights(P, ws)
         # The projections (HBM-bound, ~300 MB of features) must reach the SMs BEFORE the narrow layer-1 SpMM (L2-bound, fills
         # every register file if it arrives first): they start right after the weight prep, while the side stream first does
@@ -324,7 +334,11 @@ class EliMRec(BasicModel):
             if lazy:
                 # the loss reads the layer-mean output at the instance rows only: mark them, and keep E_u of THIS forward
                 # (Adam overwrites the parameter) for tables materialised later
-                ops.inst_rows(users, pos, neg, U, ws["inst_rows"], mask)
+                # Two hops: the last layer's wide SpMM reads layer L-1 only at the neighbours of its instance rows, the
+                # mean epilogue at the instance rows themselves -> need2 = those rows of the other side.
+                ops.inst_rows(users, pos, neg, U, ws["inst_rows"], mask, need2)
+                if L >= 2:
+                    ops.mark_neighbors(g.ui if sL_w == "u" else g.iu, mask_of[sL_w], need2_of[sL_o])
             ops.copy_2d(Eu, ws["X0_u"], U, D)
             ops.copy_2d(Ei, X0_i, I, D)          # layer 0, item side: [E_i | P_v | P_a | P_t]
             ev_copy = torch.cuda.Event()
@@ -342,7 +356,10 @@ class EliMRec(BasicModel):
                 Yw, Yn = ws["XW"][k], ws["XN"][k]
                 with torch.cuda.stream(side):
                     ops.spmm(half_n, narrow_in, Yn, D)
-                ops.spmm(half_w, wide_in, Yw, Fw)
+                sparse2 = lazy and k == L - 1          # only the rows the last layer will read
+                ops.spmm(half_w, wide_in, Yw, Fw, row_mask=need2_of[sL_o] if sparse2 else None)
+                if sparse2:
+                    ws["pre_last_layer"] = (half_w, wide_in, Yw)
                 if users_wide:
                     prev_u.append((Yw, Fw)); prev_i.append((Yn, D))
                 else:
@@ -357,9 +374,9 @@ class EliMRec(BasicModel):
                 s_w, s_n = ("u", "i") if users_wide else ("i", "u")
                 with torch.cuda.stream(side):
                     ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv),
-                             row_mask=mask_of[s_n] if lazy else None)
+                             row_mask=mask_of[s_n] if lazy else None, density=ws["density"][s_n])
                 ops.spmm(half_w, wide_in, None, Fw, ops.mean_epilogue(pw, out_w, Fw, inv),
-                         row_mask=mask_of[s_w] if lazy else None)
+                         row_mask=mask_of[s_w] if lazy else None, density=ws["density"][s_w])
                 if lazy:   # what completes the last layer on demand (every row, same inputs)
                     ws["last_layer"] = (half_n, narrow_in, pn, out_n, half_w, wide_in, pw, out_w, inv)
             ops.join_side(side)
@@ -439,6 +456,9 @@ class EliMRec(BasicModel):
                 Fw = ws["F"]
                 # the training step produced the last layer at its instance rows only: complete it (every row, from the
                 # layer inputs of that same forward), then the fusion Linear + heads with that forward's weights
+                if self.n_layers >= 2:
+                    half_p, in_p, out_p = ws["pre_last_layer"]
+                    ops.spmm(half_p, in_p, out_p, Fw)
                 half_n, narrow_in, pn, out_n, half_w, wide_in, pw, out_w, inv = ws["last_layer"]
                 ops.spmm(half_n, narrow_in, None, D, ops.mean_epilogue(pn, out_n, Fw, inv))
                 ops.spmm(half_w, wide_in, None, Fw, ops.mean_epilogue(pw, out_w, Fw, inv))
@@ -469,10 +489,10 @@ class EliMRec(BasicModel):
             gr["embedding_user_after_GCN.weight"], gr["embedding_item_after_GCN.weight"],
             gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
             [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods], ws["inst_ws"], part=part)
-        side_w = ops.fork_side(5)
+        ib(1)
+        side_w = ops.fork_side(5)     # forked after d O[inst]: the weight gradients must not delay it
         with torch.cuda.stream(side_w):
             ib(2)
-        ib(1)
         # layer-mean gradient G = dO / (L+1), row-sparse; it enters every layer of the chain
         inv = 1.0 / (L + 1)
         lo = {"u": (0, U, 0), "i": (U, N, U)}
@@ -487,6 +507,7 @@ class EliMRec(BasicModel):
         dWc, dNc = ws["dW"][0][:nrows[s_w]], ws["dN"][0][:nrows[s_n]]
         lazy = self.lazy_tables
         mask_of = {"u": ws["mask"][:U], "i": ws["mask"][U:]}
+        need2_of = {"u": ws["need2"][:U], "i": ws["need2"][U:]}
         if lazy:     # d x_L is non-zero at the instance rows only: zero just those, the first SpMMs skip all other columns
             for dst, sd, w in ((dWc, s_w, Fw), (dNc, s_n, D)):
                 a, b, off = lo[sd]
@@ -507,8 +528,15 @@ class EliMRec(BasicModel):
                 # d x_{k-1}[s, narrow] = A[s,o] @ d x_k[o, narrow]
                 ops.spmm(half_s, dNc, nN, D, col_mask=mask_of[o] if sparse_in else None)
                 add_G(nN, s, False)
-            # d x_{k-1}[o, wide]   = A[o,s] @ d x_k[s, wide]
-            ops.spmm(half_o, dWc, nW, Fw, col_mask=mask_of[s] if sparse_in else None)
+            # d x_{k-1}[o, wide]   = A[o,s] @ d x_k[s, wide].  Row-sparse step: d x_L lives on the instance rows, so
+            # d x_{L-1}[o, wide] is non-zero only on need2 (their neighbours + the instance rows of that side, which get G):
+            # layer L writes just those rows and layer L-1 reads just those columns.
+            if sparse_in:
+                ops.spmm(half_o, dWc, nW, Fw, col_mask=mask_of[s], row_mask=need2_of[o] if L >= 2 else None)
+            elif lazy and k == L - 1:
+                ops.spmm(half_o, dWc, nW, Fw, col_mask=need2_of[s])
+            else:
+                ops.spmm(half_o, dWc, nW, Fw)
             add_G(nW, o, True)
             ops.join_side(side)
             dWc, dNc, flip = nW, nN, flip ^ 1

@@ -43,10 +43,10 @@ def join_side(side):
 
 
 
-def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, row_mask=None, col_mask=None):
+def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, row_mask=None, col_mask=None, density=50):
     """Y[rows of half] = A_half @ X  (+ optional fused layer-mean epilogue).  The split (Zipf-head) rows run as their
     own launch on a side stream, concurrently with the whole rows.  ``row_mask`` / ``col_mask`` (uint8 per row / column
-    of this half): the row-sparse last-layer variant, elimrec_spmm_masked."""
+    of this half): the row-sparse last-layer variant, elimrec_spmm_masked; ``density`` = expected % of marked rows."""
     masked = row_mask is not None or col_mask is not None
 
     def go(part, launches):
@@ -54,10 +54,11 @@ def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, 
                 ptr(half.col), ptr(half.val), ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0),
                 ptr(half.partial), (C.byref(epi) if epi is not None else None)]
         if masked:
-            call("elimrec_spmm_masked", *args, ptr(row_mask, torch.uint8, True), ptr(col_mask, torch.uint8, True), stream(),
+            call("elimrec_spmm_masked", *args, ptr(row_mask, torch.uint8, True), ptr(col_mask, torch.uint8, True), int(density), stream(),
                  launches=launches, tag=f"spmm{width}m")
         else:
-            call("elimrec_spmm", *args, stream(), launches=launches, tag=f"spmm{width}")
+            # "w": the half has no split rows -> ONE launch of the whole-row kernel, timed exactly by its event pair
+            call("elimrec_spmm", *args, stream(), launches=launches, tag=f"spmm{width}" + ("w" if half.n_heavy_seg == 0 else ""))
 
     if half.n_heavy_seg == 0:
         go(0, 1)
@@ -82,10 +83,16 @@ def mark_rows(rows, mask):
     call("elimrec_mark_rows", rows.numel(), ptr(rows, torch.int32), mask.numel(), ptr(mask, torch.uint8), stream(), launches=2)
 
 
-def inst_rows(users, pos, neg, num_users, rows, mask=None):
+def inst_rows(users, pos, neg, num_users, rows, mask=None, mask2=None):
     call("elimrec_inst_rows", users.numel(), ptr(users, torch.int64), ptr(pos, torch.int64), ptr(neg, torch.int64), num_users,
-         ptr(rows, torch.int32), (mask.numel() if mask is not None else 0), ptr(mask, torch.uint8, True), stream(),
-         launches=2 if mask is not None else 1)
+         ptr(rows, torch.int32), (mask.numel() if mask is not None else 0), ptr(mask, torch.uint8, True),
+         ptr(mask2, torch.uint8, True), stream(), launches=1 + (mask is not None) + (mask2 is not None))
+
+
+def mark_neighbors(half, row_mask, out_mask):
+    """out_mask[col] = 1 for every edge of the rows of ``half`` with row_mask != 0."""
+    call("elimrec_mark_neighbors", half.n_seg, ptr(half.seg), ptr(half.col), ptr(row_mask, torch.uint8),
+         ptr(out_mask, torch.uint8), stream())
 
 
 def zero_rows(rows, lo, hi, off, dst, width):

@@ -79,13 +79,18 @@ int elimrec_spmm(int width, int part /* 0 = all rows, 1 = split rows only, 2 = w
 int elimrec_spmm_masked(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy,
                         int32_t* counter, const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y,
                         int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi, const uint8_t* row_mask,
-                        const uint8_t* col_mask, elimrec_stream_t stream);
+                        const uint8_t* col_mask, int row_density_pct /* expected % of marked rows: scheduling hint only */,
+                        elimrec_stream_t stream);
 /* mask[0:n_nodes] = 0; mask[rows[r]] = 1 */
 int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream);
 /* rows[0:3B] = [users | num_users + pos | num_users + neg]  (node ids of the batch, models/EliMRec.py:120-122 gathers
- * exactly these rows); mask (may be NULL): mask[0:n_nodes] = 0 then mask[rows] = 1 */
+ * exactly these rows); mask, mask2 (each may be NULL): m[0:n_nodes] = 0 then m[rows] = 1 */
 int elimrec_inst_rows(int B, const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t num_users,
-                      int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream);
+                      int32_t* rows, int64_t n_nodes, uint8_t* mask, uint8_t* mask2, elimrec_stream_t stream);
+/* out_mask[col] = 1 for every edge (row, col) of this CSR half with row_mask[row] != 0: the rows of the other side
+ * that the marked rows gather (two-hop support of the batch; seg = the same segment list elimrec_spmm takes) */
+int elimrec_mark_neighbors(int n_seg, const int32_t* seg, const int32_t* col, const uint8_t* row_mask, uint8_t* out_mask,
+                           elimrec_stream_t stream);
 /* dst[rows[r] - row_offset, 0:width] = 0 for row_lo <= rows[r] < row_hi */
 int elimrec_zero_rows(int n_rows, const int32_t* rows, int32_t row_lo, int32_t row_hi, int32_t row_offset, float* dst,
                       int64_t dst_ld, int width, elimrec_stream_t stream);

@@ -68,10 +68,11 @@ def test_spmm_masked_bit_identical(dev, width):
         rm[[3, 10]] = 1
         rm[11] = 0
         rmd = rm.to(dev)
-        Yr = torch.full_like(Y, 7.0)
-        ops.spmm(half, X, Yr, width, row_mask=rmd)
-        assert torch.equal(Yr[rmd.bool()], Y[rmd.bool()])
-        assert float((Yr[~rmd.bool()] - 7.0).abs().max()) == 0
+        for density in (5, 50):   # 256 / 32 segments per CTA in the sparse whole-row kernel
+            Yr = torch.full_like(Y, 7.0)
+            ops.spmm(half, X, Yr, width, row_mask=rmd, density=density)
+            assert torch.equal(Yr[rmd.bool()], Y[rmd.bool()])
+            assert float((Yr[~rmd.bool()] - 7.0).abs().max()) == 0
         # (b) column mask: equals the dense launch on X with the unmarked rows zeroed; NaNs in dropped rows are never read
         cm = (torch.rand(n_in, generator=gen) < 0.15).to(torch.uint8).to(dev)
         Xz = X * cm.float()[:, None]
@@ -90,6 +91,11 @@ def test_spmm_masked_bit_identical(dev, width):
     neg = torch.randint(0, I, (B,), generator=gen).to(dev)
     rows = torch.empty(3 * B, dtype=torch.int32, device=dev); mask = torch.full((U + I,), 9, dtype=torch.uint8, device=dev)
     ops.inst_rows(users, pos, neg, U, rows, mask)
+    m2 = torch.zeros(U + I, dtype=torch.uint8, device=dev)
+    ops.mark_neighbors(g.ui, mask[:U], m2[U:])
+    A = sp.csr_matrix((g.ui.vals_host, g.ui.indices_host, g.ui.indptr_host), shape=(U, I))
+    ref2 = np.zeros(I, dtype=np.uint8); ref2[A[mask[:U].bool().cpu().numpy()].indices] = 1
+    assert np.array_equal(m2[U:].cpu().numpy(), ref2) and int(m2[:U].sum()) == 0
     ref_rows = torch.cat([users, pos + U, neg + U]).int()
     assert torch.equal(rows, ref_rows)
     ref_mask = torch.zeros(U + I, dtype=torch.uint8, device=dev); ref_mask[ref_rows.long()] = 1

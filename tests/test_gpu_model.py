@@ -198,7 +198,7 @@ def test_lazy_tables_identical_results(golden):
     """lazy_tables=True: a step computes the fused / head embeddings of the sampled rows only; the full tables are built
     on first access from the same slab and the weights of that forward.  Everything observable must be IDENTICAL to
     the eager mode bit for bit (same kernels, same inputs), including after the optimizer has already stepped."""
-    eager, _ = _golden_model(golden)
+    eager, _ = _golden_model(golden, lazy_tables=False)
     lazy, _ = _golden_model(golden, lazy_tables=True)
     for m in (eager, lazy):
         m.make_optimizer(lr=1e-3, weight_decay=1e-4)
