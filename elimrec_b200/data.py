@@ -86,12 +86,12 @@ def csr_rows_to_dict(m: sp.csr_matrix) -> dict:
 class Dataset:
     """Same public surface as the reference ``Dataset`` for the fields the hot path reads."""
 
-    def __init__(self, conf=None, *, interactions=None, features=None, name=None):
+    def __init__(self, conf=None, *, interactions=None, features=None, name=None, words=None):
         self.conf = conf
         self.userids = self.itemids = None
         if interactions is not None:
             self.dataset_name = name or (conf["data.input.dataset"] if conf is not None else "synthetic")
-            self._from_arrays(interactions.train, interactions.valid, interactions.test, features)
+            self._from_arrays(interactions.train, interactions.valid, interactions.test, features, words)
         else:
             self.dataset_name = conf["data.input.dataset"]
             self._load_files(conf)
@@ -104,20 +104,22 @@ class Dataset:
         train, valid, test = rd(prefix + ".train"), rd(prefix + ".valid"), rd(prefix + ".test")
         path = conf["data.input.path"]
         feats = [None, None, None]
+        words = None
         if "with_item_vat" not in conf or conf["with_item_vat"]:
             if self.dataset_name == "tiktok":
-                raise NotImplementedError(
-                    "the literal 'tiktok' word-id text branch (dataset.py:164-174) is SURVEY.md row f1; "
-                    "use the generic .npy feature branch (any other dataset name)")
-            if self.dataset_name == "kwai":
+                # dataset.py:164-174: visual / audio tensors by raw item id, text as [2 x n] (raw item id, word id) pairs
+                feats[0] = torch.load(os.path.join(path, "tiktok_visual_feat.pt")).numpy()
+                feats[1] = torch.load(os.path.join(path, "tiktok_audio_feat.pt")).numpy()
+                words = torch.load(os.path.join(path, "tiktok_textual_feat.pt")).detach().cpu().numpy()
+            elif self.dataset_name == "kwai":
                 feats[0] = torch.load(os.path.join(path, "kwai_feat_v.pt")).numpy()
             else:
                 feats[0] = np.load(os.path.join(path, f"{self.dataset_name}_FeatureVideo_normal.npy"))
                 feats[1] = np.load(os.path.join(path, f"{self.dataset_name}_FeatureAudio_avg_normal.npy"))
                 feats[2] = np.load(os.path.join(path, f"{self.dataset_name}_FeatureText_stl_normal.npy"))
-        self._from_arrays(train, valid, test, feats)
+        self._from_arrays(train, valid, test, feats, words)
 
-    def _from_arrays(self, train, valid, test, feats):
+    def _from_arrays(self, train, valid, test, feats, words=None):
         # reference order of concatenation is [train, test, valid] (dataset.py:219)
         all_u = np.concatenate([train[:, 0], test[:, 0], valid[:, 0]])
         all_i = np.concatenate([train[:, 1], test[:, 1], valid[:, 1]])
@@ -146,6 +148,12 @@ class Dataset:
         for nm, f in zip(names, feats if feats is not None else [None] * 3):
             if f is not None:
                 setattr(self, nm, torch.from_numpy(np.ascontiguousarray(f[raw_i])))
+        if words is not None:
+            # literal 'tiktok' (dataset.py:166-173): keep the pairs whose raw item id is known, in file order, item id remapped
+            w = np.asarray(words, dtype=np.int64)
+            pos = np.minimum(np.searchsorted(uq_i, w[0]), uq_i.size - 1)
+            known = uq_i[pos] == w[0]
+            self.words_tensor = torch.from_numpy(np.stack([rk_i[pos[known]], w[1][known]]).astype(np.int64))
 
     # ---- accessors (same names as the reference) ------------------------------------------------
     def get_user_train_dict(self, by_time=False):

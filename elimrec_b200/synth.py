@@ -123,3 +123,25 @@ def write_reference_files(path: str, name: str, inter: Interactions, feats) -> N
         np.save(os.path.join(path, f"{name}_FeatureVideo_normal.npy"), v)
         np.save(os.path.join(path, f"{name}_FeatureAudio_avg_normal.npy"), a)
         np.save(os.path.join(path, f"{name}_FeatureText_stl_normal.npy"), t)
+
+
+def make_words(num_items: int, seed: int = 2022, vocab: int = 11574, max_words: int = 6) -> np.ndarray:
+    """``[2 x n_pairs]`` int64 (raw item id, word id) - the layout of ``tiktok_textual_feat.pt``
+    (``data/dataset.py:166-173``); every item has 1..max_words words, in shuffled pair order."""
+    rng = np.random.default_rng(seed + 2)
+    cnt = rng.integers(1, max_words + 1, size=num_items)
+    item = np.repeat(np.arange(num_items, dtype=np.int64), cnt)
+    word = rng.integers(0, vocab, size=item.size, dtype=np.int64)
+    perm = rng.permutation(item.size)
+    return np.stack([item[perm], word[perm]])
+
+
+def write_tiktok_files(path: str, inter: Interactions, v, a, words) -> None:
+    """The literal ``tiktok`` layout: CSV splits + ``tiktok_{visual,audio,textual}_feat.pt`` (``dataset.py:164-166``)."""
+    import torch
+    os.makedirs(path, exist_ok=True)
+    for split in ("train", "valid", "test"):
+        np.savetxt(os.path.join(path, f"tiktok.{split}"), getattr(inter, split), fmt="%d", delimiter=",")
+    torch.save(torch.from_numpy(v), os.path.join(path, "tiktok_visual_feat.pt"))
+    torch.save(torch.from_numpy(a), os.path.join(path, "tiktok_audio_feat.pt"))
+    torch.save(torch.from_numpy(words), os.path.join(path, "tiktok_textual_feat.pt"))

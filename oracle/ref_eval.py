@@ -65,20 +65,28 @@ def metric_rows(topk: np.ndarray, truth: list, metrics, k: int) -> np.ndarray:
 
 
 def evaluate(predict_fn, user_train: dict, user_test: dict, metrics=("Precision", "Recall", "NDCG"),
-             top_k=(20,), batch_size=128, return_rows=False):
-    """uni_evaluator.py:104-203.  ``predict_fn(list_of_users) -> [B x I] fp32 ndarray``."""
+             top_k=(20,), batch_size=128, return_rows=False, user_neg: dict | None = None, test_users=None):
+    """uni_evaluator.py:104-203.  ``predict_fn(list_of_users) -> [B x I] fp32 ndarray``.
+
+    ``user_neg`` (candidate-negatives mode, ``:132-140``): the reference hands ``predict`` a candidate list per user,
+    ``EliMRec.predict`` ignores it (``models/EliMRec.py:96``) and returns all I scores, so what the evaluator ranks is
+    the full UNMASKED row against the truth ``set(range(len(pos_test[u])))`` - restated literally."""
     mids = [METRIC_ID[m] for m in metrics]
     max_top = top_k if isinstance(top_k, int) else max(top_k)
     top_show = np.arange(max_top) + 1 if isinstance(top_k, int) else np.sort(top_k)
-    users = list(user_test.keys())
+    users = list(user_test.keys()) if test_users is None else list(test_users)
     rows = []
     for b in range(0, len(users), batch_size):
         bu = users[b:b + batch_size]
         sc = np.array(predict_fn(bu), dtype=np.float32)
-        for r, u in enumerate(bu):
-            sc[r, user_train.get(u, [])] = -np.inf
+        if user_neg is not None:
+            truth = [list(range(len(user_test[u]))) for u in bu]
+        else:
+            truth = [user_test[u] for u in bu]
+            for r, u in enumerate(bu):
+                sc[r, user_train.get(u, [])] = -np.inf
         tk = topk_lowest_index(sc, max_top)
-        rows.append(metric_rows(tk, [user_test[u] for u in bu], mids, max_top))
+        rows.append(metric_rows(tk, truth, mids, max_top))
     allrows = np.concatenate(rows, axis=0)
     final = np.mean(allrows, axis=0).reshape(len(mids), max_top)[:, top_show - 1].reshape(-1)
     buf = "\t".join([("%.8f" % x).ljust(12) for x in final])
