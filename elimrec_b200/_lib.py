@@ -61,6 +61,10 @@ _SIGS = {
     "elimrec_gather_rows": [i32, vp, vp, i64, vp, i64, i32, vp],
     "elimrec_broadcast_cols": [i64, vp, i64, vp, i64, i32, vp],
     "elimrec_copy_2d": [i64, i32, vp, i64, vp, i64, vp],
+    "elimrec_tie_blocks": [i64, vp, i64, vp, i64, i32, f32, vp],
+    "elimrec_fold_blocks": [i64, vp, i64, i32, f32, vp, i64, vp],
+    "elimrec_axpy_rows": [i64, i32, vp, vp, i64, vp, i64, vp],
+    "elimrec_layer_mean": [i64, i32, i32, C.POINTER(vp), C.POINTER(i64), f32, vp, i64, vp],
     "elimrec_gemm": [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, vp, vp, vp],
     "elimrec_colsum": [i64, i64, vp, i64, vp, vp, i32, vp, vp],
     "elimrec_linear_tf32_fwd": [i64, i64, vp, i64, vp, vp, vp, i64, vp],

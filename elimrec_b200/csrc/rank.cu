@@ -28,9 +28,32 @@ struct RankT {
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
+// t.mode = predict mode (0 'normal', 1 'TE', 2 'TIE') + 4 * score fusion (0 'rubi', 1 'hm', 2 'sum'); reference
+// general_cm_fusion, models/EliMRec.py:171-210, eps = 1e-12 (:13).  hm / sum always use every head handed in.
+__device__ __forceinline__ float fuse_fn(float x, const float* d, int n_mod, int fm) {
+    if (fm == 1) {            // hm: z = ((sigmoid(x) * z_v) * z_a) * z_t ;  log(z + eps) - log1p(z)
+        float z = sigm(x);
+#pragma unroll
+        for (int m = 0; m < ELIMREC_MAX_MODS; ++m)
+            if (m < n_mod) z *= sigm(d[m + 1]);
+        return logf(z + 1e-12f) - log1pf(z);
+    }
+    float z = x;              // sum: log(sigmoid(((x + c_v) + c_a) + c_t) + eps), raw cosines
+#pragma unroll
+    for (int m = 0; m < ELIMREC_MAX_MODS; ++m)
+        if (m < n_mod) z += d[m + 1];
+    return logf(sigm(z) + 1e-12f);
+}
+
 __device__ __forceinline__ float score_fn(const float* d, int n_mod, int mode, float mean) {
+    const int pm = mode & 3, fm = mode >> 2;
     const float ui = sigm(d[0]);
-    if (mode == 0) return sigm(ui);
+    if (pm == 0) return sigm(ui);
+    if (fm != 0) {
+        const float te = fuse_fn(ui, d, n_mod, fm);
+        if (pm == 1) return sigm(te);
+        return sigm(te - fuse_fn(mean, d, n_mod, fm));
+    }
     float z = ui, nd = mean;
 #pragma unroll
     for (int m = 0; m < ELIMREC_MAX_MODS; ++m) {
@@ -40,7 +63,7 @@ __device__ __forceinline__ float score_fn(const float* d, int n_mod, int mode, f
             nd *= zs;     // ((mean * z_v) * z_a) * z_t
         }
     }
-    if (mode == 1) return sigm(z);
+    if (pm == 1) return sigm(z);
     return sigm(z - nd);
 }
 
@@ -57,7 +80,7 @@ __global__ void __launch_bounds__(256)
 rank_kernel(RankT t, int n_eval, const int* __restrict__ eval_users, const float* __restrict__ mean_in,
             float* __restrict__ out, TopkArgs tk) {
     extern __shared__ float smem[];
-    const int ntab = (MODE == RK_MEAN) ? 1 : 1 + (t.mode == 0 ? 0 : t.n_mod);
+    const int ntab = (MODE == RK_MEAN) ? 1 : 1 + ((t.mode & 3) == 0 ? 0 : t.n_mod);
     float* us = smem;                          // [NTMAX][TU][RS]
     float* is = us + NTMAX * TU * RS;          // [NTMAX][TI][RS]
     float* sc = is + NTMAX * TI * RS;          // [TU][TI+1]
@@ -77,7 +100,7 @@ rank_kernel(RankT t, int n_eval, const int* __restrict__ eval_users, const float
         *reinterpret_cast<float4*>(us + (tb * TU + r) * RS + c4 * 4) = v;
     }
     float mean2[2] = {0.f, 0.f};
-    if (MODE != RK_MEAN && t.mode == 2) {
+    if (MODE != RK_MEAN && (t.mode & 3) == 2) {
 #pragma unroll
         for (int h = 0; h < 2; ++h)
             if (u0 + ty + 16 * h < n_eval) mean2[h] = __ldg(mean_in + u0 + ty + 16 * h);
@@ -354,7 +377,7 @@ __global__ void metric_colsum_kernel(int n_rows, int n_cols, const float* __rest
 
 int fill_tables(const elimrec_rank_tables_t* t, RankT* r) {
     if (t == nullptr) return -1;
-    if (t->n_mod < 0 || t->n_mod > ELIMREC_MAX_MODS || t->mode < 0 || t->mode > 2) return -1;
+    if (t->n_mod < 0 || t->n_mod > ELIMREC_MAX_MODS || t->mode < 0 || (t->mode & 3) > 2 || (t->mode >> 2) > 2) return -1;
     r->U = t->num_users; r->I = t->num_items; r->n_mod = t->n_mod; r->mode = t->mode;
     for (int i = 0; i < NTMAX; ++i) { r->user_tab[i] = nullptr; r->item_tab[i] = nullptr; }
     r->user_tab[0] = t->f_user;
@@ -406,7 +429,7 @@ ELIMREC_API int elimrec_rank_scores(const elimrec_rank_tables_t* t, int n_eval, 
                                     const float* ui_mean, float* scores, elimrec_stream_t stream) {
     RankT r;
     ER_CHECK_ARG(fill_tables(t, &r) == 0, "bad table descriptor");
-    ER_CHECK_ARG(t->mode != 2 || ui_mean != nullptr, "TIE needs ui_mean");
+    ER_CHECK_ARG((t->mode & 3) != 2 || ui_mean != nullptr, "TIE needs ui_mean");
     if (n_eval <= 0) return 0;
     TopkArgs tk{};
     if (launch_rank<RK_SCORES>(r, n_eval, eval_users, ui_mean, scores, tk, er_stream(stream)) != 0) return -3;
@@ -420,7 +443,7 @@ ELIMREC_API int elimrec_rank_topk(const elimrec_rank_tables_t* t, int n_eval, co
     RankT r;
     ER_CHECK_ARG(fill_tables(t, &r) == 0, "bad table descriptor");
     ER_CHECK_ARG(K >= 1 && K <= 32, "K must be in [1, 32]");
-    ER_CHECK_ARG(t->mode != 2 || ui_mean != nullptr, "TIE needs ui_mean");
+    ER_CHECK_ARG((t->mode & 3) != 2 || ui_mean != nullptr, "TIE needs ui_mean");
     if (n_eval <= 0) return 0;
     TopkArgs tk{(const long long*)train_ptr, train_items, K, topk_idx, topk_val};
     if (launch_rank<RK_TOPK>(r, n_eval, eval_users, ui_mean, nullptr, tk, er_stream(stream)) != 0) return -3;

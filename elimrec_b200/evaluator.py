@@ -55,12 +55,14 @@ class UniEvaluator(AbstractEvaluator):
         for m in metric:
             if m not in metric_dict:
                 raise ValueError("There is not the metric named '%s'!" % metric)
-        if user_neg_test is not None:
-            raise NotImplementedError("candidate-negatives evaluation (uni_evaluator.py:132-140) is SURVEY.md row f3")
         self.dataset = dataset
         self.user_pos_train = user_train_dict
         self.user_pos_test = user_test_dict
-        self.user_neg_test = None
+        # Candidate-negatives mode (uni_evaluator.py:132-140).  The reference passes per-user candidate lists to
+        # model.predict, EliMRec.predict ignores them (models/EliMRec.py:96) and returns all I scores, pad_sequences leaves
+        # the equal-length rows alone, and the metrics are taken against test_items = set(range(len(pos_test[u]))) with NO
+        # train masking.  Reproduced literally: full unmasked ranking, truth = the first len(pos) item ids.
+        self.user_neg_test = user_neg_test
         self.metrics_num = len(metric)
         self.metrics = [metric_dict[m] for m in metric]
         self.num_thread = num_thread
@@ -73,13 +75,20 @@ class UniEvaluator(AbstractEvaluator):
         show = ['\t'.join([("%s@" % re_metric_dict[m] + str(k)).ljust(12) for k in self.top_show]) for m in self.metrics]
         return "metrics:\t%s" % '\t'.join(show)
 
+    def _truth(self, users):
+        if self.user_neg_test is None:
+            return self.user_pos_test
+        return {u: range(len(self.user_pos_test[u])) for u in users}
+
     def _device_state(self, model):
         if self._dev is None:
             dev = model.device_
             users = list(self.user_pos_test.keys())
-            tptr, titems = _dict_to_csr(self.user_pos_test, users)
+            tptr, titems = _dict_to_csr(self._truth(users), users)
             U = model.num_users
-            trptr, tritems = _dict_to_csr(self.user_pos_train, range(U))
+            trptr, tritems = _dict_to_csr(self.user_pos_train if self.user_neg_test is None else {}, range(U))
+            if tritems.size == 0:
+                tritems = np.zeros(1, dtype=np.int32)
             self._dev = dict(
                 users=torch.tensor(users, dtype=torch.int32, device=dev),
                 truth_ptr=torch.from_numpy(tptr).to(dev), truth_items=torch.from_numpy(titems).to(dev),
@@ -96,7 +105,7 @@ class UniEvaluator(AbstractEvaluator):
                 raise TypeError("'test_user' must be a list, tuple, set or numpy array!")
             users_l = list(test_users)
             users = torch.tensor(users_l, dtype=torch.int32, device=dev)
-            tptr, titems = _dict_to_csr(self.user_pos_test, users_l)
+            tptr, titems = _dict_to_csr(self._truth(users_l), users_l)
             truth_ptr, truth_items = torch.from_numpy(tptr).to(dev), torch.from_numpy(titems).to(dev)
         else:
             users, truth_ptr, truth_items = st["users"], st["truth_ptr"], st["truth_items"]
@@ -115,6 +124,8 @@ class UniEvaluator(AbstractEvaluator):
             val = torch.empty(n, K, dtype=torch.float32, device=dev)
             mean = torch.empty(n, dtype=torch.float32, device=dev) if model.predict_type == "TIE" else None
             backend = model.config["rank_backend"] if "rank_backend" in model.config else "tc"
+            if getattr(model, "fusion_mode", "rubi") != "rubi":
+                backend = "fp32"     # the hm / sum score fusions are epilogues of the exact-fp32 rank kernel
             if backend == "tc":      # tensor cores, fp16 hi/lo operand pairs (fp32-class accuracy)
                 tables = model.rank_tc_tables()
                 if mean is not None:
@@ -142,13 +153,56 @@ class UniEvaluator(AbstractEvaluator):
         return final, buf
 
 
+class GroupedEvaluator(AbstractEvaluator):
+    """``evaluator/grouped_evaluator.py:12-112``: users are grouped by their number of TRAINING interactions
+    (``group_view=[10,30]`` -> ``(0,10]``, ``(10,30]``; users above the last bound are dropped) and each group is
+    evaluated on its own; the result is the multi-line string the reference documents.
+
+    As shipped the reference class cannot be constructed (it calls ``UniEvaluator`` without its ``dataset`` argument,
+    ``grouped_evaluator.py:55-58``, which trips ``typeassert``); this is the documented behaviour with that call fixed."""
+
+    def __init__(self, user_train_dict, user_test_dict, user_neg_test=None, metric=None, group_view=None, top_k=50,
+                 batch_size=1024, num_thread=8, dataset=None):
+        if not isinstance(user_train_dict, dict) or not isinstance(user_test_dict, dict):
+            raise TypeError("user_train_dict / user_test_dict must be dict")
+        if not isinstance(group_view, list):
+            raise TypeError("The type of 'group_view' must be `list`!")
+        self.evaluator = UniEvaluator(dataset, user_train_dict, user_test_dict, user_neg_test, metric=metric, top_k=top_k,
+                                      batch_size=batch_size, num_thread=num_thread)
+        self.user_pos_train = user_train_dict
+        self.user_pos_test = user_test_dict
+        bounds = [0] + group_view
+        info = [("(%d,%d]:" % (lo, hi)).ljust(12) for lo, hi in zip(bounds[:-1], bounds[1:])]
+        users = list(user_test_dict.keys())
+        n_train = [len(user_train_dict[u]) for u in users]
+        gid = np.searchsorted(bounds[1:], n_train)       # side='left': (lo, hi]
+        self.grouped_user = {}
+        for g in np.unique(gid):                         # pandas groupby order = ascending group id
+            if g < len(info):
+                self.grouped_user[info[g]] = [u for u, k in zip(users, gid) if k == g]
+        if not self.grouped_user:
+            raise ValueError("The splitting of user groups is not suitable!")
+
+    def metrics_info(self):
+        return self.evaluator.metrics_info()
+
+    def evaluate(self, model):
+        out = ""
+        for group, users in self.grouped_user.items():
+            out = "%s\n%s\t%s" % (out, group, self.evaluator.evaluate(model, users))
+        return out
+
+
 class ProxyEvaluator(AbstractEvaluator):
     def __init__(self, dataset, user_train_dict, user_test_dict, user_neg_test=None, metric=None, group_view=None,
                  top_k=50, batch_size=1024, num_thread=8):
         if not isinstance(user_train_dict, dict) or not isinstance(user_test_dict, dict):
             raise TypeError("user_train_dict / user_test_dict must be dict")
         if group_view is not None:
-            raise NotImplementedError("GroupedEvaluator (broken as shipped in the reference) is SURVEY.md row f3")
+            self.evaluator = GroupedEvaluator(user_train_dict, user_test_dict, user_neg_test, metric=metric,
+                                              group_view=group_view, top_k=top_k, batch_size=batch_size,
+                                              num_thread=num_thread, dataset=dataset)
+            return
         self.evaluator = UniEvaluator(dataset, user_train_dict, user_test_dict, user_neg_test, metric=metric,
                                       top_k=top_k, batch_size=batch_size, num_thread=num_thread)
 

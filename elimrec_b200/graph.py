@@ -7,9 +7,11 @@ the two off-diagonal blocks are kept as separate CSR halves
     ui : user rows -> item columns   [U x I]      iu : item rows -> user columns   [I x U]
 
 because every propagation layer only ever multiplies one block at a time (the graph is bipartite),
-which is also what makes the 4-graph dedup possible.  Edge values are
-``fl32(fl32(d_r * 1) * d_c)`` with ``d = deg^-1/2`` computed in numpy fp32 exactly as scipy does in
-the reference, so the arrays are bit-equal to the reference COO (tests/test_graph.py).
+which is also what makes the 4-graph dedup possible.  Edge values for the default
+``adj_type='pre'`` are ``fl32(fl32(d_r * 1) * d_c)`` with ``d = deg^-1/2`` computed in numpy fp32 exactly as
+scipy does in the reference, so the arrays are bit-equal to the reference COO; the other ``adj_type``s
+(plain / gcmc: still bipartite; norm / mean: plus a diagonal kept as a separate vector) follow the same rule
+(tests/test_host_logic.py checks all five against the reference's own COO).
 
 One-time, host-side (vectorised numpy); only the result lives on the device.
 """
@@ -45,6 +47,14 @@ class CsrHalf:
         self.col = torch.from_numpy(self.indices_host).to(device)
         self.val = torch.from_numpy(self.vals_host).to(device)
         self.indptr = torch.from_numpy(self.indptr_host).to(device)
+
+    def with_values(self, vals: np.ndarray) -> "CsrHalf":
+        """Same structure, work-lists and scratch (never used concurrently with this one), different edge values."""
+        import copy
+        other = copy.copy(self)
+        other.vals_host = vals.astype(np.float32)
+        other.val = torch.from_numpy(other.vals_host).to(self.val.device)
+        return other
 
 
 def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: int | None = None,
@@ -87,11 +97,20 @@ def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: in
     return np.ascontiguousarray(seg), heavy, n_hseg
 
 
+ADJ_TYPES = ("plain", "norm", "gcmc", "pre", "mean")
+
+
 def normalized_halves(train_csr: sp.csr_matrix, adj_type: str = "pre"):
-    """(indptr, indices, vals) of both blocks of D^-1/2 A D^-1/2; bit-equal to the reference COO."""
-    if adj_type != "pre":
-        raise NotImplementedError(f"adj_type={adj_type!r}: only 'pre' (the conf/EliMRec.properties default) is built; "
-                                  "plain/norm/gcmc/mean are SURVEY.md row f2")
+    """Both off-diagonal blocks of the propagation matrix of ``create_adj_mat`` (models/EliMRec.py:309-354), values
+    bit-equal to the reference COO.  Returns a dict:
+
+        ui, iu        (indptr, indices, vals) of the user-row / item-row block of A_hat
+        ui_t, iu_t    vals of the same blocks of A_hat^T (the backward pass), or None when A_hat is symmetric
+        self_u/self_i the diagonal of A_hat per user / item (adj_type 'norm' / 'mean'), or None
+
+    'plain': A.  'pre': D^-1/2 A D^-1/2.  'gcmc': D^-1 A.  'norm': (D+I)^-1 (A+I).  'mean' (the reference's else
+    branch, any other string): D^-1 A + I.  scipy's dtypes are followed: float32 throughout, except 'norm' whose
+    ``sp.eye`` promotes the row sums to float64 before the final float32 cast (EliMRec.py:81-83)."""
     m = train_csr.tocsr().astype(np.float32)
     m.sum_duplicates()
     m.sort_indices()
@@ -100,36 +119,75 @@ def normalized_halves(train_csr: sp.csr_matrix, adj_type: str = "pre"):
     mt.sort_indices()
     deg_u = np.asarray(m.sum(1), dtype=np.float32).ravel()
     deg_i = np.asarray(mt.sum(1), dtype=np.float32).ravel()
-    with np.errstate(divide="ignore"):
-        du = np.power(deg_u, np.float32(-0.5)).astype(np.float32)
-        di = np.power(deg_i, np.float32(-0.5)).astype(np.float32)
-    du[np.isinf(du)] = 0.0
-    di[np.isinf(di)] = 0.0
-    one = np.float32(1.0)
     row_u = np.repeat(np.arange(m.shape[0]), np.diff(m.indptr))
-    val_ui = ((du[row_u] * one) * di[m.indices]).astype(np.float32)
     row_i = np.repeat(np.arange(mt.shape[0]), np.diff(mt.indptr))
-    val_iu = ((di[row_i] * one) * du[mt.indices]).astype(np.float32)
-    return (m.indptr, m.indices, val_ui), (mt.indptr, mt.indices, val_iu)
+    one = np.float32(1.0)
+    out = dict(ui_t=None, iu_t=None, self_u=None, self_i=None)
+
+    def inv(deg, power, dtype=np.float32):
+        with np.errstate(divide="ignore"):
+            d = np.power(deg.astype(dtype), dtype(power) if power != -1 else -1)
+        d[np.isinf(d)] = 0.0
+        return d
+
+    if adj_type == "pre":
+        du, di = inv(deg_u, -0.5), inv(deg_i, -0.5)
+        val_ui = ((du[row_u] * one) * di[m.indices]).astype(np.float32)
+        val_iu = ((di[row_i] * one) * du[mt.indices]).astype(np.float32)
+    elif adj_type == "plain":
+        val_ui = np.ones(m.nnz, dtype=np.float32)
+        val_iu = np.ones(mt.nnz, dtype=np.float32)
+    else:
+        if adj_type == "norm":      # rows of A + I, normalised in float64, stored as float32
+            du = inv(deg_u.astype(np.float64) + 1.0, -1, np.float64).astype(np.float32)
+            di = inv(deg_i.astype(np.float64) + 1.0, -1, np.float64).astype(np.float32)
+            out["self_u"], out["self_i"] = du.copy(), di.copy()
+        else:                       # 'gcmc', and 'mean' = gcmc + I
+            du, di = inv(deg_u, -1), inv(deg_i, -1)
+            if adj_type != "gcmc":
+                out["self_u"] = np.ones(m.shape[0], dtype=np.float32)
+                out["self_i"] = np.ones(mt.shape[0], dtype=np.float32)
+        val_ui = (du[row_u] * one).astype(np.float32)       # A_hat[u, i] = d_u
+        val_iu = (di[row_i] * one).astype(np.float32)       # A_hat[i, u] = d_i
+        out["ui_t"] = di[m.indices].astype(np.float32)      # A_hat^T[u, i] = A_hat[i, u]
+        out["iu_t"] = du[mt.indices].astype(np.float32)
+    out["ui"] = (m.indptr, m.indices, val_ui)
+    out["iu"] = (mt.indptr, mt.indices, val_iu)
+    return out
 
 
 class BipartiteGraph:
     def __init__(self, train_csr: sp.csr_matrix, device, adj_type: str = "pre", seg_len: int = SEG_LEN,
                  user_rows=None, item_rows=None):
         self.num_users, self.num_items = train_csr.shape
-        (pu, iu_, vu), (pi, ii_, vi) = normalized_halves(train_csr, adj_type)
+        self.adj_type = adj_type
+        h = normalized_halves(train_csr, adj_type)
+        (pu, iu_, vu), (pi, ii_, vi) = h["ui"], h["iu"]
         ur = user_rows or (0, self.num_users)
         ir = item_rows or (0, self.num_items)
         self.ui = CsrHalf(pu, iu_, vu, self.num_items, device, seg_len, *ur)
         self.iu = CsrHalf(pi, ii_, vi, self.num_users, device, seg_len, *ir)
+        # blocks of A_hat^T for the backward pass: same structure (and work-lists), other values when A_hat is asymmetric
+        self.ui_t = self.ui if h["ui_t"] is None else self.ui.with_values(h["ui_t"])
+        self.iu_t = self.iu if h["iu_t"] is None else self.iu.with_values(h["iu_t"])
+        self.symmetric = h["ui_t"] is None
+        # diagonal of A_hat ('norm' / 'mean'): one vector over all N nodes, users first
+        self.self_loops = h["self_u"] is not None
+        self.self_host = np.concatenate([h["self_u"], h["self_i"]]).astype(np.float32) if self.self_loops else None
+        self.self_all = torch.from_numpy(self.self_host).to(device) if self.self_loops else None
         self.nnz = self.ui.nnz + self.iu.nnz
 
     def as_coo(self):
-        """(row, col, val) in the reference's (U+I)^2 indexing, row-major - for parity tests."""
+        """(row, col, val) in the reference's (U+I)^2 indexing, row-major, columns sorted - for parity tests."""
         U = self.num_users
         ru = np.repeat(np.arange(U), np.diff(self.ui.indptr_host))
         ri = np.repeat(np.arange(self.num_items), np.diff(self.iu.indptr_host)) + U
         row = np.concatenate([ru, ri]).astype(np.int64)
         col = np.concatenate([self.ui.indices_host.astype(np.int64) + U, self.iu.indices_host.astype(np.int64)])
         val = np.concatenate([self.ui.vals_host, self.iu.vals_host])
+        if self.self_loops:
+            n = np.arange(U + self.num_items, dtype=np.int64)
+            row, col, val = np.concatenate([row, n]), np.concatenate([col, n]), np.concatenate([val, self.self_host])
+            order = np.lexsort((col, row))
+            row, col, val = row[order], col[order], val[order]
         return row, col, val

@@ -38,6 +38,13 @@ from .graph import BipartiteGraph
 
 D = 64
 PREDICT_MODE = {"normal": 0, "TE": 1, "TIE": 2}
+FUSION_MODE = {"rubi": 0, "hm": 1, "sum": 2}      # s_fusion_mode; elimrec_rank_tables_t.mode = predict + 4 * fusion
+N_WORDS, WORD_DIM = 11574, 128                    # literal 'tiktok' text branch (EliMRec.py:374-375)
+
+
+def _require_cuda(dev):
+    if dev.type != "cuda":
+        raise ElimrecError("elimrec_b200 has no CPU path: config.device must be a CUDA device")
 
 
 def _cfg(config, key, default):
@@ -113,8 +120,10 @@ class EliMRec(BasicModel):
         self.predict_type = _cfg(cfg, "predict_type", "TIE")
         self.mm_fusion_mode = _cfg(cfg, "mm_fusion_mode", "concat")
         self.fusion_mode = _cfg(cfg, "s_fusion_mode", "rubi")
-        if self.mm_fusion_mode != "concat" or self.fusion_mode != "rubi":
-            raise NotImplementedError("mm_fusion_mode='mean' / s_fusion_mode in {'hm','sum'} are SURVEY.md row f4")
+        if self.mm_fusion_mode not in ("concat", "mean"):       # EliMRec.py:221-226
+            raise ElimrecError(f"mm_fusion_mode={self.mm_fusion_mode!r}: expected 'concat' or 'mean'")
+        if self.fusion_mode not in FUSION_MODE:                 # EliMRec.py:171-210
+            raise ElimrecError(f"s_fusion_mode={self.fusion_mode!r}: expected 'rubi', 'hm' or 'sum'")
         self.modality = _cfg(cfg, "modality", "vat")
         # 'tf32': modal projections on the tcgen05 tensor cores (1e-3 parity class); 'fp32': exact FFMA path (1e-5)
         self.proj_precision = _cfg(cfg, "proj_precision", "tf32")
@@ -136,11 +145,15 @@ class EliMRec(BasicModel):
         # once per step.  lazy_tables=False runs the reference's schedule (every row, every step).
         self.lazy_tables = bool(_cfg(cfg, "lazy_tables", True))
         self.kwai = cfg["data.input.dataset"] == "kwai"
+        # literal 'tiktok' (EliMRec.py:371-378): the text feature is the mean word embedding of the item's words, computed
+        # ONCE from the initial word_embedding; the parameter keeps receiving gradients / Adam updates that never reach
+        # the outputs.  word_grad=False drops that dead gradient (the parameter then only stays at its initial value).
+        self.tiktok = cfg["data.input.dataset"] == "tiktok" and hasattr(ds, "words_tensor")
+        self.word_grad = bool(_cfg(cfg, "word_grad", True))
         self.mods = "v" if self.kwai else "vat"
         dev = _cfg(cfg, "device", None)
         dev = torch.device(dev) if dev is not None else torch.device("cuda", torch.cuda.current_device())
-        if dev.type != "cuda":
-            raise ElimrecError("elimrec_b200 has no CPU path: config.device must be a CUDA device")
+        _require_cuda(dev)
         self.device_ = dev
 
         self.embedding_user = nn.Embedding(self.num_users, D)
@@ -148,12 +161,20 @@ class EliMRec(BasicModel):
         nn.init.xavier_uniform_(self.embedding_user.weight)
         nn.init.xavier_uniform_(self.embedding_item.weight)
         # item features, L2-row-normalised once (EliMRec.py:366-381); constant afterwards
-        self._feat = {m: F.normalize(getattr(ds, f"{m}_feat").to(dev).float(), dim=1).contiguous() for m in self.mods}
+        self._feat = {m: F.normalize(getattr(ds, f"{m}_feat").to(dev).float(), dim=1).contiguous() for m in self.mods
+                      if not (self.tiktok and m == "t")}
+        if self.tiktok:
+            self.words_tensor = ds.words_tensor.to(dev)
+            self.word_embedding = nn.Embedding(N_WORDS, WORD_DIM)
+            nn.init.xavier_normal_(self.word_embedding.weight)
+            self._build_word_graph()
+            self._feat["t"] = torch.empty(self.num_items, WORD_DIM, dtype=torch.float32, device=dev)
+            self.rebuild_text_feature()
         for m in self.mods:
             setattr(self, f"{m}_feat", self._feat[m])
         for m in self.mods:
             setattr(self, f"{m}_dense", nn.Linear(self._feat[m].shape[1], D))
-        self.item_feat_dim = D * (1 + len(self.mods))
+        self.item_feat_dim = D * (1 + len(self.mods)) if self.mm_fusion_mode == "concat" else D
         for m in self.mods:
             nn.init.xavier_uniform_(getattr(self, f"{m}_dense").weight)
         self.embedding_user_after_GCN = nn.Linear(self.item_feat_dim, D)
@@ -163,6 +184,11 @@ class EliMRec(BasicModel):
         self._all_users = self._all_items = self._all_s_embs = None
         self._tables_pending = False
         self.graph = BipartiteGraph(ds.train_matrix, dev, cfg["adj_type"])
+        # adj_type 'norm' / 'mean' put a diagonal into A_hat: user rows then depend on user rows, the bipartite dedup and
+        # the row-sparse step no longer apply -> generic schedule (every layer F wide on both sides, every row)
+        self._generic = self.graph.self_loops
+        if self._generic:
+            self.lazy_tables = False
         self.f = nn.Sigmoid()
         self.s_dense_v = nn.Linear(D, D)
         self.s_dense_a = nn.Linear(D, D)
@@ -172,6 +198,31 @@ class EliMRec(BasicModel):
         nn.init.xavier_uniform_(self.s_dense_t.weight)
         self._ws = None
         self._adam = None
+
+    # ---- literal 'tiktok' text branch ---------------------------------------------------------------
+    def _build_word_graph(self):
+        """t_feat = M @ word_embedding with M[i, w] = (#times word w is listed for item i) / (#words of item i): the
+        scatter-mean of EliMRec.py:377-378 as a CSR SpMM, and M^T for the gradient that flows back into word_embedding."""
+        import scipy.sparse as sp
+        from .graph import CsrHalf
+        w = self.words_tensor.cpu().numpy()
+        I = self.num_items
+        cnt = np.bincount(w[0], minlength=I).astype(np.float32)
+        m = sp.csr_matrix(((np.float32(1.0) / cnt[w[0]]).astype(np.float32), (w[0], w[1])), shape=(I, N_WORDS))
+        m.sum_duplicates()
+        m.sort_indices()
+        mt = m.T.tocsr()
+        mt.sort_indices()
+        self._word_half = CsrHalf(m.indptr, m.indices, m.data, N_WORDS, self.device_)
+        self._word_half_t = CsrHalf(mt.indptr, mt.indices, mt.data, I, self.device_)
+
+    @torch.no_grad()
+    def rebuild_text_feature(self):
+        """Re-derive t_feat from the CURRENT word_embedding.  The reference does this exactly once, inside its constructor
+        (EliMRec.py:376-378); call it after loading a state_dict whose word_embedding differs from this model's init."""
+        w = self.word_embedding.weight.detach().to(self.device_, torch.float32).contiguous()
+        ops.spmm(self._word_half, w, self._feat["t"], WORD_DIM)
+        self.__dict__.pop("_feat_tf32", None)
 
     def _feat_tc(self, m):
         """Features pre-rounded (to nearest) to TF32 once; what the tensor-core projections stream."""
@@ -213,6 +264,8 @@ class EliMRec(BasicModel):
     @property
     def _param_names(self):
         names = ["embedding_user.weight", "embedding_item.weight"]
+        if self.tiktok and self.word_grad:
+            names.append("word_embedding.weight")
         for m in self.mods:
             names += [f"{m}_dense.weight", f"{m}_dense.bias"]
         names += ["embedding_user_after_GCN.weight", "embedding_user_after_GCN.bias",
@@ -237,17 +290,25 @@ class EliMRec(BasicModel):
         Fw = D * G
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         ws = dict(B=B, G=G, F=Fw)
-        ws["X0_i"] = e(I, Fw)
+        if not self._generic:
+            ws["X0_i"] = e(I, Fw)
         ws["X0_u"] = e(U, D)                                              # E_u as of the last forward (lazy tables)
         ws["mask"] = torch.zeros(N, dtype=torch.uint8, device=dev)        # 1 on the <= 3B instance rows of the step
         ws["need2"] = torch.zeros(N, dtype=torch.uint8, device=dev)       # instance rows + the rows they gather (2 hops)
         ws["density"] = {"u": min(100, 100 * B // max(U, 1) + 1), "i": min(100, 200 * B // max(I, 1) + 1)}   # % rows marked
         rows = lambda side: U if side == "u" else I
         ws["XW"], ws["XN"] = {}, {}
-        for k in range(1, L):  # layer L is consumed by the fused mean epilogue and never stored
-            side = "u" if k % 2 == 1 else "i"
-            ws["XW"][k] = e(rows(side), Fw)
-            ws["XN"][k] = e(rows("i" if side == "u" else "u"), D)
+        if self._generic:
+            # self loops: every layer is a full [N x F] slab (users first); layer 0's item rows are the projection slab
+            ws["GX"] = [e(N, Fw) for _ in range(L + 1)]
+            ws["X0_i"] = ws["GX"][0][U:]
+            ws["GdX"] = [e(N, Fw), e(N, Fw)]
+            ws["dE_u"] = e(U, D)
+        else:
+            for k in range(1, L):  # layer L is consumed by the fused mean epilogue and never stored
+                side = "u" if k % 2 == 1 else "i"
+                ws["XW"][k] = e(rows(side), Fw)
+                ws["XN"][k] = e(rows("i" if side == "u" else "u"), D)
         ws["O"] = e(N, Fw)
         ws["F_all"] = e(N, D)
         ws["S"] = [e(N, D) for _ in self.mods]
@@ -260,8 +321,14 @@ class EliMRec(BasicModel):
         ws["O_inst"] = e(3 * B, Fw)
         ws["dO_inst"] = e(3 * B, Fw)
         R = max(U, I)
-        ws["dW"] = [e(R, Fw), e(R, Fw)]
-        ws["dN"] = [e(R, D), e(R, D)]
+        if not self._generic:
+            ws["dW"] = [e(R, Fw), e(R, Fw)]
+            ws["dN"] = [e(R, D), e(R, D)]
+        if self.mm_fusion_mode == "mean":   # tied fusion weights [W/G | ... | W/G] and the gradient w.r.t. them
+            ws["W_eff"] = {"u": e(D, Fw), "i": e(D, Fw)}
+            ws["g_eff"] = {"u": e(D, Fw), "i": e(D, Fw)}
+        if self.tiktok and self.word_grad:
+            ws["dT"] = e(I, WORD_DIM)
         # gradients of the small parameters
         ws["g"] = {n: torch.zeros_like(p, device=dev) for n, p in self._params().items()
                    if not n.startswith("embedding_user.w") and not n.startswith("embedding_item.w")}
@@ -287,7 +354,8 @@ class EliMRec(BasicModel):
             ws["snap_names"] += (["embedding_user_after_GCN.weight", "embedding_item_after_GCN.weight"] +
                                  [f"s_dense_{m}.weight" for m in self.mods])
         Pn = self._params()
-        ws["snap"] = {n: torch.empty_like(Pn[n], device=dev) for n in ws["snap_names"]}
+        ws["snap"] = {n: (e(D, Fw) if n.endswith("after_GCN.weight") else torch.empty_like(Pn[n], device=dev))
+                      for n in ws["snap_names"]}
         ws["snap_dst"] = [ws["snap"][n] for n in ws["snap_names"]]
         ws["W_split"] = {"u": (e(D, Fw), e(D, Fw)), "i": (e(D, Fw), e(D, Fw))}
         for m in self.mods:
@@ -309,6 +377,9 @@ class EliMRec(BasicModel):
         ws = self._workspace(B)
         G, Fw = ws["G"], ws["F"]
         g = self.graph
+        if self._generic:
+            self._forward_generic(P, ws, users, pos, neg)
+            return self._loss(P, ws, users, pos, neg)
         Eu = P["embedding_user.weight"].detach()
         Ei = P["embedding_item.weight"].detach()
         X0_i = ws["X0_i"]
@@ -381,6 +452,11 @@ class EliMRec(BasicModel):
                     ws["last_layer"] = (half_n, narrow_in, pn, out_n, half_w, wide_in, pw, out_w, inv)
             ops.join_side(side)
         self._tables_version = getattr(self, "_tables_version", 0) + 1
+        return self._loss(P, ws, users, pos, neg)
+
+    def _loss(self, P, ws, users, pos, neg):
+        """fusion Linear + heads + the 1+M BPR losses on the layer-mean slab (EliMRec.py:261-272,144-153,115-142)"""
+        U, B, Fw, O = self.num_users, ws["B"], ws["F"], ws["O"]
         if self.kwai:
             self.modality = "v"  # EliMRec.py:133-134
         alpha = float(self.config.alpha)
@@ -396,7 +472,7 @@ class EliMRec(BasicModel):
             ops.gather_rows(ws["inst_rows"], O, ws["O_inst"], Fw)
         else:
             # only the sampled rows: gather O[inst], fusion + heads on 3B rows, BPR on the compact tables
-            torch._foreach_copy_(ws["snap_dst"], [P[n].detach() for n in ws["snap_names"]])   # weights of THIS forward
+            self._snapshot(P, ws)       # weights of THIS forward
             rows = ws["inst_rows"]
             ops.gather_rows(rows, O, ws["O_inst"], Fw)
             su_ = ops.fork_side(6)
@@ -408,6 +484,19 @@ class EliMRec(BasicModel):
                     ws["inst_grad"], ws["terms"])
             self._tables_pending = True
         return ws["loss"][0]
+
+    def _fusion_weights(self, P, ws):
+        """[64 x F] weights of the fusion Linear as the concat kernels see them: the parameters themselves, or for
+        mm_fusion_mode='mean' the tied form [W/G | ... | W/G] refreshed by _prep_weights (EliMRec.py:224-225)."""
+        if self.mm_fusion_mode == "mean":
+            return ws["W_eff"]["u"], ws["W_eff"]["i"]
+        return P["embedding_user_after_GCN.weight"].detach(), P["embedding_item_after_GCN.weight"].detach()
+
+    def _snapshot(self, P, ws):
+        """keep the fusion / head weights and biases THIS forward used (lazily built tables must use them)"""
+        Wu, Wi = self._fusion_weights(P, ws)
+        eff = {"embedding_user_after_GCN.weight": Wu, "embedding_item_after_GCN.weight": Wi}
+        torch._foreach_copy_(ws["snap_dst"], [eff[n] if n in eff else P[n].detach() for n in ws["snap_names"]])
 
     def _fuse_heads_rows(self, ws, O_rows, Fout, Sout, who):
         """fusion Linear + heads on a block of rows, with the weights snapshotted / split by this forward"""
@@ -433,7 +522,7 @@ class EliMRec(BasicModel):
         U, I = self.num_users, self.num_items
         O, F_all = ws["O"], ws["F_all"]
         if not from_snapshot:
-            torch._foreach_copy_(ws["snap_dst"], [P[n].detach() for n in ws["snap_names"]])
+            self._snapshot(P, ws)
         if self.fuse_precision == "x3":
             sp, sn = ws["W_split"], ws["snap"]
             ops.fuse_heads_x3_all(U, I, O, sp["u"], sn["embedding_user_after_GCN.bias"], sp["i"],
@@ -481,18 +570,25 @@ class EliMRec(BasicModel):
         sk = ws["split_inst"]
         if gscale is not None:
             gscale = gscale.reshape(1)
-        Wu, Wi = P["embedding_user_after_GCN.weight"].detach(), P["embedding_item_after_GCN.weight"].detach()
+        Wu, Wi = self._fusion_weights(P, ws)
+        tied = self.mm_fusion_mode == "mean"
+        gWu = ws["g_eff"]["u"] if tied else gr["embedding_user_after_GCN.weight"]
+        gWi = ws["g_eff"]["i"] if tied else gr["embedding_item_after_GCN.weight"]
         # fusion Linear + heads, backward on the instance rows: dO[inst], all weight and bias gradients (3 launches)
         # part 1 (d O[inst]) seeds the propagation backward; part 2 (weight / bias gradients) only feeds Adam -> side stream
         ib = lambda part: ops.inst_backward(
             B, nt, Fw, ig, Oin, gscale, Wu, Wi, [P[f"s_dense_{m}.weight"].detach() for m in self.mods], dOin,
-            gr["embedding_user_after_GCN.weight"], gr["embedding_item_after_GCN.weight"],
-            gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
+            gWu, gWi, gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
             [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods], ws["inst_ws"], part=part)
         ib(1)
         side_w = ops.fork_side(5)     # forked after d O[inst]: the weight gradients must not delay it
         with torch.cuda.stream(side_w):
             ib(2)
+            if tied:    # d W = (1/G) * sum of the G column blocks of the tied weight's gradient
+                ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
+                ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
+        if self._generic:
+            return self._backward_generic(ws, side_w)
         # layer-mean gradient G = dO / (L+1), row-sparse; it enters every layer of the chain
         inv = 1.0 / (L + 1)
         lo = {"u": (0, U, 0), "i": (U, N, U)}
@@ -520,7 +616,7 @@ class EliMRec(BasicModel):
         for k in range(L, 0, -1):
             s = "u" if k % 2 == 1 else "i"    # wide side of layer k
             o = "i" if s == "u" else "u"
-            half_o, half_s = (g.iu, g.ui) if s == "u" else (g.ui, g.iu)
+            half_o, half_s = (g.iu_t, g.ui_t) if s == "u" else (g.ui_t, g.iu_t)     # blocks of A_hat^T
             nW, nN = ws["dW"][flip][:nrows[o]], ws["dN"][flip][:nrows[s]]
             side = ops.fork_side()
             sparse_in = lazy and k == L
@@ -543,21 +639,92 @@ class EliMRec(BasicModel):
         # now dWc = d x_0[item rows, wide] = [dE_i | dP_v | dP_a | dP_t], dNc = d x_0[user rows] = dE_u
         grads = {"embedding_user.weight": dNc, "embedding_item.weight": dWc[:, :D]}
         self._proj_wgrad(ws, dWc, 0, I)
+        self._word_wgrad(ws, dWc)
         ops.join_side(side_w)
         grads.update(gr)
+        return grads
+
+    def _word_wgrad(self, ws, dX0_i):
+        """literal 'tiktok': d t_feat = d P_t @ W_t, then d word_embedding = M^T @ d t_feat (the gradient the reference
+        keeps sending into word_embedding through the t_feat it built at construction, EliMRec.py:376-378)."""
+        if not (self.tiktok and self.word_grad):
+            return
+        Fw, I = ws["F"], self.num_items
+        Wt = self.t_dense.weight.detach()
+        c0 = D * (1 + self.mods.index("t"))
+        ops.gemm(I, WORD_DIM, D, dX0_i, Fw, 1, Wt, WORD_DIM, 1, ws["dT"], WORD_DIM, 1, a_off=c0, tag="word_dgrad")
+        ops.spmm(self._word_half_t, ws["dT"], ws["g"]["word_embedding.weight"], WORD_DIM)
+
+    # ------------------------------------------------------------------------------------------
+    # generic schedule: A_hat with a diagonal (adj_type 'norm' / 'mean', EliMRec.py:332-334,349-352)
+    #   x_k = A_bip x_{k-1} + s * x_{k-1} on every row and every graph block; no dedup, no row sparsity
+    # ------------------------------------------------------------------------------------------
+    def _forward_generic(self, P, ws, users, pos, neg):
+        U, I, L = self.num_users, self.num_items, self.n_layers
+        N, G, Fw = U + I, ws["G"], ws["F"]
+        g = self.graph
+        X = ws["GX"]
+        self._prep_weights(P, ws)
+        side = ops.fork_side()
+        with torch.cuda.stream(side):
+            ops.broadcast_cols(P["embedding_user.weight"].detach(), X[0][:U], U, G)   # the same E_u feeds every graph
+            ops.copy_2d(P["embedding_item.weight"].detach(), X[0][U:], I, D)
+        self._proj_forward(P, ws, ws["X0_i"], 0, I)
+        ops.join_side(side)
+        for k in range(1, L + 1):
+            side = ops.fork_side()
+            with torch.cuda.stream(side):
+                ops.spmm(g.iu, X[k - 1][:U], X[k][U:], Fw)
+            ops.spmm(g.ui, X[k - 1][U:], X[k][:U], Fw)
+            ops.join_side(side)
+            ops.axpy_rows(g.self_all, X[k - 1], X[k], Fw)
+        ops.layer_mean(X, ws["O"], Fw, 1.0 / (L + 1))
+        self._tables_version = getattr(self, "_tables_version", 0) + 1
+
+    def _backward_generic(self, ws, side_w):
+        U, I, L = self.num_users, self.num_items, self.n_layers
+        N, G, Fw = U + I, ws["G"], ws["F"]
+        g = self.graph
+        rows, dOin = ws["inst_rows"], ws["dO_inst"]
+        inv = 1.0 / (L + 1)
+        add_G = lambda dst: ops.scatter_add_rows(rows, 0, N, 0, dOin, Fw, dst, Fw, inv)
+        cur, flip = ws["GdX"][0], 1
+        cur.zero_()
+        add_G(cur)                                   # d x_L = G (layer-mean gradient, on the instance rows)
+        for k in range(L, 0, -1):                    # d x_{k-1} = A_hat^T d x_k + G
+            nxt = ws["GdX"][flip]
+            side = ops.fork_side()
+            with torch.cuda.stream(side):
+                ops.spmm(g.iu_t, cur[:U], nxt[U:], Fw)
+            ops.spmm(g.ui_t, cur[U:], nxt[:U], Fw)
+            ops.join_side(side)
+            ops.axpy_rows(g.self_all, cur, nxt, Fw)
+            add_G(nxt)
+            cur, flip = nxt, flip ^ 1
+        ops.fold_blocks(cur[:U], ws["dE_u"], G)      # the user table fed all G graphs
+        dX0_i = cur[U:]
+        grads = {"embedding_user.weight": ws["dE_u"], "embedding_item.weight": dX0_i[:, :D]}
+        self._proj_wgrad(ws, dX0_i, 0, I)
+        self._word_wgrad(ws, dX0_i)
+        ops.join_side(side_w)
+        grads.update(ws["g"])
         return grads
 
     # projections over item rows [r0, r1) - the whole table on one GPU, the owned block when row-sharded
     def _prep_weights(self, P, ws):
         """TF32 rounding (projections) and hi/lo split (fusion, heads) of the small weights, one launch."""
         prep = []
+        if self.mm_fusion_mode == "mean":
+            G = ws["G"]
+            ops.tie_blocks(P["embedding_user_after_GCN.weight"].detach(), ws["W_eff"]["u"], G, 1.0 / G)
+            ops.tie_blocks(P["embedding_item_after_GCN.weight"].detach(), ws["W_eff"]["i"], G, 1.0 / G)
         if self.proj_precision == "tf32":
             prep += [(P[f"{m}_dense.weight"].detach(), ws["W_tf32"][m], None) for m in self.mods
                      if self._feat[m].shape[1] % 4 == 0]
         if self.fuse_precision == "x3":
             sp = ws["W_split"]
-            prep += [(P["embedding_user_after_GCN.weight"].detach(), *sp["u"]),
-                     (P["embedding_item_after_GCN.weight"].detach(), *sp["i"])]
+            Wu, Wi = self._fusion_weights(P, ws)
+            prep += [(Wu, *sp["u"]), (Wi, *sp["i"])]
             prep += [(P[f"s_dense_{m}.weight"].detach(), *sp[m]) for m in self.mods]
         if prep:
             ops.prep_weights_tf32(prep)
@@ -715,6 +882,8 @@ class EliMRec(BasicModel):
     def _active_mods(self):
         if self.predict_type == "normal":
             return []
+        if self.fusion_mode != "rubi":      # hm / sum multiply in every modality, whatever `modality` says (EliMRec.py:190-210)
+            return list(range(len(self.mods)))
         return [j for j, m in enumerate(self.mods) if m in self.modality]
 
     def rank_tables(self):
@@ -735,10 +904,13 @@ class EliMRec(BasicModel):
         fu, fi = ws["rank_f"]
         su = [ws["S_norm"][j][0] for j in act]
         si = [ws["S_norm"][j][1] for j in act]
-        return ops.rank_tables(self.num_users, self.num_items, PREDICT_MODE[self.predict_type], fu, fi, su, si)
+        mode = PREDICT_MODE[self.predict_type] + 4 * FUSION_MODE[self.fusion_mode]
+        return ops.rank_tables(self.num_users, self.num_items, mode, fu, fi, su, si)
 
     def rank_tc_tables(self):
         """fp16 hi/lo split of the cached tables for the tensor-core evaluator (rebuilt once per training forward)."""
+        if self.fusion_mode != "rubi":
+            raise ElimrecError("the tensor-core evaluator implements the 'rubi' score fusion; hm / sum run on the fp32 rank path")
         self.rank_tables()                      # refreshes the normalised single-modal tables
         ws = self._ws
         key = (self._tables_version, self.predict_type, self.modality)

@@ -128,6 +128,34 @@ def copy_2d(src, dst, n_rows, width):
     call("elimrec_copy_2d", n_rows, width, ptr(src, F32), src.stride(0), ptr(dst, F32), dst.stride(0), stream())
 
 
+def broadcast_cols(src, dst, n_rows, n_rep):
+    """dst[r, 64g + c] = src[r, c] for g < n_rep."""
+    call("elimrec_broadcast_cols", n_rows, ptr(src, F32), src.stride(0), ptr(dst, F32), dst.stride(0), n_rep, stream())
+
+
+def tie_blocks(src, dst, n_rep, scale):
+    """dst[r, 64g + c] = scale * src[r, c]  (tied weight of mm_fusion_mode='mean')."""
+    call("elimrec_tie_blocks", src.shape[0], ptr(src, F32), src.stride(0), ptr(dst, F32), dst.stride(0), n_rep, scale, stream())
+
+
+def fold_blocks(src, dst, n_rep, scale=1.0):
+    """dst[r, c] = scale * sum_g src[r, 64g + c]."""
+    call("elimrec_fold_blocks", src.shape[0], ptr(src, F32), src.stride(0), n_rep, scale, ptr(dst, F32), dst.stride(0), stream())
+
+
+def axpy_rows(row_scale, X, Y, width):
+    """Y[r, :width] += row_scale[r] * X[r, :width]  (self-loop term of adj_type 'norm' / 'mean')."""
+    call("elimrec_axpy_rows", X.shape[0], width, ptr(row_scale, F32), ptr(X, F32), X.stride(0), ptr(Y, F32), Y.stride(0),
+         stream())
+
+
+def layer_mean(layers, out, width, scale):
+    n = len(layers)
+    lp = (C.c_void_p * n)(*[ptr(t, F32) for t in layers])
+    ld = (C.c_int64 * n)(*[t.stride(0) for t in layers])
+    call("elimrec_layer_mean", out.shape[0], width, n, lp, ld, scale, ptr(out, F32), out.stride(0), stream())
+
+
 def gemm(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, Cm, c_sm, c_sn, bias=None, accumulate=False, split_k=1, ws=None,
          scale=None, a_off=0, b_off=0, c_off=0, tag=None):
     """C(m,n) = [C +] scale * sum_k A(m,k) B(k,n) [+ bias(n)]; *_off are element offsets into the tensors."""

@@ -45,6 +45,9 @@ class ShardedEliMRec(EliMRec):
             raise ElimrecError("ShardedEliMRec needs an initialised torch.distributed process group")
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         super()._init_weight()
+        if self._generic or not self.graph.symmetric or self.mm_fusion_mode != "concat" or self.tiktok:
+            raise NotImplementedError("ShardedEliMRec covers the default configuration (symmetric adj_type, concat fusion, "
+                                      "feature-file text modality); the SURVEY.md 8f variants run on EliMRec")
         U, I, G = self.num_users, self.num_items, self.world
         self.Ub, self.Ib = -(-U // G), -(-I // G)
         self.u0, self.u1 = min(U, self.rank * self.Ub), min(U, (self.rank + 1) * self.Ub)

@@ -111,6 +111,25 @@ int elimrec_copy_2d(int64_t n_rows, int width, const float* src, int64_t src_ld,
                     elimrec_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * column-block helpers of the non-default model variants (csrc/blocks.cu)
+ * ------------------------------------------------------------------------------------------------ */
+/* dst[r, g*64 + c] = scale * src[r, c], g < n_rep.  mm_fusion_mode='mean' (models/EliMRec.py:224-225):
+ * W.mean(stack(reps)) == [W/G | ... | W/G].cat(reps), so the mean fusion runs on the concat kernels with a tied weight. */
+int elimrec_tie_blocks(int64_t n_rows, const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int n_rep, float scale,
+                       elimrec_stream_t stream);
+/* dst[r, c] = scale * sum_{g < n_rep} src[r, g*64 + c]   (gradient of a tied weight; d E_u summed over the graphs) */
+int elimrec_fold_blocks(int64_t n_rows, const float* src, int64_t src_ld, int n_rep, float scale, float* dst, int64_t dst_ld,
+                        elimrec_stream_t stream);
+/* Y[r, :] += row_scale[r] * X[r, :] - the diagonal of adj_type 'norm' / 'mean' (models/EliMRec.py:332-334,349-352),
+ * applied after the bipartite SpMM of the layer */
+int elimrec_axpy_rows(int64_t n_rows, int width, const float* row_scale, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                      elimrec_stream_t stream);
+/* out = scale * (((x_0 + x_1) + x_2) + ...) over n_layers slabs (torch.stack + torch.mean, models/EliMRec.py:246-247);
+ * used when the mean cannot be fused into the last SpMM.  layers_host / ld_host are HOST arrays of device pointers / strides. */
+int elimrec_layer_mean(int64_t n_rows, int width, int n_layers, const float* const* layers_host, const int64_t* ld_host,
+                       float scale, float* out, int64_t ld_out, elimrec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * gemm - replaces nn.Linear forward/backward for v_dense/a_dense/t_dense (models/EliMRec.py:233-236),
  * embedding_{user,item}_after_GCN (:261-270) and s_dense_* (:146-151).
  *
@@ -260,12 +279,15 @@ int elimrec_sample_triples_device(uint64_t seed, uint64_t epoch, int64_t num_sam
                                   elimrec_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * rank - replaces EliMRec.predict + general_cm_fusion (models/EliMRec.py:96-113,155-188), the
+ * rank - replaces EliMRec.predict + general_cm_fusion (models/EliMRec.py:96-113,155-212), the
  * train-item masking loop (uni_evaluator.py:149-154) and cpp_evaluate_matrix / metric.h
  * (evaluator/backend/cpp/include/evaluate.h:45-64, metric.h:17-114).
  *
- * mode: 0 = 'normal' sigmoid(sigmoid(u.i)), 1 = 'TE', 2 = 'TIE'.  s_user/s_item: L2-row-normalised
- * single-modal tables of the ACTIVE modalities (n_mod of them, reference order v,a,t).
+ * mode = predict mode + 4 * score-fusion mode.  Predict mode: 0 = 'normal' sigmoid(sigmoid(u.i)), 1 = 'TE', 2 = 'TIE'.
+ * Score fusion (s_fusion_mode, EliMRec.py:171-210): 0 = 'rubi' x * prod sigmoid(cos_m); 1 = 'hm'
+ * log(z + 1e-12) - log1p(z), z = sigmoid(x) * prod sigmoid(cos_m); 2 = 'sum' log(sigmoid(x + sum cos_m) + 1e-12).
+ * s_user/s_item: L2-row-normalised single-modal tables of the ACTIVE modalities (n_mod of them, reference order
+ * v,a,t; hm / sum use every modality, as the reference does).  The tensor-core evaluator takes rubi only.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
     int32_t num_users, num_items, n_mod, mode;

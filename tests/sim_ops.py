@@ -1,0 +1,352 @@
+"""TEST INFRASTRUCTURE - a torch-CPU stand-in for ``elimrec_b200.ops`` (the tensor-level wrappers of the C-ABI).
+
+It states, in a few lines of torch each, WHAT every entry point computes.  ``tests/test_schedule_sim.py`` swaps it
+in for the real wrappers so that the host-side schedule of ``elimrec_b200/model.py`` / ``evaluator.py`` / ``optim.py``
+(which halves, which rows, which masks, which epilogues, in which order) can be checked against the oracle in the
+GPU-less build container.  It is never imported by the package, by ``bench.py`` or by the ``-m gpu`` tests: the product
+path has no CPU implementation, and nothing here says anything about the CUDA kernels themselves (those are compared
+with the oracle on the B200, ``tests/test_gpu_*.py``).  Tensor-core paths are simulated in exact fp32.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_eval
+
+LAUNCH_LOG = []          # names of the simulated entry points, in call order
+
+
+def _log(name):
+    LAUNCH_LOG.append(name)
+
+
+# ---- streams: the simulator is sequential ------------------------------------------------------------------------------
+def fork_side(slot=0):
+    return None
+
+
+def join_side(side):
+    return None
+
+
+class _Epi:
+    def __init__(self, prev, out, width, scale):
+        self.prev, self.out, self.width, self.scale = prev, out, width, scale
+
+
+def mean_epilogue(prev, out, width, scale):
+    return _Epi(list(prev), out, width, scale)
+
+
+def _csr(half):
+    n = half.n_rows
+    crow = torch.from_numpy(half.indptr_host.astype(np.int64))
+    return torch.sparse_csr_tensor(crow, half.col.long(), half.val, size=(n, half.n_cols))
+
+
+def spmm(half, X, Y, width, epi=None, row_mask=None, col_mask=None, density=50):
+    _log(f"spmm{width}" + ("m" if row_mask is not None or col_mask is not None else ""))
+    Xs = X[:, :width]
+    if col_mask is not None:     # edges to unmarked columns are dropped before the gather (their rows may hold garbage)
+        Xs = torch.where(col_mask.bool().unsqueeze(1), Xs, torch.zeros_like(Xs))
+    acc = torch.sparse.mm(_csr(half), Xs.contiguous())
+    rows = torch.arange(half.n_rows) if row_mask is None else torch.nonzero(row_mask).flatten()
+    if Y is not None:
+        Y[rows, :width] = acc[rows]
+    if epi is not None:
+        reps = epi.width // width
+        s = None
+        for t, w in epi.prev:    # ((x0 + x1) + ...) + x_L, narrow layers broadcast over the graph blocks
+            v = t[:, :w]
+            v = v.repeat(1, epi.width // w) if w != epi.width else v
+            s = v.clone() if s is None else s + v
+        s = s + (acc.repeat(1, reps) if reps > 1 else acc)
+        epi.out[rows, :epi.width] = (s * epi.scale)[rows]
+
+
+def inst_rows(users, pos, neg, num_users, rows, mask=None, mask2=None):
+    _log("inst_rows")
+    r = torch.cat([users, num_users + pos, num_users + neg]).to(torch.int32)
+    rows.copy_(r)
+    for m in (mask, mask2):
+        if m is not None:
+            m.zero_()
+            m[r.long()] = 1
+
+
+def mark_rows(rows, mask):
+    mask.zero_()
+    mask[rows.long()] = 1
+
+
+def mark_neighbors(half, row_mask, out_mask):
+    _log("mark_neighbors")
+    ptr = half.indptr_host
+    for r in torch.nonzero(row_mask).flatten().tolist():
+        out_mask[half.col[ptr[r]:ptr[r + 1]].long()] = 1
+
+
+def zero_rows(rows, lo, hi, off, dst, width):
+    _log("zero_rows")
+    r = rows.long()
+    r = r[(r >= lo) & (r < hi)] - off
+    dst[r, :width] = 0
+
+
+def scatter_add_rows(rows, lo, hi, off, src, src_width, dst, width, scale):
+    _log("scatter_add_rows")
+    fold = src_width // width
+    r = rows.long()
+    sel = (r >= lo) & (r < hi)
+    v = src[sel, :src_width].reshape(-1, fold, width).sum(1) * scale
+    dst[:, :width].index_add_(0, r[sel] - off, v)
+
+
+def gather_rows(rows, src, dst, width):
+    _log("gather_rows")
+    dst[:, :width] = src[rows.long(), :width]
+
+
+def copy_2d(src, dst, n_rows, width):
+    _log("copy_2d")
+    dst[:n_rows, :width] = src[:n_rows, :width]
+
+
+def broadcast_cols(src, dst, n_rows, n_rep):
+    _log("broadcast_cols")
+    dst[:n_rows, :64 * n_rep] = src[:n_rows, :64].repeat(1, n_rep)
+
+
+def tie_blocks(src, dst, n_rep, scale):
+    _log("tie_blocks")
+    dst[:, :64 * n_rep] = (src[:, :64] * scale).repeat(1, n_rep)
+
+
+def fold_blocks(src, dst, n_rep, scale=1.0):
+    _log("fold_blocks")
+    dst[:, :64] = src[:, :64 * n_rep].reshape(src.shape[0], n_rep, 64).sum(1) * scale
+
+
+def axpy_rows(row_scale, X, Y, width):
+    _log("axpy_rows")
+    Y[:, :width] += row_scale.unsqueeze(1) * X[:, :width]
+
+
+def layer_mean(layers, out, width, scale):
+    _log("layer_mean")
+    s = layers[0][:, :width].clone()
+    for t in layers[1:]:
+        s = s + t[:, :width]
+    out[:, :width] = s * scale
+
+
+def _view(t, off, shape, strides):
+    return torch.as_strided(t, shape, strides, t.storage_offset() + off)
+
+
+def gemm(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, Cm, c_sm, c_sn, bias=None, accumulate=False, split_k=1, ws=None,
+         scale=None, a_off=0, b_off=0, c_off=0, tag=None):
+    _log(tag or "gemm")
+    a = _view(A, a_off, (M, K), (a_sm, a_sk))
+    b = _view(B, b_off, (K, N), (b_sk, b_sn))
+    c = _view(Cm, c_off, (M, N), (c_sm, c_sn))
+    r = a @ b
+    if scale is not None:
+        r = r * scale
+    if bias is not None:
+        r = r + bias
+    c.copy_(c + r if accumulate else r)
+
+
+def linear_tf32_fwd_multi(problems, tag="proj_fwd_tc"):
+    _log(tag)
+    for X, W, b, Y, col in problems:
+        Y[:, col:col + 64] = X @ W.t() + (b if b is not None else 0)
+
+
+def linear_tf32_fwd(X, W, b, Y, col=0, tag="proj_fwd_tc"):
+    linear_tf32_fwd_multi([(X, W, b, Y, col)], tag)
+
+
+def linear_tf32_wgrad(dY, X, dW, ws, col=0, tag="proj_wgrad_tc"):
+    _log(tag)
+    dW.copy_(dY[:, col:col + 64].t() @ X)
+
+
+def linear_tf32_wgrad_ws_floats(M, K):
+    return 1
+
+
+def colsum_ws_floats(M, N):
+    return 1
+
+
+def inst_backward_ws_floats(B, nt, Fw):
+    return 1
+
+
+def round_tf32(src, dst):
+    dst.copy_(src)
+
+
+def prep_weights_tf32(items):
+    _log("prep_weights")
+    for src, hi, lo in items:
+        hi.copy_(src)
+        if lo is not None:
+            lo.zero_()
+
+
+def fuse_heads_x3(O_rows, Wf_hi, Wf_lo, bf, Ws_hi, Ws_lo, bs, F_out, S_out, tag="fuse_heads_x3"):
+    _log(tag)
+    F_out.copy_(O_rows @ (Wf_hi + Wf_lo).t() + bf)
+    for m in range(len(Ws_hi)):
+        S_out[m].copy_(O_rows[:, 64 * (m + 1):64 * (m + 2)] @ (Ws_hi[m] + Ws_lo[m]).t() + bs[m])
+
+
+def fuse_heads_x3_all(U, I, O, Wu, bu, Wi, bi, Ws_hi, Ws_lo, bs, F_out, S_out, tag="fuse_heads_x3_all"):
+    fuse_heads_x3(O[:U], Wu[0], Wu[1], bu, Ws_hi, Ws_lo, bs, F_out[:U], [s[:U] for s in S_out], tag)
+    fuse_heads_x3(O[U:U + I], Wi[0], Wi[1], bi, Ws_hi, Ws_lo, bs, F_out[U:U + I], [s[U:U + I] for s in S_out], tag)
+
+
+def colsum(M, N, A, ld, out, ws, accumulate=False, scale=None, a_off=0):
+    _log("colsum")
+    s = _view(A, a_off, (M, N), (ld, 1)).sum(0)
+    if scale is not None:
+        s = s * scale
+    out[:N] = out[:N] + s if accumulate else s
+
+
+def bpr(tables, weights, users, pos, neg, num_users, loss_out, inst_rows_out, inst_grad, terms):
+    """1 + M normalised-cosine BPR losses (EliMRec.py:291-297) and their gradient w.r.t. the gathered rows."""
+    _log("bpr")
+    B = users.numel()
+    total = 0
+    for t, (tab, w) in enumerate(zip(tables, weights)):
+        rows = [tab[users], tab[num_users + pos], tab[num_users + neg]]
+        with torch.enable_grad():       # (called from inside an autograd.Function forward, where grad mode is off)
+            rows = [r.detach().clone().requires_grad_(True) for r in rows]
+            u, p, n = (F.normalize(r, dim=1) for r in rows)
+            loss = torch.mean(F.softplus(torch.sum(u * n, 1) - torch.sum(u * p, 1)))
+            gs = torch.autograd.grad(loss, rows)
+        for k in range(3):
+            inst_grad[k * B:(k + 1) * B, 64 * t:64 * (t + 1)] = w * gs[k]
+        total = total + w * loss.detach()
+    loss_out[0] = total
+    inst_rows_out.copy_(torch.cat([users, num_users + pos, num_users + neg]).to(torch.int32))
+
+
+def inst_backward(B, nt, Fw, inst_grad, O_inst, gscale, Wu, Wi, Ws, dO_inst, dWu, dWi, dbu, dbi, dWs, dbs, ws, part=3):
+    _log(f"inst_backward{part}")
+    g = 1.0 if gscale is None else float(gscale)
+    ig = inst_grad * g
+    if part & 1:
+        dO_inst[:B] = ig[:B, :64] @ Wu
+        dO_inst[B:] = ig[B:, :64] @ Wi
+        for m in range(nt - 1):
+            blk = slice(64 * (m + 1), 64 * (m + 2))
+            dO_inst[:, blk] += ig[:, blk] @ Ws[m]
+    if part & 2:
+        dWu.copy_(ig[:B, :64].t() @ O_inst[:B])
+        dWi.copy_(ig[B:, :64].t() @ O_inst[B:])
+        dbu.copy_(ig[:B, :64].sum(0))
+        dbi.copy_(ig[B:, :64].sum(0))
+        for m in range(nt - 1):
+            blk = slice(64 * (m + 1), 64 * (m + 2))
+            dWs[m].copy_(ig[:, blk].t() @ O_inst[:, blk])
+            dbs[m].copy_(ig[:, blk].sum(0))
+
+
+def adam_tick(step_dev, consts_dev, lr, b1, b2):
+    step_dev += 1
+    t = int(step_dev)
+    consts_dev[0] = lr / (1 - b1 ** t)
+    consts_dev[1] = (1 - b2 ** t) ** 0.5
+
+
+def adam_apply_multi(items, consts_dev, b1, b2, eps, wd):
+    _log("adam")
+    step_size, bc2_sqrt = float(consts_dev[0]), float(consts_dev[1])
+    for p, g, m, v in items:
+        g = g.reshape(p.shape) + wd * p
+        m.lerp_(g, 1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        p.addcdiv_(m, v.sqrt() / bc2_sqrt + eps, value=-step_size)
+
+
+def row_normalize(src, dst):
+    dst.copy_(F.normalize(src, dim=1))
+
+
+# ---- rank ---------------------------------------------------------------------------------------------------------------
+class _RankTables:
+    pass
+
+
+def rank_tables(num_users, num_items, mode, f_user, f_item, s_user, s_item):
+    t = _RankTables()
+    t.mode, t.f_user, t.f_item, t.s_user, t.s_item = mode, f_user, f_item, list(s_user), list(s_item)
+    return t
+
+
+def _ui(t, users):
+    return torch.sigmoid(t.f_user[users.long()] @ t.f_item.t())
+
+
+def rank_rowmean(t, eval_users, out):
+    _log("rank_rowmean")
+    out.copy_(_ui(t, eval_users).mean(1))
+
+
+def _scores(t, users, mean):
+    pm, fm = t.mode & 3, t.mode >> 2
+    ui = _ui(t, users)
+    if pm == 0:
+        return torch.sigmoid(ui)
+    cos = [su[users.long()] @ si.t() for su, si in zip(t.s_user, t.s_item)]
+
+    def fuse(x):
+        if fm == 0:
+            for c in cos:
+                x = x * torch.sigmoid(c)
+            return x
+        if fm == 1:
+            z = torch.sigmoid(x)
+            for c in cos:
+                z = z * torch.sigmoid(c)
+            return torch.log(z + 1e-12) - torch.log1p(z)
+        for c in cos:
+            x = x + c
+        return torch.log(torch.sigmoid(x) + 1e-12)
+
+    if pm == 1:
+        return torch.sigmoid(fuse(ui))
+    return torch.sigmoid(fuse(ui) - fuse(mean.unsqueeze(1).expand_as(ui)))
+
+
+def rank_scores(t, eval_users, ui_mean, out):
+    _log("rank_scores")
+    out.copy_(_scores(t, eval_users, ui_mean))
+
+
+def rank_topk(t, eval_users, ui_mean, train_ptr, train_items, K, idx, val):
+    _log("rank_topk")
+    sc = _scores(t, eval_users, ui_mean).numpy().copy()
+    tp, ti = train_ptr.numpy(), train_items.numpy()
+    for r, u in enumerate(eval_users.tolist()):
+        sc[r, ti[tp[u]:tp[u + 1]]] = -np.inf
+    top = ref_eval.topk_lowest_index(sc, K)
+    idx.copy_(torch.from_numpy(top))
+    val.copy_(torch.from_numpy(np.take_along_axis(sc, top.astype(np.int64), 1)))
+
+
+def metric_rows(topk_idx, truth_ptr, truth_items, metric_ids, K, rows, sums):
+    _log("metric_rows")
+    tp, ti = truth_ptr.numpy(), truth_items.numpy()
+    truth = [ti[tp[r]:tp[r + 1]].tolist() for r in range(topk_idx.shape[0])]
+    out = ref_eval.metric_rows(topk_idx.numpy(), truth, list(metric_ids), K)
+    rows[:out.shape[0]] = torch.from_numpy(out)
+    if sums is not None:
+        sums += torch.from_numpy(out.astype(np.float64).sum(0))

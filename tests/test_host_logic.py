@@ -25,7 +25,9 @@ def test_dataset_remap_matches_reference(golden):
 
 def test_adjacency_halves_bit_exact(golden):
     U, I = int(golden["num_users"]), int(golden["num_items"])
-    (pu, iu, vu), (pi, ii, vi) = G.normalized_halves(csr_from_golden(golden, "train"))
+    h = G.normalized_halves(csr_from_golden(golden, "train"))
+    (pu, iu, vu), (pi, ii, vi) = h["ui"], h["iu"]
+    assert h["ui_t"] is None and h["self_u"] is None
     ru = np.repeat(np.arange(U), np.diff(pu))
     ri = np.repeat(np.arange(I), np.diff(pi)) + U
     row = np.concatenate([ru, ri])
@@ -33,6 +35,46 @@ def test_adjacency_halves_bit_exact(golden):
     val = np.concatenate([vu, vi])
     assert np.array_equal(row, golden["adj_row"]) and np.array_equal(col, golden["adj_col"])
     assert np.array_equal(val.view(np.uint32), golden["adj_val"].view(np.uint32))
+
+
+@pytest.mark.parametrize("adj", ["plain", "norm", "gcmc", "mean"])
+def test_other_adj_types_bit_exact(adj):
+    """models/EliMRec.py:329-352: every adj_type against the COO the reference itself built (next.npz), plus A_hat^T."""
+    from conftest import load_golden
+    base, nxt = load_golden("generic"), load_golden("next")
+    U, I = int(base["num_users"]), int(base["num_items"])
+    g = G.BipartiteGraph(csr_from_golden(base, "train"), "cpu", adj)
+    row, col, val = g.as_coo()
+    # scipy leaves the columns of a row unsorted after `adj + sp.eye` ('norm'): compare in canonical (row, col) order
+    rr, rc, rv = nxt[f"adj_{adj}/row"], nxt[f"adj_{adj}/col"], nxt[f"adj_{adj}/val"]
+    o = np.lexsort((rc, rr))
+    assert np.array_equal(row, rr[o]) and np.array_equal(col, rc[o])
+    assert np.array_equal(val.view(np.uint32), rv[o].view(np.uint32))
+    assert g.self_loops == (adj in ("norm", "mean")) and g.symmetric == (adj == "plain")
+    # the transposed blocks really are the transpose
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, (row, col)), shape=(U + I, U + I))
+    At = A.T.tocsr()
+    ui_t = sp.csr_matrix((g.ui_t.vals_host, g.ui_t.indices_host, g.ui_t.indptr_host), shape=(U, I))
+    iu_t = sp.csr_matrix((g.iu_t.vals_host, g.iu_t.indices_host, g.iu_t.indptr_host), shape=(I, U))
+    assert abs(At[:U, U:] - ui_t).max() == 0 and abs(At[U:, :U] - iu_t).max() == 0
+
+
+def test_grouped_evaluator_groups():
+    """evaluator/grouped_evaluator.py:61-75: (lo, hi] groups by number of training items, larger users dropped."""
+    from elimrec_b200.evaluator import GroupedEvaluator, ProxyEvaluator
+    train = {u: list(range(n)) for u, n in enumerate([1, 3, 3, 4, 7, 9, 30])}
+    test = {u: [50] for u in train}
+    ge = GroupedEvaluator(train, test, None, metric=["Recall"], group_view=[3, 8], top_k=[5])
+    assert list(ge.grouped_user.keys()) == ["(0,3]:".ljust(12), "(3,8]:".ljust(12)]
+    assert list(ge.grouped_user.values()) == [[0, 1, 2], [3, 4]]
+    assert ge.metrics_info() == "metrics:\t" + "Recall@5".ljust(12)
+    with pytest.raises(ValueError):
+        GroupedEvaluator(train, {6: [50]}, None, metric=["Recall"], group_view=[3, 8], top_k=[5])
+    with pytest.raises(TypeError):
+        GroupedEvaluator(train, test, None, group_view=(3, 8))
+    assert isinstance(ProxyEvaluator(None, train, test, None, metric=["Recall"], group_view=[3, 8], top_k=5).evaluator,
+                      GroupedEvaluator)
 
 
 @pytest.mark.parametrize("seg_len", [4, 64])

@@ -1,0 +1,289 @@
+"""Host-side schedule of the model / evaluator / optimizer, checked WITHOUT a GPU.
+
+``tests/sim_ops.py`` (a few lines of torch per C-ABI entry point) replaces ``elimrec_b200.ops``; everything above it -
+which CSR half a layer uses, the wide / narrow dedup, the two-hop row masks of the row-sparse step, the instance-row
+backward, the tied weights of ``mm_fusion_mode='mean'``, the transposed values of the asymmetric ``adj_type``s, the
+self-loop schedule, the word-embedding branch, Adam, the evaluator's CSRs and modes - runs as shipped and is compared
+with the golden vectors of the reference.
+
+Every test body runs twice: ``[sim]`` here in the build container, and ``[cuda]`` (``-m gpu``) on the B200 with the real
+wrappers and kernels - same inputs, same golden vectors, same tolerances (fp32 class: 2e-5 norm-wise)."""
+import numpy as np
+import pytest
+import torch
+
+import sim_ops
+from conftest import load_golden
+from helpers import golden_dataset, golden_params
+from test_oracle_next import tiktok_setup
+
+TOL = 2e-5
+
+
+DEV = {"dev": torch.device("cpu")}
+
+
+def rel(a, b):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(params=["sim", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request, monkeypatch):
+    if request.param == "cuda":
+        DEV["dev"] = torch.device("cuda:0")
+        return "cuda"
+    DEV["dev"] = torch.device("cpu")
+    return _install_sim(monkeypatch)
+
+
+@pytest.fixture()
+def sim(monkeypatch):
+    DEV["dev"] = torch.device("cpu")
+    return _install_sim(monkeypatch)
+
+
+def _install_sim(monkeypatch):
+    import elimrec_b200.evaluator as ev
+    import elimrec_b200.model as md
+    import elimrec_b200.optim as op
+
+    class _Ev:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, *a):
+            pass
+
+    class _St:
+        def wait_event(self, *a):
+            pass
+
+    for mod in (md, ev, op):
+        monkeypatch.setattr(mod, "ops", sim_ops)
+    monkeypatch.setattr(md, "_require_cuda", lambda dev: None)
+    monkeypatch.setattr(torch.cuda, "Event", _Ev)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: _St())
+    sim_ops.LAUNCH_LOG.clear()
+    return sim_ops
+
+
+def build(ds, params, name="synthg", **cfg):
+    from elimrec_b200.data import Config
+    from elimrec_b200.model import EliMRec
+    conf = Config(**{"data.input.dataset": name, "topks": [20], "device": DEV["dev"], "alpha": 0.5,
+                     "test_batch_size": 16, "rank_backend": "fp32", "proj_precision": "fp32", **cfg})
+    model = EliMRec(conf, ds).to(DEV["dev"])
+    missing = model.load_state_dict({k: torch.as_tensor(v) for k, v in params.items()}, strict=False)
+    assert not missing.unexpected_keys and not missing.missing_keys, missing
+    return model
+
+
+def batch(g, i, pre=""):
+    return tuple(torch.as_tensor(g[f"{pre}batch{i}_{k}"]) for k in ("users", "pos", "neg"))
+
+
+def check_grads(model, g, pre):
+    n = 0
+    for name, p in model.named_parameters():
+        key = f"{pre}grad0/{name}"
+        if key in g:
+            assert p.grad is not None, name
+            assert rel(p.grad, g[key]) < TOL, name
+            n += 1
+        else:
+            assert p.grad is None, name
+    assert n >= 8
+
+
+def check_steps(model, g, pre, steps=3, subset=None, worst=1e-4, frac=1e-3):
+    """Weights after Adam steps.  Adam divides by sqrt(v)+eps: an element whose gradient is within rounding noise of zero
+    can move by a sizeable fraction of lr in either implementation (gradients themselves are gated at TOL in check_grads),
+    hence: nearly all elements within 1e-5 norm-wise, every element within `worst`."""
+    model.make_optimizer(lr=1e-3, weight_decay=1e-4)
+    losses = [float(model.train_step(*batch(g, i, pre))) for i in range(steps)]
+    np.testing.assert_allclose(losses, g[f"{pre}losses"][:steps], rtol=2e-5)
+    for k, v in model.state_dict().items():
+        want = g[f"{pre}sd3/{k}"]
+        got = v if subset is None or k not in subset else v[subset[k].to(v.device)]
+        d = np.abs(got.detach().double().cpu().numpy() - want) / np.abs(want).max()
+        assert d.max() < worst and (d > 1e-5).mean() < frac, (k, d.max(), (d > 1e-5).mean())
+
+
+# ---- the default configuration: both schedules ------------------------------------------------------------------------------
+@pytest.mark.parametrize("lazy", [True, False])
+def test_default_schedule_vs_golden(backend, golden, lazy):
+    name = "kwai" if golden["_name"] == "kwai" else "synthg"
+    model = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy)
+    loss = model.bpr_loss(*batch(golden, 0))
+    loss.backward(retain_graph=True)
+    assert abs(float(loss) - float(golden["loss0"])) < TOL * abs(float(golden["loss0"]))
+    check_grads(model, golden, "")
+    assert rel(model.all_users, golden["all_users"]) < TOL and rel(model.all_items, golden["all_items"]) < TOL
+    model.eval()
+    for pt in ("TIE", "TE", "normal"):
+        model.predict_type = pt
+        assert rel(model.predict(golden["predict_users"].tolist(), None), golden[f"predict_{pt}"]) < TOL
+        np.testing.assert_allclose(model.evaluate()[0], golden[f"evaluate_{pt}"], atol=5e-5)
+    model.predict_type = "TIE"
+    model2 = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy)
+    check_steps(model2, golden, "")
+
+
+def test_row_sparse_step_skips_dead_rows(sim, golden):
+    """lazy_tables: the last layer runs under row masks, the full tables only on demand."""
+    name = "kwai" if golden["_name"] == "kwai" else "synthg"
+    model = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=True)
+    model.make_optimizer()
+    sim.LAUNCH_LOG.clear()
+    model.train_step(*batch(golden, 0))
+    step_log = list(sim.LAUNCH_LOG)
+    assert any(x.endswith("m") and x.startswith("spmm") for x in step_log) and "fuse_heads_x3_all" not in step_log
+    sim.LAUNCH_LOG.clear()
+    model.all_users
+    assert "fuse_heads_x3_all" in sim.LAUNCH_LOG
+
+
+# ---- f2: adjacency types --------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def base():
+    g = load_golden("generic")
+    g["_name"] = "generic"
+    return g
+
+
+@pytest.fixture(scope="module")
+def nxt():
+    return load_golden("next")
+
+
+@pytest.mark.parametrize("adj", ["plain", "gcmc", "norm", "mean"])
+def test_adj_types(backend, base, nxt, adj):
+    pre = f"adj_{adj}/"
+    model = build(golden_dataset(base), golden_params(nxt, pre + "sd0/"), adj_type=adj)
+    assert model._generic == (adj in ("norm", "mean"))
+    loss = model.bpr_loss(*batch(nxt, 0, pre))
+    loss.backward(retain_graph=True)
+    assert abs(float(loss) - float(nxt[pre + "loss0"])) < TOL * abs(float(nxt[pre + "loss0"]))
+    check_grads(model, nxt, pre)
+    model.eval()
+    assert rel(model.predict(nxt[pre + "predict_users"].tolist(), None), nxt[pre + "predict_TIE"]) < TOL
+    if adj != "plain":
+        np.testing.assert_allclose(model.evaluate()[0], nxt[pre + "evaluate_TIE"], atol=5e-5)
+    else:
+        # un-normalised propagation saturates the sigmoids: whole groups of items score exactly 1.0f and the reference's
+        # partial_sort order inside a tie group is unspecified -> compare with the oracle under the lowest-index rule
+        from oracle import ref_eval, ref_model
+        from helpers import csr_from_golden, dict_from_csr, golden_feats
+        o = ref_model.OracleEliMRec(golden_params(nxt, pre + "sd0/"), golden_feats(base), csr_from_golden(base, "train"),
+                                    int(base["num_users"]), int(base["num_items"]), alpha=0.5, adj_type=adj)
+        o.bpr_loss(*batch(nxt, 0, pre))
+        want, _ = ref_eval.evaluate(lambda us: o.predict(us, "TIE").numpy(), dict_from_csr(csr_from_golden(base, "train")),
+                                    dict_from_csr(csr_from_golden(base, "valid")), top_k=[20], batch_size=16)
+        np.testing.assert_allclose(model.evaluate()[0], want, atol=5e-5)
+    # 'plain' propagates un-normalised sums: huge activations, tiny (noise-dominated) gradients on the fusion weights
+    # (and so, more mildly, does 'mean', whose identity term is not normalised either)
+    tol = dict(worst=2e-3, frac=2e-2) if adj == "plain" else dict(worst=5e-4) if adj == "mean" else {}
+    check_steps(build(golden_dataset(base), golden_params(nxt, pre + "sd0/"), adj_type=adj), nxt, pre, **tol)
+
+
+# ---- f4: mean fusion, score fusion modes -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lazy,fuse", [(True, "x3"), (False, "x3"), (True, "fp32"), (False, "fp32")])
+def test_mm_fusion_mean(backend, base, nxt, lazy, fuse):
+    pre = "mm_mean/"
+    mk = lambda: build(golden_dataset(base), golden_params(nxt, pre + "sd0/"), mm_fusion_mode="mean", lazy_tables=lazy,
+                       fuse_precision=fuse)
+    model = mk()
+    assert tuple(model.embedding_user_after_GCN.weight.shape) == (64, 64)
+    loss = model.bpr_loss(*batch(nxt, 0, pre))
+    loss.backward(retain_graph=True)
+    assert abs(float(loss) - float(nxt[pre + "loss0"])) < TOL * abs(float(nxt[pre + "loss0"]))
+    check_grads(model, nxt, pre)
+    assert rel(model.all_users, nxt[pre + "all_users"]) < TOL and rel(model.all_items, nxt[pre + "all_items"]) < TOL
+    model.eval()
+    for pt in ("TIE", "TE"):
+        model.predict_type = pt
+        assert rel(model.predict(nxt[pre + "predict_users"].tolist(), None), nxt[pre + f"predict_{pt}"]) < TOL
+    check_steps(mk(), nxt, pre)
+
+
+@pytest.mark.parametrize("pre,fm,modality", [("s_hm/", "hm", "vat"), ("s_sum/", "sum", "vat"), ("s_hm_va/", "hm", "va")])
+def test_score_fusion_modes(backend, base, nxt, pre, fm, modality):
+    model = build(golden_dataset(base), golden_params(nxt, pre + "sd0/"), s_fusion_mode=fm, modality=modality)
+    loss = model.bpr_loss(*batch(nxt, 0, pre))
+    assert abs(float(loss) - float(nxt[pre + "loss0"])) < TOL * abs(float(nxt[pre + "loss0"]))
+    model.eval()
+    for pt in ("TIE", "TE", "normal"):
+        if pre + f"predict_{pt}" not in nxt:
+            continue
+        model.predict_type = pt
+        assert rel(model.predict(nxt[pre + "predict_users"].tolist(), None), nxt[pre + f"predict_{pt}"]) < TOL
+        np.testing.assert_allclose(model.evaluate()[0], nxt[pre + f"evaluate_{pt}"], atol=5e-5)
+
+
+# ---- f3: candidate negatives, all metrics, groups ------------------------------------------------------------------------------
+def test_candidate_negatives_all_metrics_groups(backend, base, nxt):
+    from elimrec_b200.evaluator import ProxyEvaluator
+    ds = golden_dataset(base)
+    model = build(ds, golden_params(nxt, "cand/sd0/"))
+    model.bpr_loss(*batch(nxt, 0, "cand/"))
+    model.eval()
+    train, test = ds.get_user_train_dict(), ds.get_user_test_dict()
+    neg = {u: n.tolist() for u, n in zip(nxt["cand/users"].tolist(), nxt["cand/neg"])}
+    allm = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
+    kw = dict(metric=allm, top_k=[5, 20], batch_size=16, num_thread=4)
+    for rank_backend in (["fp32", "tc"] if backend == "cuda" else ["fp32"]):
+        model.config["rank_backend"] = rank_backend
+        res, buf = ProxyEvaluator(ds, train, test, neg, **kw).evaluate(model)
+        np.testing.assert_allclose(res, nxt["cand/result"], atol=1e-6)
+        res, buf = ProxyEvaluator(ds, train, test, None, **kw).evaluate(model)
+        np.testing.assert_allclose(res, nxt["allmetrics/result"], atol=1e-6)
+    model.config["rank_backend"] = "fp32"
+    ev = ProxyEvaluator(ds, train, test, None, metric=["MAP", "MRR"], top_k=7, batch_size=16, num_thread=4)
+    np.testing.assert_allclose(ev.evaluate(model)[0], nxt["topk_int/result"], atol=1e-6)
+    assert ev.metrics_info() == str(nxt["topk_int/info"])
+    # grouped view: every group's line is the plain evaluation restricted to that group's users
+    gv = ProxyEvaluator(ds, train, test, None, metric=["Recall"], group_view=[4, 8, 100], top_k=[20], batch_size=16)
+    text = gv.evaluate(model)
+    lines = text.split("\n")[1:]
+    groups = gv.evaluator.grouped_user
+    assert len(lines) == len(groups) and sum(len(v) for v in groups.values()) <= len(test)
+    uni = ProxyEvaluator(ds, train, test, None, metric=["Recall"], top_k=[20], batch_size=16).evaluator
+    for line, (name, users) in zip(lines, groups.items()):
+        assert line.startswith(name + "\t")
+        assert str(uni.evaluate(model, users)) == line[len(name) + 1:]
+
+
+# ---- f1: the literal tiktok branch ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lazy", [True, False])
+def test_tiktok_word_branch(backend, lazy):
+    tk = load_golden("tiktok")
+    ds, params = tiktok_setup(tk)
+    rows = torch.as_tensor(tk["word_rows"])
+
+    def mk():
+        m = build(ds, params("tiktok/sd0/"), "tiktok", lazy_tables=lazy)
+        m.rebuild_text_feature()        # the fixture's initial word_embedding, not this process's random one
+        return m
+    model = mk()
+    assert list(model.state_dict().keys())[:4] == ["embedding_user.weight", "embedding_item.weight",
+                                                   "word_embedding.weight", "v_dense.weight"]
+    assert rel(model.t_feat, tk["t_feat"]) < 1e-6
+    loss = model.bpr_loss(*batch(tk, 0, "tiktok/"))
+    loss.backward(retain_graph=True)
+    assert abs(float(loss) - float(tk["tiktok/loss0"])) < TOL * abs(float(tk["tiktok/loss0"]))
+    for name, p in model.named_parameters():
+        got = p.grad[rows.to(p.grad.device)] if name == "word_embedding.weight" else p.grad
+        assert rel(got, tk[f"tiktok/grad0/{name}"]) < TOL, name
+    model.eval()
+    assert rel(model.predict(tk["tiktok/predict_users"].tolist(), None), tk["tiktok/predict_TIE"]) < TOL
+    check_steps(mk(), tk, "tiktok/", subset={"word_embedding.weight": rows})
+    # word_grad=False: the dead gradient is dropped, everything that reaches the outputs is unchanged
+    m2 = build(ds, params("tiktok/sd0/"), "tiktok", lazy_tables=lazy, word_grad=False)
+    m2.rebuild_text_feature()
+    l2 = m2.bpr_loss(*batch(tk, 0, "tiktok/"))
+    l2.backward()
+    assert m2.word_embedding.weight.grad is None and abs(float(l2) - float(loss)) < 1e-7
+    assert rel(m2.v_dense.weight.grad, tk["tiktok/grad0/v_dense.weight"]) < TOL
