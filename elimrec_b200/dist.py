@@ -28,23 +28,43 @@ def is_dist():
 class GradBucket:
     """Flat fp32 buffer holding every gradient tensor back to back; ``views[name]`` has the parameter's shape."""
 
-    def __init__(self, shapes: dict, device):
-        self.names = list(shapes)
-        sizes = [int(torch.Size(shapes[n]).numel()) for n in self.names]
+    def __init__(self, shapes: dict, device, tail_flat=None, tail_views=None):
+        """Part 0 (``head``): the tensors of ``shapes``, packed back to back into an owned flat buffer.  Part 1 (``tail``,
+        optional): an EXISTING flat buffer whose views ``tail_views`` the backward pass writes directly (no packing).
+        The parts are all-reduced separately (``all_reduce_mean_part``): the embedding-table gradients (part 0) are final
+        before the weight gradients (part 1) are even started, so their all-reduce goes on the wire first and overlaps
+        the rest of the backward pass."""
+        self.head_names = list(shapes)
+        sizes = [int(torch.Size(shapes[n]).numel()) for n in self.head_names]
         self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
         self.views, o = {}, 0
-        for n, sz in zip(self.names, sizes):
+        for n, sz in zip(self.head_names, sizes):
             self.views[n] = self.flat[o:o + sz].view(shapes[n])
             o += sz
+        self.tail_flat = tail_flat
+        self.tail_names = list(tail_views) if tail_views else []
+        self.views.update(tail_views or {})
+        self.names = self.head_names + self.tail_names
 
-    def pack(self, grads: dict):
-        for n, v in self.views.items():
-            v.copy_(grads[n])          # strided gradient views are fine
+    def pack(self, grads: dict, names=None):
+        for n in (self.names if names is None else names):
+            if grads[n].data_ptr() != self.views[n].data_ptr():
+                self.views[n].copy_(grads[n])          # strided gradient views are fine
+
+    def _mean(self, t, async_op=False):
+        if t is None or t.numel() == 0:
+            return None
+        if dist.get_backend() == "gloo":   # gloo has no AVG (CPU tests): synchronous
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.div_(dist.get_world_size())
+            return None
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+
+    def all_reduce_mean_part(self, part: int, async_op: bool = False):
+        """mean over ranks of part 0 (packed head) or part 1 (in-place tail); returns the work handle when async"""
+        return self._mean(self.flat if part == 0 else self.tail_flat, async_op)
 
     def all_reduce_mean(self):
-        if dist.get_backend() == "gloo":   # gloo has no AVG
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(dist.get_world_size())
-        else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        self._mean(self.flat)
+        self._mean(self.tail_flat)
         return self.views

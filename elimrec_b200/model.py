@@ -330,11 +330,22 @@ class EliMRec(BasicModel):
         if self.tiktok and self.word_grad:
             ws["dT"] = e(I, WORD_DIM)
         # gradients of the small parameters
-        ws["g"] = {n: torch.zeros_like(p, device=dev) for n, p in self._params().items()
-                   if not n.startswith("embedding_user.w") and not n.startswith("embedding_item.w")}
-        ws["g_proj_bias"] = torch.zeros(D * len(self.mods), dtype=torch.float32, device=dev)
-        for j, m in enumerate(self.mods):   # the projection bias gradients are views of one buffer (one column-sum pass)
+        # every small gradient is a view of ONE flat buffer (no packing before the data-parallel all-reduce); it starts
+        # with the projection bias gradients, contiguous so that one column-sum pass writes all of them
+        small = {n: p for n, p in self._params().items()
+                 if not n.startswith("embedding_user.w") and not n.startswith("embedding_item.w")}
+        nb = D * len(self.mods)
+        ws["g_flat"] = torch.zeros(nb + sum(p.numel() for n, p in small.items() if not n.endswith("_dense.bias") or
+                                            n.startswith("s_dense")), dtype=torch.float32, device=dev)
+        ws["g_proj_bias"] = ws["g_flat"][:nb]
+        ws["g"], o = {}, nb
+        for j, m in enumerate(self.mods):
             ws["g"][f"{m}_dense.bias"] = ws["g_proj_bias"][D * j:D * (j + 1)]
+        for n, p in small.items():
+            if n not in ws["g"]:
+                ws["g"][n] = ws["g_flat"][o:o + p.numel()].view(p.shape)
+                o += p.numel()
+        assert o == ws["g_flat"].numel()
         # split-K plan + workspaces
         dmax = max(self._feat[m].shape[1] for m in self.mods)
         ws["split_proj"] = max(1, min(256, (I + 1023) // 1024))
@@ -556,8 +567,11 @@ class EliMRec(BasicModel):
     # ------------------------------------------------------------------------------------------
     # backward: instance rows -> fusion/head weights -> 2L SpMMs -> projection weights
     # ------------------------------------------------------------------------------------------
-    def _backward(self, gscale=None):
-        """Returns {param name: gradient view}.  ``gscale``: 1-element device tensor (upstream grad) or None."""
+    def _backward(self, gscale=None, split=False):
+        """Returns {param name: gradient view}.  ``gscale``: 1-element device tensor (upstream grad) or None.
+        ``split``: stop once the two embedding-table gradients are final and return only those; the weight gradients
+        (fusion / heads / projections / word table) are then produced by ``_backward_weights()`` - data-parallel
+        replicas put the table gradients' all-reduce on the wire in between (``make_graphed_step``)."""
         P = self._params()
         ws = self._ws
         U, I, L, B = self.num_users, self.num_items, self.n_layers, ws["B"]
@@ -580,15 +594,48 @@ class EliMRec(BasicModel):
             B, nt, Fw, ig, Oin, gscale, Wu, Wi, [P[f"s_dense_{m}.weight"].detach() for m in self.mods], dOin,
             gWu, gWi, gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
             [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods], ws["inst_ws"], part=part)
-        ib(1)
-        side_w = ops.fork_side(5)     # forked after d O[inst]: the weight gradients must not delay it
-        with torch.cuda.stream(side_w):
+        def inst_weights():
             ib(2)
             if tied:    # d W = (1/G) * sum of the G column blocks of the tied weight's gradient
                 ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
                 ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
+
+        ib(1)
+        side_w = None
+        if not split:
+            side_w = ops.fork_side(5)     # forked after d O[inst]: the weight gradients must not delay it
+            with torch.cuda.stream(side_w):
+                inst_weights()
         if self._generic:
-            return self._backward_generic(ws, side_w)
+            dE_u, dX0_i = self._backward_generic(ws)
+        else:
+            dE_u, dX0_i = self._backward_prop(ws)
+        grads = {"embedding_user.weight": dE_u, "embedding_item.weight": dX0_i[:, :D]}
+        ws["bw_pending"] = (inst_weights, dX0_i, side_w)
+        if split:
+            return grads
+        grads.update(self._backward_weights())
+        return grads
+
+    def _backward_weights(self):
+        """second half of the backward: every gradient that is not an embedding table's"""
+        ws = self._ws
+        inst_weights, dX0_i, side_w = ws.pop("bw_pending")
+        if side_w is None:      # split backward: the instance-row weight gradients run beside the projection ones
+            side_w = ops.fork_side(5)
+            with torch.cuda.stream(side_w):
+                inst_weights()
+        self._proj_wgrad(ws, dX0_i, 0, self.num_items)
+        self._word_wgrad(ws, dX0_i)
+        ops.join_side(side_w)
+        return ws["g"]
+
+    def _backward_prop(self, ws):
+        """propagation backward of the bipartite schedule: returns (d E_u, d x_0[item rows] = [dE_i | dP_v | dP_a | dP_t])"""
+        U, I, L = self.num_users, self.num_items, self.n_layers
+        N, Fw = U + I, ws["F"]
+        g = self.graph
+        rows, dOin = ws["inst_rows"], ws["dO_inst"]
         # layer-mean gradient G = dO / (L+1), row-sparse; it enters every layer of the chain
         inv = 1.0 / (L + 1)
         lo = {"u": (0, U, 0), "i": (U, N, U)}
@@ -637,12 +684,7 @@ class EliMRec(BasicModel):
             ops.join_side(side)
             dWc, dNc, flip = nW, nN, flip ^ 1
         # now dWc = d x_0[item rows, wide] = [dE_i | dP_v | dP_a | dP_t], dNc = d x_0[user rows] = dE_u
-        grads = {"embedding_user.weight": dNc, "embedding_item.weight": dWc[:, :D]}
-        self._proj_wgrad(ws, dWc, 0, I)
-        self._word_wgrad(ws, dWc)
-        ops.join_side(side_w)
-        grads.update(gr)
-        return grads
+        return dNc, dWc
 
     def _word_wgrad(self, ws, dX0_i):
         """literal 'tiktok': d t_feat = d P_t @ W_t, then d word_embedding = M^T @ d t_feat (the gradient the reference
@@ -681,7 +723,7 @@ class EliMRec(BasicModel):
         ops.layer_mean(X, ws["O"], Fw, 1.0 / (L + 1))
         self._tables_version = getattr(self, "_tables_version", 0) + 1
 
-    def _backward_generic(self, ws, side_w):
+    def _backward_generic(self, ws):
         U, I, L = self.num_users, self.num_items, self.n_layers
         N, G, Fw = U + I, ws["G"], ws["F"]
         g = self.graph
@@ -702,13 +744,7 @@ class EliMRec(BasicModel):
             add_G(nxt)
             cur, flip = nxt, flip ^ 1
         ops.fold_blocks(cur[:U], ws["dE_u"], G)      # the user table fed all G graphs
-        dX0_i = cur[U:]
-        grads = {"embedding_user.weight": ws["dE_u"], "embedding_item.weight": dX0_i[:, :D]}
-        self._proj_wgrad(ws, dX0_i, 0, I)
-        self._word_wgrad(ws, dX0_i)
-        ops.join_side(side_w)
-        grads.update(ws["g"])
-        return grads
+        return ws["dE_u"], cur[U:]
 
     # projections over item rows [r0, r1) - the whole table on one GPU, the owned block when row-sharded
     def _prep_weights(self, P, ws):
@@ -822,8 +858,10 @@ class EliMRec(BasicModel):
         ws = self._ws
         if "bucket" not in ws:
             P = self._params()
-            ws["bucket"] = GradBucket({n: tuple(P[n].shape) for n in self._param_names if n in grads}, self.device_)
-        ws["bucket"].pack(grads)
+            head = self._param_names[:2]           # the two embedding tables: packed (dE_i is a strided slab view)
+            ws["bucket"] = GradBucket({n: tuple(P[n].shape) for n in head}, self.device_, tail_flat=ws["g_flat"],
+                                      tail_views={n: ws["g"][n] for n in self._param_names[2:]})
+        ws["bucket"].pack(grads, ws["bucket"].head_names)
         return ws["bucket"].all_reduce_mean()
 
     # -- whole step as one CUDA graph (launch-bound otherwise: ~60 small launches per step) ------------
@@ -848,18 +886,29 @@ class EliMRec(BasicModel):
                 loss = self.train_step(su, sp_, sn)
             graphs = (graph,)
         else:
-            # data-parallel replicas: graph 1 = forward + backward + gradient packing, then ONE eager NCCL all-reduce of
-            # the flat bucket, then graph 2 = Adam on the averaged bucket (collectives stay outside the captures)
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
+            # data-parallel replicas, three graphs around two NCCL all-reduces:
+            #   A = forward + backward down to the embedding-table gradients (29 of the 30 MB), packed -> all-reduce #1 goes
+            #       on the wire (NCCL's own stream) ...
+            #   B = ... while the weight gradients (instance rows, projections: one more pass over the features) are
+            #       computed and packed -> all-reduce #2 (1 MB)
+            #   C = Adam on the averaged tables (only needs all-reduce #1, and hides #2), D = Adam on the small tensors.
+            # Collectives stay outside the captures.
+            gA, gB, gC, gD = (torch.cuda.CUDAGraph() for _ in range(4))
+            bucket = self._ws["bucket"]
+            with torch.cuda.graph(gA):
                 with torch.no_grad():
                     loss = self._forward(su, sp_, sn)
-                    grads = self._backward(None)
-                    self._ws["bucket"].pack(grads)
-            with torch.cuda.graph(g2, pool=g1.pool()):
+                    bucket.pack(self._backward(None, split=True), bucket.head_names)
+            with torch.cuda.graph(gB, pool=gA.pool()):
                 with torch.no_grad():
-                    self._adam.apply(self._ws["bucket"].views)
-            graphs = (g1, g2)
+                    self._backward_weights()        # writes straight into the bucket's tail (ws["g_flat"])
+            with torch.cuda.graph(gC, pool=gA.pool()):
+                with torch.no_grad():
+                    self._adam.apply({n: bucket.views[n] for n in bucket.head_names})
+            with torch.cuda.graph(gD, pool=gA.pool()):
+                with torch.no_grad():
+                    self._adam.apply({n: bucket.views[n] for n in bucket.tail_names}, tick=False)
+            graphs = (gA, gB, gC, gD)
         n_launch = CALLS["launches"] - before + 2  # + the two memsets of the backward seeds
 
         class _Runner:
@@ -870,8 +919,16 @@ class EliMRec(BasicModel):
                 su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
                 graphs[0].replay()
                 if dp:
-                    model._ws["bucket"].all_reduce_mean()
+                    bucket = model._ws["bucket"]
+                    w1 = bucket.all_reduce_mean_part(0, async_op=True)
                     graphs[1].replay()
+                    w2 = bucket.all_reduce_mean_part(1, async_op=True)
+                    if w1 is not None:
+                        w1.wait()          # stream-level waits: the launching thread never blocks
+                    graphs[2].replay()
+                    if w2 is not None:
+                        w2.wait()
+                    graphs[3].replay()
                 return loss
 
         return _Runner()

@@ -30,10 +30,12 @@ class FusedAdam:
             self.state[name] = st
         return st
 
-    def apply(self, grads: dict):
-        """One Adam step from a {name: gradient view} dict (EliMRec._backward output)."""
+    def apply(self, grads: dict, tick: bool = True):
+        """One Adam step from a {name: gradient view} dict (EliMRec._backward output).  ``tick=False``: a second group of
+        tensors of the SAME step (the step counter and bias corrections were advanced by the first call)."""
         P = self.model._params()
-        ops.adam_tick(self.step_dev, self.consts, self.lr, self.betas[0], self.betas[1])
+        if tick:
+            ops.adam_tick(self.step_dev, self.consts, self.lr, self.betas[0], self.betas[1])
         items = []
         for name, g in grads.items():
             p = P[name]

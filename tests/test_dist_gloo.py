@@ -24,14 +24,21 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         # (1) gradient bucket: mean over ranks, strided inputs, views keep the parameter shapes
-        shapes = {"embedding_user.weight": (50, 64), "v_dense.weight": (64, 16), "v_dense.bias": (64,)}
-        b = GradBucket(shapes, "cpu")
+        # head = packed (strided table gradient), tail = an existing flat buffer the backward writes in place
+        tail = torch.zeros(64 * 16 + 64)
+        tail_views = {"v_dense.weight": tail[:1024].view(64, 16), "v_dense.bias": tail[1024:]}
+        b = GradBucket({"embedding_user.weight": (50, 64)}, "cpu", tail_flat=tail, tail_views=tail_views)
         g = torch.Generator().manual_seed(rank)
         wide = torch.randn(50, 256, generator=g)
-        grads = {"embedding_user.weight": wide[:, 64:128], "v_dense.weight": torch.randn(64, 16, generator=g),
-                 "v_dense.bias": torch.full((64,), float(rank + 1))}
+        tail_views["v_dense.weight"].copy_(torch.randn(64, 16, generator=g))
+        tail_views["v_dense.bias"].fill_(float(rank + 1))
+        grads = {"embedding_user.weight": wide[:, 64:128], **tail_views}
         b.pack(grads)
-        out = b.all_reduce_mean()
+        assert b.names == ["embedding_user.weight", "v_dense.weight", "v_dense.bias"]
+        w = b.all_reduce_mean_part(0, async_op=True)
+        assert w is None        # gloo: synchronous
+        b.all_reduce_mean_part(1)
+        out = b.views
         exp_bias = sum(range(1, world + 1)) / world
         ok1 = bool(torch.allclose(out["v_dense.bias"], torch.full((64,), exp_bias)))
         mine = grads["embedding_user.weight"].clone()
