@@ -151,7 +151,11 @@ class EliMRec(BasicModel):
         self.tiktok = cfg["data.input.dataset"] == "tiktok" and hasattr(ds, "words_tensor")
         self.word_grad = bool(_cfg(cfg, "word_grad", True))
         self.mods = "v" if self.kwai else "vat"
-        dev = _cfg(cfg, "device", None)
+        # main.py:36 sets `config.device` as a plain ATTRIBUTE of the Configurator (not a key: `"device" in config` is False)
+        try:
+            dev = cfg.device
+        except (KeyError, AttributeError):
+            dev = None
         dev = torch.device(dev) if dev is not None else torch.device("cuda", torch.cuda.current_device())
         _require_cuda(dev)
         self.device_ = dev
@@ -421,6 +425,12 @@ class EliMRec(BasicModel):
                 ops.inst_rows(users, pos, neg, U, ws["inst_rows"], mask, need2)
                 if L >= 2:
                     ops.mark_neighbors(g.ui if sL_w == "u" else g.iu, mask_of[sL_w], need2_of[sL_o])
+                # off the critical path, on a stream of their own: the weights this forward uses (for tables completed
+                # later) and the zeroed instance rows of the backward's seed slabs
+                aux = ops.fork_side(7)
+                with torch.cuda.stream(aux):
+                    self._snapshot(P, ws)
+                    self._zero_seed_rows(ws)
             ops.copy_2d(Eu, ws["X0_u"], U, D)
             ops.copy_2d(Ei, X0_i, I, D)          # layer 0, item side: [E_i | P_v | P_a | P_t]
             ev_copy = torch.cuda.Event()
@@ -462,6 +472,8 @@ class EliMRec(BasicModel):
                 if lazy:   # what completes the last layer on demand (every row, same inputs)
                     ws["last_layer"] = (half_n, narrow_in, pn, out_n, half_w, wide_in, pw, out_w, inv)
             ops.join_side(side)
+        if lazy:
+            ops.join_side(aux)
         self._tables_version = getattr(self, "_tables_version", 0) + 1
         return self._loss(P, ws, users, pos, neg)
 
@@ -483,7 +495,6 @@ class EliMRec(BasicModel):
             ops.gather_rows(ws["inst_rows"], O, ws["O_inst"], Fw)
         else:
             # only the sampled rows: gather O[inst], fusion + heads on 3B rows, BPR on the compact tables
-            self._snapshot(P, ws)       # weights of THIS forward
             rows = ws["inst_rows"]
             ops.gather_rows(rows, O, ws["O_inst"], Fw)
             su_ = ops.fork_side(6)
@@ -630,6 +641,16 @@ class EliMRec(BasicModel):
         ops.join_side(side_w)
         return ws["g"]
 
+    def _zero_seed_rows(self, ws):
+        """zero the instance rows of d x_L's two slabs (the rest of those slabs is never read: column masks)"""
+        U, I, L = self.num_users, self.num_items, self.n_layers
+        N, Fw, rows = U + I, ws["F"], ws["inst_rows"]
+        s_w = "u" if L % 2 == 1 else "i"
+        for dst, sd, w in ((ws["dW"][0], s_w, Fw), (ws["dN"][0], "i" if s_w == "u" else "u", D)):
+            a, b, off = (0, U, 0) if sd == "u" else (U, N, U)
+            ops.zero_rows(rows, a, b, off, dst, w)
+        ws["seed_zeroed"] = True
+
     def _backward_prop(self, ws):
         """propagation backward of the bipartite schedule: returns (d E_u, d x_0[item rows] = [dE_i | dP_v | dP_a | dP_t])"""
         U, I, L = self.num_users, self.num_items, self.n_layers
@@ -652,9 +673,8 @@ class EliMRec(BasicModel):
         mask_of = {"u": ws["mask"][:U], "i": ws["mask"][U:]}
         need2_of = {"u": ws["need2"][:U], "i": ws["need2"][U:]}
         if lazy:     # d x_L is non-zero at the instance rows only: zero just those, the first SpMMs skip all other columns
-            for dst, sd, w in ((dWc, s_w, Fw), (dNc, s_n, D)):
-                a, b, off = lo[sd]
-                ops.zero_rows(rows, a, b, off, dst, w)
+            if not ws.pop("seed_zeroed", False):     # normally done by the forward, off the critical path
+                self._zero_seed_rows(ws)
         else:
             dWc.zero_(); dNc.zero_()
         add_G(dWc, s_w, True)
