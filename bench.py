@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cuda-graph", type=int, default=1)
     ap.add_argument("--lazy-tables", type=int, default=1,
                     help="1: build all_users/all_items/all_s_embs on demand (at evaluation) instead of every step")
+    ap.add_argument("--fused-layer-grad", type=int, default=0,
+                    help="1: layer-mean gradient added in the backward SpMM epilogues; 0 (default, measured faster): a scatter "
+                         "kernel after each SpMM, hidden under the other stream's SpMM")
     ap.add_argument("--parallel", default="dp", choices=["dp", "rowshard"],
                     help="N>1: data-parallel replicas (weak scaling, default) or the row-sharded all-gather design "
                          "(strong scaling: every rank works on the SAME batch)")
@@ -216,7 +219,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ds, name = build_dataset(args.workload)
     conf = Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH,
-                     "lazy_tables": bool(args.lazy_tables)})
+                     "lazy_tables": bool(args.lazy_tables), "fused_layer_grad": bool(args.fused_layer_grad)})
     torch.manual_seed(2022)
     rowshard = world > 1 and args.parallel == "rowshard"
     if rowshard:

@@ -52,7 +52,8 @@ class RankTcTables(C.Structure):
 
 _SIGS = {
     "elimrec_spmm": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
-    "elimrec_spmm_masked": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp, vp, i32, vp],
+    "elimrec_spmm_masked": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp, vp, i32,
+                            vp, i64, vp, vp],
     "elimrec_mark_rows": [i32, vp, i64, vp, vp],
     "elimrec_inst_rows": [i32, vp, vp, vp, i32, vp, i64, vp, vp, vp],
     "elimrec_mark_neighbors": [i32, vp, vp, vp, vp, vp],

@@ -24,6 +24,25 @@ struct MeanEpi {
     float scale;
 };
 
+// optional additive epilogue of the masked variants: Y[row] += g[row] where mask[row] != 0 (mask NULL: every row).
+// Backward pass: the row-sparse layer-mean gradient G enters every layer of the chain (d x_{k-1} = A^T d x_k + G); G lives
+// in a slab that is only valid on the <= 3B instance rows, which is what `mask` marks.
+struct AddEpi {
+    const float* g;
+    long long ld;
+    const unsigned char* mask;
+};
+
+template <int F>
+__device__ __forceinline__ void seg_add(int row, float4 (&acc)[(F >= 128) ? F / 128 : 1], const AddEpi& add, int lane) {
+    constexpr int NV = (F >= 128) ? F / 128 : 1;
+    if (add.g == nullptr || (add.mask != nullptr && __ldg(add.mask + row) == 0)) return;
+    const int l = (F == 64) ? (lane & 15) : lane;
+    const float4* gp = reinterpret_cast<const float4*>(add.g + (long long)row * add.ld) + l;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) add4(acc[i], __ldg(gp + i * 32));
+}
+
 // HEAVY = false: segments [seg_base, n_seg) are whole rows (lean path, tuned for FULL occupancy: 32 registers, 64 warps/SM -
 // the gather is latency-bound until ~11 TB/s of L2->SM traffic, measured: 2 fetches in flight x 64 warps beats 8 x 16).
 // HEAVY = true : segments [0, n_heavy_seg) belong to split rows, one CTA = 8 segments of one row.
@@ -140,7 +159,8 @@ __global__ void __launch_bounds__(256, MINB)
 spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int2* __restrict__ heavy, int* __restrict__ counter,
                 const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
                 long long ldx, float* __restrict__ Y, long long ldy, float* __restrict__ partial, MeanEpi epi,
-                const unsigned char* __restrict__ row_mask = nullptr, const unsigned char* __restrict__ col_mask = nullptr) {
+                const unsigned char* __restrict__ row_mask = nullptr, const unsigned char* __restrict__ col_mask = nullptr,
+                AddEpi add = AddEpi{nullptr, 0, nullptr}) {
     constexpr int NV = (F >= 128) ? F / 128 : 1;    // float4 per lane
     const unsigned full = 0xffffffffu;
     const int warp = seg_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -208,6 +228,7 @@ spmm_seg_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int
         }
     }
 
+    if (MASK) seg_add<F>(sg.x, acc, add, lane);
     seg_store<F, MEAN>(sg.x, acc, Y, ldy, epi, lane);
 }
 
@@ -222,7 +243,7 @@ __global__ void __launch_bounds__(256, 2)
 spmm_light_sparse_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, const int* __restrict__ col,
                          const float* __restrict__ val, const float* __restrict__ X, long long ldx, float* __restrict__ Y,
                          long long ldy, MeanEpi epi, const unsigned char* __restrict__ row_mask,
-                         const unsigned char* __restrict__ col_mask) {
+                         const unsigned char* __restrict__ col_mask, AddEpi add) {
     constexpr int NV = (F >= 128) ? F / 128 : 1;
     __shared__ int4 list[SEGS];
     __shared__ int n_list;
@@ -242,6 +263,7 @@ spmm_light_sparse_kernel(int seg_base, int n_seg, const int4* __restrict__ seg, 
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         seg_accumulate<F, 4, true>(sg, col, val, X, ldx, col_mask, lane, acc);
+        seg_add<F>(sg.x, acc, add, lane);
         seg_store<F, MEAN>(sg.x, acc, Y, ldy, epi, lane);
     }
 }
@@ -339,7 +361,8 @@ namespace {
 int spmm_launch(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy, int32_t* counter,
                 const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy,
                 float* partial, const elimrec_mean_epilogue_t* epi, const unsigned char* row_mask,
-                const unsigned char* col_mask, int density_hint, elimrec_stream_t stream) {
+                const unsigned char* col_mask, int density_hint, elimrec_stream_t stream, const float* addend = nullptr,
+                long long ld_add = 0, const unsigned char* add_mask = nullptr) {
     // whole rows under a mask: segments per CTA - 256 when only a few % of the rows are marked, else 32
     const int chunk = (row_mask != nullptr && density_hint <= 10) ? 256 : 32;
     ER_CHECK_ARG(width == 64 || width == 128 || width == 256, "width must be 64, 128 or 256");
@@ -367,7 +390,9 @@ int spmm_launch(int width, int part, int n_seg, int n_heavy_seg, const int32_t* 
     const int2* hv = reinterpret_cast<const int2*>(heavy);
     cudaStream_t st = er_stream(stream);
     const bool mean = me.out != nullptr;
-    const bool masked = row_mask != nullptr || col_mask != nullptr;
+    const bool masked = row_mask != nullptr || col_mask != nullptr || addend != nullptr;
+    ER_CHECK_ARG(addend == nullptr || ld_add % 4 == 0, "addend stride must be a multiple of 4 floats");
+    const AddEpi add{addend, ld_add, add_mask};
     ER_CHECK_ARG(n_heavy_seg >= 0 && n_heavy_seg % 8 == 0 && n_heavy_seg <= n_seg, "n_heavy_seg must be a multiple of 8");
     const int hb = n_heavy_seg / 8;                      // CTAs of split rows
     const int lb = (n_seg - n_heavy_seg + 7) / 8;        // CTAs of whole rows
@@ -375,17 +400,18 @@ int spmm_launch(int width, int part, int n_seg, int n_heavy_seg, const int32_t* 
     do {                                                                                                                  \
         if (hb > 0 && part != 2)                                                                                          \
             spmm_seg_kernel<F, MEAN, true, 2, 5, MASK><<<hb, 256, 0, st>>>(0, n_heavy_seg, sg, hv, counter, col, val, X,  \
-                                                                           ldx, Y, ldy, partial, me, row_mask, col_mask); \
+                                                                           ldx, Y, ldy, partial, me, row_mask, col_mask, add); \
         if (lb > 0 && part != 1) {                                                                                        \
-            if (!MASK || (row_mask == nullptr && F == 64)) /* measured: narrow col-mask-only is faster one warp per segment */ \
+            /* measured: narrow col-mask-only is faster one warp per segment; so is anything without a mask to compact */ \
+            if (!MASK || (row_mask == nullptr && (F == 64 || col_mask == nullptr)))                                       \
                 spmm_seg_kernel<F, MEAN, false, 2, (MEAN ? 6 : 8), MASK><<<lb, 256, 0, st>>>(                             \
-                    n_heavy_seg, n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me, nullptr, col_mask);       \
+                    n_heavy_seg, n_seg, sg, hv, counter, col, val, X, ldx, Y, ldy, partial, me, nullptr, col_mask, add);  \
             else if (chunk == 256)                                                                                        \
                 spmm_light_sparse_kernel<F, MEAN, 256><<<(n_seg - n_heavy_seg + 255) / 256, 256, 0, st>>>(                \
-                    n_heavy_seg, n_seg, sg, col, val, X, ldx, Y, ldy, me, row_mask, col_mask);                            \
+                    n_heavy_seg, n_seg, sg, col, val, X, ldx, Y, ldy, me, row_mask, col_mask, add);                       \
             else                                                                                                          \
                 spmm_light_sparse_kernel<F, MEAN, 32><<<(n_seg - n_heavy_seg + 31) / 32, 256, 0, st>>>(                   \
-                    n_heavy_seg, n_seg, sg, col, val, X, ldx, Y, ldy, me, row_mask, col_mask);                            \
+                    n_heavy_seg, n_seg, sg, col, val, X, ldx, Y, ldy, me, row_mask, col_mask, add);                       \
         }                                                                                                                 \
     } while (0)
 #define LAUNCH_W(F)                                                                  \
@@ -414,9 +440,9 @@ ELIMREC_API int elimrec_spmm_masked(int width, int part, int n_seg, int n_heavy_
                                     int32_t* counter, const int32_t* col, const float* val, const float* X, int64_t ldx,
                                     float* Y, int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi,
                                     const uint8_t* row_mask, const uint8_t* col_mask, int row_density_pct,
-                                    elimrec_stream_t stream) {
+                                    const float* addend, int64_t ld_add, const uint8_t* add_mask, elimrec_stream_t stream) {
     return spmm_launch(width, part, n_seg, n_heavy_seg, seg, heavy, counter, col, val, X, ldx, Y, ldy, partial, epi, row_mask,
-                       col_mask, row_density_pct, stream);
+                       col_mask, row_density_pct, stream, addend, ld_add, add_mask);
 }
 
 ELIMREC_API int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream) {

@@ -43,19 +43,22 @@ def join_side(side):
 
 
 
-def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, row_mask=None, col_mask=None, density=50):
+def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, row_mask=None, col_mask=None, density=50,
+         addend=None, add_mask=None):
     """Y[rows of half] = A_half @ X  (+ optional fused layer-mean epilogue).  The split (Zipf-head) rows run as their
     own launch on a side stream, concurrently with the whole rows.  ``row_mask`` / ``col_mask`` (uint8 per row / column
-    of this half): the row-sparse last-layer variant, elimrec_spmm_masked; ``density`` = expected % of marked rows."""
-    masked = row_mask is not None or col_mask is not None
+    of this half): the row-sparse last-layer variant, elimrec_spmm_masked; ``density`` = expected % of marked rows.
+    ``addend`` / ``add_mask``: Y[row] += addend[row] on the rows add_mask marks (fused layer-mean gradient)."""
+    masked = row_mask is not None or col_mask is not None or addend is not None
 
     def go(part, launches):
         args = [width, part, half.n_seg, half.n_heavy_seg, ptr(half.seg), ptr(half.heavy), ptr(half.counter),
                 ptr(half.col), ptr(half.val), ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0),
                 ptr(half.partial), (C.byref(epi) if epi is not None else None)]
         if masked:
-            call("elimrec_spmm_masked", *args, ptr(row_mask, torch.uint8, True), ptr(col_mask, torch.uint8, True), int(density), stream(),
-                 launches=launches, tag=f"spmm{width}m")
+            call("elimrec_spmm_masked", *args, ptr(row_mask, torch.uint8, True), ptr(col_mask, torch.uint8, True), int(density),
+                 ptr(addend, F32, True), (addend.stride(0) if addend is not None else 0), ptr(add_mask, torch.uint8, True),
+                 stream(), launches=launches, tag=f"spmm{width}m")
         else:
             # "w": the half has no split rows -> ONE launch of the whole-row kernel, timed exactly by its event pair
             call("elimrec_spmm", *args, stream(), launches=launches, tag=f"spmm{width}" + ("w" if half.n_heavy_seg == 0 else ""))

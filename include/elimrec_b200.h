@@ -75,12 +75,15 @@ int elimrec_spmm(int width, int part /* 0 = all rows, 1 = split rows only, 2 = w
  *   backward: col_mask[col] == 0  -> the edge is dropped before the gather (d x_L is zero outside the sampled rows)
  * Masks are byte arrays over the rows / columns of this CSR half; either may be NULL.  Surviving edges keep their
  * order: rows are bit-identical to elimrec_spmm on the same inputs (width 64 + col_mask: the two half-warps of a warp
- * split the surviving edges differently, so those sums agree to fp32 rounding instead). */
+ * split the surviving edges differently, so those sums agree to fp32 rounding instead).
+ * Additive epilogue (addend may be NULL): Y[row, :] += addend[row, 0:width] for rows with add_mask[row] != 0 (add_mask NULL:
+ * every row) - the layer-mean gradient G that enters every layer of the backward chain, d x_{k-1} = A^T d x_k + G
+ * (torch.mean over the stacked layers, models/EliMRec.py:246-247); G is only valid on the sampled rows add_mask marks. */
 int elimrec_spmm_masked(int width, int part, int n_seg, int n_heavy_seg, const int32_t* seg, const int32_t* heavy,
                         int32_t* counter, const int32_t* col, const float* val, const float* X, int64_t ldx, float* Y,
                         int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi, const uint8_t* row_mask,
                         const uint8_t* col_mask, int row_density_pct /* expected % of marked rows: scheduling hint only */,
-                        elimrec_stream_t stream);
+                        const float* addend, int64_t ld_add, const uint8_t* add_mask, elimrec_stream_t stream);
 /* mask[0:n_nodes] = 0; mask[rows[r]] = 1 */
 int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream);
 /* rows[0:3B] = [users | num_users + pos | num_users + neg]  (node ids of the batch, models/EliMRec.py:120-122 gathers

@@ -46,12 +46,15 @@ def _csr(half):
     return torch.sparse_csr_tensor(crow, half.col.long(), half.val, size=(n, half.n_cols))
 
 
-def spmm(half, X, Y, width, epi=None, row_mask=None, col_mask=None, density=50):
-    _log(f"spmm{width}" + ("m" if row_mask is not None or col_mask is not None else ""))
+def spmm(half, X, Y, width, epi=None, row_mask=None, col_mask=None, density=50, addend=None, add_mask=None):
+    _log(f"spmm{width}" + ("m" if row_mask is not None or col_mask is not None or addend is not None else ""))
     Xs = X[:, :width]
     if col_mask is not None:     # edges to unmarked columns are dropped before the gather (their rows may hold garbage)
         Xs = torch.where(col_mask.bool().unsqueeze(1), Xs, torch.zeros_like(Xs))
     acc = torch.sparse.mm(_csr(half), Xs.contiguous())
+    if addend is not None:       # Y[row] += addend[row] on the marked rows only (elsewhere the addend slab holds garbage)
+        sel = torch.ones(half.n_rows, dtype=torch.bool) if add_mask is None else add_mask.bool()
+        acc[sel] += addend[sel, :width]
     rows = torch.arange(half.n_rows) if row_mask is None else torch.nonzero(row_mask).flatten()
     if Y is not None:
         Y[rows, :width] = acc[rows]

@@ -137,3 +137,38 @@ def test_word_graph_scatter_mean(dev):
     ops.spmm(CsrHalf(mt.indptr, mt.indices, mt.data, I, dev), dT, dW, 128)
     ref = torch.from_numpy(mt.astype(np.float64) @ dT.double().cpu().numpy())
     assert rel_err(dW, ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("width", [64, 256])
+@pytest.mark.parametrize("masks", ["none", "col", "row+col"])
+def test_spmm_additive_epilogue(dev, width, masks):
+    """elimrec_spmm_masked addend: Y[row] += G[row] on the rows add_mask marks, for whole rows, split rows, every mask mix;
+    the addend slab holds NaN outside the marked rows (it is only valid there)."""
+    from elimrec_b200 import ops
+    from elimrec_b200.graph import BipartiteGraph
+    from test_gpu_kernels import _rand_graph
+    U, I = 700, 500
+    m = _rand_graph(U, I, 6000, [(3, 480), (10, 130), (11, 65)], seed=width)
+    g = BipartiteGraph(m, dev, seg_len=8 if width == 64 else 64)
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    for half, n_in in ((g.ui, I), (g.iu, U)):
+        X = torch.randn(n_in, width, generator=gen).to(dev)
+        add_mask = (torch.rand(half.n_rows, generator=gen) < 0.3).to(torch.uint8).to(dev)
+        add_mask[3] = 1                                          # a split row gets the addend too
+        G = torch.full((half.n_rows, width + 64), float("nan"), device=dev)
+        G[add_mask.bool(), :width] = torch.randn(int(add_mask.sum()), width, generator=gen).to(dev)
+        col_mask = (torch.rand(n_in, generator=gen) < 0.5).to(torch.uint8).to(dev) if "col" in masks else None
+        row_mask = (torch.rand(half.n_rows, generator=gen) < 0.4).to(torch.uint8).to(dev) if "row" in masks else None
+        kw = dict(row_mask=row_mask, col_mask=col_mask)
+        Y0 = torch.full((half.n_rows, width), 7.0, device=dev)
+        if col_mask is None and row_mask is None:
+            ops.spmm(half, X, Y0, width)
+        else:
+            ops.spmm(half, X, Y0, width, **kw)
+        Y1 = torch.full((half.n_rows, width), 7.0, device=dev)
+        ops.spmm(half, X, Y1, width, addend=G, add_mask=add_mask, **kw)
+        want = Y0.clone()
+        sel = add_mask.bool() if row_mask is None else (add_mask.bool() & row_mask.bool())
+        want[sel] += G[sel, :width]
+        assert not torch.isnan(Y1).any()
+        assert torch.equal(Y1, want)

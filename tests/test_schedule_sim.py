@@ -113,10 +113,10 @@ def check_steps(model, g, pre, steps=3, subset=None, worst=1e-4, frac=1e-3):
 
 
 # ---- the default configuration: both schedules ------------------------------------------------------------------------------
-@pytest.mark.parametrize("lazy", [True, False])
-def test_default_schedule_vs_golden(backend, golden, lazy):
+@pytest.mark.parametrize("lazy,fused", [(True, True), (True, False), (False, False)])
+def test_default_schedule_vs_golden(backend, golden, lazy, fused):
     name = "kwai" if golden["_name"] == "kwai" else "synthg"
-    model = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy)
+    model = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy, fused_layer_grad=fused)
     loss = model.bpr_loss(*batch(golden, 0))
     loss.backward(retain_graph=True)
     assert abs(float(loss) - float(golden["loss0"])) < TOL * abs(float(golden["loss0"]))
@@ -128,7 +128,7 @@ def test_default_schedule_vs_golden(backend, golden, lazy):
         assert rel(model.predict(golden["predict_users"].tolist(), None), golden[f"predict_{pt}"]) < TOL
         np.testing.assert_allclose(model.evaluate()[0], golden[f"evaluate_{pt}"], atol=5e-5)
     model.predict_type = "TIE"
-    model2 = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy)
+    model2 = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy, fused_layer_grad=fused)
     check_steps(model2, golden, "")
 
 
@@ -181,9 +181,19 @@ def test_adj_types(backend, base, nxt, adj):
         o = ref_model.OracleEliMRec(golden_params(nxt, pre + "sd0/"), golden_feats(base), csr_from_golden(base, "train"),
                                     int(base["num_users"]), int(base["num_items"]), alpha=0.5, adj_type=adj)
         o.bpr_loss(*batch(nxt, 0, pre))
-        want, _ = ref_eval.evaluate(lambda us: o.predict(us, "TIE").numpy(), dict_from_csr(csr_from_golden(base, "train")),
-                                    dict_from_csr(csr_from_golden(base, "valid")), top_k=[20], batch_size=16)
-        np.testing.assert_allclose(model.evaluate()[0], want, atol=5e-5)
+        train, valid = dict_from_csr(csr_from_golden(base, "train")), dict_from_csr(csr_from_golden(base, "valid"))
+        if backend == "sim":
+            want, _ = ref_eval.evaluate(lambda us: o.predict(us, "TIE").numpy(), train, valid, top_k=[20], batch_size=16)
+            np.testing.assert_allclose(model.evaluate()[0], want, atol=5e-5)
+        else:   # on the GPU the scores differ from torch-CPU's in the last bits, which reorders near-ties: every difference
+            #     in the top-K sets must be explained by scores closer than the fp32 tolerance
+            from gpu_util import topk_sets_match
+            ev = model.valid_evaluator.evaluator
+            ev.evaluate(model)
+            users = list(valid.keys())
+            exact, explained, bad = topk_sets_match(ev.last_topk[0].cpu().numpy(), o.predict(users, "TIE").numpy(),
+                                                    [train.get(u, []) for u in users], 20, tol=1e-4)
+            assert bad == 0 and exact + explained == len(users), (exact, explained, bad)
     # 'plain' propagates un-normalised sums: huge activations, tiny (noise-dominated) gradients on the fusion weights
     # (the row-normalised types sit between that and 'pre': a handful of near-zero-gradient elements move by ~2e-4)
     tol = dict(worst=2e-3, frac=2e-2) if adj == "plain" else dict(worst=5e-4)
