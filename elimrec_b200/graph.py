@@ -17,13 +17,24 @@ One-time, host-side (vectorised numpy); only the result lives on the device.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
 
-SEG_LEN = 64        # rows with at most this many edges are ONE warp work item
-HEAVY_SEG_LEN = 16  # longer rows are split into segments of this many edges (8 per CTA, deterministic 2-stage reduce):
-                    # short segments keep the per-warp dependent-load chain short and the launch at full occupancy
+SEG_LEN = 96        # rows with at most this many edges are ONE warp work item
+HEAVY_SEG_LEN = 96  # longer rows are split into a multiple of 8 segments of at most this many edges (8 per CTA, reduced in
+                    # shared memory; rows needing several CTAs add a deterministic 2-stage reduce through scratch)
+HEAVY_BALANCED = True   # a split row's edges are dealt EVENLY over its segments: no empty padding segments, and every row
+                        # of up to 8 * HEAVY_SEG_LEN edges is exactly ONE CTA (no partials, no counter).
+# Measured on B200 (ms / train step, tiktok | kwai | movielens shapes):
+#   64, 16, fixed-length  0.682 | 1.137 | 0.815      (short segments: most mid-degree rows paid the 2-stage reduce)
+#   64, 64, balanced      0.661 | 0.882 | 0.723
+#   96, 96, balanced      0.661 | 0.875 | 0.717      128, 32, balanced  0.685 | 0.958 | 0.759
+if os.environ.get("ELIMREC_SEG"):   # tuning sweeps: "seg_len,heavy_seg_len,balanced"
+    _a, _b, _c = os.environ["ELIMREC_SEG"].split(",")
+    SEG_LEN, HEAVY_SEG_LEN, HEAVY_BALANCED = int(_a), int(_b), bool(int(_c))
 
 
 class CsrHalf:
@@ -77,6 +88,9 @@ def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: in
     h_deg = deg[heavy_mask][order]
     h_nseg = nseg[heavy_mask][order]
     h_nseg_pad = -(-h_nseg // 8) * 8            # one CTA (8 warps) = 8 segments of ONE row; pad with empty segments
+    h_len = np.full(h_rows.size, hsl, dtype=np.int64)
+    if HEAVY_BALANCED:                          # ... or none: equal shares of the row for all of its segments
+        h_len = -(-h_deg // h_nseg_pad)
     n_hseg = int(h_nseg_pad.sum())
     segs = []
     heavy = np.zeros((h_rows.size, 2), dtype=np.int32)
@@ -87,8 +101,9 @@ def build_segments(indptr: np.ndarray, seg_len: int, row_lo: int = 0, row_hi: in
         hid = np.repeat(np.arange(h_rows.size), h_nseg_pad)
         k = np.arange(n_hseg) - np.repeat(first, h_nseg_pad)
         row_end = np.repeat(h_beg + h_deg, h_nseg_pad)
-        sb = np.minimum(np.repeat(h_beg, h_nseg_pad) + k * hsl, row_end)
-        se = np.minimum(sb + hsl, row_end)
+        ln = np.repeat(h_len, h_nseg_pad)
+        sb = np.minimum(np.repeat(h_beg, h_nseg_pad) + k * ln, row_end)
+        se = np.minimum(sb + ln, row_end)
         segs.append(np.stack([np.repeat(h_rows, h_nseg_pad), sb, se, hid], axis=1))
     l_rows = rows[~heavy_mask]
     l_beg = beg[~heavy_mask]
