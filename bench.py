@@ -329,11 +329,20 @@ def main():
         g = model.graph
         # dominant kernel: spmm_seg_kernel<Fw> (whole rows).  Timed on the launches that are exactly ONE such kernel - the
         # user-row half has no split rows, so its event pair brackets a single launch on the launching stream.
+        alg_of = lambda h: float(h.nnz * 8 + (h.n_rows + 1) * 4 + (h.n_cols + h.n_rows) * Fw * 4)
         half = g.ui if g.ui.n_heavy_seg == 0 else (g.iu if g.iu.n_heavy_seg == 0 else None)
         tag = f"spmm{Fw}w"
         if tag in agg and half is not None:
+            alg, what = alg_of(half), f"spmm_seg_kernel<{Fw}> (whole rows, {'user' if half is g.ui else 'item'}-row half)"
+        elif f"spmm{Fw}" in agg:
+            # both halves have split rows (kwai / movielens shapes): the unmasked wide SpMM runs once per half and step, each
+            # as a whole-row launch + a split-row launch side by side; one event pair brackets the pair of launches
+            tag, alg = f"spmm{Fw}", 0.5 * (alg_of(g.ui) + alg_of(g.iu))
+            what = f"spmm_seg_kernel<{Fw}> (whole-row + split-row launch of one half, mean over the two halves)"
+        else:
+            tag = None
+        if tag is not None:
             # algorithmic bytes per launch: nnz*(4+4) + (rows_out+1)*4 + (rows_in + rows_out)*F*4
-            alg = float(half.nnz * 8 + (half.n_rows + 1) * 4 + (half.n_cols + half.n_rows) * Fw * 4)
             avg_s = 1e-3 * sum(agg[tag]) / len(agg[tag])
             ach = alg / avg_s / 1e9
             traffic = None
@@ -344,12 +353,13 @@ def main():
                 pass
             fam = sum(sum(v) for k, v in agg.items() if k.startswith("spmm"))
             tot = sum(sum(v) for v in agg.values())
-            roofline = {"kernel": f"spmm_seg_kernel<{Fw}> (whole rows, user-row half)", "bound": "hbm", "achieved": ach, "peak": peak,
+            roofline = {"kernel": what, "bound": "hbm", "achieved": ach, "peak": peak,
                         "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": which, "bytes_per_launch": alg,
                         "avg_launch_us": 1e6 * avg_s, "launches_timed": len(agg[tag]),
                         "share_of_step": sum(sum(v) for k, v in agg.items() if k.startswith(f"spmm{Fw}")) / tot,
                         "spmm_family_share_of_step": fam / tot,
-                        "note": "operand slab is L2-resident: the kernel is bound by L2->SM gather bandwidth (~11 TB/s), see DESIGN.md 3.1"}
+                        "note": "operand slab is L2-resident: the kernel is bound by L2->SM gather bandwidth (measured ~10-11 TB/s "
+                                "of a ~12.4 TB/s L2 slice cap), not by HBM; see DESIGN.md 3.1"}
     clk = clocks.stop() if rank == 0 else None
     sync_all()
     if world > 1:   # the profile pass above stepped rank 0 only: put every replica back on the same weights

@@ -146,6 +146,30 @@ def test_row_sparse_step_skips_dead_rows(sim, golden):
     assert "fuse_heads_x3_all" in sim.LAUNCH_LOG
 
 
+def test_split_backward_and_bucket(sim, golden):
+    """data-parallel step: backward split at the embedding-table gradients; the small gradients are views of one flat
+    buffer (the bucket's tail, all-reduced in place), the table gradients are packed into the bucket's head."""
+    from elimrec_b200.dist import GradBucket
+    name = "kwai" if golden["_name"] == "kwai" else "synthg"
+    model = build(golden_dataset(golden), golden_params(golden), name)
+    with torch.no_grad():
+        model._forward(*model._triples(*batch(golden, 0)))
+        head = model._backward(None, split=True)
+        assert list(head) == ["embedding_user.weight", "embedding_item.weight"]
+        tail = model._backward_weights()
+    ws = model._ws
+    assert all(v.data_ptr() >= ws["g_flat"].data_ptr() and
+               v.data_ptr() + 4 * v.numel() <= ws["g_flat"].data_ptr() + 4 * ws["g_flat"].numel() for v in tail.values())
+    assert sum(v.numel() for v in tail.values()) == ws["g_flat"].numel()
+    P = model._params()
+    bucket = GradBucket({n: tuple(P[n].shape) for n in head}, "cpu", tail_flat=ws["g_flat"],
+                        tail_views={n: ws["g"][n] for n in model._param_names[2:]})
+    bucket.pack({**head, **tail}, bucket.head_names)
+    assert bucket.names == model._param_names
+    for n in model._param_names:
+        assert rel(bucket.views[n], golden["grad0/" + n]) < TOL, n
+
+
 # ---- f2: adjacency types --------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def base():
