@@ -55,7 +55,9 @@ def spmm(half, X, Y, width, epi=None, row_mask=None, col_mask=None, density=50, 
     if addend is not None:       # Y[row] += addend[row] on the marked rows only (elsewhere the addend slab holds garbage)
         sel = torch.ones(half.n_rows, dtype=torch.bool) if add_mask is None else add_mask.bool()
         acc[sel] += addend[sel, :width]
-    rows = torch.arange(half.n_rows) if row_mask is None else torch.nonzero(row_mask).flatten()
+    rows = torch.unique(half.seg[:, 0].long())       # the work-list's rows: all of them, or a rank's block when row-sharded
+    if row_mask is not None:
+        rows = rows[row_mask[rows].bool()]
     if Y is not None:
         Y[rows, :width] = acc[rows]
     if epi is not None:

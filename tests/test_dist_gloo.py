@@ -1,6 +1,9 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU host logic: user sharding of the evaluator and the
 data-parallel gradient bucket."""
 import os
+import queue as _queue
+import sys
+import time
 
 import numpy as np
 import torch
@@ -75,3 +78,107 @@ def test_bucket_and_eval_sharding_world2():
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(all(r[1:]) for r in res), res
+
+
+# ---- the multi-GPU training / evaluation modes end to end on 2 gloo ranks, kernels stood in for by tests/sim_ops.py ----------
+def _install_sim():
+    import sim_ops
+    import elimrec_b200.evaluator as ev
+    import elimrec_b200.model as md
+    import elimrec_b200.optim as op
+    import elimrec_b200.sharded as sh
+
+    class _Ev:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, *a):
+            pass
+
+    class _St:
+        def wait_event(self, *a):
+            pass
+    for mod in (md, ev, op, sh):
+        mod.ops = sim_ops
+    md._require_cuda = lambda dev: None
+    torch.cuda.Event = _Ev
+    torch.cuda.current_stream = lambda *a: _St()
+
+
+def _model_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from conftest import load_golden
+        from helpers import golden_dataset, golden_params
+        from elimrec_b200.data import Config
+        from elimrec_b200.model import EliMRec
+        from elimrec_b200.sharded import ShardedEliMRec
+        _install_sim()
+        g = load_golden("generic")
+        g["_name"] = "generic"
+        ds = golden_dataset(g)
+        cfg = lambda **kw: Config(**{"data.input.dataset": "synthg", "topks": [20], "device": torch.device("cpu"), "alpha": 0.5,
+                                     "test_batch_size": 16, "rank_backend": "fp32", "proj_precision": "fp32", **kw})
+        load = lambda m: m.load_state_dict({k: torch.as_tensor(v) for k, v in golden_params(g).items()}, strict=False)
+        batch = lambda i: tuple(torch.as_tensor(g[f"batch{i}_{k}"]) for k in ("users", "pos", "neg"))
+        rel = lambda a, b: float((a.double() - torch.as_tensor(b).double()).abs().max() / torch.as_tensor(b).double().abs().max())
+        # (1) data-parallel replicas, a different batch per rank == one replica stepping on the MEAN gradient
+        model = EliMRec(cfg(), ds)
+        load(model)
+        model.make_optimizer(lr=1e-3, weight_decay=1e-4)
+        model.enable_data_parallel()
+        model.train_step(*batch(rank))
+        ref = EliMRec(cfg(), ds)
+        load(ref)
+        opt = ref.make_optimizer(lr=1e-3, weight_decay=1e-4)
+        for i in range(world):
+            (ref.bpr_loss(*batch(i)) / world).backward()
+        opt.step()
+        worst_dp = max(rel(a, b) for a, b in zip(model.state_dict().values(), ref.state_dict().values()))
+        # (2) user-sharded evaluation: all-reduced metric sums == the reference's numbers
+        model = EliMRec(cfg(), ds)
+        load(model)
+        model.bpr_loss(*batch(0))
+        model.eval()
+        ok_eval = bool(np.abs(model.evaluate()[0] - g["evaluate_TIE"]).max() < 5e-5)
+        # (3) row-sharded propagation (all-gather per layer): golden losses / parameters / metrics
+        sm = ShardedEliMRec(cfg(), ds)
+        load(sm)
+        sm.make_optimizer(lr=1e-3, weight_decay=1e-4)
+        l0 = float(sm._forward(*sm._triples(*batch(0))))
+        sm.eval()
+        ok_seval = bool(np.abs(sm.evaluate()[0] - g["evaluate_TIE"]).max() < 5e-5)
+        losses = [float(sm.train_step(*batch(i))) for i in range(3)]
+        ok_loss = bool(np.allclose(losses, g["losses"], rtol=2e-5)) and abs(l0 - float(g["loss0"])) < 1e-5
+        worst_sh = max(rel(v, g["sd3/" + k]) for k, v in sm.state_dict().items())
+        q.put((rank, worst_dp, ok_eval, ok_seval, ok_loss, worst_sh))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_and_row_sharded_models_world2():
+    """N>1 host logic without a GPU: data-parallel replicas (gradient bucket, split all-reduce), user-sharded evaluation and
+    the row-sharded model (per-layer all-gathers, instance-row all-reduce, sharded Adam, state_dict gather) on 2 gloo ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29100 + (os.getpid() % 300)
+    procs = [ctx.Process(target=_model_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res, t0 = [], time.time()
+    while len(res) < len(procs):        # fail fast if a worker dies
+        try:
+            res.append(q.get(timeout=2))
+        except _queue.Empty:
+            if any(not p.is_alive() and p.exitcode not in (0, None) for p in procs) or time.time() - t0 > 400:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError(f"worker failed (exit codes {[p.exitcode for p in procs]})")
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, worst_dp, ok_eval, ok_seval, ok_loss, worst_sh in res:
+        assert worst_dp < 1e-4 and ok_eval and ok_seval and ok_loss and worst_sh < 1e-4, res
