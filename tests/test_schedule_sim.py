@@ -322,3 +322,104 @@ def test_tiktok_word_branch(backend, lazy):
     l2.backward()
     assert m2.word_embedding.weight.grad is None and abs(float(l2) - float(loss)) < 1e-7
     assert rel(m2.v_dense.weight.grad, tk["tiktok/grad0/v_dense.weight"]) < TOL
+
+
+# ---- ragged / degenerate batches (host schedule only; sim) ---------------------------------------------------------------------
+def _oracle_for(golden):
+    from oracle import ref_model
+    from helpers import csr_from_golden, golden_feats
+    return ref_model.OracleEliMRec(golden_params(golden), golden_feats(golden), csr_from_golden(golden, "train"),
+                                   int(golden["num_users"]), int(golden["num_items"]), kwai=golden["_name"] == "kwai", alpha=0.5)
+
+
+@pytest.mark.parametrize("lazy", [True, False])
+def test_ragged_and_degenerate_batches(sim, golden, lazy):
+    """main.py's last batch of an epoch is short (DataIterator drop_last=False): batch sizes change between steps, users
+    repeat inside a batch, a sampled negative may equal another triple's positive.  Loss and gradients vs the oracle."""
+    name = "kwai" if golden["_name"] == "kwai" else "synthg"
+    model = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy)
+    U, I = model.num_users, model.num_items
+    rng = np.random.default_rng(5)
+    batches = [batch(golden, 0),                                                   # 128
+               tuple(torch.as_tensor(rng.integers(0, n, 37)) for n in (U, I, I)),   # short, random
+               (torch.zeros(5, dtype=torch.int64), torch.tensor([1, 1, 2, 3, 3]), torch.tensor([3, 2, 1, 1, 0])),  # one user x5
+               tuple(torch.as_tensor(rng.integers(0, n, 1)) for n in (U, I, I))]    # a single triple
+    for u, p, n in batches:
+        o = _oracle_for(golden)
+        lo = o.bpr_loss(u, p, n)
+        og = o.grads(lo)
+        for prm in model.parameters():
+            prm.grad = None
+        loss = model.bpr_loss(u, p, n)
+        loss.backward(retain_graph=True)
+        assert abs(float(loss) - float(lo)) < TOL * abs(float(lo)), (u.numel(), float(loss), float(lo))
+        for nm, prm in model.named_parameters():
+            if nm in og:
+                assert rel(prm.grad, og[nm].numpy()) < TOL, (u.numel(), nm)
+        # the tables completed after this (possibly row-sparse) step are the dense ones
+        assert rel(model.all_users, o.cache["users"].detach().numpy()) < TOL
+        assert rel(model.all_items, o.cache["items"].detach().numpy()) < TOL
+
+
+def test_double_backward_and_predict_type_normal(sim, golden):
+    """`retain_graph=True` (main.py:100) allows a second backward of the same forward: same gradients again;
+    predict_type='normal' trains on the fusion loss only (EliMRec.py:125-126)."""
+    name = "kwai" if golden["_name"] == "kwai" else "synthg"
+    model = build(golden_dataset(golden), golden_params(golden), name)
+    loss = model.bpr_loss(*batch(golden, 0))
+    loss.backward(retain_graph=True)
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    for p in model.parameters():
+        p.grad = None
+    loss.backward(retain_graph=True)
+    for n, p in model.named_parameters():
+        if n in g1:
+            assert rel(p.grad, g1[n].numpy()) < 1e-6, n
+    model2 = build(golden_dataset(golden), golden_params(golden), name, predict_type="normal")
+    o = _oracle_for(golden)
+    o.predict_type = "normal"
+    lo = o.bpr_loss(*batch(golden, 0))
+    l2 = model2.bpr_loss(*batch(golden, 0))
+    l2.backward()
+    assert abs(float(l2) - float(lo)) < TOL * abs(float(lo))
+    og = o.grads(lo)
+    for nm, prm in model2.named_parameters():
+        if nm in og and not nm.startswith("s_dense"):
+            assert rel(prm.grad, og[nm].numpy()) < TOL, nm
+
+
+@pytest.mark.parametrize("top_k", [1, [1, 7, 32], 32])
+def test_evaluator_edge_cases(sim, golden, top_k):
+    """users without any training item (uni_evaluator.py:150-153), users whose train list covers most items, K = 1 and the
+    largest supported K, every metric; against the oracle evaluator on the same dicts."""
+    from oracle import ref_eval
+    from elimrec_b200.evaluator import UniEvaluator
+    name = "kwai" if golden["_name"] == "kwai" else "synthg"
+    ds = golden_dataset(golden)
+    model = build(ds, golden_params(golden), name)
+    model.bpr_loss(*batch(golden, 0))
+    model.eval()
+    o = _oracle_for(golden)
+    o.bpr_loss(*batch(golden, 0))
+    train, test = ds.get_user_train_dict(), ds.get_user_test_dict()
+    users = list(test.keys())
+    del train[users[0]]                                                        # no training items at all
+    I = ds.num_items
+    train[users[1]] = sorted(set(range(I)) - set(test[users[1]]) - {0, 1, 2})  # nearly everything masked: < K candidates left
+    allm = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
+    for pt in ("TIE", "TE", "normal"):
+        model.predict_type = pt
+        ev = UniEvaluator(ds, train, test, None, metric=allm, top_k=top_k, batch_size=16, num_thread=2)
+        got, buf = ev.evaluate(model)
+        want, wbuf = ref_eval.evaluate(lambda us: o.predict(us, pt).numpy(), train, test, metrics=allm, top_k=top_k, batch_size=16)
+        np.testing.assert_allclose(got, want, atol=2e-6)
+        assert len(buf.split("\t")) == len(wbuf.split("\t"))
+        sub = users[3:9]
+        got, _ = ev.evaluate(model, test_users=sub)
+        want, _ = ref_eval.evaluate(lambda us: o.predict(us, pt).numpy(), train, test, metrics=allm, top_k=top_k, batch_size=16,
+                                    test_users=sub)
+        np.testing.assert_allclose(got, want, atol=2e-6)
+    with pytest.raises(TypeError):
+        ev.evaluate(model, test_users=5)
+    with pytest.raises(ValueError):
+        UniEvaluator(ds, train, test, None, metric=["Recal"], top_k=5)
