@@ -593,14 +593,9 @@ class EliMRec(BasicModel):
         replicas put the table gradients' all-reduce on the wire in between (``make_graphed_step``)."""
         P = self._params()
         ws = self._ws
-        U, I, L, B = self.num_users, self.num_items, self.n_layers, ws["B"]
-        N, G, Fw, nt = U + I, ws["G"], ws["F"], ws["nt"]
-        g = self.graph
-        O, ig, rows = ws["O"], ws["inst_grad"], ws["inst_rows"]
-        ld = D * nt
+        B, G, Fw, nt = ws["B"], ws["G"], ws["F"], ws["nt"]
+        ig, gr = ws["inst_grad"], ws["g"]
         Oin, dOin = ws["O_inst"], ws["dO_inst"]
-        gws, cws, gr = ws["gemm_ws"], ws["colsum_ws"], ws["g"]
-        sk = ws["split_inst"]
         if gscale is not None:
             gscale = gscale.reshape(1)
         Wu, Wi = self._fusion_weights(P, ws)
@@ -931,11 +926,11 @@ class EliMRec(BasicModel):
                 loss = self.train_step(su, sp_, sn)
             graphs = (graph,)
         else:
-            # data-parallel replicas, three graphs around two NCCL all-reduces:
+            # data-parallel replicas, four graphs around two NCCL all-reduces:
             #   A = forward + backward down to the embedding-table gradients (29 of the 30 MB), packed -> all-reduce #1 goes
             #       on the wire (NCCL's own stream) ...
             #   B = ... while the weight gradients (instance rows, projections: one more pass over the features) are
-            #       computed and packed -> all-reduce #2 (1 MB)
+            #       computed straight into the bucket's tail -> all-reduce #2 (1 MB)
             #   C = Adam on the averaged tables (only needs all-reduce #1, and hides #2), D = Adam on the small tensors.
             # Collectives stay outside the captures.
             gA, gB, gC, gD = (torch.cuda.CUDAGraph() for _ in range(4))
