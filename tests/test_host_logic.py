@@ -153,3 +153,38 @@ def test_eval_csr_helper():
     from elimrec_b200.evaluator import _dict_to_csr
     ptr, flat = _dict_to_csr({3: [5, 1], 9: [2]}, [9, 3, 4])
     assert ptr.tolist() == [0, 1, 3, 3] and flat.tolist() == [2, 1, 5]
+
+
+def test_dataset_from_reference_file_layout(golden, tmp_path):
+    """Dataset(conf) reads the reference's on-disk layout (data/dataset.py:164-185,207-212): CSV splits + generic .npy
+    features / kwai_feat_v.pt; same id remap, CSRs and feature rows as the reference's own Dataset (golden)."""
+    from elimrec_b200 import synth
+    from elimrec_b200.data import Config, Dataset
+    kwai = golden["_name"] == "kwai"
+    name = "kwai" if kwai else "synthg"
+    inter = synth.Interactions(int(golden["num_users"]), int(golden["num_items"]), golden["raw_train"], golden["raw_valid"],
+                               golden["raw_test"])
+    feats = [golden.get(f"raw_feat_{m}") for m in "vat"]
+    synth.write_reference_files(str(tmp_path), name, inter, feats)
+    ds = Dataset(Config(**{"data.input.path": str(tmp_path), "data.input.dataset": name}))
+    assert ds.num_users == int(golden["num_users"]) and ds.num_items == int(golden["num_items"])
+    for split in ("train", "valid", "test"):
+        m = getattr(ds, f"{split}_matrix")
+        assert np.array_equal(m.indptr, golden[f"{split}_indptr"]) and np.array_equal(m.indices, golden[f"{split}_indices"])
+    for m, f in golden_feats(golden).items():
+        assert np.array_equal(getattr(ds, f"{m}_feat").numpy(), f)
+    u, i = ds.get_train_interactions()
+    assert len(u) == ds.train_matrix.nnz == len(i)
+
+
+def test_tiktok_file_layout(tmp_path):
+    """the literal 'tiktok' layout: tiktok_{visual,audio,textual}_feat.pt; word pairs remapped like dataset.py:166-173"""
+    from conftest import load_golden
+    from elimrec_b200 import synth
+    from elimrec_b200.data import Config, Dataset
+    tk = load_golden("tiktok")
+    inter = synth.Interactions(int(tk["num_users"]), int(tk["num_items"]), tk["raw_train"], tk["raw_valid"], tk["raw_test"])
+    synth.write_tiktok_files(str(tmp_path), inter, tk["raw_feat_v"], tk["raw_feat_a"], tk["raw_words"])
+    ds = Dataset(Config(**{"data.input.path": str(tmp_path), "data.input.dataset": "tiktok"}))
+    assert np.array_equal(ds.words_tensor.numpy(), tk["words_tensor"]) and not hasattr(ds, "t_feat")
+    assert ds.v_feat.shape == (ds.num_items, tk["raw_feat_v"].shape[1])
