@@ -920,11 +920,29 @@ class EliMRec(BasicModel):
         torch.cuda.synchronize()
         dp = getattr(self, "_dp", False)
         before = CALLS["launches"]
+        single = bool(_cfg(self.config, "dp_single_graph", False))
         if not dp:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 loss = self.train_step(su, sp_, sn)
             graphs = (graph,)
+        elif single:
+            # EXPERIMENTAL (dp_single_graph=True, not yet run on hardware - DESIGN.md section 8 item 1): the same schedule with
+            # the two all-reduces captured INSIDE one graph, so the four graph launches (and the ~85 us they cost) become one.
+            graph = torch.cuda.CUDAGraph()
+            bucket = self._ws["bucket"]
+            with torch.cuda.graph(graph):
+                with torch.no_grad():
+                    loss = self._forward(su, sp_, sn)
+                    bucket.pack(self._backward(None, split=True), bucket.head_names)
+                    w1 = bucket.all_reduce_mean_part(0, async_op=True)
+                    self._backward_weights()
+                    w2 = bucket.all_reduce_mean_part(1, async_op=True)
+                    w1.wait()
+                    self._adam.apply({n: bucket.views[n] for n in bucket.head_names})
+                    w2.wait()
+                    self._adam.apply({n: bucket.views[n] for n in bucket.tail_names}, tick=False)
+            graphs, dp = (graph,), False       # the runner just replays it
         else:
             # data-parallel replicas, four graphs around two NCCL all-reduces:
             #   A = forward + backward down to the embedding-table gradients (29 of the 30 MB), packed -> all-reduce #1 goes
