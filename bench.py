@@ -392,7 +392,7 @@ def main():
               "topk": TOPK, "predict_type": "TIE", "result": [float(x) for x in res]}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # reported at N=1 only (the other ranks would idle for it)
         r = cpu_port_run(ds, name, steps=2, warmup=1, budget_s=45.0)
         cpu = {"value": BATCH / r["step_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "sample": f"{r['timed_steps']} full train steps (batch {BATCH}) of the same {args.workload}-shape graph after 1 warm-up; "
