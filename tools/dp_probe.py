@@ -2,6 +2,7 @@
 without collectives, with serial collectives, and of each all-reduce alone.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_probe.py
+    ELIMREC_DP_SINGLE=1 timeout 120 python -m torch.distributed.run ... tools/dp_probe.py      # experimental one-graph step
 """
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +17,9 @@ torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 inter, feats = synth.make_shape("tiktok")
 ds = Dataset(None, interactions=inter, features=feats, name="tiktok_shape")
-conf = Config(**{"data.input.dataset": "tiktok_shape", "topks": [20], "device": dev, "alpha": 0.5, "batch_size": 2048})
+single = bool(int(os.environ.get("ELIMREC_DP_SINGLE", "0")))     # 1: the experimental one-graph step with captured collectives
+conf = Config(**{"data.input.dataset": "tiktok_shape", "topks": [20], "device": dev, "alpha": 0.5, "batch_size": 2048,
+                 "dp_single_graph": single})
 torch.manual_seed(2022)
 model = EliMRec(conf, ds).to(dev); model.make_optimizer(); model.enable_data_parallel()
 B = 2048
@@ -33,7 +36,10 @@ def timeit(fn, label):
     for b in bt[5:55]: fn(b)
     e1.record(); torch.cuda.synchronize()
     print(f"rank {rank} {label}: {e0.elapsed_time(e1)/50:.4f} ms/step", flush=True)
-timeit(lambda b: run(*b), "full dp step")
+timeit(lambda b: run(*b), "full dp step" + (" (single graph)" if single else ""))
+if single:      # the variants below patch the eager collectives, which the single graph no longer calls
+    dist.destroy_process_group()
+    sys.exit(0)
 bucket = model._ws["bucket"]
 # variants: patch the bucket's collective
 orig = bucket.all_reduce_mean_part
