@@ -423,3 +423,43 @@ def test_evaluator_edge_cases(sim, golden, top_k):
         ev.evaluate(model, test_users=5)
     with pytest.raises(ValueError):
         UniEvaluator(ds, train, test, None, metric=["Recal"], top_k=5)
+
+
+# ---- configuration sweep against the (pinned) oracle: host schedule for every layer count / variant combination -------------
+@pytest.mark.parametrize("layers", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [dict(), dict(lazy_tables=False), dict(adj_type="gcmc"), dict(adj_type="norm"),
+                                     dict(mm_fusion_mode="mean"), dict(modality="va"), dict(modality="t", lazy_tables=False),
+                                     dict(adj_type="gcmc", mm_fusion_mode="mean", fused_layer_grad=True)],
+                         ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
+def test_layer_count_and_variant_sweep(sim, golden, layers, variant):
+    from oracle import ref_model
+    from helpers import csr_from_golden, golden_feats
+    kwai = golden["_name"] == "kwai"
+    name = "kwai" if kwai else "synthg"
+    params = golden_params(golden)
+    if variant.get("mm_fusion_mode") == "mean":      # [64 x 64] fusion weights
+        rng = np.random.default_rng(1)
+        for s_ in ("user", "item"):
+            params[f"embedding_{s_}_after_GCN.weight"] = (rng.standard_normal((64, 64)) * 0.1).astype(np.float32)
+    okw = {k: v for k, v in variant.items() if k in ("adj_type", "mm_fusion_mode", "modality")}
+    o = ref_model.OracleEliMRec(params, golden_feats(golden), csr_from_golden(golden, "train"), int(golden["num_users"]),
+                                int(golden["num_items"]), kwai=kwai, alpha=0.5, n_layers=layers, **okw)
+    model = build(golden_dataset(golden), params, name, layer_num=layers, **variant)
+    u, p, n = batch(golden, 1)
+    lo = o.bpr_loss(u, p, n)
+    og = o.grads(lo)
+    loss = model.bpr_loss(u, p, n)
+    loss.backward()
+    assert abs(float(loss) - float(lo)) < TOL * abs(float(lo))
+    for nm, prm in model.named_parameters():
+        if nm in og:     # (bias gradients are sums with heavy cancellation: summation order shows at a few 1e-5)
+            assert rel(prm.grad, og[nm].numpy()) < (5e-5 if nm.endswith("bias") else TOL), nm
+        else:
+            assert prm.grad is None or not prm.grad.any(), nm
+    assert rel(model.all_users, o.cache["users"].detach().numpy()) < TOL
+    assert rel(model.all_items, o.cache["items"].detach().numpy()) < TOL
+    model.eval()
+    users = golden["predict_users"].tolist()
+    for pt in ("TIE", "TE"):
+        model.predict_type = pt
+        assert rel(model.predict(users, None), o.predict(users, pt).numpy()) < TOL
