@@ -39,6 +39,15 @@ class LinearDesc(C.Structure):
     _fields_ = [("M", i64), ("K", i64), ("X", vp), ("ldx", i64), ("W", vp), ("b", vp), ("Y", vp), ("ldy", i64)]
 
 
+class LinLayers(C.Structure):
+    _fields_ = [("n", i32), ("user", vp * (MAX_LAYERS + 1)), ("item", vp * (MAX_LAYERS + 1)),
+                ("user_ld", i64 * (MAX_LAYERS + 1)), ("item_ld", i64 * (MAX_LAYERS + 1))]
+
+
+class PackProj(C.Structure):
+    _fields_ = [("W", vp), ("b", vp), ("dst", vp), ("Dm", i64), ("Kp", i64)]
+
+
 class RankTables(C.Structure):
     _fields_ = [("num_users", i32), ("num_items", i32), ("n_mod", i32), ("mode", i32), ("f_user", vp),
                 ("f_item", vp), ("s_user", vp * MAX_MODS), ("s_item", vp * MAX_MODS)]
@@ -66,6 +75,10 @@ _SIGS = {
     "elimrec_fold_blocks": [i64, vp, i64, i32, f32, vp, i64, vp],
     "elimrec_axpy_rows": [i64, i32, vp, vp, i64, vp, i64, vp],
     "elimrec_layer_mean": [i64, i32, i32, C.POINTER(vp), C.POINTER(i64), f32, vp, i64, vp],
+    "elimrec_lin_assemble": [i64, vp, i32, C.POINTER(LinLayers), f32, i32, i32, vp, i64, vp],
+    "elimrec_lin_seed": [i32, vp, i32, i32, vp, i64, i32, f32, vp, i64, vp],
+    "elimrec_pack_proj_weights": [i32, C.POINTER(PackProj), i32, vp],
+    "elimrec_axpy_2d": [i64, i32, f32, vp, i64, vp, i64, i32, vp],
     "elimrec_gemm": [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, vp, vp, vp],
     "elimrec_colsum": [i64, i64, vp, i64, vp, vp, i32, vp, vp],
     "elimrec_linear_tf32_fwd": [i64, i64, vp, i64, vp, vp, vp, i64, vp],

@@ -1,0 +1,304 @@
+"""The LINEAR schedule of the training step (default where it applies; ``linear_schedule=False`` switches it off).
+
+What the reference computes every step (``models/EliMRec.py:228-258``): four graphs ``x^g_0 = [E_u ; Z_g]`` with
+``Z_id = E_i`` and ``Z_m = X_m W_m^T + b_m``, three propagation layers each, ``light_out_g = mean_k A_hat^k x^g_0``.
+Propagation is linear and the item features ``X_m`` are constants of the dataset, so for a modality graph
+
+    light_out_m = mean_k A_hat^k [E_u ; 0]  +  (mean_k A_hat^k [0 ; X_m | 1]) [W_m | b_m]^T
+                = (parity part of p)        +            Zbar_m               W'_m^T
+
+where ``p_k = A_hat^k [E_u ; E_i]`` is the id graph's own 64-wide propagation: ``A_hat`` is bipartite, so
+``A_hat^k [E_u ; 0]`` lives on the user rows for even k and on the item rows for odd k - exactly the rows of ``p_k`` that
+do not depend on ``E_i``.  ``Zbar_m`` ([N x (D_m + 1)], the bias rides along as a column of ones) is built once
+(``_lin_build_zbar``).  A step then is
+
+    forward   ONE 64-wide propagation (layers L-1 / L only at the rows the loss reaches), Zbar rows gathered at the 3B
+              instance rows, a [3B x D_m] x [D_m x 64] GEMM per modality, ``lin_assemble`` -> O[inst rows]
+    backward  dW'_m = dO_m[inst]^T Zbar_m[inst] (one small GEMM: weight AND bias gradient), one 64-wide backward chain
+              seeded by ``lin_seed`` -> dE_u, dE_i
+
+instead of one 64-wide plus three 256-wide propagations and two passes over the feature matrices (311 MB each at the
+Tiktok shape).  Same loss and gradients up to fp32 reassociation (gated at the fp32 tolerance against the reference's
+golden vectors, tests/test_linear_schedule.py).  The full tables for evaluation are completed on demand from the same
+pieces (``_lin_materialize``).  Applies to the bipartite adjacency types ('pre', 'plain', 'gcmc') with ``lazy_tables``;
+the self-loop types and the literal-tiktok dead word gradient keep the slab schedules of model.py.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+D = 64
+
+
+def _cfg(config, key, default):
+    return config[key] if key in config else default
+
+
+class LinearSchedule:
+    """Mixin of ``EliMRec`` (model.py): everything specific to the linear schedule."""
+
+    # ---- construction ---------------------------------------------------------------------------------------------------
+    def _lin_init(self):
+        want = bool(_cfg(self.config, "linear_schedule", True))
+        self.linear = bool(want and self.lazy_tables and not self._generic and not (self.tiktok and self.word_grad))
+        if not self.linear:
+            return
+        dims = [self._feat[m].shape[1] for m in self.mods]
+        self._lin_Kp = [((d + 1 + 3) // 4) * 4 for d in dims]          # [X_m | 1 | 0-pad] : multiple of 4 floats (TMA)
+        self._lin_koff = [sum(self._lin_Kp[:j]) for j in range(len(dims))]
+        self._lin_Ktot = sum(self._lin_Kp)
+        self._lin_build_zbar()
+
+    @torch.no_grad()
+    def _lin_build_zbar(self):
+        """Zbar [N x Ktot] (users first), block m = mean_k A_hat^k [0 ; X_m | 1 | 0] - constant.  Built with the propagation
+        kernel itself, 256 / 128 / 64 columns at a time; in TF32 mode it is rounded (to nearest) once, like the features."""
+        U, I, L, dev = self.num_users, self.num_items, self.n_layers, self.device_
+        g, inv = self.graph, 1.0 / (self.n_layers + 1)
+        Z = torch.zeros(U + I, self._lin_Ktot, dtype=torch.float32, device=dev)
+        tmp = {}
+        for j, m in enumerate(self.mods):
+            X = self._feat[m]
+            Dm, Kp, koff = X.shape[1], self._lin_Kp[j], self._lin_koff[j]
+            Kc = -(-Kp // 64) * 64
+            T0 = torch.zeros(I, Kc, dtype=torch.float32, device=dev)
+            T0[:, :Dm].copy_(X)
+            T0[:, Dm] = 1.0
+            c0 = 0
+            while c0 < Kc:
+                w = 256 if Kc - c0 >= 256 else (128 if Kc - c0 >= 128 else 64)
+                wa = min(w, Kp - c0)                 # columns of this chunk that exist in Zbar (the rest is padding)
+                if w not in tmp:
+                    tmp[w] = (torch.empty(U, w, dtype=torch.float32, device=dev), torch.empty(I, w, dtype=torch.float32, device=dev))
+                tu, ti = tmp[w]
+                zc = koff + c0
+                cur = T0[:, c0:c0 + w]               # layer 0 lives on the item rows
+                ops.axpy_2d(cur, Z[U:, zc:], I, wa, inv, accumulate=False)
+                on_items = True
+                for k in range(1, L + 1):
+                    if on_items:
+                        ops.spmm(g.ui, cur, tu, w)
+                        ops.axpy_2d(tu, Z[:U, zc:], U, wa, inv, accumulate=(k > 1))
+                        cur = tu
+                    else:
+                        ops.spmm(g.iu, cur, ti, w)
+                        ops.axpy_2d(ti, Z[U:, zc:], I, wa, inv, accumulate=True)
+                        cur = ti
+                    on_items = not on_items
+                c0 += w
+            del T0
+        if self.proj_precision == "tf32":
+            ops.round_tf32(Z, Z)
+        self._zbar = Z
+
+    # ---- workspace ------------------------------------------------------------------------------------------------------
+    def _lin_workspace_shared(self, ws):
+        dev, U, I, L = self.device_, self.num_users, self.num_items, self.n_layers
+        N = U + I
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        ws["P"] = [None] + [e(N, D) for _ in range(L)]      # p_1 .. p_L (users first); p_0 are the embedding tables themselves
+        ws["H"] = [e(N, D), e(N, D)]                        # backward chain, ping-pong
+        ws["E0"] = e(N, D)                                  # [E_u ; E_i] as THIS forward saw them (Adam overwrites the tables)
+        ws["Wp"] = {m: e(D, kp) for m, kp in zip(self.mods, self._lin_Kp)}     # [W_m | b_m | 0] of this forward
+        # gradients of the small parameters, one flat buffer (what the data-parallel all-reduce sends in place): first the
+        # packed projection gradients d[W_m | b_m] (weight and bias gradients are strided views of them), then the rest
+        small = {n: p for n, p in self._params().items()
+                 if not n.startswith("embedding_user.w") and not n.startswith("embedding_item.w")}
+        n_pack = sum(D * kp for kp in self._lin_Kp)
+        rest = [n for n in small if "_dense." not in n or n.startswith("s_dense")]
+        ws["g_flat"] = torch.zeros(n_pack + sum(small[n].numel() for n in rest), dtype=torch.float32, device=dev)
+        ws["g"], ws["dWp"], o = {}, {}, 0
+        for m, kp in zip(self.mods, self._lin_Kp):
+            blk = ws["g_flat"][o:o + D * kp].view(D, kp)
+            dm = self._feat[m].shape[1]
+            ws["dWp"][m] = blk
+            ws["g"][f"{m}_dense.weight"], ws["g"][f"{m}_dense.bias"] = blk[:, :dm], blk[:, dm]
+            o += D * kp
+        for n in rest:
+            ws["g"][n] = ws["g_flat"][o:o + small[n].numel()].view(small[n].shape)
+            o += small[n].numel()
+        assert o == ws["g_flat"].numel()
+        ws["split_proj"], ws["dmax"] = 64, max(self._lin_Kp)       # sizes the split-K scratch of the exact-fp32 GEMMs
+
+    def _lin_workspace_batch(self, ws, B):
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device_)
+        ws["Zg"] = e(3 * B, self._lin_Ktot)                 # Zbar gathered at the instance rows
+        ws["lin_wgrad_ws"] = {m: e(max(1, ops.linear_tf32_wgrad_ws_floats(3 * B, kp))) for m, kp in zip(self.mods, self._lin_Kp)}
+
+    def _lin_tc(self):
+        return self.proj_precision == "tf32"
+
+    def _lin_tables(self, ws, p0_u, p0_i):
+        U = self.num_users
+        return [(p0_u, p0_i)] + [(p[:U], p[U:]) for p in ws["P"][1:]]
+
+    def _lin_modal_gemm(self, ws, Zrows, out, n_rows):
+        """out[:, 64(1+j) : 64(2+j)] = Zrows[:, block j] @ W'_j^T for every modality (bias included: ones column)"""
+        Fw = ws["F"]
+        if self._lin_tc():
+            ops.linear_tf32_fwd_multi([(Zrows[:, ko:ko + kp], ws["Wp"][m], None, out, D * (j + 1))
+                                       for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff))],
+                                      tag="lin_modal_tc")
+        else:
+            ld = Zrows.stride(0)
+            for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
+                ops.gemm(n_rows, D, kp, Zrows, ld, 1, ws["Wp"][m], 1, kp, out, out.stride(0), 1, a_off=ko, c_off=D * (j + 1),
+                         tag="lin_modal")
+
+    # ---- forward --------------------------------------------------------------------------------------------------------
+    def _lin_forward(self, users, pos, neg):
+        P = self._params()
+        U, I, L = self.num_users, self.num_items, self.n_layers
+        B = int(users.numel())
+        ws = self._workspace(B)
+        g = self.graph
+        Eu = P["embedding_user.weight"].detach()
+        Ei = P["embedding_item.weight"].detach()
+        mask, need2 = ws["mask"], ws["need2"]
+        rows = ws["inst_rows"]
+        self._prep_weights(P, ws, proj=False)
+        ops.pack_proj_weights([(P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach(), ws["Wp"][m]) for m in self.mods],
+                              self._lin_tc())
+        # side stream: instance rows and their masks, Zbar gathered at them and the modality GEMMs (none of it depends on the
+        # propagation); a third stream keeps what tables completed later must use and zeroes the backward's seed rows
+        side = ops.fork_side()
+        with torch.cuda.stream(side):
+            ops.inst_rows(users, pos, neg, U, rows, mask, need2)
+            ev_rows = torch.cuda.Event()
+            ev_rows.record(side)
+            if L >= 2:    # layer L-1 is read at the graph neighbours of the instance rows (both sides are 64 wide here)
+                ops.mark_neighbors(g.ui, mask[:U], need2[U:])
+                ops.mark_neighbors(g.iu, mask[U:], need2[:U])
+            ev_masks = torch.cuda.Event()
+            ev_masks.record(side)
+            ops.gather_rows(rows, self._zbar, ws["Zg"], self._lin_Ktot)
+            self._lin_modal_gemm(ws, ws["Zg"], ws["O_inst"], 3 * B)
+        aux = ops.fork_side(7)
+        with torch.cuda.stream(aux):
+            self._snapshot(P, ws)
+            ops.copy_2d(Eu, ws["E0"][:U], U, D)
+            ops.copy_2d(Ei, ws["E0"][U:], I, D)
+            torch.cuda.current_stream().wait_event(ev_rows)
+            ops.zero_rows(rows, 0, U + I, 0, ws["H"][0], D)
+            ws["seed_zeroed"] = True
+        # the propagation: p_k = A_hat p_{k-1}, both halves 64 wide, on two streams
+        in_u, in_i = Eu, Ei
+        cur = torch.cuda.current_stream()
+        for k in range(1, L + 1):
+            out = ws["P"][k]
+            rm = mask if k == L else (need2 if k == L - 1 else None)
+            if rm is not None:
+                cur.wait_event(ev_rows if k == L else ev_masks)
+            dens = ws["density"] if k == L else {"u": 50, "i": 50}
+            s2 = ops.fork_side(3)
+            with torch.cuda.stream(s2):
+                ops.spmm(g.iu, in_u, out[U:], D, row_mask=rm[U:] if rm is not None else None, density=dens["i"])
+            ops.spmm(g.ui, in_i, out[:U], D, row_mask=rm[:U] if rm is not None else None, density=dens["u"])
+            ops.join_side(s2)
+            in_u, in_i = out[:U], out[U:]
+        ops.join_side(side)
+        lay = ops.lin_layers(self._lin_tables(ws, Eu, Ei))
+        ops.lin_assemble(rows, U, lay, 1.0 / (L + 1), len(self.mods), True, ws["O_inst"])
+        ops.join_side(aux)
+        self._tables_version = getattr(self, "_tables_version", 0) + 1
+        return self._loss(P, ws, users, pos, neg, gathered=True)
+
+    # ---- backward -------------------------------------------------------------------------------------------------------
+    def _lin_backward(self, gscale=None, split=False):
+        P = self._params()
+        ws = self._ws
+        U, I, L = self.num_users, self.num_items, self.n_layers
+        B, G, Fw, nt = ws["B"], ws["G"], ws["F"], ws["nt"]
+        g = self.graph
+        ig, gr = ws["inst_grad"], ws["g"]
+        Oin, dOin, rows = ws["O_inst"], ws["dO_inst"], ws["inst_rows"]
+        if gscale is not None:
+            gscale = gscale.reshape(1)
+        Wu, Wi = self._fusion_weights(P, ws)
+        tied = self.mm_fusion_mode == "mean"
+        gWu = ws["g_eff"]["u"] if tied else gr["embedding_user_after_GCN.weight"]
+        gWi = ws["g_eff"]["i"] if tied else gr["embedding_item_after_GCN.weight"]
+        ib = lambda part: ops.inst_backward(
+            B, nt, Fw, ig, Oin, gscale, Wu, Wi, [P[f"s_dense_{m}.weight"].detach() for m in self.mods], dOin,
+            gWu, gWi, gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
+            [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods], ws["inst_ws"], part=part)
+
+        def weights():
+            """every gradient that is not an embedding table's: fusion / heads (instance rows) and d[W_m | b_m] =
+            dO_m[inst]^T Zbar_m[inst] - none of it waits for the propagation backward"""
+            ib(2)
+            if tied:
+                ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
+                ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
+            Zg, ldz = ws["Zg"], ws["Zg"].stride(0)
+            for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
+                if self._lin_tc():
+                    ops.linear_tf32_wgrad(dOin, Zg[:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
+                                          tag="lin_wgrad_tc")
+                else:
+                    ops.gemm(kp, D, 3 * B, Zg, 1, ldz, dOin, Fw, 1, ws["dWp"][m], 1, kp, split_k=ws["split_inst"], ws=ws["gemm_ws"],
+                             a_off=ko, b_off=D * (j + 1), tag="lin_wgrad")
+
+        ib(1)
+        side_w = None
+        if not split:
+            side_w = ops.fork_side(5)
+            with torch.cuda.stream(side_w):
+                weights()
+        # the 64-wide backward chain: h_L = g_L, h_{k-1} = A_hat^T h_k + g_{k-1}; g_k (lin_seed) lives on the instance rows
+        inv, nm = 1.0 / (L + 1), len(self.mods)
+        h, flip = ws["H"][0], 1
+        if not ws.pop("seed_zeroed", False):      # normally done by the forward, off the critical path
+            ops.zero_rows(rows, 0, U + I, 0, h, D)
+        ops.lin_seed(rows, U, L, dOin, nm, inv, h)
+        mask, need2 = ws["mask"], ws["need2"]
+        for k in range(L, 0, -1):
+            nxt = ws["H"][flip]
+            # h_L is valid on the instance rows only, h_{L-1} on need2 only: the first two hops drop every other column
+            cm = mask if k == L else (need2 if k == L - 1 else None)
+            rm = need2 if (k == L and L >= 2) else None
+            s2 = ops.fork_side(3)
+            with torch.cuda.stream(s2):
+                ops.spmm(g.iu_t, h[:U], nxt[U:], D, col_mask=cm[:U] if cm is not None else None,
+                         row_mask=rm[U:] if rm is not None else None)
+            ops.spmm(g.ui_t, h[U:], nxt[:U], D, col_mask=cm[U:] if cm is not None else None,
+                     row_mask=rm[:U] if rm is not None else None)
+            ops.join_side(s2)
+            ops.lin_seed(rows, U, k - 1, dOin, nm, inv, nxt)
+            h, flip = nxt, flip ^ 1
+        grads = {"embedding_user.weight": h[:U], "embedding_item.weight": h[U:]}
+        ws["bw_pending"] = (weights, side_w)
+        if split:
+            return grads
+        grads.update(self._lin_backward_weights())
+        return grads
+
+    def _lin_backward_weights(self):
+        ws = self._ws
+        weights, side_w = ws.pop("bw_pending")
+        if side_w is None:
+            weights()
+        else:
+            ops.join_side(side_w)
+        dead = self._dead_params()
+        return {n: gv for n, gv in ws["g"].items() if n not in dead} if dead else ws["g"]
+
+    # ---- full tables for evaluation, on demand ------------------------------------------------------------------------------
+    def _lin_materialize(self):
+        """O over ALL rows from the pieces of the last forward: the masked layers completed (every row, same inputs), the
+        modality blocks as Zbar W'^T with that forward's packed weights, then the fusion Linear + heads."""
+        ws = self._ws
+        U, I, L = self.num_users, self.num_items, self.n_layers
+        N, g = U + I, self.graph
+        E0 = ws["E0"]
+        for k in range(max(1, L - 1), L + 1):
+            src = E0 if k == 1 else ws["P"][k - 1]
+            out = ws["P"][k]
+            ops.spmm(g.iu, src[:U], out[U:], D)
+            ops.spmm(g.ui, src[U:], out[:U], D)
+        self._lin_modal_gemm(ws, self._zbar, ws["O"], N)
+        lay = ops.lin_layers(self._lin_tables(ws, E0[:U], E0[U:]))
+        ops.lin_assemble(None, U, lay, 1.0 / (L + 1), len(self.mods), True, ws["O"], n_rows=N)
+        self._dense_tables(None, ws, from_snapshot=True)

@@ -35,6 +35,7 @@ from torch import nn
 from . import ops
 from ._lib import CALLS, ElimrecError
 from .graph import BipartiteGraph
+from .linear import LinearSchedule
 
 D = 64
 PREDICT_MODE = {"normal": 0, "TE": 1, "TIE": 2}
@@ -100,7 +101,7 @@ class _StepFunction(torch.autograd.Function):
             (grads[n].clone() if grads.get(n) is not None else None) for n in ctx.names)
 
 
-class EliMRec(BasicModel):
+class EliMRec(LinearSchedule, BasicModel):
     def __init__(self, config, dataset):
         super().__init__(dataset, config)
         self._init_weight()
@@ -207,6 +208,8 @@ class EliMRec(BasicModel):
         nn.init.xavier_uniform_(self.s_dense_t.weight)
         self._ws = None
         self._adam = None
+        # linear schedule (linear.py): the modality graphs by linearity from one 64-wide propagation + constant tables
+        self._lin_init()
 
     # ---- literal 'tiktok' text branch ---------------------------------------------------------------
     def _build_word_graph(self):
@@ -232,6 +235,8 @@ class EliMRec(BasicModel):
         w = self.word_embedding.weight.detach().to(self.device_, torch.float32).contiguous()
         ops.spmm(self._word_half, w, self._feat["t"], WORD_DIM)
         self.__dict__.pop("_feat_tf32", None)
+        if getattr(self, "linear", False):      # the constant tables of the linear schedule derive from the features
+            self._lin_build_zbar()
 
     def _feat_tc(self, m):
         """Features pre-rounded (to nearest) to TF32 once; what the tensor-core projections stream."""
@@ -290,21 +295,70 @@ class EliMRec(BasicModel):
     # ------------------------------------------------------------------------------------------
     # workspace: every buffer of a step, allocated once (static addresses => CUDA-graph friendly)
     # ------------------------------------------------------------------------------------------
+    # keys of the workspace that depend on the batch size (everything else - slabs, tables, gradient buffers, ~all of the
+    # memory - is allocated once and shared by every batch size; PairwiseSamplerV2 has drop_last=False, so the last batch of
+    # an epoch is short) and keys that describe the LAST forward
+    _WS_PER_BATCH = ("B", "density", "terms", "inst_rows", "inst_grad", "O_inst", "dO_inst", "split_inst", "gemm_ws", "inst_ws",
+                     "inst_dummy", "F_c", "S_c", "c_users", "c_pos", "c_neg", "Zg", "lin_wgrad_ws")
+    _WS_PER_FORWARD = ("pre_last_layer", "last_layer", "seed_zeroed", "bw_pending")
+
     def _workspace(self, B):
         ws = self._ws
         if ws is not None and ws["B"] == B:
+            return ws
+        by_B = self.__dict__.setdefault("_ws_by_B", {})
+        if B in by_B:
+            self._ws = by_B[B]
+            return self._ws
+        if by_B:      # another batch size: share every batch-independent buffer, allocate only the 3B-row ones
+            ws = {k: v for k, v in next(iter(by_B.values())).items()
+                  if k not in self._WS_PER_BATCH and k not in self._WS_PER_FORWARD}
+            self._workspace_batch(ws, B)
+            by_B[B] = self._ws = ws
             return ws
         dev, U, I, L = self.device_, self.num_users, self.num_items, self.n_layers
         N, G = U + I, 1 + len(self.mods)
         Fw = D * G
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        ws = dict(B=B, G=G, F=Fw)
+        ws = dict(G=G, F=Fw, nt=G, cache={})  # cache: tables derived from the last forward (normalised heads, fp16 splits, DP bucket)
+        ws["mask"] = torch.zeros(N, dtype=torch.uint8, device=dev)        # 1 on the <= 3B instance rows of the step
+        ws["need2"] = torch.zeros(N, dtype=torch.uint8, device=dev)       # instance rows + the rows they gather (2 hops)
+        ws["O"] = e(N, Fw)
+        ws["F_all"] = e(N, D)
+        ws["S"] = [e(N, D) for _ in self.mods]
+        ws["loss"] = e(1)
+        if self.mm_fusion_mode == "mean":   # tied fusion weights [W/G | ... | W/G] and the gradient w.r.t. them
+            ws["W_eff"] = {"u": e(D, Fw), "i": e(D, Fw)}
+            ws["g_eff"] = {"u": e(D, Fw), "i": e(D, Fw)}
+        # snapshot of the fusion / head weights and biases used by the last forward (what lazily built tables must use)
+        ws["snap_names"] = (["embedding_user_after_GCN.bias", "embedding_item_after_GCN.bias"] +
+                            [f"s_dense_{m}.bias" for m in self.mods])
+        if self.fuse_precision != "x3":
+            ws["snap_names"] += (["embedding_user_after_GCN.weight", "embedding_item_after_GCN.weight"] +
+                                 [f"s_dense_{m}.weight" for m in self.mods])
+        Pn = self._params()
+        ws["snap"] = {n: (e(D, Fw) if n.endswith("after_GCN.weight") else torch.empty_like(Pn[n], device=dev))
+                      for n in ws["snap_names"]}
+        ws["snap_dst"] = [ws["snap"][n] for n in ws["snap_names"]]
+        ws["W_split"] = {"u": (e(D, Fw), e(D, Fw)), "i": (e(D, Fw), e(D, Fw))}
+        for m in self.mods:
+            ws["W_split"][m] = (e(D, D), e(D, D))
+        if self.linear:
+            self._lin_workspace_shared(ws)
+        else:
+            self._workspace_shared(ws)
+        self._workspace_batch(ws, B)
+        by_B[B] = self._ws = ws
+        return ws
+
+    def _workspace_shared(self, ws):
+        """batch-independent buffers of the slab schedules (reference / row-sparse / generic)"""
+        dev, U, I, L = self.device_, self.num_users, self.num_items, self.n_layers
+        N, Fw = U + I, ws["F"]
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         if not self._generic:
             ws["X0_i"] = e(I, Fw)
         ws["X0_u"] = e(U, D)                                              # E_u as of the last forward (lazy tables)
-        ws["mask"] = torch.zeros(N, dtype=torch.uint8, device=dev)        # 1 on the <= 3B instance rows of the step
-        ws["need2"] = torch.zeros(N, dtype=torch.uint8, device=dev)       # instance rows + the rows they gather (2 hops)
-        ws["density"] = {"u": min(100, 100 * B // max(U, 1) + 1), "i": min(100, 200 * B // max(I, 1) + 1)}   # % rows marked
         rows = lambda side: U if side == "u" else I
         ws["XW"], ws["XN"] = {}, {}
         if self._generic:
@@ -318,17 +372,6 @@ class EliMRec(BasicModel):
                 side = "u" if k % 2 == 1 else "i"
                 ws["XW"][k] = e(rows(side), Fw)
                 ws["XN"][k] = e(rows("i" if side == "u" else "u"), D)
-        ws["O"] = e(N, Fw)
-        ws["F_all"] = e(N, D)
-        ws["S"] = [e(N, D) for _ in self.mods]
-        nt = 1 + len(self.mods)
-        ws["nt"] = nt
-        ws["loss"] = e(1)
-        ws["terms"] = e(nt * B)
-        ws["inst_rows"] = torch.empty(3 * B, dtype=torch.int32, device=dev)
-        ws["inst_grad"] = e(3 * B, D * nt)
-        ws["O_inst"] = e(3 * B, Fw)
-        ws["dO_inst"] = e(3 * B, Fw)
         R = max(U, I)
         if not self._generic:
             ws["dW"] = [e(R, Fw), e(R, Fw)]
@@ -336,9 +379,6 @@ class EliMRec(BasicModel):
             if self.lazy_tables and self.fused_layer_grad:
                 # G wide / G folded over the graph blocks, for all N nodes; only the instance rows are ever written or read
                 ws["Gw"], ws["Gn"] = e(N, Fw), e(N, D)
-        if self.mm_fusion_mode == "mean":   # tied fusion weights [W/G | ... | W/G] and the gradient w.r.t. them
-            ws["W_eff"] = {"u": e(D, Fw), "i": e(D, Fw)}
-            ws["g_eff"] = {"u": e(D, Fw), "i": e(D, Fw)}
         if self.tiktok and self.word_grad:
             ws["dT"] = e(I, WORD_DIM)
         # gradients of the small parameters
@@ -361,39 +401,41 @@ class EliMRec(BasicModel):
         # split-K plan + workspaces
         dmax = max(self._feat[m].shape[1] for m in self.mods)
         ws["split_proj"] = max(1, min(256, (I + 1023) // 1024))
-        ws["split_inst"] = max(1, min(64, (3 * B + 127) // 128))
-        need = max(ws["split_proj"] * dmax * D, ws["split_inst"] * Fw * D)
-        ws["gemm_ws"] = e(need)
+        ws["dmax"] = dmax
         ws["W_tf32"] = {m: e(D, self._feat[m].shape[1]) for m in self.mods}
+        ws["wgrad_ws_m"] = {m: e(max(1, ops.linear_tf32_wgrad_ws_floats(I, self._feat[m].shape[1]))) for m in self.mods}
+        ws["gemm_ws_m"] = {m: (e(ws["split_proj"] * self._feat[m].shape[1] * D) if self.proj_precision == "fp32"
+                               or self._feat[m].shape[1] % 4 else None) for m in self.mods}
+        ws["colsum_ws"] = e(ops.colsum_ws_floats(I, D * len(self.mods)))
+
+    def _workspace_batch(self, ws, B):
+        """the buffers whose size follows the batch: everything indexed by the 3B instance rows"""
+        dev, U, I = self.device_, self.num_users, self.num_items
+        Fw, nt = ws["F"], ws["nt"]
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        ws["B"] = B
+        ws["density"] = {"u": min(100, 100 * B // max(U, 1) + 1), "i": min(100, 200 * B // max(I, 1) + 1)}   # % rows marked
+        ws["terms"] = e(nt * B)
+        ws["inst_rows"] = torch.empty(3 * B, dtype=torch.int32, device=dev)
+        ws["inst_grad"] = e(3 * B, D * nt)
+        ws["O_inst"] = e(3 * B, Fw)
+        ws["dO_inst"] = e(3 * B, Fw)
+        ws["split_inst"] = max(1, min(64, (3 * B + 127) // 128))
+        ws["gemm_ws"] = e(max(ws["split_proj"] * ws["dmax"] * D, ws["split_inst"] * Fw * D))
         ws["inst_ws"] = e(ops.inst_backward_ws_floats(B, nt, Fw))
         ws["inst_dummy"] = torch.empty(3 * B, dtype=torch.int32, device=dev)
         ws["F_c"], ws["S_c"] = e(3 * B, D), [e(3 * B, D) for _ in self.mods]
         ar = torch.arange(B, dtype=torch.int64, device=dev)
         ws["c_users"], ws["c_pos"], ws["c_neg"] = ar.clone(), ar.clone(), ar + B
-        # snapshot of the fusion / head weights and biases used by the last forward (what lazily built tables must use)
-        ws["snap_names"] = (["embedding_user_after_GCN.bias", "embedding_item_after_GCN.bias"] +
-                            [f"s_dense_{m}.bias" for m in self.mods])
-        if self.fuse_precision != "x3":
-            ws["snap_names"] += (["embedding_user_after_GCN.weight", "embedding_item_after_GCN.weight"] +
-                                 [f"s_dense_{m}.weight" for m in self.mods])
-        Pn = self._params()
-        ws["snap"] = {n: (e(D, Fw) if n.endswith("after_GCN.weight") else torch.empty_like(Pn[n], device=dev))
-                      for n in ws["snap_names"]}
-        ws["snap_dst"] = [ws["snap"][n] for n in ws["snap_names"]]
-        ws["W_split"] = {"u": (e(D, Fw), e(D, Fw)), "i": (e(D, Fw), e(D, Fw))}
-        for m in self.mods:
-            ws["W_split"][m] = (e(D, D), e(D, D))
-        ws["wgrad_ws_m"] = {m: e(max(1, ops.linear_tf32_wgrad_ws_floats(I, self._feat[m].shape[1]))) for m in self.mods}
-        ws["gemm_ws_m"] = {m: (e(ws["split_proj"] * self._feat[m].shape[1] * D) if self.proj_precision == "fp32"
-                               or self._feat[m].shape[1] % 4 else None) for m in self.mods}
-        ws["colsum_ws"] = e(ops.colsum_ws_floats(I, D * len(self.mods)))
-        self._ws = ws
-        return ws
+        if self.linear:
+            self._lin_workspace_batch(ws, B)
 
     # ------------------------------------------------------------------------------------------
     # forward  (compute + gcn_cf + bpr losses; EliMRec.py:228-272,144-153,115-142)
     # ------------------------------------------------------------------------------------------
     def _forward(self, users, pos, neg):
+        if self.linear:
+            return self._lin_forward(users, pos, neg)
         P = self._params()
         U, I, L = self.num_users, self.num_items, self.n_layers
         B = int(users.numel())
@@ -485,16 +527,13 @@ class EliMRec(BasicModel):
         self._tables_version = getattr(self, "_tables_version", 0) + 1
         return self._loss(P, ws, users, pos, neg)
 
-    def _loss(self, P, ws, users, pos, neg):
-        """fusion Linear + heads + the 1+M BPR losses on the layer-mean slab (EliMRec.py:261-272,144-153,115-142)"""
+    def _loss(self, P, ws, users, pos, neg, gathered=False):
+        """fusion Linear + heads + the 1+M BPR losses on the layer-mean slab (EliMRec.py:261-272,144-153,115-142);
+        ``gathered``: O[instance rows] is already in ws["O_inst"] (linear schedule)"""
         U, B, Fw, O = self.num_users, ws["B"], ws["F"], ws["O"]
         if self.kwai:
             self.modality = "v"  # EliMRec.py:133-134
-        alpha = float(self.config.alpha)
-        if self.predict_type == "normal":
-            weights = [1.0] + [0.0] * len(self.mods)
-        else:
-            weights = [1.0] + [alpha * self.modality.count(m) for m in self.mods]
+        weights = self._loss_weights()
         if not self.lazy_tables:
             # fusion Linear (concat) and single-modal heads over ALL rows, as the reference does every step
             self._dense_tables(P, ws)
@@ -504,7 +543,8 @@ class EliMRec(BasicModel):
         else:
             # only the sampled rows: gather O[inst], fusion + heads on 3B rows, BPR on the compact tables
             rows = ws["inst_rows"]
-            ops.gather_rows(rows, O, ws["O_inst"], Fw)
+            if not gathered:
+                ops.gather_rows(rows, O, ws["O_inst"], Fw)
             su_ = ops.fork_side(6)
             with torch.cuda.stream(su_):
                 self._fuse_heads_rows(ws, ws["O_inst"][:B], ws["F_c"][:B], [s_[:B] for s_ in ws["S_c"]], "u")
@@ -514,6 +554,22 @@ class EliMRec(BasicModel):
                     ws["inst_grad"], ws["terms"])
             self._tables_pending = True
         return ws["loss"][0]
+
+    def _loss_weights(self):
+        """weight of the fused BPR term and of each single-modal term in the loss (EliMRec.py:125-142)"""
+        if self.predict_type == "normal":
+            return [1.0] + [0.0] * len(self.mods)
+        alpha = float(self.config.alpha)
+        return [1.0] + [alpha * self.modality.count(m) for m in self.mods]
+
+    def _dead_params(self):
+        """Heads whose loss term has weight 0 (predict_type='normal', modality ablations): the reference never calls them,
+        their .grad stays None and Adam skips them - so no gradient is handed out for them here either."""
+        dead = set()
+        for m, w in zip(self.mods, self._loss_weights()[1:]):
+            if w == 0:
+                dead |= {f"s_dense_{m}.weight", f"s_dense_{m}.bias"}
+        return dead
 
     def _fusion_weights(self, P, ws):
         """[64 x F] weights of the fusion Linear as the concat kernels see them: the parameters themselves, or for
@@ -571,6 +627,8 @@ class EliMRec(BasicModel):
     def _materialize_tables(self):
         if self._tables_pending:
             with torch.no_grad():
+                if self.linear:
+                    return self._lin_materialize()
                 ws = self._ws
                 Fw = ws["F"]
                 # the training step produced the last layer at its instance rows only: complete it (every row, from the
@@ -591,6 +649,8 @@ class EliMRec(BasicModel):
         ``split``: stop once the two embedding-table gradients are final and return only those; the weight gradients
         (fusion / heads / projections / word table) are then produced by ``_backward_weights()`` - data-parallel
         replicas put the table gradients' all-reduce on the wire in between (``make_graphed_step``)."""
+        if self.linear:
+            return self._lin_backward(gscale, split)
         P = self._params()
         ws = self._ws
         B, G, Fw, nt = ws["B"], ws["G"], ws["F"], ws["nt"]
@@ -633,6 +693,8 @@ class EliMRec(BasicModel):
 
     def _backward_weights(self):
         """second half of the backward: every gradient that is not an embedding table's"""
+        if self.linear:
+            return self._lin_backward_weights()
         ws = self._ws
         inst_weights, dX0_i, side_w = ws.pop("bw_pending")
         if side_w is None:      # split backward: the instance-row weight gradients run beside the projection ones
@@ -642,7 +704,8 @@ class EliMRec(BasicModel):
         self._proj_wgrad(ws, dX0_i, 0, self.num_items)
         self._word_wgrad(ws, dX0_i)
         ops.join_side(side_w)
-        return ws["g"]
+        dead = self._dead_params()
+        return {n: g for n, g in ws["g"].items() if n not in dead} if dead else ws["g"]
 
     def _zero_seed_rows(self, ws):
         """zero the instance rows of d x_L's two slabs (the rest of those slabs is never read: column masks)"""
@@ -787,14 +850,14 @@ class EliMRec(BasicModel):
         return ws["dE_u"], cur[U:]
 
     # projections over item rows [r0, r1) - the whole table on one GPU, the owned block when row-sharded
-    def _prep_weights(self, P, ws):
+    def _prep_weights(self, P, ws, proj=True):
         """TF32 rounding (projections) and hi/lo split (fusion, heads) of the small weights, one launch."""
         prep = []
         if self.mm_fusion_mode == "mean":
             G = ws["G"]
             ops.tie_blocks(P["embedding_user_after_GCN.weight"].detach(), ws["W_eff"]["u"], G, 1.0 / G)
             ops.tie_blocks(P["embedding_item_after_GCN.weight"].detach(), ws["W_eff"]["i"], G, 1.0 / G)
-        if self.proj_precision == "tf32":
+        if proj and self.proj_precision == "tf32":
             prep += [(P[f"{m}_dense.weight"].detach(), ws["W_tf32"][m], None) for m in self.mods
                      if self._feat[m].shape[1] % 4 == 0]
         if self.fuse_precision == "x3":
@@ -861,8 +924,16 @@ class EliMRec(BasicModel):
             raise ElimrecError("model parameters are not on config.device; call .to(config.device)")
         return _StepFunction.apply(self, users, pos, neg, *[P[n] for n in self._param_names])
 
+    @torch.no_grad()
     def getEmbedding(self, users, pos_items, neg_items):
-        raise NotImplementedError("row gathers are fused into bpr_loss (elimrec_bpr_forward_backward)")
+        """models/EliMRec.py:274-289: runs the propagation (``compute()``), caches ``all_users`` / ``all_items`` and returns
+        their rows at the batch plus the three raw ("ego") embedding lookups.  No autograd history: training goes through
+        ``bpr_loss`` / ``train_step``, whose fused kernel does these gathers itself (elimrec_bpr_forward_backward)."""
+        users, pos, neg = self._triples(users, pos_items, neg_items)
+        self._forward(users, pos, neg)
+        au, ai = self.all_users, self.all_items           # completed on demand (every row), as the reference caches them
+        Eu, Ei = self.embedding_user.weight.detach(), self.embedding_item.weight.detach()
+        return au[users], ai[pos], ai[neg], Eu[users], Ei[pos], Ei[neg]
 
     def make_optimizer(self, lr=None, weight_decay=None, betas=(0.9, 0.999), eps=1e-8):
         from .optim import FusedAdam
@@ -896,13 +967,15 @@ class EliMRec(BasicModel):
         """One flat bucket (embedding tables + every small gradient), one all-reduce(AVG)."""
         from .dist import GradBucket
         ws = self._ws
+        ws = ws["cache"]
         if "bucket" not in ws:
             P = self._params()
             head = self._param_names[:2]           # the two embedding tables: packed (dE_i is a strided slab view)
-            ws["bucket"] = GradBucket({n: tuple(P[n].shape) for n in head}, self.device_, tail_flat=ws["g_flat"],
-                                      tail_views={n: ws["g"][n] for n in self._param_names[2:]})
+            ws["bucket"] = GradBucket({n: tuple(P[n].shape) for n in head}, self.device_, tail_flat=self._ws["g_flat"],
+                                      tail_views={n: self._ws["g"][n] for n in self._param_names[2:]})
         ws["bucket"].pack(grads, ws["bucket"].head_names)
-        return ws["bucket"].all_reduce_mean()
+        views = ws["bucket"].all_reduce_mean()
+        return {n: views[n] for n in grads}      # heads the loss does not use stay without a gradient
 
     # -- whole step as one CUDA graph (launch-bound otherwise: ~60 small launches per step) ------------
     def make_graphed_step(self, batch_size=None):
@@ -914,11 +987,28 @@ class EliMRec(BasicModel):
         model = self
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):   # warm-up outside capture: allocates workspace + Adam state
+        # warm-up outside capture (allocates workspace + Adam state, loads kernels).  It is a real step on a dummy batch, so
+        # parameters, Adam moments and the device step counter are put back afterwards: building the runner changes nothing.
+        ad = self._adam
+        saved_p = {n: p.detach().clone() for n, p in self.named_parameters()}
+        saved_st = {n: (m.clone(), v.clone()) for n, (m, v) in ad.state.items()}
+        saved_step, saved_consts = ad.step_dev.clone(), ad.consts.clone()
+        with torch.cuda.stream(side):
             self.train_step(su, sp_, sn)
         torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():
+            for n, p in self.named_parameters():
+                p.copy_(saved_p[n])
+            for n, (m, v) in ad.state.items():
+                if n in saved_st:
+                    m.copy_(saved_st[n][0]); v.copy_(saved_st[n][1])
+                else:
+                    m.zero_(); v.zero_()
+            ad.step_dev.copy_(saved_step); ad.consts.copy_(saved_consts)
+        del saved_p, saved_st
         torch.cuda.synchronize()
         dp = getattr(self, "_dp", False)
+        dead = self._dead_params()
         before = CALLS["launches"]
         single = bool(_cfg(self.config, "dp_single_graph", False))
         if not dp:
@@ -930,7 +1020,7 @@ class EliMRec(BasicModel):
             # EXPERIMENTAL (dp_single_graph=True, not yet run on hardware - DESIGN.md section 8 item 1): the same schedule with
             # the two all-reduces captured INSIDE one graph, so the four graph launches (and the ~85 us they cost) become one.
             graph = torch.cuda.CUDAGraph()
-            bucket = self._ws["bucket"]
+            bucket = self._ws["cache"]["bucket"]
             with torch.cuda.graph(graph):
                 with torch.no_grad():
                     loss = self._forward(su, sp_, sn)
@@ -941,7 +1031,7 @@ class EliMRec(BasicModel):
                     w1.wait()
                     self._adam.apply({n: bucket.views[n] for n in bucket.head_names})
                     w2.wait()
-                    self._adam.apply({n: bucket.views[n] for n in bucket.tail_names}, tick=False)
+                    self._adam.apply({n: bucket.views[n] for n in bucket.tail_names if n not in dead}, tick=False)
             graphs, dp = (graph,), False       # the runner just replays it
         else:
             # data-parallel replicas, four graphs around two NCCL all-reduces:
@@ -952,7 +1042,7 @@ class EliMRec(BasicModel):
             #   C = Adam on the averaged tables (only needs all-reduce #1, and hides #2), D = Adam on the small tensors.
             # Collectives stay outside the captures.
             gA, gB, gC, gD = (torch.cuda.CUDAGraph() for _ in range(4))
-            bucket = self._ws["bucket"]
+            bucket = self._ws["cache"]["bucket"]
             with torch.cuda.graph(gA):
                 with torch.no_grad():
                     loss = self._forward(su, sp_, sn)
@@ -965,7 +1055,7 @@ class EliMRec(BasicModel):
                     self._adam.apply({n: bucket.views[n] for n in bucket.head_names})
             with torch.cuda.graph(gD, pool=gA.pool()):
                 with torch.no_grad():
-                    self._adam.apply({n: bucket.views[n] for n in bucket.tail_names}, tick=False)
+                    self._adam.apply({n: bucket.views[n] for n in bucket.tail_names if n not in dead}, tick=False)
             graphs = (gA, gB, gC, gD)
         n_launch = CALLS["launches"] - before + 2  # + the two memsets of the backward seeds
 
@@ -977,7 +1067,7 @@ class EliMRec(BasicModel):
                 su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
                 graphs[0].replay()
                 if dp:
-                    bucket = model._ws["bucket"]
+                    bucket = model._ws["cache"]["bucket"]
                     w1 = bucket.all_reduce_mean_part(0, async_op=True)
                     graphs[1].replay()
                     w2 = bucket.all_reduce_mean_part(1, async_op=True)
@@ -987,6 +1077,12 @@ class EliMRec(BasicModel):
                     if w2 is not None:
                         w2.wait()
                     graphs[3].replay()
+                # what _forward / _loss do on the host besides launching: a replay is a new training forward, so every
+                # table cached from the previous one (all_users / all_items / all_s_embs, normalised heads, fp16 splits)
+                # is stale
+                model._tables_version = getattr(model, "_tables_version", 0) + 1
+                if model.lazy_tables:
+                    model._tables_pending = True
                 return loss
 
         return _Runner()
@@ -1006,7 +1102,7 @@ class EliMRec(BasicModel):
         refreshed once per training forward, not per batch)."""
         if self.all_users is None:
             raise TypeError("'NoneType' object is not subscriptable (predict before any bpr_loss, as in the reference)")
-        ws = self._ws
+        ws = self._ws["cache"]
         if ws.get("S_norm_version") != self._tables_version:
             fu, fi, su, si = self._tables()
             ws["S_norm"] = [(torch.empty_like(a), torch.empty_like(b)) for a, b in zip(su, si)]
@@ -1027,7 +1123,7 @@ class EliMRec(BasicModel):
         if self.fusion_mode != "rubi":
             raise ElimrecError("the tensor-core evaluator implements the 'rubi' score fusion; hm / sum run on the fp32 rank path")
         self.rank_tables()                      # refreshes the normalised single-modal tables
-        ws = self._ws
+        ws = self._ws["cache"]
         key = (self._tables_version, self.predict_type, self.modality)
         if ws.get("rank_tc_key") != key:
             fu, fi = ws["rank_f"]

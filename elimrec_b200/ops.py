@@ -159,6 +159,44 @@ def layer_mean(layers, out, width, scale):
     call("elimrec_layer_mean", out.shape[0], width, n, lp, ld, scale, ptr(out, F32), out.stride(0), stream())
 
 
+def lin_layers(tables):
+    """tables: list over k = 0..L of (user rows [U x 64], item rows [I x 64]) of p_k = A_hat^k [E_u ; E_i]"""
+    lay = _lib.LinLayers()
+    lay.n = len(tables)
+    for k, (tu, ti) in enumerate(tables):
+        lay.user[k], lay.user_ld[k] = ptr(tu, F32), tu.stride(0)
+        lay.item[k], lay.item_ld[k] = ptr(ti, F32), ti.stride(0)
+    lay._keepalive = tables
+    return lay
+
+
+def lin_assemble(rows, num_users, layers, scale, n_mod, accumulate, out, n_rows=None):
+    """out[j, 0:64] = scale * sum_k p_k[rows[j]];  out[j, 64(1+m):64(2+m)] (+)= scale * (parity layers) - elimrec_lin_assemble.
+    rows None: out row j = node j (n_rows of them)."""
+    n = rows.numel() if rows is not None else n_rows
+    call("elimrec_lin_assemble", n, ptr(rows, torch.int32, True), num_users, C.byref(layers), scale, n_mod, int(accumulate),
+         ptr(out, F32), out.stride(0), stream())
+
+
+def lin_seed(rows, num_users, layer, dO, n_mod, scale, dst):
+    """dst[rows[j]] += scale * (dO[j, :64] + [parity] * sum_m dO[j, 64(1+m):64(2+m)])  (adjoint of lin_assemble, layer `layer`)"""
+    call("elimrec_lin_seed", rows.numel(), ptr(rows, torch.int32), num_users, layer, ptr(dO, F32), dO.stride(0), n_mod, scale,
+         ptr(dst, F32), dst.stride(0), stream())
+
+
+def pack_proj_weights(items, round_tf32):
+    """items: list of (W [64 x Dm], b [64], dst [64 x Kp]) -> dst = [W | b | 0..], one launch"""
+    arr = (_lib.PackProj * len(items))()
+    for k, (W, b, dst) in enumerate(items):
+        arr[k].W, arr[k].b, arr[k].dst, arr[k].Dm, arr[k].Kp = ptr(W, F32), ptr(b, F32), ptr(dst, F32), W.shape[1], dst.shape[1]
+    call("elimrec_pack_proj_weights", len(items), arr, int(round_tf32), stream())
+
+
+def axpy_2d(X, Y, n_rows, width, scale=1.0, accumulate=True):
+    """Y[:, :width] = [Y +] scale * X[:, :width]"""
+    call("elimrec_axpy_2d", n_rows, width, scale, ptr(X, F32), X.stride(0), ptr(Y, F32), Y.stride(0), int(accumulate), stream())
+
+
 def gemm(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, Cm, c_sm, c_sn, bias=None, accumulate=False, split_k=1, ws=None,
          scale=None, a_off=0, b_off=0, c_off=0, tag=None):
     """C(m,n) = [C +] scale * sum_k A(m,k) B(k,n) [+ bias(n)]; *_off are element offsets into the tensors."""
@@ -280,8 +318,12 @@ def adam_apply_multi(items, consts_dev, b1, b2, eps, wd):
     for k, (p, g, m, v) in enumerate(items):
         row_len = p.shape[-1]
         arr[k].param, arr[k].grad, arr[k].exp_avg, arr[k].exp_avg_sq = ptr(p, F32), ptr(g, F32), ptr(m, F32), ptr(v, F32)
+        if g.dim() == 1 and g.numel() > 1 and g.stride(0) != 1:      # a column of a wider matrix (packed [W | b] gradient)
+            row_len, gld = 1, g.stride(0)
+        else:
+            gld = g.stride(0) if g.dim() == 2 else row_len
         arr[k].numel, arr[k].row_len = p.numel(), row_len
-        arr[k].grad_ld = g.stride(0) if g.dim() == 2 else row_len
+        arr[k].grad_ld = gld
     call("elimrec_adam_apply_multi", len(items), arr, ptr(consts_dev, torch.float64), b1, b2, eps, wd, stream())
 
 

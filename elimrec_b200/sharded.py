@@ -40,6 +40,9 @@ from .model import D, EliMRec, ElimrecError
 
 
 class ShardedEliMRec(EliMRec):
+    def _lin_init(self):
+        self.linear = False      # the wide/narrow slab schedule, row-sharded
+
     def _init_weight(self):
         if not (dist.is_available() and dist.is_initialized()):
             raise ElimrecError("ShardedEliMRec needs an initialised torch.distributed process group")
@@ -79,7 +82,7 @@ class ShardedEliMRec(EliMRec):
         Gm = 1 + len(self.mods)
         Fw = D * Gm
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        ws = dict(B=B, G=Gm, F=Fw, nt=Gm)
+        ws = dict(B=B, G=Gm, F=Fw, nt=Gm, cache={})
         ws["Eu"], ws["X0_i"] = z(Up, D), z(Ip, Fw)
         rows = lambda side: Up if side == "u" else Ip
         ws["XW"], ws["XN"] = {}, {}

@@ -133,6 +133,47 @@ int elimrec_layer_mean(int64_t n_rows, int width, int n_layers, const float* con
                        float scale, float* out, int64_t ld_out, elimrec_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * linear schedule (csrc/linsched.cu) - compute_graph x4 + mm_fusion inputs (models/EliMRec.py:238-258) by linearity.
+ *
+ * light_out_m = mean_k A_hat^k [E_u ; X_m W_m^T + b_m] = mean_k A_hat^k [E_u ; 0] + Zbar_m [W_m | b_m]^T, where
+ * Zbar_m = mean_k A_hat^k [0 ; X_m | 1] is a CONSTANT of the dataset (item features are never trained), and the first
+ * term is read off the id graph's own layers p_k = A_hat^k [E_u ; E_i]: A_hat is bipartite, so it sits on the user rows
+ * of the even layers and on the item rows of the odd ones.  One 64-wide propagation per step instead of one 64-wide plus
+ * three 256-wide ones, and no pass over the features.
+ *
+ * elimrec_lin_assemble: for output row j (node = rows[j], or j when rows == NULL; users first):
+ *   out[j, 0:64]                 = scale * ((p_0 + p_1) + ... + p_L)[node]            (light_out of the id graph)
+ *   out[j, 64(1+m) : 64(2+m)]  (+)= scale * sum_{k : k even (user) / odd (item)} p_k[node]    for m < n_mod
+ * accumulate != 0: the modality blocks already hold Zbar_m[node] W'_m^T (written by the GEMM) and are added to.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t n;                                       /* L + 1 tables p_0 .. p_L */
+    const float* user[ELIMREC_MAX_LAYERS + 1];       /* p_k, user rows [U x 64] */
+    const float* item[ELIMREC_MAX_LAYERS + 1];       /* p_k, item rows [I x 64] */
+    int64_t user_ld[ELIMREC_MAX_LAYERS + 1];
+    int64_t item_ld[ELIMREC_MAX_LAYERS + 1];
+} elimrec_lin_layers_t;
+int elimrec_lin_assemble(int64_t n_rows, const int32_t* rows /* may be NULL */, int32_t num_users,
+                         const elimrec_lin_layers_t* layers, float scale, int n_mod, int accumulate, float* out, int64_t ldo,
+                         elimrec_stream_t stream);
+/* adjoint of elimrec_lin_assemble w.r.t. layer `layer` of the chain, on the instance rows (atomic: nodes repeat):
+ *   dst[rows[j], 0:64] += scale * (dO[j, 0:64] + [layer even (user row) / odd (item row)] * sum_m dO[j, 64(1+m):64(2+m)]) */
+int elimrec_lin_seed(int n_rows, const int32_t* rows, int32_t num_users, int layer, const float* dO, int64_t ldo, int n_mod,
+                     float scale, float* dst /* [N x 64], users first */, int64_t ldd, elimrec_stream_t stream);
+/* dst_m [64 x Kp] = [ W_m [64 x Dm] | b_m | 0 .. ]: the projection weight with its bias as one more input column (the
+ * matching column of Zbar_m is mean_k A_hat^k [0 ; 1]); round_tf32 != 0 rounds to nearest TF32 for the tensor-core GEMM */
+typedef struct {
+    const float* W;
+    const float* b;
+    float* dst;
+    int64_t Dm, Kp;
+} elimrec_pack_proj_t;
+int elimrec_pack_proj_weights(int n, const elimrec_pack_proj_t* tensors_host, int round_tf32, elimrec_stream_t stream);
+/* Y[r, 0:width] = [Y +] scale * X[r, 0:width]  (accumulating the constant Zbar tables, once per model) */
+int elimrec_axpy_2d(int64_t n_rows, int width, float scale, const float* X, int64_t ldx, float* Y, int64_t ldy, int accumulate,
+                    elimrec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * gemm - replaces nn.Linear forward/backward for v_dense/a_dense/t_dense (models/EliMRec.py:233-236),
  * embedding_{user,item}_after_GCN (:261-270) and s_dense_* (:146-151).
  *

@@ -31,9 +31,10 @@ def main(which, data_dir, out_file):
         sys.path.insert(0, os.path.join(REPO, "dropin"))
         import sim_ops
         import elimrec_b200.evaluator as ev
+        import elimrec_b200.linear as ln
         import elimrec_b200.model as md
         import elimrec_b200.optim as op
-        for mod in (md, ev, op):
+        for mod in (md, ev, op, ln):
             mod.ops = sim_ops
         md._require_cuda = lambda dev: None
 

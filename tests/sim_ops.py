@@ -147,6 +147,49 @@ def layer_mean(layers, out, width, scale):
     out[:, :width] = s * scale
 
 
+def lin_layers(tables):
+    return list(tables)
+
+
+def lin_assemble(rows, num_users, layers, scale, n_mod, accumulate, out, n_rows=None):
+    _log("lin_assemble")
+    node = rows.long() if rows is not None else torch.arange(n_rows)
+    is_user = node < num_users
+    sa = sp = None
+    for k, (tu, ti) in enumerate(layers):
+        v = torch.where(is_user.unsqueeze(1), tu[torch.where(is_user, node, 0), :64], ti[torch.where(is_user, 0, node - num_users), :64])
+        sa = v.clone() if sa is None else sa + v
+        par = torch.where(is_user, k % 2 == 0, k % 2 == 1).unsqueeze(1)
+        sp = torch.where(par, v, torch.zeros_like(v)) if sp is None else sp + torch.where(par, v, torch.zeros_like(v))
+    out[:, :64] = sa * scale
+    for m in range(n_mod):
+        blk = slice(64 * (m + 1), 64 * (m + 2))
+        out[:, blk] = (out[:, blk] if accumulate else 0) + sp * scale
+
+
+def lin_seed(rows, num_users, layer, dO, n_mod, scale, dst):
+    _log("lin_seed")
+    node = rows.long()
+    par = torch.where(node < num_users, layer % 2 == 0, layer % 2 == 1).unsqueeze(1)
+    v = dO[:, :64].clone()
+    if n_mod:
+        v = v + torch.where(par, dO[:, 64:64 * (1 + n_mod)].reshape(-1, n_mod, 64).sum(1), torch.zeros_like(v))
+    dst[:, :64].index_add_(0, node, v * scale)
+
+
+def pack_proj_weights(items, round_tf32):
+    _log("pack_proj")
+    for W, b, dst in items:
+        dm = W.shape[1]
+        dst.zero_()
+        dst[:, :dm] = W
+        dst[:, dm] = b
+
+
+def axpy_2d(X, Y, n_rows, width, scale=1.0, accumulate=True):
+    Y[:n_rows, :width] = (Y[:n_rows, :width] if accumulate else 0) + scale * X[:n_rows, :width]
+
+
 def _view(t, off, shape, strides):
     return torch.as_strided(t, shape, strides, t.storage_offset() + off)
 

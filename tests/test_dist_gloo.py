@@ -84,6 +84,7 @@ def test_bucket_and_eval_sharding_world2():
 def _install_sim():
     import sim_ops
     import elimrec_b200.evaluator as ev
+    import elimrec_b200.linear as ln
     import elimrec_b200.model as md
     import elimrec_b200.optim as op
     import elimrec_b200.sharded as sh
@@ -98,7 +99,7 @@ def _install_sim():
     class _St:
         def wait_event(self, *a):
             pass
-    for mod in (md, ev, op, sh):
+    for mod in (md, ev, op, sh, ln):
         mod.ops = sim_ops
     md._require_cuda = lambda dev: None
     torch.cuda.Event = _Ev

@@ -47,6 +47,7 @@ def sim(monkeypatch):
 
 def _install_sim(monkeypatch):
     import elimrec_b200.evaluator as ev
+    import elimrec_b200.linear as ln
     import elimrec_b200.model as md
     import elimrec_b200.optim as op
 
@@ -61,7 +62,7 @@ def _install_sim(monkeypatch):
         def wait_event(self, *a):
             pass
 
-    for mod in (md, ev, op):
+    for mod in (md, ev, op, ln):
         monkeypatch.setattr(mod, "ops", sim_ops)
     monkeypatch.setattr(md, "_require_cuda", lambda dev: None)
     monkeypatch.setattr(torch.cuda, "Event", _Ev)
@@ -112,11 +113,17 @@ def check_steps(model, g, pre, steps=3, subset=None, worst=1e-4, frac=1e-3):
         assert d.max() < worst and (d > 1e-5).mean() < frac, (k, d.max(), (d > 1e-5).mean())
 
 
-# ---- the default configuration: both schedules ------------------------------------------------------------------------------
-@pytest.mark.parametrize("lazy,fused", [(True, True), (True, False), (False, False)])
-def test_default_schedule_vs_golden(backend, golden, lazy, fused):
+# ---- the default configuration: every schedule -------------------------------------------------------------------------------
+SCHEDULES = {"linear": dict(), "rowsparse": dict(linear_schedule=False), "rowsparse_fused": dict(linear_schedule=False, fused_layer_grad=True),
+             "reference": dict(lazy_tables=False)}
+
+
+@pytest.mark.parametrize("sched", list(SCHEDULES))
+def test_default_schedule_vs_golden(backend, golden, sched):
     name = "kwai" if golden["_name"] == "kwai" else "synthg"
-    model = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy, fused_layer_grad=fused)
+    kw = SCHEDULES[sched]
+    model = build(golden_dataset(golden), golden_params(golden), name, **kw)
+    assert model.linear == (sched == "linear")
     loss = model.bpr_loss(*batch(golden, 0))
     loss.backward(retain_graph=True)
     assert abs(float(loss) - float(golden["loss0"])) < TOL * abs(float(golden["loss0"]))
@@ -128,14 +135,14 @@ def test_default_schedule_vs_golden(backend, golden, lazy, fused):
         assert rel(model.predict(golden["predict_users"].tolist(), None), golden[f"predict_{pt}"]) < TOL
         np.testing.assert_allclose(model.evaluate()[0], golden[f"evaluate_{pt}"], atol=5e-5)
     model.predict_type = "TIE"
-    model2 = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=lazy, fused_layer_grad=fused)
+    model2 = build(golden_dataset(golden), golden_params(golden), name, **kw)
     check_steps(model2, golden, "")
 
 
 def test_row_sparse_step_skips_dead_rows(sim, golden):
     """lazy_tables: the last layer runs under row masks, the full tables only on demand."""
     name = "kwai" if golden["_name"] == "kwai" else "synthg"
-    model = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=True)
+    model = build(golden_dataset(golden), golden_params(golden), name, lazy_tables=True, linear_schedule=False)
     model.make_optimizer()
     sim.LAUNCH_LOG.clear()
     model.train_step(*batch(golden, 0))
@@ -160,7 +167,9 @@ def test_split_backward_and_bucket(sim, golden):
     ws = model._ws
     assert all(v.data_ptr() >= ws["g_flat"].data_ptr() and
                v.data_ptr() + 4 * v.numel() <= ws["g_flat"].data_ptr() + 4 * ws["g_flat"].numel() for v in tail.values())
-    assert sum(v.numel() for v in tail.values()) == ws["g_flat"].numel()
+    # (linear schedule: the packed d[W_m | b_m | 0-pad] blocks carry their alignment padding along)
+    pad = 64 * sum(kp - model._feat[m].shape[1] - 1 for m, kp in zip(model.mods, model._lin_Kp)) if model.linear else 0
+    assert sum(v.numel() for v in tail.values()) == ws["g_flat"].numel() - pad
     P = model._params()
     bucket = GradBucket({n: tuple(P[n].shape) for n in head}, "cpu", tail_flat=ws["g_flat"],
                         tail_views={n: ws["g"][n] for n in model._param_names[2:]})
@@ -427,7 +436,8 @@ def test_evaluator_edge_cases(sim, golden, top_k):
 
 # ---- configuration sweep against the (pinned) oracle: host schedule for every layer count / variant combination -------------
 @pytest.mark.parametrize("layers", [1, 2, 3, 4])
-@pytest.mark.parametrize("variant", [dict(), dict(lazy_tables=False), dict(adj_type="gcmc"), dict(adj_type="norm"),
+@pytest.mark.parametrize("variant", [dict(), dict(linear_schedule=False), dict(lazy_tables=False), dict(adj_type="gcmc"),
+                                     dict(adj_type="gcmc", linear_schedule=False), dict(adj_type="norm"),
                                      dict(mm_fusion_mode="mean"), dict(modality="va"), dict(modality="t", lazy_tables=False),
                                      dict(adj_type="gcmc", mm_fusion_mode="mean", fused_layer_grad=True)],
                          ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")

@@ -40,7 +40,7 @@ timeit(lambda b: run(*b), "full dp step" + (" (single graph)" if single else "")
 if single:      # the variants below patch the eager collectives, which the single graph no longer calls
     dist.destroy_process_group()
     sys.exit(0)
-bucket = model._ws["bucket"]
+bucket = model._ws["cache"]["bucket"]
 # variants: patch the bucket's collective
 orig = bucket.all_reduce_mean_part
 bucket.all_reduce_mean_part = lambda part, async_op=False: None
