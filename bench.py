@@ -4,9 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiktok] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  Contract: see the task statement; in short
-  value        whole-job triples/s of K train steps (fwd + bwd + Adam), inputs resident in HBM
-  e2e          same metric through the public API with HOST triples: per step H2D of the batch from
-               pinned memory and a D2H read of the loss are inside the timed region
+  value        whole-job triples/s of K train steps, each = sample the batch (device Philox sampler, inside the step's CUDA
+               graph) + fwd + bwd + Adam; dataset and parameters resident in HBM
+  e2e          same metric through the reference-facing API exactly as main.py:92-102 drives it: whole epochs of
+               `for users, pos, neg in PairwiseSamplerV2: loss = step(...); loss.item()` with the HOST compat sampler
+               (bit-exact libc stream + numpy shuffle) INSIDE the timed region - overlapped on a prefetch thread
+               (`e2e.value`) and serial (`e2e.serial_sampler_value`) - per step H2D of the batch from pinned memory and
+               a D2H read of the loss
   eval         users/s of one full `evaluate()` (TIE, K=20, Precision/Recall/NDCG), device + e2e
   roofline     the propagation SpMM (wide launch) against the measured HBM copy bandwidth
   cpu_baseline the oracle port (torch-CPU restatement of the reference) timed on this host, rank 0
@@ -51,6 +55,9 @@ def parse():
     ap.add_argument("--cuda-graph", type=int, default=1)
     ap.add_argument("--lazy-tables", type=int, default=1,
                     help="1: build all_users/all_items/all_s_embs on demand (at evaluation) instead of every step")
+    ap.add_argument("--linear", type=int, default=1,
+                    help="1 (default): linear schedule - modality graphs by linearity from one 64-wide propagation + constant "
+                         "tables; 0: the row-sparse slab schedule of round 1")
     ap.add_argument("--fused-layer-grad", type=int, default=0,
                     help="1: layer-mean gradient added in the backward SpMM epilogues; 0 (default, measured faster): a scatter "
                          "kernel after each SpMM, hidden under the other stream's SpMM")
@@ -170,6 +177,96 @@ def cpu_port_run(ds, name, steps, warmup, budget_s, eval_users=256):
                 threads=torch.get_num_threads())
 
 
+def load_peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return pk["hbm_gbs"], pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1384.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1384.0, "fallback (B200_PROFILING.md)"
+
+
+def rooflines_of(model, agg, workload, B, prefix=""):
+    """Per-kernel rooflines from the serialised CUDA-event profile `agg` {tag: [ms, ...]} of a few training steps.
+    Returns (headline roofline of the dominant propagation kernel, list for every family that has a stated bound)."""
+    hbm, tf_bf16, which = load_peaks()
+    g = model.graph
+    U, I = model.num_users, model.num_items
+    M = len(model.mods)
+    Fw = 64 if model.linear else 64 * (1 + M)
+    tot = sum(sum(v) for v in agg.values())
+    out, head = [], None
+    avg_s = lambda tag: 1e-3 * sum(agg[tag]) / len(agg[tag])
+
+    def add(kernel, tag, bound, units, peak, unit, **extra):
+        if tag not in agg:
+            return None
+        t = avg_s(tag)
+        ach = units / t / (1e9 if unit == "GB/s" else 1e12)
+        r = {"kernel": prefix + kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+             "avg_launch_us": 1e6 * t, "launches_timed": len(agg[tag]), "share_of_step": sum(agg[tag]) / tot,
+             ("bytes_per_launch" if unit == "GB/s" else "flops_per_launch"): units, **extra}
+        out.append(r)
+        return r
+
+    # propagation SpMM, algorithmic bytes per launch (DESIGN.md 3.1): nnz*(4+4) + (rows_out+1)*4 + (rows_in + rows_out)*F*4.
+    # Timed on launches that are exactly ONE kernel: the half without split rows ("w" tag).  Where both halves have split
+    # rows, one event pair brackets the whole-row + split-row launches of a half (they run side by side).
+    alg_of = lambda h: float(h.nnz * 8 + (h.n_rows + 1) * 4 + (h.n_cols + h.n_rows) * Fw * 4)
+    half = g.ui if g.ui.n_heavy_seg == 0 else (g.iu if g.iu.n_heavy_seg == 0 else None)
+    traffic = None
+    try:      # L2->SM / DRAM bytes per launch from the committed ncu --set full capture of this kernel (tiktok shape)
+        if workload == "tiktok":
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json"))).get(f"dram_bytes_per_launch_w{Fw}")
+    except Exception:
+        pass
+    fam = sum(sum(v) for k, v in agg.items() if k.startswith("spmm"))
+    common = dict(traffic=traffic, peak_source=which, spmm_family_share_of_step=fam / tot)
+    if f"spmm{Fw}w" in agg and half is not None:
+        head = add(f"spmm_seg_kernel<{Fw}> (whole rows, {'user' if half is g.ui else 'item'}-row half, unmasked)", f"spmm{Fw}w",
+                   "hbm", alg_of(half), hbm, "GB/s", **common)
+        other = g.iu if half is g.ui else g.ui
+        add(f"spmm_seg_kernel<{Fw}> (whole-row + split-row launch, {'item' if half is g.ui else 'user'}-row half, unmasked)",
+            f"spmm{Fw}", "hbm", alg_of(other), hbm, "GB/s", peak_source=which)
+    elif f"spmm{Fw}" in agg:
+        head = add(f"spmm_seg_kernel<{Fw}> (whole-row + split-row launch of one half, mean over the two halves)", f"spmm{Fw}",
+                   "hbm", 0.5 * (alg_of(g.ui) + alg_of(g.iu)), hbm, "GB/s", **common)
+    if head is not None:
+        slab_mb = (U + I) * Fw * 4 / 1e6
+        head["note"] = (f"operand slab {slab_mb:.0f} MB " + ("fits the 126 MB L2: the gather is bound by L2->SM bandwidth, DRAM carries "
+                        "only the compulsory bytes" if slab_mb < 100 else "exceeds the 126 MB L2: the gather misses to HBM at "
+                        "row granularity") + "; achieved = algorithmic bytes / launch time (DESIGN.md 3.1)")
+    # Adam: 7 streams x 4 B per parameter element (read p, g, m, v; write p, m, v)
+    n_par = sum(p.numel() for p in model._params().values())
+    add("adam_multi_kernel (all parameters, one launch)", "elimrec_adam_apply_multi", "hbm", 28.0 * n_par, hbm, "GB/s",
+        peak_source=which)
+    if model.linear:
+        Kt = model._lin_Ktot
+        add("gather_rows_kernel (Zbar rows at the 3B instance rows)", "elimrec_gather_rows", "hbm", 2.0 * 3 * B * Kt * 4, hbm, "GB/s",
+            peak_source=which)
+        # TF32 runs at half the bf16 rate
+        add("linear_tf32_fwd_kernel (modality blocks on the instance rows, tcgen05 kind::tf32)", "lin_modal_tc", "tensor",
+            2.0 * 3 * B * 64 * Kt, tf_bf16 / 2, "TFLOP/s", peak_source=which + ", TF32 = bf16 / 2",
+            note="3B x Ktot x 64 per step: launch-latency sized, not a throughput kernel")
+    else:
+        feat_b = float(sum(model._feat[m].shape[1] for m in model.mods) * I * 4 + I * 64 * 4 * M)
+        flops = 2.0 * I * 64 * sum(model._feat[m].shape[1] for m in model.mods)
+        r = add("linear_tf32_fwd_kernel (all modal projections, one persistent launch): feature stream", "proj_fwd_tc", "hbm",
+                feat_b, hbm, "GB/s", peak_source=which)
+        if r is not None:
+            r["tensor_tflops"] = flops / (r["avg_launch_us"] * 1e-6) / 1e12
+            r["tensor_frac_of_tf32_peak"] = r["tensor_tflops"] / (tf_bf16 / 2)
+            r["note"] = "32 flop per fp32 feature byte: HBM-bound on the feature stream, the tensor pipe only has to keep up"
+        if "proj_wgrad_tc" in agg:      # one launch pair per modality; report the largest (text / visual) one
+            dmax = max(model._feat[m].shape[1] for m in model.mods)
+            t_big = max(agg["proj_wgrad_tc"])
+            out.append({"kernel": prefix + f"linear_tf32_wgrad_kernel + reduce (widest modality, D={dmax})", "bound": "hbm",
+                        "achieved": (I * dmax * 4 + I * 64 * 4) / (1e-3 * t_big) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": (I * dmax * 4 + I * 64 * 4) / (1e-3 * t_big) / 1e9 / hbm, "avg_launch_us": 1e3 * t_big,
+                        "share_of_step": sum(agg["proj_wgrad_tc"]) / tot, "peak_source": which,
+                        "tensor_tflops": 2.0 * I * 64 * dmax / (1e-3 * t_big) / 1e12})
+    return head, out
+
+
 def main():
     args = parse()
     # stdout carries exactly ONE JSON line: route everything else a library may print there (e.g. NCCL's version
@@ -219,7 +316,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ds, name = build_dataset(args.workload)
     conf = Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH,
-                     "lazy_tables": bool(args.lazy_tables), "fused_layer_grad": bool(args.fused_layer_grad)})
+                     "lazy_tables": bool(args.lazy_tables), "fused_layer_grad": bool(args.fused_layer_grad),
+                     "linear_schedule": bool(args.linear)})
     torch.manual_seed(2022)
     rowshard = world > 1 and args.parallel == "rowshard"
     if rowshard:
@@ -234,24 +332,25 @@ def main():
     # data-parallel: every rank draws its own triples; row-sharded: all ranks work on the same batch
     sampler_dev = PairwiseSamplerV2(ds, batch_size=BATCH, mode="device", device=dev, seed=2022 + (0 if rowshard else rank))
     sampler_host = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat")
-    n_steps = args.warmup + args.steps
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm: triples already in HBM ---------------------------------------------
-    u, p, n = sampler_dev.sample_epoch_device(n_steps * BATCH)
-    batches = [(u[i * BATCH:(i + 1) * BATCH], p[i * BATCH:(i + 1) * BATCH], n[i * BATCH:(i + 1) * BATCH]) for i in range(n_steps)]
+    # ---- device arm: every step = draw its batch on the device (Philox, inside the graph) + fwd + bwd + Adam ---------------
     use_graph = bool(args.cuda_graph) and not rowshard
-    runner = model.make_graphed_step() if use_graph else None
+    runner = model.make_graphed_step(device_sampler=sampler_dev) if use_graph else None
+    bu, bp, bn = (torch.empty(BATCH, dtype=torch.int64, device=dev) for _ in range(3))
 
-    def step(b):
-        return runner(*b) if runner is not None else model.train_step(*b)
+    def step_sampled():
+        if runner is not None:
+            return runner()
+        sampler_dev.sample_batch_device(model._adam.step_dev, bu, bp, bn)
+        return model.train_step(bu, bp, bn)
 
-    for b in batches[:args.warmup]:
-        step(b)
+    for _ in range(args.warmup):
+        step_sampled()
     sync_all()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -259,12 +358,12 @@ def main():
     _lib.CALLS["launches"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for b in batches[args.warmup:]:
-        loss = step(b)
+    for _ in range(args.steps):
+        loss = step_sampled()
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    log(f"[bench] rank {rank}: device-resident arm {ms / args.steps:.3f} ms/step")
+    log(f"[bench] rank {rank}: device arm {ms / args.steps:.3f} ms/step")
     launches = _lib.CALLS["launches"] if runner is None else runner.launches_per_step * args.steps
     tms = torch.tensor([ms], device=dev)
     if world > 1:
@@ -274,36 +373,80 @@ def main():
     value = units * BATCH * args.steps / (ms / 1e3)
     final_loss = float(loss)
 
-    # ---- e2e arm: host triples, H2D + loss D2H every step ----------------------------------------
-    hu, hp, hn = sampler_host.sample_epoch_host()
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a[:n_steps * BATCH])).pin_memory()
-    hu, hp, hn = pin(hu), pin(hp), pin(hn)
-    du, dp_, dn = (torch.empty(BATCH, dtype=torch.int64, device=dev) for _ in range(3))
+    # ---- sampler throughput on its own --------------------------------------------------------------------
+    samp = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        hu_, hp_, hn_ = sampler_host.sample_epoch_host()
+        t_draw = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        perm = np.random.permutation(hu_.size)
+        _ = hu_[perm], hp_[perm], hn_[perm]
+        t_shuf = time.perf_counter() - t0
+        sampler_dev.sample_epoch_device()
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        sampler_dev.sample_epoch_device()
+        b_.record()
+        torch.cuda.synchronize()
+        samp = {"compat_triples_per_s": hu_.size / (t_draw + t_shuf), "compat_draw_s": t_draw, "compat_shuffle_s": t_shuf,
+                "device_triples_per_s": hu_.size / (a_.elapsed_time(b_) / 1e3), "epoch_triples": int(hu_.size),
+                "note": "compat = bit-exact replay of the reference's libc rand() stream (sequential by construction) + one numpy "
+                        "permutation; device = Philox4x32-10, one thread per triple"}
+        del hu_, hp_, hn_, perm
 
-    def e2e_step(i):
-        sl = slice(i * BATCH, (i + 1) * BATCH)
-        du.copy_(hu[sl], non_blocking=True)
-        dp_.copy_(hp[sl], non_blocking=True)
-        dn.copy_(hn[sl], non_blocking=True)
-        return float(step((du, dp_, dn)))  # .item(): the D2H read main.py:102 does
+    # ---- e2e arm: main.py:92-102 as written - host sampler, per-batch H2D, loss.item() every step ---------------------------
+    runner_h = model.make_graphed_step() if use_graph else None
+    steps_per_epoch = len(sampler_host)
 
-    for i in range(args.warmup):
-        e2e_step(i)
+    def run_epochs(sampler, n_epochs):
+        n = 0
+        for _ in range(n_epochs):
+            for hu, hp, hn in sampler:
+                if hu.numel() != BATCH:           # the short last batch of an epoch (drop_last=False): eager step
+                    float(model.train_step(hu, hp, hn))
+                else:
+                    float(runner_h(hu, hp, hn) if runner_h is not None else model.train_step(hu, hp, hn))   # .item(): main.py:102
+                n += int(hu.numel())
+        return n
+
+    e2e_epochs = max(1, -(-args.steps // steps_per_epoch))
+    np.random.seed(2022 + (0 if rowshard else rank))
+    sampler_pf = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat", prefetch=True, pin=True)
+    sampler_pf.rng.seed(1 + (0 if rowshard else rank))        # replicas draw different triples
+    run_epochs(sampler_pf, 1)                     # warm-up epoch; leaves the next epoch being sampled on the thread
     sync_all()
     t0 = time.perf_counter()
-    for i in range(args.warmup, n_steps):
-        e2e_step(i)
+    n_e2e = run_epochs(sampler_pf, e2e_epochs)
     sync_all()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev)
+    if sampler_pf._next is not None:
+        sampler_pf._next[0].join()
+    sampler_se = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat", prefetch=False, pin=True)
+    sampler_se.rng.seed(101 + (0 if rowshard else rank))
+    sync_all()
+    t0 = time.perf_counter()
+    n_ser = run_epochs(sampler_se, e2e_epochs)
+    sync_all()
+    ser_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, ser_s], device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = units * BATCH * args.steps / float(te)
-    log(f"[bench] rank {rank}: e2e arm done")
+    e2e_value = units * n_e2e / float(te[0])
+    e2e_serial = units * n_ser / float(te[1])
+    e2e_steps = e2e_epochs * steps_per_epoch
+    log(f"[bench] rank {rank}: e2e arm done ({e2e_steps} steps: {1e3 * float(te[0]) / e2e_steps:.3f} ms/step overlapped, "
+        f"{1e3 * float(te[1]) / e2e_steps:.3f} serial)")
+
+    # fixed batches for the per-kernel profile and the reference-schedule comparison
+    u, p, n = sampler_dev.sample_epoch_device((args.warmup + args.steps) * BATCH)
+    n_steps = args.warmup + args.steps
+    batches = [(u[i * BATCH:(i + 1) * BATCH], p[i * BATCH:(i + 1) * BATCH], n[i * BATCH:(i + 1) * BATCH]) for i in range(n_steps)]
 
     # ---- per-kernel CUDA-event profile + roofline of the wide SpMM -------------------------------
     kernels = {}
-    roofline = None
+    roofline, rooflines = None, []
     if rank == 0 and not rowshard:
         # rank-local, serialised launches, NO collective (the other ranks do not take part in this pass)
         dp_saved, model._dp = getattr(model, "_dp", False), False
@@ -319,47 +462,7 @@ def main():
         nprof = min(5, args.steps)
         kernels = {k: {"ms_per_step": round(sum(v) / nprof, 4), "launches_per_step": len(v) // nprof,
                        "avg_us": round(1e3 * sum(v) / len(v), 2)} for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))}
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        Fw = 64 * (1 + len(model.mods))
-        g = model.graph
-        # dominant kernel: spmm_seg_kernel<Fw> (whole rows).  Timed on the launches that are exactly ONE such kernel - the
-        # user-row half has no split rows, so its event pair brackets a single launch on the launching stream.
-        alg_of = lambda h: float(h.nnz * 8 + (h.n_rows + 1) * 4 + (h.n_cols + h.n_rows) * Fw * 4)
-        half = g.ui if g.ui.n_heavy_seg == 0 else (g.iu if g.iu.n_heavy_seg == 0 else None)
-        tag = f"spmm{Fw}w"
-        if tag in agg and half is not None:
-            alg, what = alg_of(half), f"spmm_seg_kernel<{Fw}> (whole rows, {'user' if half is g.ui else 'item'}-row half)"
-        elif f"spmm{Fw}" in agg:
-            # both halves have split rows (kwai / movielens shapes): the unmasked wide SpMM runs once per half and step, each
-            # as a whole-row launch + a split-row launch side by side; one event pair brackets the pair of launches
-            tag, alg = f"spmm{Fw}", 0.5 * (alg_of(g.ui) + alg_of(g.iu))
-            what = f"spmm_seg_kernel<{Fw}> (whole-row + split-row launch of one half, mean over the two halves)"
-        else:
-            tag = None
-        if tag is not None:
-            # algorithmic bytes per launch: nnz*(4+4) + (rows_out+1)*4 + (rows_in + rows_out)*F*4
-            avg_s = 1e-3 * sum(agg[tag]) / len(agg[tag])
-            ach = alg / avg_s / 1e9
-            traffic = None
-            try:   # DRAM bytes per wide launch from the committed ncu --set full capture (Tiktok shape only)
-                if args.workload == "tiktok":
-                    traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json")))["avg_wide_launch_bytes"]
-            except Exception:
-                pass
-            fam = sum(sum(v) for k, v in agg.items() if k.startswith("spmm"))
-            tot = sum(sum(v) for v in agg.values())
-            roofline = {"kernel": what, "bound": "hbm", "achieved": ach, "peak": peak,
-                        "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": which, "bytes_per_launch": alg,
-                        "avg_launch_us": 1e6 * avg_s, "launches_timed": len(agg[tag]),
-                        "share_of_step": sum(sum(v) for k, v in agg.items() if k.startswith(f"spmm{Fw}")) / tot,
-                        "spmm_family_share_of_step": fam / tot,
-                        "note": "operand slab is L2-resident: the kernel is bound by L2->SM gather bandwidth (measured ~10-11 TB/s "
-                                "of a ~12.4 TB/s L2 slice cap), not by HBM; see DESIGN.md 3.1"}
+        roofline, rooflines = rooflines_of(model, agg, args.workload, BATCH)
     clk = clocks.stop() if rank == 0 else None
     sync_all()
     if world > 1:   # the profile pass above stepped rank 0 only: put every replica back on the same weights
@@ -377,19 +480,38 @@ def main():
             users = users[:args.eval_users]
         kw = dict(test_users=users) if args.eval_users else {}
         evalr.evaluate(model, **kw)  # warm-up (device CSR upload, smem opt-in)
-        sync_all()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        a.record()
-        res, buf = evalr.evaluate(model, **kw)   # returns host ndarray: the D2H of the result is inside
-        b_.record()
-        sync_all()
-        wall = time.perf_counter() - t0
-        tm = torch.tensor([a.elapsed_time(b_) / 1e3, wall], device=dev)
-        if world > 1:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ev = {"value": len(users) / float(tm[0]), "unit": "users/s", "n_users": len(users), "e2e_value": len(users) / float(tm[1]),
-              "topk": TOPK, "predict_type": "TIE", "result": [float(x) for x in res]}
+
+        def timed_eval():
+            sync_all()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            res_, _ = evalr.evaluate(model, **kw)   # returns host ndarray: the D2H of the result is inside
+            b_.record()
+            sync_all()
+            tm = torch.tensor([a.elapsed_time(b_) / 1e3, time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return float(tm[0]), float(tm[1]), res_
+
+        # what main.py:111-127 does: evaluate right after training steps - the tables of the last forward are completed
+        # (masked layers over every row, modality blocks, fusion Linear + heads), normalised and split inside the timed call
+        step_sampled()
+        t_dev, t_wall, res = timed_eval()
+        c_dev, c_wall, _ = timed_eval()          # again without a step in between: cached tables
+        M_ = len(model.mods)
+        flops = 2.0 * len(users) * ds.num_items * 64 * ((1 + M_) * 3 + 3)      # fp16 hi/lo: 3 MMA terms per dot product; + row-mean pass
+        _, tfp, _ = load_peaks()
+        ev = {"value": len(users) / t_dev, "unit": "users/s", "n_users": len(users), "e2e_value": len(users) / t_wall,
+              "cached_tables_value": len(users) / c_dev, "ms": 1e3 * t_dev, "ms_cached_tables": 1e3 * c_dev,
+              "topk": TOPK, "predict_type": "TIE", "result": [float(x) for x in res],
+              "note": "value: evaluate() right after a training step, table completion included; cached_tables_value: a second "
+                      "evaluate() of the same forward",
+              "roofline": {"kernel": "rank_tc_kernel (tcgen05 kind::f16 hi/lo pairs; row-mean pass + TIE pass)", "bound": "tensor",
+                           "achieved": flops / c_dev / 1e12, "peak": tfp, "unit": "TFLOP/s", "frac": flops / c_dev / 1e12 / tfp,
+                           "flops_per_launch": flops,
+                           "note": "MUFU-bound (1+M exp + 1 rcp per user-item pair), see DESIGN.md 3.6 and profiles/ for the "
+                                   "tensor-pipe / XU-pipe percentages of the ncu capture"}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # reported at N=1 only (the other ranks would idle for it)
@@ -417,25 +539,52 @@ def main():
         d1.record()
         torch.cuda.synchronize()
         dms = d0.elapsed_time(d1) / args.steps
-        dense = {"ms_per_step": dms, "value": BATCH / (dms / 1e3), "unit": UNIT, "final_loss": float(ld),
-                 "note": "lazy_tables=False: all rows of the last layer, fusion + heads over all U+I rows each step"}
+        _lib.PROFILE["on"], _lib.PROFILE["events"] = True, []
+        for b in batches[args.warmup:args.warmup + 3]:
+            md.train_step(*b)
+        torch.cuda.synchronize()
+        _lib.PROFILE["on"] = False
+        agg_d = {}
+        for tag, a, b_ in _lib.PROFILE["events"]:
+            agg_d.setdefault(tag, []).append(a.elapsed_time(b_))
+        rl_d, rls_d = rooflines_of(md, agg_d, args.workload, BATCH, prefix="reference schedule: ")
+        dense = {"ms_per_step": dms, "value": BATCH / (dms / 1e3), "unit": UNIT, "final_loss": float(ld), "roofline": rl_d,
+                 "note": "lazy_tables=False: the reference's schedule - four graphs propagated (64 + 256 wide), every row of every "
+                         "layer, projections over all items, fusion + heads over all U+I rows, every step"}
+        rooflines += rls_d
         del md, rd
 
     if rank == 0:
+        N_ = ds.num_users + ds.num_items
+        if model.linear:
+            ws_mb = (N_ * 64 * 4 * (1 + 2 + 1 + model.n_layers + 2) + 2 * 3 * BATCH * model._lin_Ktot * 4) / 1e6
+            sched = ("linear: the modality graphs by linearity from ONE 64-wide propagation + constant Zbar tables (built once); "
+                     "layers L-1 / L and the fusion / head tables only at the rows the loss reads; identical loss / gradients / "
+                     "parameters up to fp32 reassociation; full tables completed at evaluation")
+        else:
+            ws_mb = 900.0
+            sched = ("row-sparse: loss-dead rows of the last two layers and of the fusion/head tables are not computed in the step"
+                     if args.lazy_tables else "reference: every row of every layer and table, every step")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": ("strong" if rowshard else "weak"), "vs_baseline": None,
-                "dtype": "f32 (tf32 tensor-core projections, 3xTF32 fusion/heads)", "data": "synthetic",
+                "dtype": "f32 (fp32 propagation / loss / Adam; TF32 tensor-core modality GEMMs, 3xTF32 fusion + heads)", "data": "synthetic",
                 "config": {"workload": f"{args.workload}-shape EliMRec train step (sample + fwd + bwd + Adam), batch {BATCH}/GPU, "
                                        f"layer_num 3, recdim 64, U={ds.num_users} I={ds.num_items} E_train={ds.train_matrix.nnz}",
                            "parallelism": (f"rowshard{world} (all-gather per GCN layer)" if rowshard else f"dp{world}") if world > 1 else "single",
-                           "l2_policy": "per-step working set (features + propagation slabs, >0.9 GB) exceeds the 126 MB L2; no flush",
+                           "l2_policy": f"no flush: the per-step working set ({ws_mb:.0f} MB: embedding tables + Adam moments + "
+                                        "propagation / gradient slabs + gathered constant rows) exceeds the 126 MB L2",
                            "cuda_graph": bool(runner is not None), "lazy_tables": bool(args.lazy_tables),
-                           "row_sparse_step": ("loss-dead rows of the last two layers and of the fusion/head tables are not computed "
-                                               "in the step (identical loss / gradients / parameters); full tables are completed "
-                                               "at evaluation" if args.lazy_tables else "off"), "sampler": "device Philox (value) / compat libc stream (e2e)"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "eval": ev,
-                "kernels": kernels, "final_loss": final_loss, "dense_schedule": dense}
+                           "schedule": sched,
+                           "triples_per_optimizer_step": BATCH * units,
+                           "sampler": "value: device Philox sampler inside every step's graph; e2e: host compat sampler (bit-exact "
+                                      "libc stream) + numpy shuffle, whole epochs, inside the timed region"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4,
+                        "steps": e2e_steps, "epochs": e2e_epochs, "serial_sampler_value": e2e_serial,
+                        "note": "main.py:92-102 loop over whole epochs; value: next epoch sampled on a prefetch thread while this one "
+                                "trains; serial_sampler_value: each epoch sampled + shuffled before its first step (as the "
+                                "reference does), both inside the timed region"},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu,
+                "eval": ev, "sampler": samp, "kernels": kernels, "final_loss": final_loss, "dense_schedule": dense}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -101,6 +101,7 @@ _SIGS = {
     "elimrec_adam_apply": [i64, vp, vp, i64, i64, vp, vp, vp, f64, f64, f32, f32, vp],
     "elimrec_sample_epoch_compat": [vp, i32, vp, vp, vp, i32, i64, vp, vp, vp],
     "elimrec_sample_triples_device": [C.c_uint64, C.c_uint64, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp],
+    "elimrec_sample_batch_device": [C.c_uint64, C.c_uint64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp],
     "elimrec_row_normalize": [i64, vp, vp, vp],
     "elimrec_rank_rowmean": [C.POINTER(RankTables), i32, vp, vp, vp],
     "elimrec_rank_scores": [C.POINTER(RankTables), i32, vp, vp, vp, vp],

@@ -114,12 +114,17 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void sample_triples_kernel(unsigned long long seed, unsigned long long epoch, long long n, int n_tu,
+// batch_index (may be NULL): device-resident batch counter; triple `t` of this launch is sample number
+// (*batch_index) * n + t of the epoch's stream, so a CUDA graph that contains this launch draws a NEW batch at every replay
+// (the counter is the optimizer's step counter, advanced by elimrec_adam_tick at the end of each step).
+__global__ void sample_triples_kernel(unsigned long long seed, unsigned long long epoch, const long long* __restrict__ batch_index,
+                                      long long n, int n_tu,
                                       const int* __restrict__ user_ids, const long long* __restrict__ row_ptr,
                                       const int* __restrict__ items, int num_items, long long* __restrict__ ou,
                                       long long* __restrict__ op, long long* __restrict__ on) {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long k = (batch_index != nullptr ? *batch_index * n : 0) + t;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t c0 = (uint32_t)k, c1 = (uint32_t)((unsigned long long)k >> 32), c3 = (uint32_t)epoch;
     uint32_t o[4];
@@ -143,9 +148,9 @@ __global__ void sample_triples_kernel(unsigned long long seed, unsigned long lon
             if (!(lo < deg && it[lo] == a)) ng = a;
         }
     }
-    ou[k] = user_ids[s];
-    op[k] = p;
-    on[k] = ng;
+    ou[t] = user_ids[s];
+    op[t] = p;
+    on[t] = ng;
 }
 
 }  // namespace
@@ -157,8 +162,21 @@ ELIMREC_API int elimrec_sample_triples_device(uint64_t seed, uint64_t epoch, int
     ER_CHECK_ARG(n_tu > 0 && num_items > 0, "empty input");
     if (num_samples <= 0) return 0;
     sample_triples_kernel<<<(unsigned)((num_samples + 255) / 256), 256, 0, er_stream(stream)>>>(
-        seed, epoch, num_samples, n_tu, user_ids, (const long long*)row_ptr, items, num_items, (long long*)out_users,
+        seed, epoch, nullptr, num_samples, n_tu, user_ids, (const long long*)row_ptr, items, num_items, (long long*)out_users,
         (long long*)out_pos, (long long*)out_neg);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_sample_batch_device(uint64_t seed, uint64_t epoch, const int64_t* batch_index_dev, int64_t batch_size,
+                                            int32_t n_tu, const int32_t* user_ids, const int64_t* row_ptr, const int32_t* items,
+                                            int32_t num_items, int64_t* out_users, int64_t* out_pos, int64_t* out_neg,
+                                            elimrec_stream_t stream) {
+    ER_CHECK_ARG(n_tu > 0 && num_items > 0 && batch_index_dev != nullptr, "empty input");
+    if (batch_size <= 0) return 0;
+    sample_triples_kernel<<<(unsigned)((batch_size + 255) / 256), 256, 0, er_stream(stream)>>>(
+        seed, epoch, (const long long*)batch_index_dev, batch_size, n_tu, user_ids, (const long long*)row_ptr, items, num_items,
+        (long long*)out_users, (long long*)out_pos, (long long*)out_neg);
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -978,7 +978,10 @@ class EliMRec(LinearSchedule, BasicModel):
         return {n: views[n] for n in grads}      # heads the loss does not use stay without a gradient
 
     # -- whole step as one CUDA graph (launch-bound otherwise: ~60 small launches per step) ------------
-    def make_graphed_step(self, batch_size=None):
+    def make_graphed_step(self, batch_size=None, device_sampler=None):
+        """The whole training step as a CUDA graph.  ``device_sampler`` (a ``PairwiseSamplerV2``): the graph starts with the
+        Philox batch sampler reading its position from the optimizer's device step counter, so ``runner()`` with no
+        arguments draws a new batch and trains on it - sampling + forward + backward + Adam in one replay."""
         B = int(batch_size or self.config["batch_size"])
         if self._adam is None:
             self.make_optimizer()
@@ -1010,10 +1013,16 @@ class EliMRec(LinearSchedule, BasicModel):
         dp = getattr(self, "_dp", False)
         dead = self._dead_params()
         before = CALLS["launches"]
+
+        def draw():
+            if device_sampler is not None:
+                device_sampler.sample_batch_device(self._adam.step_dev, su, sp_, sn)
+
         single = bool(_cfg(self.config, "dp_single_graph", False))
         if not dp:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
+                draw()
                 loss = self.train_step(su, sp_, sn)
             graphs = (graph,)
         elif single:
@@ -1023,6 +1032,7 @@ class EliMRec(LinearSchedule, BasicModel):
             bucket = self._ws["cache"]["bucket"]
             with torch.cuda.graph(graph):
                 with torch.no_grad():
+                    draw()
                     loss = self._forward(su, sp_, sn)
                     bucket.pack(self._backward(None, split=True), bucket.head_names)
                     w1 = bucket.all_reduce_mean_part(0, async_op=True)
@@ -1045,6 +1055,7 @@ class EliMRec(LinearSchedule, BasicModel):
             bucket = self._ws["cache"]["bucket"]
             with torch.cuda.graph(gA):
                 with torch.no_grad():
+                    draw()
                     loss = self._forward(su, sp_, sn)
                     bucket.pack(self._backward(None, split=True), bucket.head_names)
             with torch.cuda.graph(gB, pool=gA.pool()):
@@ -1062,9 +1073,17 @@ class EliMRec(LinearSchedule, BasicModel):
         class _Runner:
             launches_per_step = n_launch
 
-            def __call__(self, users, pos, neg):
-                u, p, n = model._triples(users, pos, neg)
-                su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
+            triples = (su, sp_, sn)          # the batch the last replay trained on
+
+            def __call__(self, users=None, pos=None, neg=None):
+                if users is None:
+                    if device_sampler is None:
+                        raise ElimrecError("runner() without a batch needs make_graphed_step(device_sampler=...)")
+                else:
+                    if device_sampler is not None:
+                        raise ElimrecError("this runner samples its own batches; call it without arguments")
+                    u, p, n = model._triples(users, pos, neg)
+                    su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
                 graphs[0].replay()
                 if dp:
                     bucket = model._ws["cache"]["bucket"]

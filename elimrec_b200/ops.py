@@ -412,3 +412,10 @@ def sample_triples_device(seed, epoch, n, user_ids, row_ptr, items, num_items, o
     call("elimrec_sample_triples_device", seed, epoch, n, user_ids.numel(), ptr(user_ids, torch.int32),
          ptr(row_ptr, torch.int64), ptr(items, torch.int32), num_items, ptr(ou, torch.int64), ptr(op, torch.int64),
          ptr(on, torch.int64), stream())
+
+
+def sample_batch_device(seed, epoch, batch_index_dev, n, user_ids, row_ptr, items, num_items, ou, op, on):
+    """one batch of the epoch's Philox stream, its position read from a device counter (graph-replayable)"""
+    call("elimrec_sample_batch_device", seed, epoch, ptr(batch_index_dev, torch.int64), n, user_ids.numel(),
+         ptr(user_ids, torch.int32), ptr(row_ptr, torch.int64), ptr(items, torch.int32), num_items, ptr(ou, torch.int64),
+         ptr(op, torch.int64), ptr(on, torch.int64), stream())

@@ -8,10 +8,14 @@
     ``set_seed`` yields the same batches.  Vectorised: no per-user / per-sample Python loops.
     ``mode='device'`` draws the epoch on the GPU (Philox4x32-10, same distribution) and yields device
     tensors - the throughput mode; its numpy restatement is ``oracle/philox_sampler.py``.
+    ``prefetch=True`` (compat mode, off by default): the NEXT epoch is sampled and shuffled on a host thread while the
+    current one trains (the C sampler releases the GIL); ``pin=True`` yields pinned torch tensors so the per-batch
+    host->device copies are asynchronous.  Both keep the stream: the draws happen in the same order, just earlier.
 """
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -44,7 +48,7 @@ def _train_csr(user_pos_dict: dict):
 
 class PairwiseSamplerV2:
     def __init__(self, dataset, neg_num=1, batch_size=1024, shuffle=True, drop_last=False, mode="compat",
-                 device=None, seed=2022):
+                 device=None, seed=2022, prefetch=False, pin=False):
         if neg_num <= 0:
             raise ValueError("'neg_num' must be a positive integer.")
         if neg_num != 1:
@@ -63,6 +67,8 @@ class PairwiseSamplerV2:
         self.seed = seed
         self.device = device
         self._dev = None
+        self.prefetch, self.pin = bool(prefetch), bool(pin)
+        self._next = None           # (thread, result holder) of the epoch being sampled ahead
 
     def __len__(self):
         n = self.num_trainings
@@ -89,13 +95,58 @@ class PairwiseSamplerV2:
         ops.sample_triples_device(self.seed, self.epoch, n, *self._dev, self.item_num, ou, op, on)
         return ou, op, on
 
+    def sample_batch_device(self, batch_index_dev, ou, op, on):
+        """One batch (``ou.numel()`` triples) of the current epoch's device stream; its position in the stream is read from
+        the device counter ``batch_index_dev`` (int64[1]) - capturable in a CUDA graph, a new batch at every replay."""
+        dev = ou.device
+        if self._dev is None:
+            self._dev = (torch.from_numpy(self.users).to(dev), torch.from_numpy(self.ptr).to(dev),
+                         torch.from_numpy(self.items).to(dev))
+        ops.sample_batch_device(self.seed, self.epoch, batch_index_dev, ou.numel(), *self._dev, self.item_num, ou, op, on)
+
+    def _host_epoch(self):
+        """sample + shuffle one epoch on the host (the two steps of data/sampler.py:336-344), optionally into pinned memory"""
+        u, p, n = self.sample_epoch_host()
+        total = u.size
+        perm = np.random.permutation(total) if self.shuffle else None
+        if self.pin:
+            out = [torch.empty(total, dtype=torch.int64).pin_memory() for _ in range(3)]
+            for src, dst in zip((u, p, n), out):
+                if perm is None:
+                    dst.numpy()[:] = src
+                else:
+                    np.take(src, perm, out=dst.numpy())
+            return tuple(out), total
+        if perm is not None:
+            u, p, n = u[perm], p[perm], n[perm]
+        return (u, p, n), total
+
+    def _start_prefetch(self):
+        box = {}
+
+        def work():
+            try:
+                box["epoch"] = self._host_epoch()
+            except BaseException as exc:      # surfaced by the consumer
+                box["error"] = exc
+        t = threading.Thread(target=work, daemon=True)
+        t.start()
+        self._next = (t, box)
+
     def __iter__(self):
         bs = self.batch_size
         if self.mode == "compat":
-            u, p, n = self.sample_epoch_host()
-            total = u.size
-            perm = np.random.permutation(total) if self.shuffle else np.arange(total)
-            u, p, n = u[perm], p[perm], n[perm]
+            if self._next is not None:
+                t, box = self._next
+                t.join()
+                self._next = None
+                if "error" in box:
+                    raise box["error"]
+                (u, p, n), total = box["epoch"]
+            else:
+                (u, p, n), total = self._host_epoch()
+            if self.prefetch:
+                self._start_prefetch()
         else:
             u, p, n = self.sample_epoch_device()
             total = u.numel()  # i.i.d. draws: already in random order, no shuffle pass needed

@@ -322,6 +322,14 @@ int elimrec_sample_triples_device(uint64_t seed, uint64_t epoch, int64_t num_sam
                                   int32_t num_items, int64_t* out_users, int64_t* out_pos, int64_t* out_neg,
                                   elimrec_stream_t stream);
 
+/* One BATCH of the same stream from inside a CUDA graph: triple t of the launch is sample (*batch_index_dev) * batch_size + t
+ * of epoch `epoch` (identical to the corresponding slice of elimrec_sample_triples_device).  batch_index_dev is a device
+ * counter the caller advances between replays - the optimizer's step counter (elimrec_adam_tick) does it for free. */
+int elimrec_sample_batch_device(uint64_t seed, uint64_t epoch, const int64_t* batch_index_dev, int64_t batch_size,
+                                int32_t n_train_users, const int32_t* user_ids, const int64_t* row_ptr, const int32_t* items,
+                                int32_t num_items, int64_t* out_users, int64_t* out_pos, int64_t* out_neg,
+                                elimrec_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * rank - replaces EliMRec.predict + general_cm_fusion (models/EliMRec.py:96-113,155-212), the
  * train-item masking loop (uni_evaluator.py:149-154) and cpp_evaluate_matrix / metric.h
