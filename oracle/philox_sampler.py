@@ -33,8 +33,9 @@ def _u64(hi, lo):
     return (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
 
 
-def sample_triples(seed, epoch, n, user_ids, row_ptr, items, num_items):
-    k = np.arange(n, dtype=np.uint64)
+def sample_triples(seed, epoch, n, user_ids, row_ptr, items, num_items, first=0):
+    """samples first .. first+n-1 of the epoch's stream (elimrec_sample_batch_device: first = batch index * batch size)"""
+    k = np.arange(first, first + n, dtype=np.uint64)
     c0, c1 = (k & MASK).astype(np.uint32), (k >> np.uint64(32)).astype(np.uint32)
     c3 = np.full(n, epoch & 0xFFFFFFFF, dtype=np.uint32)
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF

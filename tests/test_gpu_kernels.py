@@ -562,3 +562,87 @@ def test_rank_tc_matches_exact_path(dev, mode, n_mod):
     ref = _ref_scores(fu, fi, su, si, users, mode).numpy()
     exact, explained, bad = topk_sets_match(idx_t.cpu().numpy(), ref, [train[int(u)] for u in users], K, tol=2e-6)
     assert bad == 0 and float(same) > 0.97, (float(same), exact, explained, bad)
+
+
+# ---- round 2: kernels of the linear schedule and the graph-replayable batch sampler -----------------------------------------
+@pytest.mark.parametrize("n_mod,L", [(3, 3), (1, 2), (0, 1), (3, 8)])
+def test_lin_assemble_and_seed_match_restatement(dev, n_mod, L):
+    """elimrec_lin_assemble / elimrec_lin_seed against the few-line torch statements in tests/sim_ops.py (instance rows with
+    repeats, all-rows mode, accumulate on / off, strided tables)."""
+    import sim_ops
+    from elimrec_b200 import ops
+    U, I, Fw = 50, 70, 64 * (1 + max(n_mod, 1))
+    g = torch.Generator().manual_seed(L)
+    tabs = [(torch.randn(U, 64, generator=g), torch.randn(I, 96, generator=g)[:, 16:80]) for _ in range(L + 1)]
+    rows = torch.randint(0, U + I, (333,), generator=g, dtype=torch.int32)
+    rows[:7] = rows[0]
+    for acc in (False, True):
+        for rr, n_rows in ((rows, None), (None, U + I)):
+            base = torch.randn(rows.numel() if rr is not None else U + I, Fw, generator=g)
+            want = base.clone()
+            sim_ops.lin_assemble(rr, U, sim_ops.lin_layers(tabs), 0.25, n_mod, acc, want, n_rows=n_rows)
+            got = base.to(dev)
+            dt = [(a.to(dev), b.to(dev)) for a, b in tabs]
+            dt = [(a, torch.cat([torch.zeros(I, 16, device=dev), b, torch.zeros(I, 16, device=dev)], 1)[:, 16:80]) for a, b in dt]
+            ops.lin_assemble(rr.to(dev) if rr is not None else None, U, ops.lin_layers(dt), 0.25, n_mod, acc, got, n_rows=n_rows)
+            assert rel_err(got, want) < 1e-6
+    dO = torch.randn(rows.numel(), Fw, generator=g)
+    for layer in range(L + 1):
+        want = torch.randn(U + I, 64, generator=g)
+        got = want.to(dev)
+        sim_ops.lin_seed(rows, U, layer, dO, n_mod, 0.25, want)
+        ops.lin_seed(rows.to(dev), U, layer, dO.to(dev), n_mod, 0.25, got)
+        assert rel_err(got, want) < 2e-6          # atomics: order of the repeated rows
+
+
+def test_pack_proj_weights_and_axpy(dev):
+    from elimrec_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    items, want = [], []
+    for dm in (16, 100, 768):
+        kp = ((dm + 1 + 3) // 4) * 4
+        W, b = torch.randn(64, dm, generator=g), torch.randn(64, generator=g)
+        dst = torch.full((64, kp), float("nan"), device=dev)
+        items.append((W.to(dev), b.to(dev), dst))
+        w = torch.zeros(64, kp)
+        w[:, :dm], w[:, dm] = W, b
+        want.append(w)
+    ops.pack_proj_weights(items, False)
+    for (_, _, dst), w in zip(items, want):
+        assert torch.equal(dst.cpu(), w)
+    ops.pack_proj_weights(items, True)
+    for (_, _, dst), w in zip(items, want):
+        d = dst.cpu()
+        assert (d.view(torch.int32) & 0x1FFF).eq(0).all() and rel_err(d, w) < 2 ** -11      # TF32: 10 mantissa bits, to nearest
+    X, Y = torch.randn(300, 132, generator=g), torch.randn(300, 260, generator=g)
+    for acc in (True, False):
+        y = Y.to(dev)
+        ops.axpy_2d(X.to(dev)[:, 4:], y[:, 8:], 300, 120, 0.25, accumulate=acc)
+        ref = Y.clone()
+        ref[:, 8:128] = (ref[:, 8:128] if acc else 0) + 0.25 * X[:, 4:124]
+        assert rel_err(y, ref) < 1e-7
+
+
+def test_batch_sampler_is_a_slice_of_the_epoch_stream(dev):
+    """elimrec_sample_batch_device(batch index on the device) == the matching slice of elimrec_sample_triples_device == the
+    numpy restatement (oracle/philox_sampler.py), bit for bit."""
+    from elimrec_b200 import ops
+    from oracle import philox_sampler
+    rng = np.random.default_rng(3)
+    U, I, B = 200, 300, 96
+    deg = rng.integers(1, 12, U)
+    ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    items = np.concatenate([np.sort(rng.choice(I, d, replace=False)) for d in deg]).astype(np.int32)
+    uid = np.arange(U, dtype=np.int32)
+    d = lambda a: torch.from_numpy(a).to(dev)
+    eu, ep, en = (torch.empty(5 * B, dtype=torch.int64, device=dev) for _ in range(3))
+    ops.sample_triples_device(11, 2, 5 * B, d(uid), d(ptr), d(items), I, eu, ep, en)
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    for step in (0, 3, 4):
+        ctr.fill_(step)
+        bu, bp, bn = (torch.empty(B, dtype=torch.int64, device=dev) for _ in range(3))
+        ops.sample_batch_device(11, 2, ctr, B, d(uid), d(ptr), d(items), I, bu, bp, bn)
+        sl = slice(step * B, (step + 1) * B)
+        assert torch.equal(bu, eu[sl]) and torch.equal(bp, ep[sl]) and torch.equal(bn, en[sl])
+        wu, wp, wn = philox_sampler.sample_triples(11, 2, B, uid, ptr, items, I, first=step * B)
+        assert np.array_equal(bu.cpu().numpy(), wu) and np.array_equal(bp.cpu().numpy(), wp) and np.array_equal(bn.cpu().numpy(), wn)
