@@ -78,6 +78,7 @@ _SIGS = {
     "elimrec_lin_assemble": [i64, vp, i32, C.POINTER(LinLayers), f32, i32, i32, vp, i64, vp],
     "elimrec_lin_seed": [i32, vp, i32, i32, vp, i64, i32, f32, vp, i64, vp],
     "elimrec_pack_proj_weights": [i32, C.POINTER(PackProj), i32, vp],
+    "elimrec_split3_rows": [i64, i32, vp, i64, vp, i64, i32, vp],
     "elimrec_axpy_2d": [i64, i32, f32, vp, i64, vp, i64, i32, vp],
     "elimrec_gemm": [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, vp, vp, vp],
     "elimrec_colsum": [i64, i64, vp, i64, vp, vp, i32, vp, vp],

@@ -119,7 +119,44 @@ __global__ void axpy_2d_kernel(long long n_rows, int width4, float scale, const 
     *y = v;
 }
 
+// 3xTF32 by concatenation: dst = [hi ; hi ; lo] (pattern 0) or [hi ; lo ; hi] (pattern 1) of src, hi = rna_tf32(x),
+// lo = rna_tf32(x - hi).  A TF32 GEMM that reduces over the 3n stacked rows of a pattern-0 and a pattern-1 operand computes
+// hi*hi + hi*lo + lo*hi: fp32-class accuracy from the plain TF32 weight-gradient kernel.
+__global__ void split3_kernel(long long n_rows, int width4, const float* __restrict__ src, long long lds,
+                              float* __restrict__ dst, long long ldd, int pattern) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t / width4;
+    const int c = (int)(t % width4) * 4;
+    if (r >= n_rows) return;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(src + r * lds + c));
+    float4 hi, lo;
+    auto sp = [](float v, float& h, float& l) {
+        uint32_t a, b;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v));
+        h = __uint_as_float(a);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v - h));
+        l = __uint_as_float(b);
+    };
+    sp(x.x, hi.x, lo.x); sp(x.y, hi.y, lo.y); sp(x.z, hi.z, lo.z); sp(x.w, hi.w, lo.w);
+    float4* d0 = reinterpret_cast<float4*>(dst + r * ldd + c);
+    float4* d1 = reinterpret_cast<float4*>(dst + (r + n_rows) * ldd + c);
+    float4* d2 = reinterpret_cast<float4*>(dst + (r + 2 * n_rows) * ldd + c);
+    *d0 = hi;
+    *d1 = pattern ? lo : hi;
+    *d2 = pattern ? hi : lo;
+}
+
 }  // namespace
+
+ELIMREC_API int elimrec_split3_rows(int64_t n_rows, int width, const float* src, int64_t lds, float* dst, int64_t ldd,
+                                    int pattern, elimrec_stream_t stream) {
+    ER_CHECK_ARG(width % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && (pattern == 0 || pattern == 1), "bad shape");
+    if (n_rows <= 0 || width <= 0) return 0;
+    const long long threads = n_rows * (width / 4);
+    split3_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, er_stream(stream)>>>(n_rows, width / 4, src, lds, dst, ldd, pattern);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
 
 ELIMREC_API int elimrec_lin_assemble(int64_t n_rows, const int32_t* rows, int32_t num_users, const elimrec_lin_layers_t* layers,
                                      float scale, int n_mod, int accumulate, float* out, int64_t ldo,

@@ -28,6 +28,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from ._lib import ElimrecError
 
 D = 64
 
@@ -43,7 +44,11 @@ class LinearSchedule:
     def _lin_init(self):
         want = bool(_cfg(self.config, "linear_schedule", True))
         self.linear = bool(want and self.lazy_tables and not self._generic and not (self.tiktok and self.word_grad))
+        if self.proj_precision == "auto":
+            self.proj_precision = "x3" if self.linear else "tf32"
         if not self.linear:
+            if self.proj_precision == "x3":
+                raise ElimrecError("proj_precision='x3' needs the linear schedule; the slab schedules take 'tf32' or 'fp32'")
             return
         dims = [self._feat[m].shape[1] for m in self.mods]
         self._lin_Kp = [((d + 1 + 3) // 4) * 4 for d in dims]          # [X_m | 1 | 0-pad] : multiple of 4 floats (TMA)
@@ -102,6 +107,8 @@ class LinearSchedule:
         ws["H"] = [e(N, D), e(N, D)]                        # backward chain, ping-pong
         ws["E0"] = e(N, D)                                  # [E_u ; E_i] as THIS forward saw them (Adam overwrites the tables)
         ws["Wp"] = {m: e(D, kp) for m, kp in zip(self.mods, self._lin_Kp)}     # [W_m | b_m | 0] of this forward
+        if self.proj_precision == "x3":
+            ws["Wp_split"] = {m: (e(D, kp), e(D, kp)) for m, kp in zip(self.mods, self._lin_Kp)}   # its TF32 hi / lo parts
         # gradients of the small parameters, one flat buffer (what the data-parallel all-reduce sends in place): first the
         # packed projection gradients d[W_m | b_m] (weight and bias gradients are strided views of them), then the rest
         small = {n: p for n, p in self._params().items()
@@ -125,10 +132,21 @@ class LinearSchedule:
     def _lin_workspace_batch(self, ws, B):
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device_)
         ws["Zg"] = e(3 * B, self._lin_Ktot)                 # Zbar gathered at the instance rows
-        ws["lin_wgrad_ws"] = {m: e(max(1, ops.linear_tf32_wgrad_ws_floats(3 * B, kp))) for m, kp in zip(self.mods, self._lin_Kp)}
+        rows = 3 * B
+        if self.proj_precision == "x3":     # operands of the weight gradient as stacked TF32 hi / lo parts (elimrec_split3_rows)
+            rows = 9 * B
+            ws["Zg3"], ws["dO3"] = e(rows, self._lin_Ktot), e(rows, ws["F"])
+        ws["lin_wgrad_ws"] = {m: e(max(1, ops.linear_tf32_wgrad_ws_floats(rows, kp))) for m, kp in zip(self.mods, self._lin_Kp)}
 
     def _lin_tc(self):
         return self.proj_precision == "tf32"
+
+    def _lin_pack_weights(self, P, ws):
+        """[W_m | b_m | 0] of this forward (TF32-rounded in 'tf32' mode; hi / lo split by _prep_weights in 'x3' mode)"""
+        ops.pack_proj_weights([(P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach(), ws["Wp"][m]) for m in self.mods],
+                              self._lin_tc())
+        extra = [(ws["Wp"][m], *ws["Wp_split"][m]) for m in self.mods] if self.proj_precision == "x3" else []
+        self._prep_weights(P, ws, proj=False, extra=extra)
 
     def _lin_tables(self, ws, p0_u, p0_i):
         U = self.num_users
@@ -141,6 +159,10 @@ class LinearSchedule:
             ops.linear_tf32_fwd_multi([(Zrows[:, ko:ko + kp], ws["Wp"][m], None, out, D * (j + 1))
                                        for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff))],
                                       tag="lin_modal_tc")
+        elif self.proj_precision == "x3":
+            for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
+                hi, lo = ws["Wp_split"][m]
+                ops.linear_x3_fwd(Zrows[:, ko:ko + kp], hi, lo, None, out, col=D * (j + 1), tag="lin_modal_x3")
         else:
             ld = Zrows.stride(0)
             for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
@@ -158,9 +180,7 @@ class LinearSchedule:
         Ei = P["embedding_item.weight"].detach()
         mask, need2 = ws["mask"], ws["need2"]
         rows = ws["inst_rows"]
-        self._prep_weights(P, ws, proj=False)
-        ops.pack_proj_weights([(P[f"{m}_dense.weight"].detach(), P[f"{m}_dense.bias"].detach(), ws["Wp"][m]) for m in self.mods],
-                              self._lin_tc())
+        self._lin_pack_weights(P, ws)
         # side stream: instance rows and their masks, Zbar gathered at them and the modality GEMMs (none of it depends on the
         # propagation); a third stream keeps what tables completed later must use and zeroes the backward's seed rows
         side = ops.fork_side()
@@ -233,8 +253,14 @@ class LinearSchedule:
                 ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
                 ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
             Zg, ldz = ws["Zg"], ws["Zg"].stride(0)
+            if self.proj_precision == "x3":      # 3xTF32: hi*hi + hi*lo + lo*hi as ONE reduction over 9B stacked rows
+                ops.split3_rows(dOin, ws["dO3"], 3 * B, Fw, 0)
+                ops.split3_rows(Zg, ws["Zg3"], 3 * B, self._lin_Ktot, 1)
             for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
-                if self._lin_tc():
+                if self.proj_precision == "x3":
+                    ops.linear_tf32_wgrad(ws["dO3"], ws["Zg3"][:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
+                                          tag="lin_wgrad_x3")
+                elif self._lin_tc():
                     ops.linear_tf32_wgrad(dOin, Zg[:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
                                           tag="lin_wgrad_tc")
                 else:

@@ -126,10 +126,12 @@ class EliMRec(LinearSchedule, BasicModel):
         if self.fusion_mode not in FUSION_MODE:                 # EliMRec.py:171-210
             raise ElimrecError(f"s_fusion_mode={self.fusion_mode!r}: expected 'rubi', 'hm' or 'sum'")
         self.modality = _cfg(cfg, "modality", "vat")
-        # 'tf32': modal projections on the tcgen05 tensor cores (1e-3 parity class); 'fp32': exact FFMA path (1e-5)
-        self.proj_precision = _cfg(cfg, "proj_precision", "tf32")
-        if self.proj_precision not in ("tf32", "fp32"):
-            raise ElimrecError("proj_precision must be 'tf32' or 'fp32'")
+        # modal projections (v/a/t_dense): 'tf32' = tcgen05 tensor cores, TF32 operands (1e-3 parity class); 'fp32' = exact FFMA
+        # path (1e-5 class); 'x3' = 3xTF32 on the tensor cores (1e-5 class; linear schedule only, where the GEMM runs on the 3B
+        # instance rows and costs next to nothing).  Default 'auto': 'x3' with the linear schedule, else 'tf32'.
+        self.proj_precision = _cfg(cfg, "proj_precision", "auto")
+        if self.proj_precision not in ("auto", "tf32", "fp32", "x3"):
+            raise ElimrecError("proj_precision must be 'auto', 'tf32', 'x3' or 'fp32'")
         # fusion Linear + single-modal heads: 'x3' = 3xTF32 on the tensor cores (fp32-class accuracy), 'fp32' = FFMA
         self.fuse_precision = _cfg(cfg, "fuse_precision", "x3")
         if self.fuse_precision not in ("x3", "fp32"):
@@ -299,7 +301,7 @@ class EliMRec(LinearSchedule, BasicModel):
     # memory - is allocated once and shared by every batch size; PairwiseSamplerV2 has drop_last=False, so the last batch of
     # an epoch is short) and keys that describe the LAST forward
     _WS_PER_BATCH = ("B", "density", "terms", "inst_rows", "inst_grad", "O_inst", "dO_inst", "split_inst", "gemm_ws", "inst_ws",
-                     "inst_dummy", "F_c", "S_c", "c_users", "c_pos", "c_neg", "Zg", "lin_wgrad_ws")
+                     "inst_dummy", "F_c", "S_c", "c_users", "c_pos", "c_neg", "Zg", "lin_wgrad_ws", "Zg3", "dO3")
     _WS_PER_FORWARD = ("pre_last_layer", "last_layer", "seed_zeroed", "bw_pending")
 
     def _workspace(self, B):
@@ -850,9 +852,9 @@ class EliMRec(LinearSchedule, BasicModel):
         return ws["dE_u"], cur[U:]
 
     # projections over item rows [r0, r1) - the whole table on one GPU, the owned block when row-sharded
-    def _prep_weights(self, P, ws, proj=True):
+    def _prep_weights(self, P, ws, proj=True, extra=()):
         """TF32 rounding (projections) and hi/lo split (fusion, heads) of the small weights, one launch."""
-        prep = []
+        prep = list(extra)
         if self.mm_fusion_mode == "mean":
             G = ws["G"]
             ops.tie_blocks(P["embedding_user_after_GCN.weight"].detach(), ws["W_eff"]["u"], G, 1.0 / G)
@@ -987,6 +989,8 @@ class EliMRec(LinearSchedule, BasicModel):
             self.make_optimizer()
         dev = self.device_
         su, sp_, sn = (torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3))
+        if device_sampler is not None:
+            device_sampler.ensure_device(dev)
         model = self
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())

@@ -192,6 +192,11 @@ def pack_proj_weights(items, round_tf32):
     call("elimrec_pack_proj_weights", len(items), arr, int(round_tf32), stream())
 
 
+def split3_rows(src, dst, n_rows, width, pattern):
+    """dst[3 n_rows x width] = [hi ; hi ; lo] (pattern 0) / [hi ; lo ; hi] (pattern 1) TF32 parts of src"""
+    call("elimrec_split3_rows", n_rows, width, ptr(src, F32), src.stride(0), ptr(dst, F32), dst.stride(0), pattern, stream())
+
+
 def axpy_2d(X, Y, n_rows, width, scale=1.0, accumulate=True):
     """Y[:, :width] = [Y +] scale * X[:, :width]"""
     call("elimrec_axpy_2d", n_rows, width, scale, ptr(X, F32), X.stride(0), ptr(Y, F32), Y.stride(0), int(accumulate), stream())

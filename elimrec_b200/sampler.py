@@ -85,11 +85,17 @@ class PairwiseSamplerV2:
             raise _lib.ElimrecError(_lib.lib().elimrec_last_error().decode())
         return ou, op, on
 
-    def sample_epoch_device(self, n=None):
-        dev = self.device or torch.device("cuda", torch.cuda.current_device())
+    def ensure_device(self, dev=None):
+        """upload the train CSR once (must happen outside CUDA-graph capture)"""
         if self._dev is None:
+            dev = dev or self.device or torch.device("cuda", torch.cuda.current_device())
             self._dev = (torch.from_numpy(self.users).to(dev), torch.from_numpy(self.ptr).to(dev),
                          torch.from_numpy(self.items).to(dev))
+        return self._dev
+
+    def sample_epoch_device(self, n=None):
+        dev = self.device or torch.device("cuda", torch.cuda.current_device())
+        self.ensure_device(dev)
         n = self.num_trainings if n is None else n
         ou, op, on = (torch.empty(n, dtype=torch.int64, device=dev) for _ in range(3))
         ops.sample_triples_device(self.seed, self.epoch, n, *self._dev, self.item_num, ou, op, on)
@@ -98,10 +104,7 @@ class PairwiseSamplerV2:
     def sample_batch_device(self, batch_index_dev, ou, op, on):
         """One batch (``ou.numel()`` triples) of the current epoch's device stream; its position in the stream is read from
         the device counter ``batch_index_dev`` (int64[1]) - capturable in a CUDA graph, a new batch at every replay."""
-        dev = ou.device
-        if self._dev is None:
-            self._dev = (torch.from_numpy(self.users).to(dev), torch.from_numpy(self.ptr).to(dev),
-                         torch.from_numpy(self.items).to(dev))
+        self.ensure_device(ou.device)
         ops.sample_batch_device(self.seed, self.epoch, batch_index_dev, ou.numel(), *self._dev, self.item_num, ou, op, on)
 
     def _host_epoch(self):

@@ -169,6 +169,11 @@ typedef struct {
     int64_t Dm, Kp;
 } elimrec_pack_proj_t;
 int elimrec_pack_proj_weights(int n, const elimrec_pack_proj_t* tensors_host, int round_tf32, elimrec_stream_t stream);
+/* dst [3 n_rows x width] = [hi ; hi ; lo] (pattern 0) or [hi ; lo ; hi] (pattern 1) of src [n_rows x width], hi = rna_tf32(x),
+ * lo = rna_tf32(x - hi): elimrec_linear_tf32_wgrad over the 3 n_rows stacked rows of a pattern-0 dY and a pattern-1 X computes
+ * hi*hi + hi*lo + lo*hi, i.e. the weight gradient in the fp32 accuracy class on the TF32 tensor-core kernel */
+int elimrec_split3_rows(int64_t n_rows, int width, const float* src, int64_t lds, float* dst, int64_t ldd, int pattern,
+                        elimrec_stream_t stream);
 /* Y[r, 0:width] = [Y +] scale * X[r, 0:width]  (accumulating the constant Zbar tables, once per model) */
 int elimrec_axpy_2d(int64_t n_rows, int width, float scale, const float* X, int64_t ldx, float* Y, int64_t ldy, int accumulate,
                     elimrec_stream_t stream);

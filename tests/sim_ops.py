@@ -186,6 +186,20 @@ def pack_proj_weights(items, round_tf32):
         dst[:, dm] = b
 
 
+def split3_rows(src, dst, n_rows, width, pattern):
+    """(exact-fp32 simulation: hi = x, lo = 0 - the three stacked products then sum to x*y)"""
+    _log("split3")
+    z = torch.zeros(n_rows, width)
+    parts = [src[:n_rows, :width], z, src[:n_rows, :width]] if pattern else [src[:n_rows, :width], src[:n_rows, :width], z]
+    for b, part in enumerate(parts):
+        dst[b * n_rows:(b + 1) * n_rows, :width] = part
+
+
+def linear_x3_fwd(X, W_hi, W_lo, b, Y, col=0, tag="linear_x3"):
+    _log(tag)
+    Y[:, col:col + 64] = X @ (W_hi + W_lo).t() + (b if b is not None else 0)
+
+
 def axpy_2d(X, Y, n_rows, width, scale=1.0, accumulate=True):
     Y[:n_rows, :width] = (Y[:n_rows, :width] if accumulate else 0) + scale * X[:n_rows, :width]
 

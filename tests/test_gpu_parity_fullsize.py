@@ -1,12 +1,12 @@
 """-m gpu: oracle parity at BASELINE.json's FULL sizes with the bench's DEFAULT configuration.
 
 For the Tiktok, Kwai and Movielens shapes (``elimrec_b200.synth.SHAPES``): the CUDA path exactly as ``bench.py`` configures
-it (linear schedule, TF32 tensor-core modality GEMMs, 3xTF32 fusion / heads, tensor-core evaluator) and its exact-fp32
-variant, against ``oracle.ref_model.OracleEliMRec`` / ``oracle.ref_eval`` (the CPU restatement pinned to the reference by
+it (linear schedule, 3xTF32 tensor-core GEMMs, tensor-core evaluator), its TF32 and exact-FFMA variants and the round-1
+row-sparse schedule, against ``oracle.ref_model.OracleEliMRec`` / ``oracle.ref_eval`` (the CPU restatement pinned to the reference by
 tests/golden) on the same weights and the same 2048-triple batch:
 
-  * loss and every gradient: 1e-3 norm-wise in the TF32 class, 1e-5 class with ``proj_precision='fp32'``
-    (models/EliMRec.py:115-142 and its autograd);
+  * loss and every gradient: the 1e-5 class for the default (3xTF32) and the exact path, 1e-3 norm-wise with
+    ``proj_precision='tf32'`` (models/EliMRec.py:115-142 and its autograd);
   * top-20 index sets of >= 1024 users: exact / explained by a near-tie within the score tolerance / unexplained, gated at
     zero unexplained (uni_evaluator.py:104-203, evaluate.h:23-64);
   * Recall@20 / NDCG@20 (and Precision@20) identical to 4 decimals.
@@ -33,8 +33,8 @@ def setup(request):
     name = "kwai" if shape == "kwai" else shape + "shape"
     ds = Dataset(None, interactions=inter, features=feats, name=name)
     torch.manual_seed(2022)
-    model = build_model(ds, None, dataset_name=name, alpha=0.5, proj_precision="tf32")      # bench.py's defaults
-    assert model.linear and model.lazy_tables and model.fuse_precision == "x3"
+    model = build_model(ds, None, dataset_name=name, alpha=0.5, proj_precision="auto")      # bench.py's defaults
+    assert model.linear and model.lazy_tables and model.fuse_precision == "x3" and model.proj_precision == "x3"
     params = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     mods = "v" if shape == "kwai" else "vat"
     orc = OracleEliMRec(params, {m: getattr(ds, f"{m}_feat") for m in mods}, ds.train_matrix, ds.num_users, ds.num_items,
@@ -65,22 +65,29 @@ def _check_step(model, s, tol, bias_tol):
 
 
 def test_default_config_loss_and_gradients(setup):
-    """bench default (TF32 class): 1e-3"""
-    worst = _check_step(setup["model"], setup, 1e-3, 1e-3)
+    """bench default (linear schedule, 3xTF32 GEMMs): the 1e-5 class (2e-5 norm-wise, as everywhere in tests/; bias gradients
+    are column sums with heavy cancellation: 1e-4)"""
+    worst = _check_step(setup["model"], setup, 2e-5, 1e-4)
     assert len(worst) >= 8
-    assert rel_err(setup["model"].all_users, setup["orc"].cache["users"]) < 1e-3
-    assert rel_err(setup["model"].all_items, setup["orc"].cache["items"]) < 1e-3
+    print(f"[{setup['shape']}] worst gradient error {max(worst.values()):.2e} ({max(worst, key=worst.get)})")
+    assert rel_err(setup["model"].all_users, setup["orc"].cache["users"]) < 2e-5
+    assert rel_err(setup["model"].all_items, setup["orc"].cache["items"]) < 2e-5
 
 
-@pytest.mark.parametrize("linear", [True, False])
-def test_fp32_config_loss_and_gradients(setup, linear):
-    """exact-fp32 GEMMs: the 1e-5 class (2e-5 norm-wise, as everywhere in tests/; bias column sums 1e-4)"""
+@pytest.mark.parametrize("cfg", [dict(proj_precision="fp32"), dict(proj_precision="fp32", linear_schedule=False),
+                                 dict(proj_precision="tf32"), dict(proj_precision="tf32", linear_schedule=False)],
+                         ids=["fp32-linear", "fp32-rowsparse", "tf32-linear", "tf32-rowsparse"])
+def test_other_configs_loss_and_gradients(setup, cfg):
+    """exact-FFMA GEMMs: 1e-5 class; TF32 GEMMs: 1e-3; both schedules"""
     s = setup
-    model = build_model(s["ds"], s["params"], dataset_name=s["name"], alpha=0.5, proj_precision="fp32", linear_schedule=linear)
-    assert model.linear == linear
-    _check_step(model, s, 2e-5, 1e-4)
-    assert rel_err(model.all_users, s["orc"].cache["users"]) < 2e-5
-    assert rel_err(model.all_items, s["orc"].cache["items"]) < 2e-5
+    if s["shape"] == "movielens" and cfg == dict(proj_precision="fp32", linear_schedule=False):
+        pytest.skip("FFMA projections over 2048-d features of every item, twice per step: covered at the other shapes")
+    model = build_model(s["ds"], s["params"], dataset_name=s["name"], alpha=0.5, **cfg)
+    assert model.linear == cfg.get("linear_schedule", True)
+    tol, btol = (1e-3, 1e-3) if cfg["proj_precision"] == "tf32" else (2e-5, 1e-4)
+    _check_step(model, s, tol, btol)
+    assert rel_err(model.all_users, s["orc"].cache["users"]) < tol
+    assert rel_err(model.all_items, s["orc"].cache["items"]) < tol
 
 
 @pytest.mark.parametrize("pt", ["TIE", "TE"])
@@ -99,11 +106,11 @@ def test_default_config_topk_sets_and_metrics(setup, pt):
     res, _ = ev.evaluate(model, test_users=users)
     idx = ev.last_topk[0].cpu().numpy()
     ref = np.concatenate([orc.predict(users[i:i + 128], pt).numpy() for i in range(0, len(users), 128)])
-    # measured score error of this configuration (TF32-class tables through the final sigmoid) on a few users: the near-tie
-    # tolerance of the triage is twice that, and must itself stay inside the TF32 class
+    # measured score error of this configuration on a few users: the near-tie tolerance of the triage is twice that, and must
+    # itself stay inside the fp32 class
     got = model.predict(users[:32]).numpy()
     score_err = float(np.abs(got - ref[:32]).max())
-    assert score_err < 1e-3 * float(np.abs(ref[:32]).max()), score_err
+    assert score_err < 1e-5 * float(np.abs(ref[:32]).max()), score_err
     tol = max(2e-6, 2 * score_err)
     exact, explained, bad = topk_sets_match(idx, ref, [train.get(x, []) for x in users], 20, tol=tol)
     print(f"[{s['shape']} {pt}] score error {score_err:.2e}; top-20 sets: {exact} exact, {explained} near-tie (<= {tol:.1e}), "

@@ -34,6 +34,22 @@ def test_linear_step_propagates_64_wide_only(sim, golden):
     assert sum(x.startswith("spmm64") for x in log) == 2 * min(2, L)
 
 
+@pytest.mark.parametrize("prec", ["x3", "tf32", "fp32", "auto"])
+def test_linear_schedule_precision_modes(backend, golden, prec):
+    """host paths of the three GEMM precisions of the linear schedule (packed / split weights, stacked hi-lo operands of the
+    weight gradient).  The simulator computes all of them exactly; on the B200 'tf32' is gated at its own class."""
+    tol = 1e-3 if (backend == "cuda" and prec == "tf32") else TOL
+    model = build(golden_dataset(golden), golden_params(golden), _name(golden), proj_precision=prec)
+    assert model.linear and model.proj_precision == ("x3" if prec == "auto" else prec)
+    loss = model.bpr_loss(*batch(golden, 0))
+    loss.backward()
+    assert abs(float(loss) - float(golden["loss0"])) < tol * abs(float(golden["loss0"]))
+    for name, p in model.named_parameters():
+        if ("grad0/" + name) in golden:
+            assert rel(p.grad, golden["grad0/" + name]) < (2 * tol if prec == "tf32" else tol), name
+    assert rel(model.all_users, golden["all_users"]) < tol and rel(model.all_items, golden["all_items"]) < tol
+
+
 def test_zbar_is_the_propagated_feature_mean(sim, golden):
     """Zbar_m = mean_k A_hat^k [0 ; X_m | 1] against a dense restatement"""
     model = build(golden_dataset(golden), golden_params(golden), _name(golden))
