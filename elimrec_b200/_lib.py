@@ -39,6 +39,11 @@ class LinearDesc(C.Structure):
     _fields_ = [("M", i64), ("K", i64), ("X", vp), ("ldx", i64), ("W", vp), ("b", vp), ("Y", vp), ("ldy", i64)]
 
 
+class Spmm64Half(C.Structure):
+    _fields_ = [("n_seg", i32), ("n_heavy_seg", i32), ("seg", vp), ("col", vp), ("val", vp), ("X", vp), ("ldx", i64), ("Y", vp),
+                ("ldy", i64), ("row_mask", vp), ("col_mask", vp), ("addend", vp), ("ld_add", i64), ("add_mask", vp)]
+
+
 class LinLayers(C.Structure):
     _fields_ = [("n", i32), ("user", vp * (MAX_LAYERS + 1)), ("item", vp * (MAX_LAYERS + 1)),
                 ("user_ld", i64 * (MAX_LAYERS + 1)), ("item_ld", i64 * (MAX_LAYERS + 1))]
@@ -63,6 +68,7 @@ _SIGS = {
     "elimrec_spmm": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
     "elimrec_spmm_masked": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp, vp, i32,
                             vp, i64, vp, vp],
+    "elimrec_spmm64_pair": [C.POINTER(Spmm64Half), C.POINTER(Spmm64Half), i32, vp],
     "elimrec_mark_rows": [i32, vp, i64, vp, vp],
     "elimrec_inst_rows": [i32, vp, vp, vp, i32, vp, i64, vp, vp, vp],
     "elimrec_mark_neighbors": [i32, vp, vp, vp, vp, vp],
@@ -77,6 +83,7 @@ _SIGS = {
     "elimrec_layer_mean": [i64, i32, i32, C.POINTER(vp), C.POINTER(i64), f32, vp, i64, vp],
     "elimrec_lin_assemble": [i64, vp, i32, C.POINTER(LinLayers), f32, i32, i32, vp, i64, vp],
     "elimrec_lin_seed": [i32, vp, i32, i32, vp, i64, i32, f32, vp, i64, vp],
+    "elimrec_lin_seed2": [i32, vp, vp, i64, i32, f32, vp, vp, i64, vp],
     "elimrec_pack_proj_weights": [i32, C.POINTER(PackProj), i32, vp],
     "elimrec_split3_rows": [i64, i32, vp, i64, vp, i64, i32, vp],
     "elimrec_axpy_2d": [i64, i32, f32, vp, i64, vp, i64, i32, vp],

@@ -75,6 +75,26 @@ lin_seed_kernel(int n_rows, const int* __restrict__ rows, int num_users, int k, 
     atomicAdd(d + 3, scale * v.w);
 }
 
+// Both seeds of the backward chain at once: GA[node] += scale * sum of ALL blocks of dO[j], GB[node] += scale * dO[j, 0:64].
+// Layer k of the chain then adds GA on the rows whose parity carries the modality graphs' E_u part (users: k even, items:
+// k odd) and GB on the others - as the additive epilogue of the propagation launch itself (elimrec_spmm64_pair).
+__global__ void __launch_bounds__(256)
+lin_seed2_kernel(int n_rows, const int* __restrict__ rows, const float* __restrict__ dO, long long ldo, int n_mod, float scale,
+                 float* __restrict__ GA, float* __restrict__ GB, long long ldg) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int l = threadIdx.x & 15;
+    if (j >= n_rows) return;
+    const long long node = __ldg(rows + j);
+    const float4* s = reinterpret_cast<const float4*>(dO + (long long)j * ldo) + l;
+    const float4 b = __ldg(s);
+    float4 a = b;
+    for (int m = 0; m < n_mod; ++m) add4(a, __ldg(s + 16 * (m + 1)));
+    float* da = GA + node * ldg + 4 * l;
+    float* db = GB + node * ldg + 4 * l;
+    atomicAdd(da + 0, scale * a.x); atomicAdd(da + 1, scale * a.y); atomicAdd(da + 2, scale * a.z); atomicAdd(da + 3, scale * a.w);
+    atomicAdd(db + 0, scale * b.x); atomicAdd(db + 1, scale * b.y); atomicAdd(db + 2, scale * b.z); atomicAdd(db + 3, scale * b.w);
+}
+
 struct PackProj {
     int n;
     const float* W[ELIMREC_MAX_MODS];
@@ -185,6 +205,16 @@ ELIMREC_API int elimrec_lin_seed(int n_rows, const int32_t* rows, int32_t num_us
     if (n_rows <= 0) return 0;
     lin_seed_kernel<<<(n_rows * 16 + 255) / 256, 256, 0, er_stream(stream)>>>(n_rows, rows, num_users, layer, dO, ldo, n_mod,
                                                                              scale, dst, ldd);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_lin_seed2(int n_rows, const int32_t* rows, const float* dO, int64_t ldo, int n_mod, float scale,
+                                  float* GA, float* GB, int64_t ldg, elimrec_stream_t stream) {
+    ER_CHECK_ARG(rows != nullptr && dO != nullptr && GA != nullptr && GB != nullptr, "NULL buffer");
+    ER_CHECK_ARG(n_mod >= 0 && n_mod <= ELIMREC_MAX_MODS && ldo % 4 == 0 && ldg % 4 == 0, "bad shape");
+    if (n_rows <= 0) return 0;
+    lin_seed2_kernel<<<(n_rows * 16 + 255) / 256, 256, 0, er_stream(stream)>>>(n_rows, rows, dO, ldo, n_mod, scale, GA, GB, ldg);
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,151 @@
+// 64-wide propagation, both CSR halves in ONE launch - the hot SpMM of the linear schedule (csrc/linsched.cu):
+// p_k = A_hat p_{k-1} (models/EliMRec.py:244 for the id graph; by linearity also the E_u part of the modality graphs).
+//
+// Why not spmm_seg_kernel<64>: with one warp per row a 64-float row (256 B) keeps only half a warp busy per edge, and every
+// row pays three DEPENDENT round trips to L2 (segment descriptor -> col/val -> neighbour rows) before its first FMA; at an
+// average degree of 8-17 that chain, not bandwidth, set the time (6 TB/s L2->SM against ~11 TB/s for the 256-wide launch).
+// Here an 8-lane GROUP owns a row (a lane holds 2 x float4 = columns [4l, 4l+4) and [32+4l, 32+4l+4)), so a warp works on
+// FOUR rows at once: the dependent chain is shared by 4 rows, a warp-level LDG.128 still covers whole 128-byte lines, and
+// UNR edges per group (2 x UNR LDG.128 per lane) are in flight.  The two halves (user rows <- item rows, item rows <- user
+// rows) are independent and go into the same grid: one launch instead of two, no tail of one half idling the machine.
+// Rows longer than the segment length (split rows) keep the CTA-cooperative path of spmm.cu (elimrec_spmm part = 1).
+// Edges are accumulated in CSR order by one group: deterministic, and a masked launch gives the bits of the dense one.
+#include "common.cuh"
+
+namespace {
+
+struct Half64 {
+    const int4* seg;       // whole-row segments of this half: {row, edge_begin, edge_end, -1}
+    int n_light;
+    const int* col;
+    const float* val;
+    const float* X;
+    long long ldx;
+    float* Y;
+    long long ldy;
+    const unsigned char* row_mask;   // NULL: every row.  else rows with 0 are skipped (output untouched)
+    const unsigned char* col_mask;   // NULL: every edge. else edges to columns with 0 are dropped before the gather
+    const float* addend;             // NULL, or Y[row] += addend[row] on the rows add_mask marks (NULL: every row)
+    long long ld_add;
+    const unsigned char* add_mask;
+};
+
+template <int UNR, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+spmm64_pair_kernel(const Half64 a, const Half64 b) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, gl = lane & 7;
+    const long long item = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * 4 + (lane >> 3);
+    const bool in_a = item < a.n_light;
+    const long long idx = in_a ? item : item - a.n_light;
+    const int4* seg = in_a ? a.seg : b.seg;
+    const int* col = in_a ? a.col : b.col;
+    const float* val = in_a ? a.val : b.val;
+    const float* X = in_a ? a.X : b.X;
+    const long long ldx = in_a ? a.ldx : b.ldx;
+    const unsigned char* rmask = in_a ? a.row_mask : b.row_mask;
+    const unsigned char* cmask = in_a ? a.col_mask : b.col_mask;
+    bool active = idx < (in_a ? a.n_light : b.n_light);
+    int4 sg = make_int4(0, 0, 0, -1);
+    if (active) {
+        sg = __ldg(seg + idx);
+        if (rmask != nullptr && __ldg(rmask + sg.x) == 0) active = false;
+    }
+    const int beg = active ? sg.y : 0, end = active ? sg.z : 0;
+    int n_it = (end - beg + 7) >> 3;
+    n_it = __reduce_max_sync(full, n_it);       // shuffles below need all four groups in step
+
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    for (int it = 0; it < n_it; ++it) {
+        const int e0 = beg + it * 8;
+        const int e = e0 + gl;
+        int c = 0;
+        float w = 0.f;
+        bool live = e < end;
+        if (live) {
+            c = __ldg(col + e);
+            w = __ldg(val + e);
+            if (cmask != nullptr && __ldg(cmask + c) == 0) live = false;
+        }
+        const unsigned alive = __ballot_sync(full, live);      // bit per lane: edge exists and its column is marked
+        const unsigned mine = (alive >> (lane & 24)) & 0xffu;  // the 8 bits of this group
+#pragma unroll
+        for (int u0 = 0; u0 < 8; u0 += UNR) {
+            if (u0 > 0 && ((alive >> u0) & (0x01010101u * ((1u << (8 - u0)) - 1u))) == 0) break;   // nothing left in any group
+            float4 v0[UNR], v1[UNR];
+            float ww[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int cc = __shfl_sync(full, c, u0 + u, 8);
+                const float wv = __shfl_sync(full, w, u0 + u, 8);
+                const bool ok = (mine >> (u0 + u)) & 1u;
+                ww[u] = ok ? wv : 0.f;
+                const float4* p = reinterpret_cast<const float4*>(X + (long long)cc * ldx) + gl;
+                v0[u] = ok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v1[u] = ok ? __ldg(p + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                fma4(acc0, ww[u], v0[u]);
+                fma4(acc1, ww[u], v1[u]);
+            }
+        }
+    }
+    if (active) {
+        const float* addend = in_a ? a.addend : b.addend;
+        if (addend != nullptr) {      // the layer-mean gradient entering this layer of the backward chain (instance rows)
+            const unsigned char* am = in_a ? a.add_mask : b.add_mask;
+            if (am == nullptr || __ldg(am + sg.x) != 0) {
+                const float4* g = reinterpret_cast<const float4*>(addend + (long long)sg.x * (in_a ? a.ld_add : b.ld_add)) + gl;
+                add4(acc0, __ldg(g));
+                add4(acc1, __ldg(g + 8));
+            }
+        }
+        float* Y = in_a ? a.Y : b.Y;
+        const long long ldy = in_a ? a.ldy : b.ldy;
+        float4* y = reinterpret_cast<float4*>(Y + (long long)sg.x * ldy) + gl;
+        y[0] = acc0;
+        y[8] = acc1;
+    }
+}
+
+int fill_half(Half64& h, const elimrec_spmm64_half_t* s, const char** err) {
+    h = Half64{};
+    if (s == nullptr) return 0;
+    if (s->n_heavy_seg < 0 || s->n_heavy_seg > s->n_seg) { *err = "n_heavy_seg out of range"; return -1; }
+    if (s->ldx % 4 != 0 || s->ldy % 4 != 0) { *err = "row strides must be multiples of 4 floats"; return -1; }
+    h.seg = reinterpret_cast<const int4*>(s->seg) + s->n_heavy_seg;
+    h.n_light = s->n_seg - s->n_heavy_seg;
+    h.col = s->col; h.val = s->val; h.X = s->X; h.ldx = s->ldx; h.Y = s->Y; h.ldy = s->ldy;
+    h.row_mask = s->row_mask; h.col_mask = s->col_mask;
+    h.addend = s->addend; h.ld_add = s->ld_add; h.add_mask = s->add_mask;
+    if (s->addend != nullptr && s->ld_add % 4 != 0) { *err = "addend stride must be a multiple of 4 floats"; return -1; }
+    if (h.n_light > 0 && (h.X == nullptr || h.Y == nullptr || h.seg == nullptr)) { *err = "NULL buffer"; return -1; }
+    return 0;
+}
+
+}  // namespace
+
+ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimrec_spmm64_half_t* b, int variant,
+                                    elimrec_stream_t stream) {
+    ER_CHECK_ARG(a != nullptr, "first half required");
+    Half64 ha, hb;
+    const char* err = nullptr;
+    if (fill_half(ha, a, &err) != 0 || fill_half(hb, b, &err) != 0) {
+        elimrec_set_error("elimrec_spmm64_pair: %s", err);
+        return -1;
+    }
+    const long long items = (long long)ha.n_light + hb.n_light;
+    if (items <= 0) return 0;
+    const unsigned blocks = (unsigned)((items + 31) / 32);      // 8 warps x 4 rows per CTA
+    cudaStream_t st = er_stream(stream);
+    switch (variant) {
+        case 1: spmm64_pair_kernel<8, 2><<<blocks, 256, 0, st>>>(ha, hb); break;
+        case 2: spmm64_pair_kernel<4, 3><<<blocks, 256, 0, st>>>(ha, hb); break;
+        case 3: spmm64_pair_kernel<2, 6><<<blocks, 256, 0, st>>>(ha, hb); break;
+        case 4: spmm64_pair_kernel<8, 3><<<blocks, 256, 0, st>>>(ha, hb); break;
+        default: spmm64_pair_kernel<4, 4><<<blocks, 256, 0, st>>>(ha, hb); break;
+    }
+    ER_LAUNCH_CHECK();
+    return 0;
+}

@@ -105,6 +105,8 @@ class LinearSchedule:
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         ws["P"] = [None] + [e(N, D) for _ in range(L)]      # p_1 .. p_L (users first); p_0 are the embedding tables themselves
         ws["H"] = [e(N, D), e(N, D)]                        # backward chain, ping-pong
+        # the two seed vectors of the chain (lin_seed2), valid on the instance rows of the current step only
+        ws["GA"], ws["GB"] = torch.zeros(N, D, dtype=torch.float32, device=dev), torch.zeros(N, D, dtype=torch.float32, device=dev)
         ws["E0"] = e(N, D)                                  # [E_u ; E_i] as THIS forward saw them (Adam overwrites the tables)
         ws["Wp"] = {m: e(D, kp) for m, kp in zip(self.mods, self._lin_Kp)}     # [W_m | b_m | 0] of this forward
         if self.proj_precision == "x3":
@@ -160,9 +162,18 @@ class LinearSchedule:
                                        for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff))],
                                       tag="lin_modal_tc")
         elif self.proj_precision == "x3":
-            for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
+            sts = []
+            for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):     # disjoint output columns: side by side
                 hi, lo = ws["Wp_split"][m]
-                ops.linear_x3_fwd(Zrows[:, ko:ko + kp], hi, lo, None, out, col=D * (j + 1), tag="lin_modal_x3")
+                go = lambda: ops.linear_x3_fwd(Zrows[:, ko:ko + kp], hi, lo, None, out, col=D * (j + 1), tag="lin_modal_x3")
+                if j == 0:
+                    go()
+                else:
+                    sts.append(ops.fork_side(10 + j, high_priority=True))
+                    with torch.cuda.stream(sts[-1]):
+                        go()
+            for st in sts:
+                ops.join_side(st)
         else:
             ld = Zrows.stride(0)
             for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
@@ -180,30 +191,35 @@ class LinearSchedule:
         Ei = P["embedding_item.weight"].detach()
         mask, need2 = ws["mask"], ws["need2"]
         rows = ws["inst_rows"]
-        self._lin_pack_weights(P, ws)
-        # side stream: instance rows and their masks, Zbar gathered at them and the modality GEMMs (none of it depends on the
-        # propagation); a third stream keeps what tables completed later must use and zeroes the backward's seed rows
-        side = ops.fork_side()
+        # Small kernels run on HIGH-PRIORITY side streams: beside a propagation launch that fills every SM they would otherwise
+        # queue behind its whole grid.
+        #   side: instance rows + masks, then Zbar gathered at them and the modality GEMMs (nothing here needs the propagation)
+        #   aux : what tables completed later must use (weights, E_u / E_i of THIS forward), zeroed seed rows of the backward
+        side = ops.fork_side(0, high_priority=True)
         with torch.cuda.stream(side):
             ops.inst_rows(users, pos, neg, U, rows, mask, need2)
             ev_rows = torch.cuda.Event()
             ev_rows.record(side)
-            if L >= 2:    # layer L-1 is read at the graph neighbours of the instance rows (both sides are 64 wide here)
+            if L >= 2:    # layer L-1 is read at the graph neighbours of the instance rows
                 ops.mark_neighbors(g.ui, mask[:U], need2[U:])
                 ops.mark_neighbors(g.iu, mask[U:], need2[:U])
             ev_masks = torch.cuda.Event()
             ev_masks.record(side)
+            self._lin_pack_weights(P, ws)
             ops.gather_rows(rows, self._zbar, ws["Zg"], self._lin_Ktot)
             self._lin_modal_gemm(ws, ws["Zg"], ws["O_inst"], 3 * B)
-        aux = ops.fork_side(7)
+        aux = ops.fork_side(7, high_priority=True)
         with torch.cuda.stream(aux):
+            if getattr(self, "_tick_early", False):      # train_step: the optimizer's step counter / bias corrections
+                self._adam.tick()
             self._snapshot(P, ws)
             ops.copy_2d(Eu, ws["E0"][:U], U, D)
             ops.copy_2d(Ei, ws["E0"][U:], I, D)
             torch.cuda.current_stream().wait_event(ev_rows)
-            ops.zero_rows(rows, 0, U + I, 0, ws["H"][0], D)
+            ops.zero_rows(rows, 0, U + I, 0, ws["GA"], D)
+            ops.zero_rows(rows, 0, U + I, 0, ws["GB"], D)
             ws["seed_zeroed"] = True
-        # the propagation: p_k = A_hat p_{k-1}, both halves 64 wide, on two streams
+        # the propagation: p_k = A_hat p_{k-1}, both halves 64 wide in one launch
         in_u, in_i = Eu, Ei
         cur = torch.cuda.current_stream()
         for k in range(1, L + 1):
@@ -211,12 +227,8 @@ class LinearSchedule:
             rm = mask if k == L else (need2 if k == L - 1 else None)
             if rm is not None:
                 cur.wait_event(ev_rows if k == L else ev_masks)
-            dens = ws["density"] if k == L else {"u": 50, "i": 50}
-            s2 = ops.fork_side(3)
-            with torch.cuda.stream(s2):
-                ops.spmm(g.iu, in_u, out[U:], D, row_mask=rm[U:] if rm is not None else None, density=dens["i"])
-            ops.spmm(g.ui, in_i, out[:U], D, row_mask=rm[:U] if rm is not None else None, density=dens["u"])
-            ops.join_side(s2)
+            ops.spmm64_pair(g.ui, g.iu, in_i, in_u, out[:U], out[U:], row_mask_u=rm[:U] if rm is not None else None,
+                            row_mask_i=rm[U:] if rm is not None else None)
             in_u, in_i = out[:U], out[U:]
         ops.join_side(side)
         lay = ops.lin_layers(self._lin_tables(ws, Eu, Ei))
@@ -245,57 +257,82 @@ class LinearSchedule:
             gWu, gWi, gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
             [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods], ws["inst_ws"], part=part)
 
-        def weights():
-            """every gradient that is not an embedding table's: fusion / heads (instance rows) and d[W_m | b_m] =
-            dO_m[inst]^T Zbar_m[inst] - none of it waits for the propagation backward"""
+        def inst_weights():
+            """fusion Linear / head weight and bias gradients (instance rows)"""
             ib(2)
             if tied:
                 ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
                 ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
+
+        def proj_weights():
+            """d[W_m | b_m] = dO_m[inst]^T Zbar_m[inst]"""
             Zg, ldz = ws["Zg"], ws["Zg"].stride(0)
             if self.proj_precision == "x3":      # 3xTF32: hi*hi + hi*lo + lo*hi as ONE reduction over 9B stacked rows
                 ops.split3_rows(dOin, ws["dO3"], 3 * B, Fw, 0)
                 ops.split3_rows(Zg, ws["Zg3"], 3 * B, self._lin_Ktot, 1)
+            sts = []
             for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
-                if self.proj_precision == "x3":
-                    ops.linear_tf32_wgrad(ws["dO3"], ws["Zg3"][:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
-                                          tag="lin_wgrad_x3")
-                elif self._lin_tc():
-                    ops.linear_tf32_wgrad(dOin, Zg[:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
-                                          tag="lin_wgrad_tc")
+                def go(j=j, m=m, kp=kp, ko=ko):
+                    if self.proj_precision == "x3":
+                        ops.linear_tf32_wgrad(ws["dO3"], ws["Zg3"][:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
+                                              tag="lin_wgrad_x3")
+                    elif self._lin_tc():
+                        ops.linear_tf32_wgrad(dOin, Zg[:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
+                                              tag="lin_wgrad_tc")
+                    else:
+                        ops.gemm(kp, D, 3 * B, Zg, 1, ldz, dOin, Fw, 1, ws["dWp"][m], 1, kp, split_k=ws["split_inst"], ws=ws["gemm_ws"],
+                                 a_off=ko, b_off=D * (j + 1), tag="lin_wgrad")
+                if j == 0 or self.proj_precision == "fp32":      # (the exact path shares one split-K scratch: in sequence)
+                    go()
                 else:
-                    ops.gemm(kp, D, 3 * B, Zg, 1, ldz, dOin, Fw, 1, ws["dWp"][m], 1, kp, split_k=ws["split_inst"], ws=ws["gemm_ws"],
-                             a_off=ko, b_off=D * (j + 1), tag="lin_wgrad")
+                    sts.append(ops.fork_side(10 + j, high_priority=True))
+                    with torch.cuda.stream(sts[-1]):
+                        go()
+            for st in sts:
+                ops.join_side(st)
+
+        def weights(fork):
+            """every gradient that is not an embedding table's - none of it waits for the propagation backward.  Two
+            independent high-priority branches beside the chain; returns what must be joined before Adam."""
+            if not fork:
+                inst_weights()
+                proj_weights()
+                return []
+            s1, s2 = ops.fork_side(5, high_priority=True), ops.fork_side(6, high_priority=True)
+            with torch.cuda.stream(s1):
+                inst_weights()
+            with torch.cuda.stream(s2):
+                proj_weights()
+            return [s1, s2]
 
         ib(1)
-        side_w = None
-        if not split:
-            side_w = ops.fork_side(5)
-            with torch.cuda.stream(side_w):
-                weights()
-        # the 64-wide backward chain: h_L = g_L, h_{k-1} = A_hat^T h_k + g_{k-1}; g_k (lin_seed) lives on the instance rows
+        pending = None if split else weights(True)
+        # the 64-wide backward chain: h_L = g_L, h_{k-1} = A_hat^T h_k + g_{k-1}.  g_k lives on the instance rows and takes two
+        # values per row: GA (all blocks of dO) where layer k carries the modality graphs' E_u part (users: k even, items:
+        # k odd), GB (id block) elsewhere.  h_L is read straight from the G slabs through the column mask; every later g_k is the
+        # additive epilogue of the propagation launch.
         inv, nm = 1.0 / (L + 1), len(self.mods)
-        h, flip = ws["H"][0], 1
+        GA, GB = ws["GA"], ws["GB"]
         if not ws.pop("seed_zeroed", False):      # normally done by the forward, off the critical path
-            ops.zero_rows(rows, 0, U + I, 0, h, D)
-        ops.lin_seed(rows, U, L, dOin, nm, inv, h)
+            ops.zero_rows(rows, 0, U + I, 0, GA, D)
+            ops.zero_rows(rows, 0, U + I, 0, GB, D)
+        ops.lin_seed2(rows, dOin, nm, inv, GA, GB)
         mask, need2 = ws["mask"], ws["need2"]
+        g_u = lambda k: (GA if k % 2 == 0 else GB)[:U]
+        g_i = lambda k: (GA if k % 2 == 1 else GB)[U:]
+        h_u, h_i, flip = g_u(L), g_i(L), 0
         for k in range(L, 0, -1):
             nxt = ws["H"][flip]
             # h_L is valid on the instance rows only, h_{L-1} on need2 only: the first two hops drop every other column
             cm = mask if k == L else (need2 if k == L - 1 else None)
             rm = need2 if (k == L and L >= 2) else None
-            s2 = ops.fork_side(3)
-            with torch.cuda.stream(s2):
-                ops.spmm(g.iu_t, h[:U], nxt[U:], D, col_mask=cm[:U] if cm is not None else None,
-                         row_mask=rm[U:] if rm is not None else None)
-            ops.spmm(g.ui_t, h[U:], nxt[:U], D, col_mask=cm[U:] if cm is not None else None,
-                     row_mask=rm[:U] if rm is not None else None)
-            ops.join_side(s2)
-            ops.lin_seed(rows, U, k - 1, dOin, nm, inv, nxt)
-            h, flip = nxt, flip ^ 1
-        grads = {"embedding_user.weight": h[:U], "embedding_item.weight": h[U:]}
-        ws["bw_pending"] = (weights, side_w)
+            ops.spmm64_pair(g.ui_t, g.iu_t, h_i, h_u, nxt[:U], nxt[U:],
+                            row_mask_u=rm[:U] if rm is not None else None, row_mask_i=rm[U:] if rm is not None else None,
+                            col_mask_u=cm[U:] if cm is not None else None, col_mask_i=cm[:U] if cm is not None else None,
+                            addend_u=g_u(k - 1), addend_i=g_i(k - 1), add_mask_u=mask[:U], add_mask_i=mask[U:])
+            h_u, h_i, flip = nxt[:U], nxt[U:], flip ^ 1
+        grads = {"embedding_user.weight": h_u, "embedding_item.weight": h_i}
+        ws["bw_pending"] = (weights, pending)
         if split:
             return grads
         grads.update(self._lin_backward_weights())
@@ -303,11 +340,12 @@ class LinearSchedule:
 
     def _lin_backward_weights(self):
         ws = self._ws
-        weights, side_w = ws.pop("bw_pending")
-        if side_w is None:
-            weights()
+        weights, pending = ws.pop("bw_pending")
+        if pending is None:
+            weights(False)
         else:
-            ops.join_side(side_w)
+            for st in pending:
+                ops.join_side(st)
         dead = self._dead_params()
         return {n: gv for n, gv in ws["g"].items() if n not in dead} if dead else ws["g"]
 
@@ -322,8 +360,7 @@ class LinearSchedule:
         for k in range(max(1, L - 1), L + 1):
             src = E0 if k == 1 else ws["P"][k - 1]
             out = ws["P"][k]
-            ops.spmm(g.iu, src[:U], out[U:], D)
-            ops.spmm(g.ui, src[U:], out[:U], D)
+            ops.spmm64_pair(g.ui, g.iu, src[U:], src[:U], out[:U], out[U:])
         self._lin_modal_gemm(ws, self._zbar, ws["O"], N)
         lay = ops.lin_layers(self._lin_tables(ws, E0[:U], E0[U:]))
         ops.lin_assemble(None, U, lay, 1.0 / (L + 1), len(self.mods), True, ws["O"], n_rows=N)

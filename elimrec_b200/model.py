@@ -949,11 +949,16 @@ class EliMRec(LinearSchedule, BasicModel):
             self.make_optimizer()
         users, pos, neg = self._triples(users, pos_items, neg_items)
         with torch.no_grad():
-            loss = self._forward(users, pos, neg)
+            # linear schedule: the step counter ticks on a side stream of the forward, off the critical path
+            early = self._tick_early = bool(self.linear)
+            try:
+                loss = self._forward(users, pos, neg)
+            finally:
+                self._tick_early = False
             grads = self._backward(None)
             if getattr(self, "_dp", False):
                 grads = self._allreduce_grads(grads)
-            self._adam.apply(grads)
+            self._adam.apply(grads, tick=not early)
         return loss
 
     # -- data-parallel replicas: each rank draws its own triples, gradients are averaged (NCCL) ----

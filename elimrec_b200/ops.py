@@ -20,14 +20,17 @@ F32 = torch.float32
 _SIDE = {}
 
 
-def fork_side(slot=0):
+def fork_side(slot=0, high_priority=False):
+    """A side stream that starts after everything queued on the current one.  ``high_priority``: for branches of SMALL kernels
+    that run beside a propagation launch - their CTAs are then placed as soon as SM slots free up instead of queueing behind
+    the big grid (stream priority is kept by the nodes of a captured CUDA graph)."""
     cur = torch.cuda.current_stream()
     if _lib.PROFILE["on"]:      # per-kernel event timing needs the launches serialised
         return cur
     key = (cur.device.index, cur.cuda_stream, slot)
     side = _SIDE.get(key)
     if side is None:
-        side = _SIDE[key] = torch.cuda.Stream(device=cur.device)
+        side = _SIDE[key] = torch.cuda.Stream(device=cur.device, priority=-1 if high_priority else 0)
     ev = torch.cuda.Event()
     ev.record(cur)
     side.wait_event(ev)
@@ -80,6 +83,39 @@ def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, 
         e1.record()
         _lib.PROFILE["on"] = True
         _lib.PROFILE["events"].append((f"spmm{width}m" if masked else f"spmm{width}", e0, e1))
+
+
+def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row_mask_i=None, col_mask_u=None, col_mask_i=None,
+                addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, variant=0):
+    """Both halves of a 64-wide propagation layer: Y_u = half_u @ X_for_u (user rows gather item rows), Y_i = half_i @ X_for_i.
+    Whole rows of both halves are ONE launch (elimrec_spmm64_pair); split rows go through the CTA-cooperative kernel on a
+    side stream.  ``col_mask_u``: mask over the COLUMNS of half_u (item rows), etc.  ``addend_*`` / ``add_mask_*``:
+    Y[row] += addend[row] on the marked rows (the gradient entering this layer of the backward chain)."""
+    def desc(h, X, Y, rm, cm, ad, am):
+        d = _lib.Spmm64Half()
+        d.n_seg, d.n_heavy_seg, d.seg, d.col, d.val = h.n_seg, h.n_heavy_seg, ptr(h.seg), ptr(h.col), ptr(h.val)
+        d.X, d.ldx, d.Y, d.ldy = ptr(X, F32), X.stride(0), ptr(Y, F32), Y.stride(0)
+        d.row_mask, d.col_mask = ptr(rm, torch.uint8, True), ptr(cm, torch.uint8, True)
+        d.addend, d.ld_add, d.add_mask = ptr(ad, F32, True), (ad.stride(0) if ad is not None else 0), ptr(am, torch.uint8, True)
+        return d
+    todo = [(half_u, X_for_u, Y_u, row_mask_u, col_mask_u, addend_u, add_mask_u),
+            (half_i, X_for_i, Y_i, row_mask_i, col_mask_i, addend_i, add_mask_i)]
+    heavy = [t for t in todo if t[0].n_heavy_seg > 0]
+    side = fork_side(1) if heavy else None
+    if heavy:
+        with torch.cuda.stream(side):
+            for h, X, Y, rm, cm, ad, am in heavy:
+                args = [64, 1, h.n_seg, h.n_heavy_seg, ptr(h.seg), ptr(h.heavy), ptr(h.counter), ptr(h.col), ptr(h.val), ptr(X, F32),
+                        X.stride(0), ptr(Y, F32), Y.stride(0), ptr(h.partial), None]
+                if rm is not None or cm is not None or ad is not None:
+                    call("elimrec_spmm_masked", *args, ptr(rm, torch.uint8, True), ptr(cm, torch.uint8, True), 50, ptr(ad, F32, True),
+                         (ad.stride(0) if ad is not None else 0), ptr(am, torch.uint8, True), stream(), launches=1, tag="spmm64_heavy")
+                else:
+                    call("elimrec_spmm", *args, stream(), launches=1, tag="spmm64_heavy")
+    da, db = desc(*todo[0]), desc(*todo[1])
+    call("elimrec_spmm64_pair", C.byref(da), C.byref(db), int(variant), stream(), tag="spmm64_pair")
+    if heavy:
+        join_side(side)
 
 
 def mark_rows(rows, mask):
@@ -182,6 +218,12 @@ def lin_seed(rows, num_users, layer, dO, n_mod, scale, dst):
     """dst[rows[j]] += scale * (dO[j, :64] + [parity] * sum_m dO[j, 64(1+m):64(2+m)])  (adjoint of lin_assemble, layer `layer`)"""
     call("elimrec_lin_seed", rows.numel(), ptr(rows, torch.int32), num_users, layer, ptr(dO, F32), dO.stride(0), n_mod, scale,
          ptr(dst, F32), dst.stride(0), stream())
+
+
+def lin_seed2(rows, dO, n_mod, scale, GA, GB):
+    """GA[rows[j]] += scale * (sum of all 64-column blocks of dO[j]);  GB[rows[j]] += scale * dO[j, :64]"""
+    call("elimrec_lin_seed2", rows.numel(), ptr(rows, torch.int32), ptr(dO, F32), dO.stride(0), n_mod, scale, ptr(GA, F32),
+         ptr(GB, F32), GA.stride(0), stream())
 
 
 def pack_proj_weights(items, round_tf32):

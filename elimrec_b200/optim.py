@@ -30,12 +30,16 @@ class FusedAdam:
             self.state[name] = st
         return st
 
+    def tick(self):
+        """advance the device step counter and refresh the bias corrections (once per step, any time before apply)"""
+        ops.adam_tick(self.step_dev, self.consts, self.lr, self.betas[0], self.betas[1])
+
     def apply(self, grads: dict, tick: bool = True):
         """One Adam step from a {name: gradient view} dict (EliMRec._backward output).  ``tick=False``: a second group of
         tensors of the SAME step (the step counter and bias corrections were advanced by the first call)."""
         P = self.model._params()
         if tick:
-            ops.adam_tick(self.step_dev, self.consts, self.lr, self.betas[0], self.betas[1])
+            self.tick()
         items = []
         for name, g in grads.items():
             p = P[name]

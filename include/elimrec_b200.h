@@ -84,6 +84,27 @@ int elimrec_spmm_masked(int width, int part, int n_seg, int n_heavy_seg, const i
                         int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi, const uint8_t* row_mask,
                         const uint8_t* col_mask, int row_density_pct /* expected % of marked rows: scheduling hint only */,
                         const float* addend, int64_t ld_add, const uint8_t* add_mask, elimrec_stream_t stream);
+/* The 64-wide propagation of BOTH CSR halves in one launch (csrc/spmm64.cu): an 8-lane group owns a row, four rows per warp.
+ * Each half: Y[row, 0:64] = sum_e val[e] * X[col[e], 0:64] over its WHOLE-row segments [n_heavy_seg, n_seg) - the split rows
+ * [0, n_heavy_seg) go through elimrec_spmm / elimrec_spmm_masked with part = 1, concurrently (they write other rows).
+ * row_mask / col_mask as in elimrec_spmm_masked (either may be NULL); masked rows carry the bits of the dense launch.
+ * `b` may be NULL.  variant: 0 = default tuning; 1..4 = other unroll / occupancy points (tools/spmm64_bench.py). */
+typedef struct {
+    int32_t n_seg, n_heavy_seg;
+    const int32_t* seg;
+    const int32_t* col;
+    const float* val;
+    const float* X;
+    int64_t ldx;
+    float* Y;
+    int64_t ldy;
+    const uint8_t* row_mask;
+    const uint8_t* col_mask;
+    const float* addend;      /* may be NULL: Y[row] += addend[row, 0:64] where add_mask[row] != 0 (add_mask NULL: every row) */
+    int64_t ld_add;
+    const uint8_t* add_mask;
+} elimrec_spmm64_half_t;
+int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimrec_spmm64_half_t* b, int variant, elimrec_stream_t stream);
 /* mask[0:n_nodes] = 0; mask[rows[r]] = 1 */
 int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream);
 /* rows[0:3B] = [users | num_users + pos | num_users + neg]  (node ids of the batch, models/EliMRec.py:120-122 gathers
@@ -160,6 +181,11 @@ int elimrec_lin_assemble(int64_t n_rows, const int32_t* rows /* may be NULL */, 
  *   dst[rows[j], 0:64] += scale * (dO[j, 0:64] + [layer even (user row) / odd (item row)] * sum_m dO[j, 64(1+m):64(2+m)]) */
 int elimrec_lin_seed(int n_rows, const int32_t* rows, int32_t num_users, int layer, const float* dO, int64_t ldo, int n_mod,
                      float scale, float* dst /* [N x 64], users first */, int64_t ldd, elimrec_stream_t stream);
+/* both seed vectors at once, for the fused form of the chain (the propagation launch adds them in its epilogue):
+ *   GA[rows[j], 0:64] += scale * sum_{all blocks} dO[j];   GB[rows[j], 0:64] += scale * dO[j, 0:64]   (atomic)
+ * layer k adds GA on user rows for even k / item rows for odd k, and GB on the other side */
+int elimrec_lin_seed2(int n_rows, const int32_t* rows, const float* dO, int64_t ldo, int n_mod, float scale, float* GA, float* GB,
+                      int64_t ldg, elimrec_stream_t stream);
 /* dst_m [64 x Kp] = [ W_m [64 x Dm] | b_m | 0 .. ]: the projection weight with its bias as one more input column (the
  * matching column of Zbar_m is mean_k A_hat^k [0 ; 1]); round_tf32 != 0 rounds to nearest TF32 for the tensor-core GEMM */
 typedef struct {

@@ -23,7 +23,7 @@ def _log(name):
 
 
 # ---- streams: the simulator is sequential ------------------------------------------------------------------------------
-def fork_side(slot=0):
+def fork_side(slot=0, high_priority=False):
     return None
 
 
@@ -69,6 +69,12 @@ def spmm(half, X, Y, width, epi=None, row_mask=None, col_mask=None, density=50, 
             s = v.clone() if s is None else s + v
         s = s + (acc.repeat(1, reps) if reps > 1 else acc)
         epi.out[rows, :epi.width] = (s * epi.scale)[rows]
+
+
+def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row_mask_i=None, col_mask_u=None, col_mask_i=None,
+                addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, variant=0):
+    spmm(half_u, X_for_u, Y_u, 64, row_mask=row_mask_u, col_mask=col_mask_u, addend=addend_u, add_mask=add_mask_u)
+    spmm(half_i, X_for_i, Y_i, 64, row_mask=row_mask_i, col_mask=col_mask_i, addend=addend_i, add_mask=add_mask_i)
 
 
 def inst_rows(users, pos, neg, num_users, rows, mask=None, mask2=None):
@@ -175,6 +181,14 @@ def lin_seed(rows, num_users, layer, dO, n_mod, scale, dst):
     if n_mod:
         v = v + torch.where(par, dO[:, 64:64 * (1 + n_mod)].reshape(-1, n_mod, 64).sum(1), torch.zeros_like(v))
     dst[:, :64].index_add_(0, node, v * scale)
+
+
+def lin_seed2(rows, dO, n_mod, scale, GA, GB):
+    _log("lin_seed2")
+    node = rows.long()
+    a = dO[:, :64 * (1 + n_mod)].reshape(-1, 1 + n_mod, 64).sum(1)
+    GA[:, :64].index_add_(0, node, a * scale)
+    GB[:, :64].index_add_(0, node, dO[:, :64] * scale)
 
 
 def pack_proj_weights(items, round_tf32):

@@ -24,7 +24,8 @@ def test_linear_step_propagates_64_wide_only(sim, golden):
     L = model.n_layers
     assert not any(x.startswith(("spmm128", "spmm256", "proj_fwd", "proj_wgrad", "colsum")) for x in log), log
     assert sum(x.startswith("spmm64") for x in log) == 4 * L          # two halves per layer, forward and backward
-    assert log.count("lin_assemble") == 1 and log.count("lin_seed") == L + 1 and log.count("gather_rows") == 1
+    # both seed vectors of the backward chain in one launch; the chain adds them in the propagation launches' epilogues
+    assert log.count("lin_assemble") == 1 and log.count("lin_seed2") == 1 and log.count("gather_rows") == 1
     assert "fuse_heads_x3_all" not in log
     # completing the tables for an evaluation: the two masked layers again (every row) + one pass over Zbar
     sim.LAUNCH_LOG.clear()

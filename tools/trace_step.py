@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Kernel timeline of ONE CUDA-graph-replayed training step (torch.profiler / CUPTI): start, duration, kernel.
-Usage (GPU box): python tools/trace_step.py [workload] [lazy] > profiles/<name>.txt"""
+Usage (GPU box): python tools/trace_step.py [workload] [linear|rowsparse|reference] > profiles/<name>.txt
+Columns: start_us duration_us stream kernel (the stream column shows which launches run side by side)."""
 import os
 import sys
 
@@ -15,10 +16,11 @@ from elimrec_b200.sampler import PairwiseSamplerV2  # noqa: E402
 
 def main():
     workload = sys.argv[1] if len(sys.argv) > 1 else "tiktok"
-    lazy = len(sys.argv) > 2 and sys.argv[2] == "lazy"
+    sched = sys.argv[2] if len(sys.argv) > 2 else "linear"
     dev = torch.device("cuda:0")
     ds, name = bench.build_dataset(workload)
-    conf = Config(**{"data.input.dataset": name, "topks": [20], "device": dev, "alpha": 0.5, "batch_size": 2048, "lazy_tables": lazy})
+    conf = Config(**{"data.input.dataset": name, "topks": [20], "device": dev, "alpha": 0.5, "batch_size": 2048, "lazy_tables": sched != "reference",
+                     "linear_schedule": sched == "linear"})
     torch.manual_seed(2022)
     model = EliMRec(conf, ds).to(dev)
     model.make_optimizer()
@@ -34,16 +36,19 @@ def main():
         for x in b[4:7]:
             run(*x)
         torch.cuda.synchronize()
-    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-    ev.sort(key=lambda e: e.time_range.start)
-    idx = [i for i, e in enumerate(ev) if "prep_multi" in e.name]
+    ev = [e for e in prof.profiler.kineto_results.events() if e.device_type() == torch.autograd.DeviceType.CUDA]
+    ev.sort(key=lambda e: e.start_ns())
+    first = "pack_proj" if model.linear else "prep_multi"
+    idx = [i for i, e in enumerate(ev) if first in e.name()]
     ev = ev[idx[-1]:] if idx else ev
-    t0 = ev[0].time_range.start
-    print(f"# one graph-replayed train step, {workload}-shape, batch 2048; columns: start_us duration_us kernel")
+    t0 = ev[0].start_ns()
+    streams = {}
+    print(f"# one graph-replayed train step ({sched} schedule), {workload}-shape, batch 2048; columns: start_us duration_us stream kernel")
     for e in ev:
-        nm = e.name.replace("(anonymous namespace)::", "").split("(")[0][:70]
-        print(f"{e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:8.1f}  {nm}")
-    print(f"# span {ev[-1].time_range.end - t0:.1f} us")
+        nm = e.name().replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0][:70]
+        sid = streams.setdefault(e.device_resource_id(), len(streams))
+        print(f"{(e.start_ns() - t0) / 1e3:9.1f} {e.duration_ns() / 1e3:8.1f}  s{sid:<2d} {nm}")
+    print(f"# span {(ev[-1].start_ns() + ev[-1].duration_ns() - t0) / 1e3:.1f} us")
 
 
 if __name__ == "__main__":
