@@ -44,6 +44,11 @@ class Spmm64Half(C.Structure):
                 ("ldy", i64), ("row_mask", vp), ("col_mask", vp), ("addend", vp), ("ld_add", i64), ("add_mask", vp)]
 
 
+class WgradProblem(C.Structure):
+    _fields_ = [("A", vp), ("lda", i64), ("B", vp), ("ldb", i64), ("K", i64), ("row_begin", i64), ("row_end", i64), ("out", vp),
+                ("ldo", i64), ("bias_out", vp), ("scale_by_g", i32)]
+
+
 class LinLayers(C.Structure):
     _fields_ = [("n", i32), ("user", vp * (MAX_LAYERS + 1)), ("item", vp * (MAX_LAYERS + 1)),
                 ("user_ld", i64 * (MAX_LAYERS + 1)), ("item_ld", i64 * (MAX_LAYERS + 1))]
@@ -81,6 +86,7 @@ _SIGS = {
     "elimrec_fold_blocks": [i64, vp, i64, i32, f32, vp, i64, vp],
     "elimrec_axpy_rows": [i64, i32, vp, vp, i64, vp, i64, vp],
     "elimrec_layer_mean": [i64, i32, i32, C.POINTER(vp), C.POINTER(i64), f32, vp, i64, vp],
+    "elimrec_wgrad_multi": [i32, C.POINTER(WgradProblem), i32, vp, vp, vp],
     "elimrec_lin_assemble": [i64, vp, i32, C.POINTER(LinLayers), f32, i32, i32, vp, i64, vp],
     "elimrec_lin_seed": [i32, vp, i32, i32, vp, i64, i32, f32, vp, i64, vp],
     "elimrec_lin_seed2": [i32, vp, vp, i64, i32, f32, vp, vp, i64, vp],
@@ -125,6 +131,7 @@ _I64_RET = {
     "elimrec_linear_tf32_wgrad_workspace_floats": [i64, i64],
     "elimrec_inst_backward_workspace_floats": [i32, i32, i32],
     "elimrec_rank_tc_workspace_bytes": [i32],
+    "elimrec_wgrad_multi_workspace_floats": [i32, C.POINTER(WgradProblem), i32],
 }
 # every symbol include/elimrec_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = sorted(list(_SIGS) + list(_I64_RET) + ["elimrec_last_error", "elimrec_abi_version",

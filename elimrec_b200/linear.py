@@ -134,14 +134,29 @@ class LinearSchedule:
     def _lin_workspace_batch(self, ws, B):
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device_)
         ws["Zg"] = e(3 * B, self._lin_Ktot)                 # Zbar gathered at the instance rows
-        rows = 3 * B
-        if self.proj_precision == "x3":     # operands of the weight gradient as stacked TF32 hi / lo parts (elimrec_split3_rows)
-            rows = 9 * B
-            ws["Zg3"], ws["dO3"] = e(rows, self._lin_Ktot), e(rows, ws["F"])
-        ws["lin_wgrad_ws"] = {m: e(max(1, ops.linear_tf32_wgrad_ws_floats(rows, kp))) for m, kp in zip(self.mods, self._lin_Kp)}
+        ws["B"] = B
+        ws["wg_splits"] = max(1, min(32, (3 * B + 255) // 256))
+        if self.mm_fusion_mode == "mean":
+            gWu, gWi = ws["g_eff"]["u"], ws["g_eff"]["i"]
+        else:
+            gWu, gWi = ws["g"]["embedding_user_after_GCN.weight"], ws["g"]["embedding_item_after_GCN.weight"]
+        ws["wg_ws"] = e(max(1, ops.wgrad_multi_ws_floats(self._lin_wgrad_problems(ws, gWu, gWi), ws["wg_splits"])))
 
     def _lin_tc(self):
         return self.proj_precision == "tf32"
+
+    def _lin_wgrad_problems(self, ws, gWu, gWi):
+        """(A, a_col, B, b_col, K, row_begin, row_end, out, bias_out, scale_by_g) for elimrec_wgrad_multi"""
+        B, Fw, gr = ws["B"], ws["F"], ws["g"]
+        ig, Oin, dOin, Zg = ws["inst_grad"], ws["O_inst"], ws["dO_inst"], ws["Zg"]
+        pr = [(ig, 0, Oin, 0, Fw, 0, B, gWu, gr["embedding_user_after_GCN.bias"], True),
+              (ig, 0, Oin, 0, Fw, B, 3 * B, gWi, gr["embedding_item_after_GCN.bias"], True)]
+        for j, m in enumerate(self.mods):
+            c = D * (j + 1)
+            pr.append((ig, c, Oin, c, D, 0, 3 * B, gr[f"s_dense_{m}.weight"], gr[f"s_dense_{m}.bias"], True))
+        for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):      # dO[inst] already carries g
+            pr.append((dOin, D * (j + 1), Zg, ko, kp, 0, 3 * B, ws["dWp"][m], None, False))
+        return pr
 
     def _lin_pack_weights(self, P, ws):
         """[W_m | b_m | 0] of this forward (TF32-rounded in 'tf32' mode; hi / lo split by _prep_weights in 'x3' mode)"""
@@ -257,53 +272,22 @@ class LinearSchedule:
             gWu, gWi, gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
             [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods], ws["inst_ws"], part=part)
 
-        def inst_weights():
-            """fusion Linear / head weight and bias gradients (instance rows)"""
-            ib(2)
-            if tied:
-                ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
-                ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
-
-        def proj_weights():
-            """d[W_m | b_m] = dO_m[inst]^T Zbar_m[inst]"""
-            Zg, ldz = ws["Zg"], ws["Zg"].stride(0)
-            if self.proj_precision == "x3":      # 3xTF32: hi*hi + hi*lo + lo*hi as ONE reduction over 9B stacked rows
-                ops.split3_rows(dOin, ws["dO3"], 3 * B, Fw, 0)
-                ops.split3_rows(Zg, ws["Zg3"], 3 * B, self._lin_Ktot, 1)
-            sts = []
-            for j, (m, kp, ko) in enumerate(zip(self.mods, self._lin_Kp, self._lin_koff)):
-                def go(j=j, m=m, kp=kp, ko=ko):
-                    if self.proj_precision == "x3":
-                        ops.linear_tf32_wgrad(ws["dO3"], ws["Zg3"][:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
-                                              tag="lin_wgrad_x3")
-                    elif self._lin_tc():
-                        ops.linear_tf32_wgrad(dOin, Zg[:, ko:ko + kp], ws["dWp"][m], ws["lin_wgrad_ws"][m], col=D * (j + 1),
-                                              tag="lin_wgrad_tc")
-                    else:
-                        ops.gemm(kp, D, 3 * B, Zg, 1, ldz, dOin, Fw, 1, ws["dWp"][m], 1, kp, split_k=ws["split_inst"], ws=ws["gemm_ws"],
-                                 a_off=ko, b_off=D * (j + 1), tag="lin_wgrad")
-                if j == 0 or self.proj_precision == "fp32":      # (the exact path shares one split-K scratch: in sequence)
-                    go()
-                else:
-                    sts.append(ops.fork_side(10 + j, high_priority=True))
-                    with torch.cuda.stream(sts[-1]):
-                        go()
-            for st in sts:
-                ops.join_side(st)
-
         def weights(fork):
-            """every gradient that is not an embedding table's - none of it waits for the propagation backward.  Two
-            independent high-priority branches beside the chain; returns what must be joined before Adam."""
+            """every gradient that is not an embedding table's, in ONE launch + its reduction (elimrec_wgrad_multi): fusion
+            Linears and heads from the instance gradients, d[W_m | b_m] = dO_m[inst]^T Zbar_m[inst] (weight AND bias: the ones
+            column of Zbar) - none of it waits for the propagation backward.  Returns what must be joined before Adam."""
+            def go():
+                ops.wgrad_multi(self._lin_wgrad_problems(ws, gWu, gWi), ws["wg_splits"], ws["wg_ws"], gscale)
+                if tied:
+                    ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
+                    ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
             if not fork:
-                inst_weights()
-                proj_weights()
+                go()
                 return []
-            s1, s2 = ops.fork_side(5, high_priority=True), ops.fork_side(6, high_priority=True)
+            s1 = ops.fork_side(5, high_priority=True)
             with torch.cuda.stream(s1):
-                inst_weights()
-            with torch.cuda.stream(s2):
-                proj_weights()
-            return [s1, s2]
+                go()
+            return [s1]
 
         ib(1)
         pending = None if split else weights(True)

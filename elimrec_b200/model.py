@@ -301,7 +301,7 @@ class EliMRec(LinearSchedule, BasicModel):
     # memory - is allocated once and shared by every batch size; PairwiseSamplerV2 has drop_last=False, so the last batch of
     # an epoch is short) and keys that describe the LAST forward
     _WS_PER_BATCH = ("B", "density", "terms", "inst_rows", "inst_grad", "O_inst", "dO_inst", "split_inst", "gemm_ws", "inst_ws",
-                     "inst_dummy", "F_c", "S_c", "c_users", "c_pos", "c_neg", "Zg", "lin_wgrad_ws", "Zg3", "dO3")
+                     "inst_dummy", "F_c", "S_c", "c_users", "c_pos", "c_neg", "Zg", "wg_splits", "wg_ws")
     _WS_PER_FORWARD = ("pre_last_layer", "last_layer", "seed_zeroed", "bw_pending")
 
     def _workspace(self, B):

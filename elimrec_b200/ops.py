@@ -359,6 +359,29 @@ def inst_backward(B, nt, F, inst_grad, O_inst, gscale, Wu, Wi, Ws, dO_inst, dWu,
          dbp, ptr(ws, F32), stream(), launches={1: 1, 2: 2, 3: 3}[part], tag=f"inst_backward{part}")
 
 
+def _wgrad_problems(problems):
+    arr = (_lib.WgradProblem * len(problems))()
+    for k, (A, a_col, B, b_col, K, r0, r1, out, bias, by_g) in enumerate(problems):
+        arr[k].A, arr[k].lda = ptr(A, F32) + 4 * a_col, A.stride(0)
+        arr[k].B, arr[k].ldb, arr[k].K = ptr(B, F32) + 4 * b_col, B.stride(0), K
+        arr[k].row_begin, arr[k].row_end = r0, r1
+        arr[k].out, arr[k].ldo, arr[k].bias_out, arr[k].scale_by_g = ptr(out, F32), out.stride(0), ptr(bias, F32, True), int(by_g)
+    return arr
+
+
+def wgrad_multi_ws_floats(problems, splits):
+    return int(_lib.lib().elimrec_wgrad_multi_workspace_floats(len(problems), _wgrad_problems(problems), splits))
+
+
+def wgrad_multi(problems, splits, ws, gscale=None):
+    """problems: list of (A, a_col, B, b_col, K, row_begin, row_end, out [64 x K], bias_out or None, scale_by_g):
+    out = g * A[r0:r1, a_col:a_col+64]^T B[r0:r1, b_col:b_col+K], bias_out = g * column sums of that A block - all problems in
+    one launch + one fixed-order reduction (elimrec_wgrad_multi)."""
+    arr = _wgrad_problems(problems)
+    call("elimrec_wgrad_multi", len(problems), arr, splits, ptr(ws, F32), ptr(gscale, F32, True), stream(), launches=2,
+         tag="wgrad_multi")
+
+
 def adam_apply_multi(items, consts_dev, b1, b2, eps, wd):
     """items: list of (param, grad_view, exp_avg, exp_avg_sq); one launch for all of them."""
     arr = (_lib.AdamTensor * len(items))()

@@ -310,6 +310,28 @@ int elimrec_inst_backward_part(int part, int B, int n_tables, int F, const float
                           const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu, float* dbi,
                           float* const* dWs_host, float* const* dbs_host, float* workspace, elimrec_stream_t stream);
 
+/* Every weight / bias gradient that contracts over the 3B instance rows in ONE launch (+ one fixed-order reduction),
+ * exact fp32 (csrc/wgrad_multi.cu):   out_p [64 x K_p] (row stride ldo) = g * A_p[r0:r1, 0:64]^T B_p[r0:r1, 0:K_p],
+ * bias_out_p [64] = g * column sums of A_p[r0:r1] (if not NULL);  g = *gscale_dev for problems with scale_by_g, else 1.
+ * Fusion Linears: A = instance gradient block 0, B = O[inst rows]; heads: block m of both; modality projections of the
+ * linear schedule: A = block m of dO[inst rows], B = Zbar_m[inst rows] (its ones column yields the bias gradient). */
+#define ELIMREC_WGRAD_MAX_PROBLEMS 12
+typedef struct {
+    const float* A;      /* [rows x >= 64], 16-byte aligned, lda % 4 == 0 */
+    int64_t lda;
+    const float* B;      /* [rows x >= K] */
+    int64_t ldb;
+    int64_t K;
+    int64_t row_begin, row_end;
+    float* out;
+    int64_t ldo;
+    float* bias_out;     /* may be NULL */
+    int32_t scale_by_g;
+} elimrec_wgrad_problem_t;
+int64_t elimrec_wgrad_multi_workspace_floats(int n, const elimrec_wgrad_problem_t* problems_host, int splits);
+int elimrec_wgrad_multi(int n, const elimrec_wgrad_problem_t* problems_host, int splits /* row ranges per tile, <= 64 */,
+                        float* workspace, const float* gscale_dev /* may be NULL */, elimrec_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * adam - replaces torch.optim.Adam(lr, weight_decay) .step() (main.py:49,101): coupled L2,
  * betas (0.9, 0.999), eps 1e-8, bias correction from the device-resident step counter.

@@ -335,6 +335,20 @@ def inst_backward(B, nt, Fw, inst_grad, O_inst, gscale, Wu, Wi, Ws, dO_inst, dWu
             dbs[m].copy_(ig[:, blk].sum(0))
 
 
+def wgrad_multi_ws_floats(problems, splits):
+    return 1
+
+
+def wgrad_multi(problems, splits, ws, gscale=None):
+    _log("wgrad_multi")
+    for A, a_col, B, b_col, K, r0, r1, out, bias, by_g in problems:
+        g = float(gscale) if (by_g and gscale is not None) else 1.0
+        a = A[r0:r1, a_col:a_col + 64]
+        out[:, :K] = g * (a.t() @ B[r0:r1, b_col:b_col + K])
+        if bias is not None:
+            bias.copy_(g * a.sum(0))
+
+
 def adam_tick(step_dev, consts_dev, lr, b1, b2):
     step_dev += 1
     t = int(step_dev)

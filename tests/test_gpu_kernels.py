@@ -646,3 +646,32 @@ def test_batch_sampler_is_a_slice_of_the_epoch_stream(dev):
         assert torch.equal(bu, eu[sl]) and torch.equal(bp, ep[sl]) and torch.equal(bn, en[sl])
         wu, wp, wn = philox_sampler.sample_triples(11, 2, B, uid, ptr, items, I, first=step * B)
         assert np.array_equal(bu.cpu().numpy(), wu) and np.array_equal(bp.cpu().numpy(), wp) and np.array_equal(bn.cpu().numpy(), wn)
+
+
+def test_wgrad_multi_matches_fp64(dev):
+    """elimrec_wgrad_multi: several skinny A^T B problems (row ranges, column blocks, a K that is not a multiple of 64 and a
+    B whose rows are not 16-byte aligned for the tail tile) + bias column sums, against fp64; deterministic."""
+    from elimrec_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    R = 1000
+    A = torch.randn(R, 256, generator=g).to(dev)
+    Bm = torch.randn(R, 300, generator=g).to(dev)
+    Z = torch.randn(R, 140, generator=g).to(dev)
+    gs = torch.tensor([0.37], device=dev)
+    outs = [torch.full((64, 256), float("nan"), device=dev), torch.full((64, 64), float("nan"), device=dev),
+            torch.full((64, 132), float("nan"), device=dev), torch.full((64, 100), float("nan"), device=dev)]
+    b0, b1 = torch.full((64,), float("nan"), device=dev), torch.full((64,), float("nan"), device=dev)
+    pr = [(A, 0, Bm, 0, 256, 0, 400, outs[0], b0, True), (A, 64, Bm, 64, 64, 0, R, outs[1], b1, True),
+          (A, 128, Z, 4, 132, 0, R, outs[2], None, False), (A, 192, Bm, 1, 100, 123, 777, outs[3], None, False)]
+    for splits in (1, 7, 24):
+        ws = torch.empty(ops.wgrad_multi_ws_floats(pr, splits), device=dev)
+        ops.wgrad_multi(pr, splits, ws, gs)
+        first = [o.clone() for o in outs]
+        for (A_, ac, B_, bc, K, r0, r1, out, bias, by_g) in pr:
+            sc = 0.37 if by_g else 1.0
+            want = sc * (A_[r0:r1, ac:ac + 64].double().t() @ B_[r0:r1, bc:bc + K].double())
+            assert rel_err(out[:, :K], want) < 2e-6
+            if bias is not None:
+                assert rel_err(bias, sc * A_[r0:r1, ac:ac + 64].double().sum(0)) < 2e-6
+        ops.wgrad_multi(pr, splits, ws, gs)
+        assert all(torch.equal(a, b) for a, b in zip(first, outs))

@@ -38,9 +38,8 @@ def main():
         torch.cuda.synchronize()
     ev = [e for e in prof.profiler.kineto_results.events() if e.device_type() == torch.autograd.DeviceType.CUDA]
     ev.sort(key=lambda e: e.start_ns())
-    first = "pack_proj" if model.linear else "prep_multi"
-    idx = [i for i, e in enumerate(ev) if first in e.name()]
-    ev = ev[idx[-1]:] if idx else ev
+    idx = [i for i, e in enumerate(ev) if "adam_multi" in e.name()]      # a step = everything between two Adam launches
+    ev = ev[idx[-2] + 1:idx[-1] + 1]
     t0 = ev[0].start_ns()
     streams = {}
     print(f"# one graph-replayed train step ({sched} schedule), {workload}-shape, batch 2048; columns: start_us duration_us stream kernel")
