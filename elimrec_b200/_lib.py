@@ -40,8 +40,9 @@ class LinearDesc(C.Structure):
 
 
 class Spmm64Half(C.Structure):
-    _fields_ = [("n_seg", i32), ("n_heavy_seg", i32), ("seg", vp), ("col", vp), ("val", vp), ("X", vp), ("ldx", i64), ("Y", vp),
-                ("ldy", i64), ("row_mask", vp), ("col_mask", vp), ("addend", vp), ("ld_add", i64), ("add_mask", vp)]
+    _fields_ = [("n_item", i32), ("n_split_item", i32), ("item", vp), ("split_rows", vp), ("counter", vp), ("partial", vp),
+                ("col", vp), ("val", vp), ("X", vp), ("ldx", i64), ("Y", vp), ("ldy", i64), ("row_mask", vp), ("col_mask", vp),
+                ("addend", vp), ("ld_add", i64), ("add_mask", vp)]
 
 
 class WgradProblem(C.Structure):

@@ -3,20 +3,27 @@
 //
 // Why not spmm_seg_kernel<64>: with one warp per row a 64-float row (256 B) keeps only half a warp busy per edge, and every
 // row pays three DEPENDENT round trips to L2 (segment descriptor -> col/val -> neighbour rows) before its first FMA; at an
-// average degree of 8-17 that chain, not bandwidth, set the time (6 TB/s L2->SM against ~11 TB/s for the 256-wide launch).
-// Here an 8-lane GROUP owns a row (a lane holds 2 x float4 = columns [4l, 4l+4) and [32+4l, 32+4l+4)), so a warp works on
-// FOUR rows at once: the dependent chain is shared by 4 rows, a warp-level LDG.128 still covers whole 128-byte lines, and
-// UNR edges per group (2 x UNR LDG.128 per lane) are in flight.  The two halves (user rows <- item rows, item rows <- user
-// rows) are independent and go into the same grid: one launch instead of two, no tail of one half idling the machine.
-// Rows longer than the segment length (split rows) keep the CTA-cooperative path of spmm.cu (elimrec_spmm part = 1).
-// Edges are accumulated in CSR order by one group: deterministic, and a masked launch gives the bits of the dense one.
+// average degree of 8-17 that chain, not bandwidth, set the time (6 TB/s L2->SM against ~11 TB/s for the 256-wide launch),
+// and the split rows were a second launch that queued behind the first.
+// Here an 8-lane GROUP owns a work item (a lane holds 2 x float4 = columns [4l, 4l+4) and [32+4l, 32+4l+4)), so a warp works
+// on FOUR items at once: the dependent chain is shared by 4 rows, a warp-level LDG.128 still covers whole 128-byte lines,
+// and UNR edges per group (2 x UNR LDG.128 per lane) are in flight.  Work items (elimrec_b200/graph.py build_segments64):
+// rows of <= 64 edges are one item, sorted by descending degree so the four rows of a warp run in lock step; longer rows are
+// dealt evenly over several items that come FIRST in the list, write partial sums to scratch, and the last-arriving item of
+// the row (atomic counter) adds the partials in item order - deterministic, no float atomics, and the reduction of the
+// hottest rows overlaps the bulk of the launch.  The two halves (user rows <- item rows, item rows <- user rows) are
+// independent and share the grid: one launch per propagation layer.
+// Edges are accumulated in CSR order: a masked launch gives the bits of the dense one.
 #include "common.cuh"
 
 namespace {
 
 struct Half64 {
-    const int4* seg;       // whole-row segments of this half: {row, edge_begin, edge_end, -1}
-    int n_light;
+    const int4* item;      // {row, edge_begin, edge_end, split_row_id or -1}; split-row items first
+    int n_item;
+    const int2* hrow;      // split row h: {first item, number of items}
+    int* counter;          // per split row, zero on entry, left zero
+    float* partial;        // [n_split_items x 64]
     const int* col;
     const float* val;
     const float* X;
@@ -35,20 +42,20 @@ __global__ void __launch_bounds__(256, MINB)
 spmm64_pair_kernel(const Half64 a, const Half64 b) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, gl = lane & 7;
-    const long long item = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * 4 + (lane >> 3);
-    const bool in_a = item < a.n_light;
-    const long long idx = in_a ? item : item - a.n_light;
-    const int4* seg = in_a ? a.seg : b.seg;
-    const int* col = in_a ? a.col : b.col;
-    const float* val = in_a ? a.val : b.val;
-    const float* X = in_a ? a.X : b.X;
-    const long long ldx = in_a ? a.ldx : b.ldx;
-    const unsigned char* rmask = in_a ? a.row_mask : b.row_mask;
-    const unsigned char* cmask = in_a ? a.col_mask : b.col_mask;
-    bool active = idx < (in_a ? a.n_light : b.n_light);
+    const long long it_all = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * 4 + (lane >> 3);
+    const bool in_a = it_all < a.n_item;
+#define SEL(f) (in_a ? a.f : b.f)                  /* kernel parameters: a select between two constant-bank values */
+    const long long idx = in_a ? it_all : it_all - a.n_item;
+    const int* col = SEL(col);
+    const float* val = SEL(val);
+    const float* X = SEL(X);
+    const long long ldx = SEL(ldx);
+    const unsigned char* cmask = SEL(col_mask);
+    bool active = idx < SEL(n_item);
     int4 sg = make_int4(0, 0, 0, -1);
     if (active) {
-        sg = __ldg(seg + idx);
+        sg = __ldg(SEL(item) + idx);
+        const unsigned char* rmask = SEL(row_mask);
         if (rmask != nullptr && __ldg(rmask + sg.x) == 0) active = false;
     }
     const int beg = active ? sg.y : 0, end = active ? sg.z : 0;
@@ -57,8 +64,7 @@ spmm64_pair_kernel(const Half64 a, const Half64 b) {
 
     float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
     for (int it = 0; it < n_it; ++it) {
-        const int e0 = beg + it * 8;
-        const int e = e0 + gl;
+        const int e = beg + it * 8 + gl;
         int c = 0;
         float w = 0.f;
         bool live = e < end;
@@ -91,36 +97,86 @@ spmm64_pair_kernel(const Half64 a, const Half64 b) {
             }
         }
     }
+
+    // split rows: partial sum to scratch; the last-arriving item of the row adds all of them in item order
+    const bool split = active && sg.w >= 0;
+    int old = -1;
+    float* partial = SEL(partial);
+    int* counter = SEL(counter);
+    if (split) {
+        float4* pp = reinterpret_cast<float4*>(partial + idx * 64) + gl;
+        pp[0] = acc0;
+        pp[8] = acc1;
+        __threadfence();
+    }
+    if (__any_sync(full, split)) {
+        if (split && gl == 0) old = atomicAdd(counter + sg.w, 1);
+        old = __shfl_sync(full, old, 0, 8);
+    }
+    if (split) {
+        const int2 hr = __ldg(SEL(hrow) + sg.w);
+        if (old != hr.y - 1) {
+            active = false;                       // somebody else finishes this row
+        } else {
+            __threadfence();
+            acc0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc1 = acc0;
+            const float4* ps = reinterpret_cast<const float4*>(partial + (long long)hr.x * 64) + gl;
+            constexpr int RU = 4;
+            for (int s = 0; s < hr.y; s += RU) {
+                float4 t0[RU], t1[RU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const bool ok = s + u < hr.y;
+                    t0[u] = ok ? __ldcg(ps + (long long)(s + u) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    t1[u] = ok ? __ldcg(ps + (long long)(s + u) * 16 + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    add4(acc0, t0[u]);
+                    add4(acc1, t1[u]);
+                }
+            }
+            if (gl == 0) counter[sg.w] = 0;     // ready for the next launch
+        }
+    }
+
     if (active) {
-        const float* addend = in_a ? a.addend : b.addend;
+        const float* addend = SEL(addend);
         if (addend != nullptr) {      // the layer-mean gradient entering this layer of the backward chain (instance rows)
-            const unsigned char* am = in_a ? a.add_mask : b.add_mask;
+            const unsigned char* am = SEL(add_mask);
             if (am == nullptr || __ldg(am + sg.x) != 0) {
-                const float4* g = reinterpret_cast<const float4*>(addend + (long long)sg.x * (in_a ? a.ld_add : b.ld_add)) + gl;
+                const float4* g = reinterpret_cast<const float4*>(addend + (long long)sg.x * SEL(ld_add)) + gl;
                 add4(acc0, __ldg(g));
                 add4(acc1, __ldg(g + 8));
             }
         }
-        float* Y = in_a ? a.Y : b.Y;
-        const long long ldy = in_a ? a.ldy : b.ldy;
-        float4* y = reinterpret_cast<float4*>(Y + (long long)sg.x * ldy) + gl;
+        float4* y = reinterpret_cast<float4*>(SEL(Y) + (long long)sg.x * SEL(ldy)) + gl;
         y[0] = acc0;
         y[8] = acc1;
     }
+#undef SEL
 }
 
 int fill_half(Half64& h, const elimrec_spmm64_half_t* s, const char** err) {
     h = Half64{};
     if (s == nullptr) return 0;
-    if (s->n_heavy_seg < 0 || s->n_heavy_seg > s->n_seg) { *err = "n_heavy_seg out of range"; return -1; }
+    if (s->n_split_item < 0 || s->n_split_item > s->n_item) { *err = "n_split_item out of range"; return -1; }
     if (s->ldx % 4 != 0 || s->ldy % 4 != 0) { *err = "row strides must be multiples of 4 floats"; return -1; }
-    h.seg = reinterpret_cast<const int4*>(s->seg) + s->n_heavy_seg;
-    h.n_light = s->n_seg - s->n_heavy_seg;
+    h.item = reinterpret_cast<const int4*>(s->item);
+    h.n_item = s->n_item;
+    h.hrow = reinterpret_cast<const int2*>(s->split_rows);
+    h.counter = s->counter;
+    h.partial = s->partial;
     h.col = s->col; h.val = s->val; h.X = s->X; h.ldx = s->ldx; h.Y = s->Y; h.ldy = s->ldy;
     h.row_mask = s->row_mask; h.col_mask = s->col_mask;
     h.addend = s->addend; h.ld_add = s->ld_add; h.add_mask = s->add_mask;
     if (s->addend != nullptr && s->ld_add % 4 != 0) { *err = "addend stride must be a multiple of 4 floats"; return -1; }
-    if (h.n_light > 0 && (h.X == nullptr || h.Y == nullptr || h.seg == nullptr)) { *err = "NULL buffer"; return -1; }
+    if (h.n_item > 0 && (h.X == nullptr || h.Y == nullptr || h.item == nullptr)) { *err = "NULL buffer"; return -1; }
+    if (s->n_split_item > 0 && (h.hrow == nullptr || h.counter == nullptr || h.partial == nullptr)) {
+        *err = "split rows need split_rows / counter / partial";
+        return -1;
+    }
     return 0;
 }
 
@@ -135,9 +191,9 @@ ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimre
         elimrec_set_error("elimrec_spmm64_pair: %s", err);
         return -1;
     }
-    const long long items = (long long)ha.n_light + hb.n_light;
+    const long long items = (long long)ha.n_item + hb.n_item;
     if (items <= 0) return 0;
-    const unsigned blocks = (unsigned)((items + 31) / 32);      // 8 warps x 4 rows per CTA
+    const unsigned blocks = (unsigned)((items + 31) / 32);      // 8 warps x 4 items per CTA
     cudaStream_t st = er_stream(stream);
     switch (variant) {
         case 1: spmm64_pair_kernel<8, 2><<<blocks, 256, 0, st>>>(ha, hb); break;

@@ -127,20 +127,29 @@ __global__ void __launch_bounds__(256) wgrad_multi_kernel(const __grid_constant_
     if (want_bias && tid < 64) a.ws[(long long)a.n_tiles * a.splits * 4096 + ((long long)tile * a.splits + split) * 64 + tid] = bsum;
 }
 
+// grid (tiles, 16): CTA y sums 256 elements of the tile over the splits, in split order
 __global__ void __launch_bounds__(256) wgrad_multi_reduce_kernel(const __grid_constant__ WgArgs a) {
     const int tile = blockIdx.x;
     const WgProblem& pr = a.p[wg_find(a, tile)];
     const int c0 = (tile - pr.tile0) * 64;
     const float g = (pr.scale_by_g && a.gscale != nullptr) ? __ldg(a.gscale) : 1.f;
     const float* part = a.ws + (long long)tile * a.splits * 4096;
-    for (int e = threadIdx.x; e < 4096; e += 256) {
+    {
+        const int e = blockIdx.y * 256 + threadIdx.x;
         const int o = e >> 6, c = e & 63;
-        if (c0 + c >= pr.K) continue;
-        float s = 0.f;
-        for (int z = 0; z < a.splits; ++z) s += part[(long long)z * 4096 + e];
-        pr.out[(long long)o * pr.ldo + c0 + c] = g * s;
+        if (c0 + c < pr.K) {
+            float s = 0.f;
+            int z = 0;
+            for (; z + 4 <= a.splits; z += 4) {
+                const float t0 = part[(long long)z * 4096 + e], t1 = part[(long long)(z + 1) * 4096 + e];
+                const float t2 = part[(long long)(z + 2) * 4096 + e], t3 = part[(long long)(z + 3) * 4096 + e];
+                s = (((s + t0) + t1) + t2) + t3;
+            }
+            for (; z < a.splits; ++z) s += part[(long long)z * 4096 + e];
+            pr.out[(long long)o * pr.ldo + c0 + c] = g * s;
+        }
     }
-    if (pr.bias != nullptr && c0 == 0 && threadIdx.x < 64) {
+    if (pr.bias != nullptr && c0 == 0 && blockIdx.y == 0 && threadIdx.x < 64) {
         const float* bp = a.ws + (long long)a.n_tiles * a.splits * 4096 + (long long)tile * a.splits * 64 + threadIdx.x;
         float s = 0.f;
         for (int z = 0; z < a.splits; ++z) s += bp[z * 64];
@@ -184,7 +193,7 @@ ELIMREC_API int elimrec_wgrad_multi(int n, const elimrec_wgrad_problem_t* proble
     cudaStream_t st = er_stream(stream);
     wgrad_multi_kernel<<<dim3(tiles, splits), 256, 0, st>>>(a);
     ER_LAUNCH_CHECK();
-    wgrad_multi_reduce_kernel<<<tiles, 256, 0, st>>>(a);
+    wgrad_multi_reduce_kernel<<<dim3(tiles, 16), 256, 0, st>>>(a);
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -37,6 +37,43 @@ if os.environ.get("ELIMREC_SEG"):   # tuning sweeps: "seg_len,heavy_seg_len,bala
     SEG_LEN, HEAVY_SEG_LEN, HEAVY_BALANCED = int(_a), int(_b), bool(int(_c))
 
 
+SEG64_LEN = 64      # work items of the 64-wide pair kernel (csrc/spmm64.cu): rows of at most this many edges are one item, longer
+                    # rows are dealt evenly over ceil(deg / SEG64_LEN) items whose partial sums the last-arriving item adds up
+
+
+def build_segments64(indptr: np.ndarray, seg_len: int = SEG64_LEN, row_lo: int = 0, row_hi: int | None = None):
+    """Work list of elimrec_spmm64_pair for one CSR half: item = (row, edge_begin, edge_end, split_row_id or -1).
+    Split rows first (longest first: their fixed-order reduction then overlaps the bulk of the launch), then the whole rows by
+    DESCENDING degree - the four rows a warp works on in lock step have the same length, and the shortest rows form the tail.
+    Returns (items [n x 4] int32, split_rows [h x 2] int32 = (first item, number of items), n_split_items)."""
+    n_rows = indptr.size - 1
+    row_hi = n_rows if row_hi is None else row_hi
+    rows = np.arange(row_lo, row_hi, dtype=np.int64)
+    beg = indptr[rows]
+    deg = indptr[rows + 1] - beg
+    heavy = deg > seg_len
+    h_order = np.argsort(-deg[heavy], kind="stable")
+    h_rows, h_beg, h_deg = rows[heavy][h_order], beg[heavy][h_order], deg[heavy][h_order]
+    h_n = -(-h_deg // seg_len)
+    h_len = -(-h_deg // np.maximum(h_n, 1))
+    n_hitems = int(h_n.sum())
+    parts = []
+    hrow = np.zeros((h_rows.size, 2), dtype=np.int32)
+    if h_rows.size:
+        first = np.concatenate([[0], np.cumsum(h_n)[:-1]])
+        hrow[:, 0], hrow[:, 1] = first, h_n
+        k = np.arange(n_hitems) - np.repeat(first, h_n)
+        ln = np.repeat(h_len, h_n)
+        row_end = np.repeat(h_beg + h_deg, h_n)
+        sb = np.minimum(np.repeat(h_beg, h_n) + k * ln, row_end)
+        parts.append(np.stack([np.repeat(h_rows, h_n), sb, np.minimum(sb + ln, row_end), np.repeat(np.arange(h_rows.size), h_n)], axis=1))
+    l_order = np.argsort(-deg[~heavy], kind="stable")
+    l_rows, l_beg, l_deg = rows[~heavy][l_order], beg[~heavy][l_order], deg[~heavy][l_order]
+    parts.append(np.stack([l_rows, l_beg, l_beg + l_deg, np.full(l_rows.size, -1)], axis=1))
+    items = np.concatenate(parts, axis=0).astype(np.int32)
+    return np.ascontiguousarray(items), hrow, n_hitems
+
+
 class CsrHalf:
     """One CSR block + its segment work-list on the device."""
 
@@ -58,6 +95,13 @@ class CsrHalf:
         self.col = torch.from_numpy(self.indices_host).to(device)
         self.val = torch.from_numpy(self.vals_host).to(device)
         self.indptr = torch.from_numpy(self.indptr_host).to(device)
+        # work list of the 64-wide pair kernel (its own split: 8-lane groups, no CTA padding)
+        it, hrow, n_hit = build_segments64(self.indptr_host, SEG64_LEN, row_lo, self.n_rows if row_hi is None else row_hi)
+        self.n_item64, self.n_split64 = int(it.shape[0]), int(n_hit)
+        self.item64 = torch.from_numpy(it if it.size else np.zeros((1, 4), np.int32)).to(device)
+        self.hrow64 = torch.from_numpy(hrow if hrow.size else np.zeros((1, 2), np.int32)).to(device)
+        self.counter64 = torch.zeros(max(1, hrow.shape[0]), dtype=torch.int32, device=device)
+        self.partial64 = torch.empty(max(1, n_hit) * 64, dtype=torch.float32, device=device)
 
     def with_values(self, vals: np.ndarray) -> "CsrHalf":
         """Same structure, work-lists and scratch (never used concurrently with this one), different edge values."""

@@ -220,11 +220,10 @@ class LinearSchedule:
                 ops.mark_neighbors(g.iu, mask[U:], need2[:U])
             ev_masks = torch.cuda.Event()
             ev_masks.record(side)
-            self._lin_pack_weights(P, ws)
             ops.gather_rows(rows, self._zbar, ws["Zg"], self._lin_Ktot)
-            self._lin_modal_gemm(ws, ws["Zg"], ws["O_inst"], 3 * B)
         aux = ops.fork_side(7, high_priority=True)
         with torch.cuda.stream(aux):
+            self._lin_pack_weights(P, ws)
             if getattr(self, "_tick_early", False):      # train_step: the optimizer's step counter / bias corrections
                 self._adam.tick()
             self._snapshot(P, ws)
@@ -234,6 +233,9 @@ class LinearSchedule:
             ops.zero_rows(rows, 0, U + I, 0, ws["GA"], D)
             ops.zero_rows(rows, 0, U + I, 0, ws["GB"], D)
             ws["seed_zeroed"] = True
+        with torch.cuda.stream(side):      # the modality GEMMs: packed weights (aux) x gathered Zbar rows (side)
+            ops.join_side(aux)
+            self._lin_modal_gemm(ws, ws["Zg"], ws["O_inst"], 3 * B)
         # the propagation: p_k = A_hat p_{k-1}, both halves 64 wide in one launch
         in_u, in_i = Eu, Ei
         cur = torch.cuda.current_stream()

@@ -85,37 +85,24 @@ def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, 
         _lib.PROFILE["events"].append((f"spmm{width}m" if masked else f"spmm{width}", e0, e1))
 
 
+def spmm64_half(h, X, Y, row_mask=None, col_mask=None, addend=None, add_mask=None):
+    d = _lib.Spmm64Half()
+    d.n_item, d.n_split_item, d.item, d.split_rows = h.n_item64, h.n_split64, ptr(h.item64), ptr(h.hrow64)
+    d.counter, d.partial, d.col, d.val = ptr(h.counter64), ptr(h.partial64), ptr(h.col), ptr(h.val)
+    d.X, d.ldx, d.Y, d.ldy = ptr(X, F32), X.stride(0), ptr(Y, F32), Y.stride(0)
+    d.row_mask, d.col_mask = ptr(row_mask, torch.uint8, True), ptr(col_mask, torch.uint8, True)
+    d.addend, d.ld_add, d.add_mask = ptr(addend, F32, True), (addend.stride(0) if addend is not None else 0), ptr(add_mask, torch.uint8, True)
+    return d
+
+
 def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row_mask_i=None, col_mask_u=None, col_mask_i=None,
                 addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, variant=0):
-    """Both halves of a 64-wide propagation layer: Y_u = half_u @ X_for_u (user rows gather item rows), Y_i = half_i @ X_for_i.
-    Whole rows of both halves are ONE launch (elimrec_spmm64_pair); split rows go through the CTA-cooperative kernel on a
-    side stream.  ``col_mask_u``: mask over the COLUMNS of half_u (item rows), etc.  ``addend_*`` / ``add_mask_*``:
-    Y[row] += addend[row] on the marked rows (the gradient entering this layer of the backward chain)."""
-    def desc(h, X, Y, rm, cm, ad, am):
-        d = _lib.Spmm64Half()
-        d.n_seg, d.n_heavy_seg, d.seg, d.col, d.val = h.n_seg, h.n_heavy_seg, ptr(h.seg), ptr(h.col), ptr(h.val)
-        d.X, d.ldx, d.Y, d.ldy = ptr(X, F32), X.stride(0), ptr(Y, F32), Y.stride(0)
-        d.row_mask, d.col_mask = ptr(rm, torch.uint8, True), ptr(cm, torch.uint8, True)
-        d.addend, d.ld_add, d.add_mask = ptr(ad, F32, True), (ad.stride(0) if ad is not None else 0), ptr(am, torch.uint8, True)
-        return d
-    todo = [(half_u, X_for_u, Y_u, row_mask_u, col_mask_u, addend_u, add_mask_u),
-            (half_i, X_for_i, Y_i, row_mask_i, col_mask_i, addend_i, add_mask_i)]
-    heavy = [t for t in todo if t[0].n_heavy_seg > 0]
-    side = fork_side(1) if heavy else None
-    if heavy:
-        with torch.cuda.stream(side):
-            for h, X, Y, rm, cm, ad, am in heavy:
-                args = [64, 1, h.n_seg, h.n_heavy_seg, ptr(h.seg), ptr(h.heavy), ptr(h.counter), ptr(h.col), ptr(h.val), ptr(X, F32),
-                        X.stride(0), ptr(Y, F32), Y.stride(0), ptr(h.partial), None]
-                if rm is not None or cm is not None or ad is not None:
-                    call("elimrec_spmm_masked", *args, ptr(rm, torch.uint8, True), ptr(cm, torch.uint8, True), 50, ptr(ad, F32, True),
-                         (ad.stride(0) if ad is not None else 0), ptr(am, torch.uint8, True), stream(), launches=1, tag="spmm64_heavy")
-                else:
-                    call("elimrec_spmm", *args, stream(), launches=1, tag="spmm64_heavy")
-    da, db = desc(*todo[0]), desc(*todo[1])
+    """Both halves of a 64-wide propagation layer in ONE launch (elimrec_spmm64_pair): Y_u = half_u @ X_for_u (user rows gather
+    item rows), Y_i = half_i @ X_for_i.  ``col_mask_u``: mask over the COLUMNS of half_u (item rows), etc.  ``addend_*`` /
+    ``add_mask_*``: Y[row] += addend[row] on the marked rows (the gradient entering this layer of the backward chain)."""
+    da = spmm64_half(half_u, X_for_u, Y_u, row_mask_u, col_mask_u, addend_u, add_mask_u)
+    db = spmm64_half(half_i, X_for_i, Y_i, row_mask_i, col_mask_i, addend_i, add_mask_i)
     call("elimrec_spmm64_pair", C.byref(da), C.byref(db), int(variant), stream(), tag="spmm64_pair")
-    if heavy:
-        join_side(side)
 
 
 def mark_rows(rows, mask):

@@ -84,14 +84,20 @@ int elimrec_spmm_masked(int width, int part, int n_seg, int n_heavy_seg, const i
                         int64_t ldy, float* partial, const elimrec_mean_epilogue_t* epi, const uint8_t* row_mask,
                         const uint8_t* col_mask, int row_density_pct /* expected % of marked rows: scheduling hint only */,
                         const float* addend, int64_t ld_add, const uint8_t* add_mask, elimrec_stream_t stream);
-/* The 64-wide propagation of BOTH CSR halves in one launch (csrc/spmm64.cu): an 8-lane group owns a row, four rows per warp.
- * Each half: Y[row, 0:64] = sum_e val[e] * X[col[e], 0:64] over its WHOLE-row segments [n_heavy_seg, n_seg) - the split rows
- * [0, n_heavy_seg) go through elimrec_spmm / elimrec_spmm_masked with part = 1, concurrently (they write other rows).
+/* The 64-wide propagation of BOTH CSR halves in one launch (csrc/spmm64.cu): an 8-lane group owns a work item, four items
+ * per warp.  Each half: Y[row, 0:64] = sum_e val[e] * X[col[e], 0:64].  Work items (elimrec_b200/graph.py build_segments64):
+ * item[i] = {row, edge_begin, edge_end, split_row_id or -1}; rows longer than 64 edges are dealt evenly over several items
+ * that come first in the list (n_split_item of them), write partial sums to `partial` ([n_split_item x 64] floats) and the
+ * last-arriving item of split row h (counter[h], zero on entry and on exit; split_rows[h] = {first item, number of items})
+ * adds them in item order - deterministic.  Whole rows follow by descending degree.
  * row_mask / col_mask as in elimrec_spmm_masked (either may be NULL); masked rows carry the bits of the dense launch.
  * `b` may be NULL.  variant: 0 = default tuning; 1..4 = other unroll / occupancy points (tools/spmm64_bench.py). */
 typedef struct {
-    int32_t n_seg, n_heavy_seg;
-    const int32_t* seg;
+    int32_t n_item, n_split_item;
+    const int32_t* item;
+    const int32_t* split_rows;
+    int32_t* counter;
+    float* partial;
     const int32_t* col;
     const float* val;
     const float* X;

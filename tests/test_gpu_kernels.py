@@ -675,3 +675,43 @@ def test_wgrad_multi_matches_fp64(dev):
                 assert rel_err(bias, sc * A_[r0:r1, ac:ac + 64].double().sum(0)) < 2e-6
         ops.wgrad_multi(pr, splits, ws, gs)
         assert all(torch.equal(a, b) for a, b in zip(first, outs))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])
+def test_spmm64_pair_matches_fp64(dev, variant):
+    """elimrec_spmm64_pair (both halves in one launch, 8-lane groups, split rows with last-arriver reduction): dense, row- and
+    column-masked, with the additive epilogue; against fp64; deterministic; masked rows carry the bits of the dense launch."""
+    from elimrec_b200 import ops
+    from elimrec_b200.graph import BipartiteGraph
+    U, I = 700, 500
+    m = _rand_graph(U, I, 6000, [(3, 480), (10, 130), (11, 65), (12, 64)], seed=variant)
+    g = BipartiteGraph(m, dev)
+    assert g.ui.n_split64 > 0 and g.iu.n_item64 >= I
+    X = torch.randn(U + I, 64, device=dev)
+    A_ui = sp.csr_matrix((g.ui.vals_host.astype(np.float64), g.ui.indices_host, g.ui.indptr_host), shape=(U, I))
+    A_iu = sp.csr_matrix((g.iu.vals_host.astype(np.float64), g.iu.indices_host, g.iu.indptr_host), shape=(I, U))
+    Xd = X.double().cpu().numpy()
+    ref = np.concatenate([A_ui @ Xd[U:], A_iu @ Xd[:U]])
+    Y = torch.full((U + I, 64), float("nan"), device=dev)
+    ops.spmm64_pair(g.ui, g.iu, X[U:], X[:U], Y[:U], Y[U:], variant=variant)
+    assert rel_err(Y, ref) < FP32_TOL
+    Y2 = torch.empty_like(Y)
+    ops.spmm64_pair(g.ui, g.iu, X[U:], X[:U], Y2[:U], Y2[U:], variant=variant)
+    assert torch.equal(Y, Y2) and int(g.ui.counter64.abs().sum()) == 0 and int(g.iu.counter64.abs().sum()) == 0
+    # row mask: marked rows = dense bits, the others untouched
+    rm = (torch.rand(U + I, device=dev) < 0.4).to(torch.uint8)
+    rm[3] = 1
+    Y3 = torch.full_like(Y, 7.0)
+    ops.spmm64_pair(g.ui, g.iu, X[U:], X[:U], Y3[:U], Y3[U:], row_mask_u=rm[:U], row_mask_i=rm[U:], variant=variant)
+    assert torch.equal(Y3[rm.bool()], Y[rm.bool()]) and (Y3[~rm.bool()] == 7.0).all()
+    # column mask: dropped columns may hold garbage; + additive epilogue on marked rows
+    cm = (torch.rand(U + I, device=dev) < 0.3).to(torch.uint8)
+    Xg = torch.where(cm.bool().unsqueeze(1), X, torch.full_like(X, float("nan")))
+    add = torch.randn(U + I, 64, device=dev)
+    am = (torch.rand(U + I, device=dev) < 0.5).to(torch.uint8)
+    Y4 = torch.empty_like(Y)
+    ops.spmm64_pair(g.ui, g.iu, Xg[U:], Xg[:U], Y4[:U], Y4[U:], col_mask_u=cm[U:], col_mask_i=cm[:U], addend_u=add[:U],
+                    addend_i=add[U:], add_mask_u=am[:U], add_mask_i=am[U:], variant=variant)
+    Xz = (X * cm.unsqueeze(1)).double().cpu().numpy()
+    ref4 = np.concatenate([A_ui @ Xz[U:], A_iu @ Xz[:U]]) + (add * am.unsqueeze(1)).double().cpu().numpy()
+    assert rel_err(Y4, ref4) < FP32_TOL

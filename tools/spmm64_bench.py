@@ -47,7 +47,8 @@ def main():
     A_iu = torch.sparse_csr_tensor(g.iu.indptr, g.iu.col.long(), g.iu.val, size=(I, U))
     ref = torch.cat([torch.sparse.mm(A_ui, X[U:]), torch.sparse.mm(A_iu, X[:U])])
     alg = g.nnz * 8 + (U + I + 2) * 4 + 2 * (U + I) * 64 * 4
-    out = {"workload": workload, "U": U, "I": I, "nnz": g.nnz, "heavy_seg": [g.ui.n_heavy_seg, g.iu.n_heavy_seg],
+    out = {"workload": workload, "U": U, "I": I, "nnz": g.nnz, "split_items": [g.ui.n_split64, g.iu.n_split64],
+           "items": [g.ui.n_item64, g.iu.n_item64],
            "algorithmic_bytes_per_layer": alg, "gathered_bytes_per_layer": g.nnz * 256}
 
     def old():
@@ -67,28 +68,6 @@ def main():
         err = float((Y1 - ref).abs().max() / ref.abs().max())
         out[f"spmm64_pair v{v}"] = {"us": round(t, 2), "alg_GBps": round(alg / t / 1e3, 1), "gather_TBps": round(g.nnz * 256 / t / 1e6, 2),
                                     "err": err}
-    # light part only (no split rows) to see what the split-row launch costs
-    for v in (0, 1):
-        import ctypes as C
-        from elimrec_b200 import _lib
-        from elimrec_b200._lib import call, ptr, stream
-
-        def light(v=v):
-            def desc(h, Xs, Ys):
-                d = _lib.Spmm64Half()
-                d.n_seg, d.n_heavy_seg, d.seg, d.col, d.val = h.n_seg, h.n_heavy_seg, ptr(h.seg), ptr(h.col), ptr(h.val)
-                d.X, d.ldx, d.Y, d.ldy = ptr(Xs), Xs.stride(0), ptr(Ys), Ys.stride(0)
-                return d
-            da, db = desc(g.ui, X[U:], Y1[:U]), desc(g.iu, X[:U], Y1[U:])
-            call("elimrec_spmm64_pair", C.byref(da), C.byref(db), v, stream())
-        out[f"spmm64_pair v{v} whole rows only"] = {"us": round(timeit(light), 2)}
-    def heavy_only():
-        ops.spmm  # split rows of the item half alone
-        h = g.iu
-        call("elimrec_spmm", 64, 1, h.n_seg, h.n_heavy_seg, ptr(h.seg), ptr(h.heavy), ptr(h.counter), ptr(h.col), ptr(h.val), ptr(X),
-             X.stride(0), ptr(Y1[U:]), 64, ptr(h.partial), None, stream())
-    out["split rows only (item half, spmm_seg_kernel<64> heavy)"] = {"us": round(timeit(heavy_only), 2), "segments": g.iu.n_heavy_seg,
-                                                                      "edges": int(sum(int(z) - int(y) for _, y, z, _ in g.iu.seg[:g.iu.n_heavy_seg].tolist()))}
     # masks: rows at ~50 % (the layer L-1 of a step), columns at ~5 % (first backward hop)
     rm = (torch.rand(U + I, device=dev) < 0.5).to(torch.uint8)
     cm = (torch.rand(U + I, device=dev) < 0.05).to(torch.uint8)
