@@ -42,7 +42,12 @@ class LinearDesc(C.Structure):
 class Spmm64Half(C.Structure):
     _fields_ = [("n_item", i32), ("n_split_item", i32), ("item", vp), ("split_rows", vp), ("counter", vp), ("partial", vp),
                 ("col", vp), ("val", vp), ("X", vp), ("ldx", i64), ("Y", vp), ("ldy", i64), ("row_mask", vp), ("col_mask", vp),
-                ("addend", vp), ("ld_add", i64), ("add_mask", vp)]
+                ("addend", vp), ("ld_add", i64), ("add_mask", vp), ("adam_param", vp), ("adam_exp_avg", vp),
+                ("adam_exp_avg_sq", vp), ("adam_old_out", vp)]
+
+
+class AdamConsts(C.Structure):
+    _fields_ = [("consts_dev", vp), ("beta1", f64), ("beta2", f64), ("eps", f32), ("weight_decay", f32)]
 
 
 class WgradProblem(C.Structure):
@@ -74,7 +79,7 @@ _SIGS = {
     "elimrec_spmm": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
     "elimrec_spmm_masked": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp, vp, i32,
                             vp, i64, vp, vp],
-    "elimrec_spmm64_pair": [C.POINTER(Spmm64Half), C.POINTER(Spmm64Half), i32, vp],
+    "elimrec_spmm64_pair": [C.POINTER(Spmm64Half), C.POINTER(Spmm64Half), C.POINTER(AdamConsts), i32, vp],
     "elimrec_mark_rows": [i32, vp, i64, vp, vp],
     "elimrec_inst_rows": [i32, vp, vp, vp, i32, vp, i64, vp, vp, vp],
     "elimrec_mark_neighbors": [i32, vp, vp, vp, vp, vp],

@@ -35,11 +35,35 @@ struct Half64 {
     const float* addend;             // NULL, or Y[row] += addend[row] on the rows add_mask marks (NULL: every row)
     long long ld_add;
     const unsigned char* add_mask;
+    // fused Adam (last hop of the backward chain: the finished row IS d loss / d table[row]): update the [rows x 64] table
+    // in place instead of storing the gradient; old_out (may be NULL) receives the parameter row as it was before the update
+    float* adam_p;
+    float* adam_m;
+    float* adam_v;
+    float* adam_old;
 };
+
+struct AdamC {
+    const double* consts;            // device: {lr / bias_correction1, sqrt(bias_correction2)} (elimrec_adam_tick)
+    float b2, omb1, omb2, eps, wd;
+};
+
+// torch.optim.Adam single-tensor math, as in adam_multi_kernel (csrc/bpr.cu)
+__device__ __forceinline__ void adam4(float4& p, const float4 g, float4& m, float4& v, const AdamC& c, float step_size, float bc2s) {
+#define ADAM1(f)                                                  \
+    {                                                             \
+        const float gr = fmaf(c.wd, p.f, g.f);                    \
+        m.f = m.f + (gr - m.f) * c.omb1;                          \
+        v.f = fmaf(c.omb2 * gr, gr, v.f * c.b2);                  \
+        p.f = p.f - step_size * (m.f / (sqrtf(v.f) / bc2s + c.eps)); \
+    }
+    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+}
 
 template <int UNR, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-spmm64_pair_kernel(const Half64 a, const Half64 b) {
+spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, gl = lane & 7;
     const long long it_all = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * 4 + (lane >> 3);
@@ -151,9 +175,28 @@ spmm64_pair_kernel(const Half64 a, const Half64 b) {
                 add4(acc1, __ldg(g + 8));
             }
         }
-        float4* y = reinterpret_cast<float4*>(SEL(Y) + (long long)sg.x * SEL(ldy)) + gl;
-        y[0] = acc0;
-        y[8] = acc1;
+        float* ap = SEL(adam_p);
+        if (ap != nullptr) {
+            const float step_size = (float)adam.consts[0], bc2s = (float)adam.consts[1];
+            const long long o = (long long)sg.x * 64;
+            float4* pp = reinterpret_cast<float4*>(ap + o) + gl;
+            float4* mp = reinterpret_cast<float4*>(SEL(adam_m) + o) + gl;
+            float4* vp = reinterpret_cast<float4*>(SEL(adam_v) + o) + gl;
+            float4 p0 = pp[0], p1 = pp[8], m0 = mp[0], m1 = mp[8], v0 = vp[0], v1 = vp[8];
+            float* oldp = SEL(adam_old);
+            if (oldp != nullptr) {
+                float4* op = reinterpret_cast<float4*>(oldp + o) + gl;
+                op[0] = p0;
+                op[8] = p1;
+            }
+            adam4(p0, acc0, m0, v0, adam, step_size, bc2s);
+            adam4(p1, acc1, m1, v1, adam, step_size, bc2s);
+            pp[0] = p0; pp[8] = p1; mp[0] = m0; mp[8] = m1; vp[0] = v0; vp[8] = v1;
+        } else {
+            float4* y = reinterpret_cast<float4*>(SEL(Y) + (long long)sg.x * SEL(ldy)) + gl;
+            y[0] = acc0;
+            y[8] = acc1;
+        }
     }
 #undef SEL
 }
@@ -172,7 +215,9 @@ int fill_half(Half64& h, const elimrec_spmm64_half_t* s, const char** err) {
     h.row_mask = s->row_mask; h.col_mask = s->col_mask;
     h.addend = s->addend; h.ld_add = s->ld_add; h.add_mask = s->add_mask;
     if (s->addend != nullptr && s->ld_add % 4 != 0) { *err = "addend stride must be a multiple of 4 floats"; return -1; }
-    if (h.n_item > 0 && (h.X == nullptr || h.Y == nullptr || h.item == nullptr)) { *err = "NULL buffer"; return -1; }
+    h.adam_p = s->adam_param; h.adam_m = s->adam_exp_avg; h.adam_v = s->adam_exp_avg_sq; h.adam_old = s->adam_old_out;
+    if (h.adam_p != nullptr && (h.adam_m == nullptr || h.adam_v == nullptr)) { *err = "fused Adam needs exp_avg / exp_avg_sq"; return -1; }
+    if (h.n_item > 0 && (h.X == nullptr || (h.Y == nullptr && h.adam_p == nullptr) || h.item == nullptr)) { *err = "NULL buffer"; return -1; }
     if (s->n_split_item > 0 && (h.hrow == nullptr || h.counter == nullptr || h.partial == nullptr)) {
         *err = "split rows need split_rows / counter / partial";
         return -1;
@@ -182,9 +227,20 @@ int fill_half(Half64& h, const elimrec_spmm64_half_t* s, const char** err) {
 
 }  // namespace
 
-ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimrec_spmm64_half_t* b, int variant,
-                                    elimrec_stream_t stream) {
+ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimrec_spmm64_half_t* b,
+                                    const elimrec_adam_consts_t* adam, int variant, elimrec_stream_t stream) {
     ER_CHECK_ARG(a != nullptr, "first half required");
+    AdamC ac{};
+    const bool fused = (a->adam_param != nullptr) || (b != nullptr && b->adam_param != nullptr);
+    ER_CHECK_ARG(!fused || (adam != nullptr && adam->consts_dev != nullptr), "fused Adam needs the optimizer constants");
+    if (adam != nullptr) {
+        ac.consts = adam->consts_dev;
+        ac.b2 = (float)adam->beta2;
+        ac.omb1 = (float)(1.0 - adam->beta1);      // python doubles rounded once, as torch does
+        ac.omb2 = (float)(1.0 - adam->beta2);
+        ac.eps = adam->eps;
+        ac.wd = adam->weight_decay;
+    }
     Half64 ha, hb;
     const char* err = nullptr;
     if (fill_half(ha, a, &err) != 0 || fill_half(hb, b, &err) != 0) {
@@ -196,11 +252,11 @@ ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimre
     const unsigned blocks = (unsigned)((items + 31) / 32);      // 8 warps x 4 items per CTA
     cudaStream_t st = er_stream(stream);
     switch (variant) {
-        case 1: spmm64_pair_kernel<8, 2><<<blocks, 256, 0, st>>>(ha, hb); break;
-        case 2: spmm64_pair_kernel<4, 3><<<blocks, 256, 0, st>>>(ha, hb); break;
-        case 3: spmm64_pair_kernel<2, 6><<<blocks, 256, 0, st>>>(ha, hb); break;
-        case 4: spmm64_pair_kernel<8, 3><<<blocks, 256, 0, st>>>(ha, hb); break;
-        default: spmm64_pair_kernel<4, 4><<<blocks, 256, 0, st>>>(ha, hb); break;
+        case 1: spmm64_pair_kernel<8, 2><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+        case 2: spmm64_pair_kernel<4, 3><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+        case 3: spmm64_pair_kernel<2, 6><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+        case 4: spmm64_pair_kernel<8, 3><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+        default: spmm64_pair_kernel<4, 4><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
     }
     ER_LAUNCH_CHECK();
     return 0;

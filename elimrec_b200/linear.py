@@ -227,8 +227,9 @@ class LinearSchedule:
             if getattr(self, "_tick_early", False):      # train_step: the optimizer's step counter / bias corrections
                 self._adam.tick()
             self._snapshot(P, ws)
-            ops.copy_2d(Eu, ws["E0"][:U], U, D)
-            ops.copy_2d(Ei, ws["E0"][U:], I, D)
+            if not getattr(self, "_fuse_adam_now", False):      # (the fused Adam epilogue writes the pre-update rows itself)
+                ops.copy_2d(Eu, ws["E0"][:U], U, D)
+                ops.copy_2d(Ei, ws["E0"][U:], I, D)
             torch.cuda.current_stream().wait_event(ev_rows)
             ops.zero_rows(rows, 0, U + I, 0, ws["GA"], D)
             ops.zero_rows(rows, 0, U + I, 0, ws["GB"], D)
@@ -255,7 +256,9 @@ class LinearSchedule:
         return self._loss(P, ws, users, pos, neg, gathered=True)
 
     # ---- backward -------------------------------------------------------------------------------------------------------
-    def _lin_backward(self, gscale=None, split=False):
+    def _lin_backward(self, gscale=None, split=False, fuse_adam=False):
+        """``fuse_adam`` (train_step on one GPU): the last hop of the chain applies Adam to both embedding tables in its
+        epilogue (their gradients are never stored) and records the pre-update rows for tables completed later."""
         P = self._params()
         ws = self._ws
         U, I, L = self.num_users, self.num_items, self.n_layers
@@ -286,13 +289,12 @@ class LinearSchedule:
             if not fork:
                 go()
                 return []
-            s1 = ops.fork_side(5, high_priority=True)
+            s1 = ops.fork_side(5)
             with torch.cuda.stream(s1):
                 go()
             return [s1]
 
         ib(1)
-        pending = None if split else weights(True)
         # the 64-wide backward chain: h_L = g_L, h_{k-1} = A_hat^T h_k + g_{k-1}.  g_k lives on the instance rows and takes two
         # values per row: GA (all blocks of dO) where layer k carries the modality graphs' E_u part (users: k even, items:
         # k odd), GB (id block) elsewhere.  h_L is read straight from the G slabs through the column mask; every later g_k is the
@@ -303,6 +305,7 @@ class LinearSchedule:
             ops.zero_rows(rows, 0, U + I, 0, GA, D)
             ops.zero_rows(rows, 0, U + I, 0, GB, D)
         ops.lin_seed2(rows, dOin, nm, inv, GA, GB)
+        pending = None if split else weights(True)      # queued behind the seeds: the chain must not wait for its big grid
         mask, need2 = ws["mask"], ws["need2"]
         g_u = lambda k: (GA if k % 2 == 0 else GB)[:U]
         g_i = lambda k: (GA if k % 2 == 1 else GB)[U:]
@@ -312,12 +315,19 @@ class LinearSchedule:
             # h_L is valid on the instance rows only, h_{L-1} on need2 only: the first two hops drop every other column
             cm = mask if k == L else (need2 if k == L - 1 else None)
             rm = need2 if (k == L and L >= 2) else None
+            kw = {}
+            if k == 1 and fuse_adam:
+                ad = self._adam
+                Eu, Ei = P["embedding_user.weight"], P["embedding_item.weight"]
+                kw = dict(adam_u=(Eu.data, *ad._st("embedding_user.weight", Eu), ws["E0"][:U]),
+                          adam_i=(Ei.data, *ad._st("embedding_item.weight", Ei), ws["E0"][U:]),
+                          adam_consts=(ad.consts, ad.betas[0], ad.betas[1], ad.eps, ad.wd))
             ops.spmm64_pair(g.ui_t, g.iu_t, h_i, h_u, nxt[:U], nxt[U:],
                             row_mask_u=rm[:U] if rm is not None else None, row_mask_i=rm[U:] if rm is not None else None,
                             col_mask_u=cm[U:] if cm is not None else None, col_mask_i=cm[:U] if cm is not None else None,
-                            addend_u=g_u(k - 1), addend_i=g_i(k - 1), add_mask_u=mask[:U], add_mask_i=mask[U:])
+                            addend_u=g_u(k - 1), addend_i=g_i(k - 1), add_mask_u=mask[:U], add_mask_i=mask[U:], **kw)
             h_u, h_i, flip = nxt[:U], nxt[U:], flip ^ 1
-        grads = {"embedding_user.weight": h_u, "embedding_item.weight": h_i}
+        grads = {} if fuse_adam else {"embedding_user.weight": h_u, "embedding_item.weight": h_i}
         ws["bw_pending"] = (weights, pending)
         if split:
             return grads

@@ -646,13 +646,13 @@ class EliMRec(LinearSchedule, BasicModel):
     # ------------------------------------------------------------------------------------------
     # backward: instance rows -> fusion/head weights -> 2L SpMMs -> projection weights
     # ------------------------------------------------------------------------------------------
-    def _backward(self, gscale=None, split=False):
+    def _backward(self, gscale=None, split=False, fuse_adam=False):
         """Returns {param name: gradient view}.  ``gscale``: 1-element device tensor (upstream grad) or None.
         ``split``: stop once the two embedding-table gradients are final and return only those; the weight gradients
         (fusion / heads / projections / word table) are then produced by ``_backward_weights()`` - data-parallel
         replicas put the table gradients' all-reduce on the wire in between (``make_graphed_step``)."""
         if self.linear:
-            return self._lin_backward(gscale, split)
+            return self._lin_backward(gscale, split, fuse_adam)
         P = self._params()
         ws = self._ws
         B, G, Fw, nt = ws["B"], ws["G"], ws["F"], ws["nt"]
@@ -951,11 +951,18 @@ class EliMRec(LinearSchedule, BasicModel):
         with torch.no_grad():
             # linear schedule: the step counter ticks on a side stream of the forward, off the critical path
             early = self._tick_early = bool(self.linear)
+            # ... and, on one GPU, Adam on the two embedding tables is the epilogue of the last backward hop (fused_adam=False
+            # keeps the separate optimizer pass; data-parallel replicas must average the gradients first)
+            fuse = self._fuse_adam_now = bool(self.linear and not getattr(self, "_dp", False) and _cfg(self.config, "fused_adam", True))
             try:
                 loss = self._forward(users, pos, neg)
             finally:
-                self._tick_early = False
-            grads = self._backward(None)
+                self._tick_early = self._fuse_adam_now = False
+            if fuse:      # moments of the tables must exist before the backward hands them to the kernel
+                P = self._params()
+                for n in ("embedding_user.weight", "embedding_item.weight"):
+                    self._adam._st(n, P[n])
+            grads = self._backward(None, fuse_adam=fuse)
             if getattr(self, "_dp", False):
                 grads = self._allreduce_grads(grads)
             self._adam.apply(grads, tick=not early)
@@ -1133,7 +1140,8 @@ class EliMRec(LinearSchedule, BasicModel):
         ws = self._ws["cache"]
         if ws.get("S_norm_version") != self._tables_version:
             fu, fi, su, si = self._tables()
-            ws["S_norm"] = [(torch.empty_like(a), torch.empty_like(b)) for a, b in zip(su, si)]
+            if "S_norm" not in ws:      # allocated once, refreshed in place after every training forward
+                ws["S_norm"] = [(torch.empty_like(a), torch.empty_like(b)) for a, b in zip(su, si)]
             for (a, b), (an, bn) in zip(zip(su, si), ws["S_norm"]):
                 ops.row_normalize(a, an)
                 ops.row_normalize(b, bn)
@@ -1158,14 +1166,18 @@ class EliMRec(LinearSchedule, BasicModel):
             act = self._active_mods()
             srcs = [(fu, fi)] + [ws["S_norm"][j] for j in act]
             out = []
+            bufs = ws.setdefault("rank_tc_bufs", {})       # fp16 hi / lo tables, allocated once and refilled
             for k, (a, b) in enumerate(srcs):
                 parts = []
                 scales = []
-                for x in (a, b):
+                for side_, x in enumerate((a, b)):
                     amax = float(x.abs().max()) if k == 0 else 1.0      # heads are L2-normalised: |x| <= 1
                     sc = 2.0 ** np.floor(np.log2(4096.0 / max(amax, 1e-30)))
-                    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
-                    lo = torch.empty_like(hi)
+                    key_ = (k, side_, tuple(x.shape))
+                    if key_ not in bufs:
+                        bufs[key_] = (torch.empty(x.shape, dtype=torch.float16, device=x.device),
+                                      torch.empty(x.shape, dtype=torch.float16, device=x.device))
+                    hi, lo = bufs[key_]
                     ops.split_fp16(x.contiguous(), float(sc), hi, lo)
                     parts += [hi, lo]
                     scales.append(sc)

@@ -85,24 +85,39 @@ def spmm(half, X: torch.Tensor, Y, width: int, epi: MeanEpilogue | None = None, 
         _lib.PROFILE["events"].append((f"spmm{width}m" if masked else f"spmm{width}", e0, e1))
 
 
-def spmm64_half(h, X, Y, row_mask=None, col_mask=None, addend=None, add_mask=None):
+def spmm64_half(h, X, Y, row_mask=None, col_mask=None, addend=None, add_mask=None, adam=None):
     d = _lib.Spmm64Half()
     d.n_item, d.n_split_item, d.item, d.split_rows = h.n_item64, h.n_split64, ptr(h.item64), ptr(h.hrow64)
     d.counter, d.partial, d.col, d.val = ptr(h.counter64), ptr(h.partial64), ptr(h.col), ptr(h.val)
-    d.X, d.ldx, d.Y, d.ldy = ptr(X, F32), X.stride(0), ptr(Y, F32), Y.stride(0)
+    d.X, d.ldx, d.Y, d.ldy = ptr(X, F32), X.stride(0), ptr(Y, F32, True), (Y.stride(0) if Y is not None else 0)
     d.row_mask, d.col_mask = ptr(row_mask, torch.uint8, True), ptr(col_mask, torch.uint8, True)
     d.addend, d.ld_add, d.add_mask = ptr(addend, F32, True), (addend.stride(0) if addend is not None else 0), ptr(add_mask, torch.uint8, True)
+    if adam is not None:
+        p, m, v, old = adam
+        for t in (p, m, v) + ((old,) if old is not None else ()):
+            if not t.is_contiguous() or t.shape[-1] != 64:
+                raise _lib.ElimrecError("fused Adam takes contiguous [rows x 64] tensors")
+        d.adam_param, d.adam_exp_avg, d.adam_exp_avg_sq, d.adam_old_out = ptr(p, F32), ptr(m, F32), ptr(v, F32), ptr(old, F32, True)
     return d
 
 
 def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row_mask_i=None, col_mask_u=None, col_mask_i=None,
-                addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, variant=0):
+                addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, adam_u=None, adam_i=None, adam_consts=None,
+                variant=0):
     """Both halves of a 64-wide propagation layer in ONE launch (elimrec_spmm64_pair): Y_u = half_u @ X_for_u (user rows gather
     item rows), Y_i = half_i @ X_for_i.  ``col_mask_u``: mask over the COLUMNS of half_u (item rows), etc.  ``addend_*`` /
-    ``add_mask_*``: Y[row] += addend[row] on the marked rows (the gradient entering this layer of the backward chain)."""
-    da = spmm64_half(half_u, X_for_u, Y_u, row_mask_u, col_mask_u, addend_u, add_mask_u)
-    db = spmm64_half(half_i, X_for_i, Y_i, row_mask_i, col_mask_i, addend_i, add_mask_i)
-    call("elimrec_spmm64_pair", C.byref(da), C.byref(db), int(variant), stream(), tag="spmm64_pair")
+    ``add_mask_*``: Y[row] += addend[row] on the marked rows (the gradient entering this layer of the backward chain).
+    ``adam_u`` / ``adam_i`` = (param, exp_avg, exp_avg_sq, old_out or None) with ``adam_consts`` = (consts_dev, beta1, beta2, eps,
+    weight_decay): the finished rows are gradients of those tables and Adam is applied in the epilogue (Y_* may be None)."""
+    da = spmm64_half(half_u, X_for_u, Y_u, row_mask_u, col_mask_u, addend_u, add_mask_u, adam_u)
+    db = spmm64_half(half_i, X_for_i, Y_i, row_mask_i, col_mask_i, addend_i, add_mask_i, adam_i)
+    ac = None
+    if adam_consts is not None:
+        ac = _lib.AdamConsts()
+        ac.consts_dev, ac.beta1, ac.beta2, ac.eps, ac.weight_decay = (ptr(adam_consts[0], torch.float64), adam_consts[1], adam_consts[2],
+                                                                     adam_consts[3], adam_consts[4])
+    call("elimrec_spmm64_pair", C.byref(da), C.byref(db), (C.byref(ac) if ac is not None else None), int(variant), stream(),
+         tag="spmm64_pair" + ("+adam" if ac is not None else ""))
 
 
 def mark_rows(rows, mask):

@@ -109,8 +109,23 @@ typedef struct {
     const float* addend;      /* may be NULL: Y[row] += addend[row, 0:64] where add_mask[row] != 0 (add_mask NULL: every row) */
     int64_t ld_add;
     const uint8_t* add_mask;
+    /* Fused Adam (adam_param != NULL; Y may then be NULL): the finished row is d loss / d table[row] - the last hop of the
+     * backward chain - and the [rows x 64] table, exp_avg and exp_avg_sq rows are updated in place instead of storing the
+     * gradient (torch.optim.Adam arithmetic, main.py:49,101).  The propagation is bound by L2->SM gathers and leaves HBM
+     * idle; the optimizer is pure HBM streaming - fused, its traffic rides along.  adam_old_out (may be NULL) receives the
+     * parameter row as it was BEFORE the update: what tables completed later for predict() must use. */
+    float* adam_param;
+    float* adam_exp_avg;
+    float* adam_exp_avg_sq;
+    float* adam_old_out;
 } elimrec_spmm64_half_t;
-int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimrec_spmm64_half_t* b, int variant, elimrec_stream_t stream);
+typedef struct {
+    const double* consts_dev; /* {lr / bias_correction1, sqrt(bias_correction2)} written by elimrec_adam_tick */
+    double beta1, beta2;
+    float eps, weight_decay;
+} elimrec_adam_consts_t;
+int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimrec_spmm64_half_t* b, const elimrec_adam_consts_t* adam /* may be NULL */,
+                        int variant, elimrec_stream_t stream);
 /* mask[0:n_nodes] = 0; mask[rows[r]] = 1 */
 int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream);
 /* rows[0:3B] = [users | num_users + pos | num_users + neg]  (node ids of the batch, models/EliMRec.py:120-122 gathers

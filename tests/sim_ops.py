@@ -72,9 +72,20 @@ def spmm(half, X, Y, width, epi=None, row_mask=None, col_mask=None, density=50, 
 
 
 def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row_mask_i=None, col_mask_u=None, col_mask_i=None,
-                addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, variant=0):
-    spmm(half_u, X_for_u, Y_u, 64, row_mask=row_mask_u, col_mask=col_mask_u, addend=addend_u, add_mask=add_mask_u)
-    spmm(half_i, X_for_i, Y_i, 64, row_mask=row_mask_i, col_mask=col_mask_i, addend=addend_i, add_mask=add_mask_i)
+                addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, adam_u=None, adam_i=None, adam_consts=None,
+                variant=0):
+    for half, X, Y, rm, cm, ad, am, adam in ((half_u, X_for_u, Y_u, row_mask_u, col_mask_u, addend_u, add_mask_u, adam_u),
+                                             (half_i, X_for_i, Y_i, row_mask_i, col_mask_i, addend_i, add_mask_i, adam_i)):
+        if adam is None:
+            spmm(half, X, Y, 64, row_mask=rm, col_mask=cm, addend=ad, add_mask=am)
+            continue
+        grad = torch.zeros(half.n_rows, 64)
+        spmm(half, X, grad, 64, row_mask=rm, col_mask=cm, addend=ad, add_mask=am)
+        p, m, v, old = adam
+        if old is not None:
+            old.copy_(p)
+        consts, b1, b2, eps, wd = adam_consts
+        adam_apply_multi([(p, grad, m, v)], consts, b1, b2, eps, wd)
 
 
 def inst_rows(users, pos, neg, num_users, rows, mask=None, mask2=None):

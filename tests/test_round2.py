@@ -147,3 +147,27 @@ def test_get_embedding(backend, golden):
     sd = golden_params(golden)
     for got, want in zip(out[3:], (sd["embedding_user.weight"][u], sd["embedding_item.weight"][p], sd["embedding_item.weight"][n])):
         assert np.array_equal(got.detach().cpu().numpy(), want)
+
+
+def test_fused_adam_epilogue_matches_separate_pass(backend, golden):
+    """linear schedule on one GPU: Adam on the two embedding tables runs in the epilogue of the last backward hop (the table
+    gradients are never stored; the pre-update rows are recorded for tables completed later).  Same parameters, same
+    moments, same evaluation as the separate optimizer pass, and both reproduce the reference's three steps."""
+    from test_schedule_sim import check_steps
+    name = _name(golden)
+    fused = build(golden_dataset(golden), golden_params(golden), name)
+    plain = build(golden_dataset(golden), golden_params(golden), name, fused_adam=False)
+    for m in (fused, plain):
+        m.make_optimizer(lr=1e-3, weight_decay=1e-4)
+    for i in range(3):
+        lf, lp = float(fused.train_step(*batch(golden, i))), float(plain.train_step(*batch(golden, i)))
+        assert abs(lf - lp) <= 1e-6 * abs(lp)
+    for (k, a), b in zip(fused.state_dict().items(), plain.state_dict().values()):
+        assert rel(a, b.detach().cpu().numpy()) < 1e-6, k
+    for n in ("embedding_user.weight", "embedding_item.weight"):
+        for a, b in zip(fused._adam.state[n], plain._adam.state[n]):
+            assert rel(a, b.detach().cpu().numpy()) < 1e-5, n
+    # tables of the LAST forward (pre-update embeddings): the fused epilogue recorded them
+    assert rel(fused.all_users, plain.all_users.detach().cpu().numpy()) < 1e-6
+    assert rel(fused.all_items, plain.all_items.detach().cpu().numpy()) < 1e-6
+    check_steps(build(golden_dataset(golden), golden_params(golden), name), golden, "")
