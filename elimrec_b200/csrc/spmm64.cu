@@ -61,12 +61,40 @@ __device__ __forceinline__ void adam4(float4& p, const float4 g, float4& m, floa
 #undef ADAM1
 }
 
-template <int UNR, int MINB>
+// COMPACT (launches with a row mask): the CTA first looks at its 32 items, keeps the marked ones (order preserved) and deals
+// them to its first groups - warps left without work exit, so a 50 % mask costs half the time instead of all of it (the four
+// items of a warp would otherwise finish only when the slowest unmasked one does).
+// ADAM (fused optimizer epilogue): the table / moment rows are fetched BEFORE the gather loop, so their HBM latency hides
+// under the L2 gathers instead of adding a dependent round trip per row.
+template <int UNR, int MINB, bool COMPACT, bool ADAM>
 __global__ void __launch_bounds__(256, MINB)
 spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, gl = lane & 7;
-    const long long it_all = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * 4 + (lane >> 3);
+    long long it_all = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * 4 + (lane >> 3);
+    bool active = true;
+    if (COMPACT) {
+        __shared__ long long list[32];
+        __shared__ int n_list;
+        if (threadIdx.x < 32) {
+            const long long mine_it = (long long)blockIdx.x * 32 + threadIdx.x;
+            const bool ia = mine_it < a.n_item;
+            const long long ix = ia ? mine_it : mine_it - a.n_item;
+            bool keep = ix < (ia ? a.n_item : b.n_item);
+            if (keep) {
+                const unsigned char* rm = ia ? a.row_mask : b.row_mask;
+                if (rm != nullptr) keep = __ldg(rm + __ldg((ia ? a.item : b.item) + ix).x) != 0;
+            }
+            const unsigned bal = __ballot_sync(full, keep);
+            if (keep) list[__popc(bal & ((1u << lane) - 1u))] = mine_it;
+            if (lane == 0) n_list = __popc(bal);
+        }
+        __syncthreads();
+        const int slot = threadIdx.x >> 3;                 // group index inside the CTA
+        if ((slot & ~3) >= n_list) return;                 // the whole warp is beyond the compacted list
+        active = slot < n_list;
+        it_all = active ? list[slot] : 0;
+    }
     const bool in_a = it_all < a.n_item;
 #define SEL(f) (in_a ? a.f : b.f)                  /* kernel parameters: a select between two constant-bank values */
     const long long idx = in_a ? it_all : it_all - a.n_item;
@@ -75,12 +103,27 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
     const float* X = SEL(X);
     const long long ldx = SEL(ldx);
     const unsigned char* cmask = SEL(col_mask);
-    bool active = idx < SEL(n_item);
+    active = active && idx < SEL(n_item);
     int4 sg = make_int4(0, 0, 0, -1);
     if (active) {
         sg = __ldg(SEL(item) + idx);
-        const unsigned char* rmask = SEL(row_mask);
-        if (rmask != nullptr && __ldg(rmask + sg.x) == 0) active = false;
+        if (!COMPACT) {
+            const unsigned char* rmask = SEL(row_mask);
+            if (rmask != nullptr && __ldg(rmask + sg.x) == 0) active = false;
+        }
+    }
+    // fused Adam: table / moment rows of a whole-row item, in flight while the neighbours are gathered
+    float4 p0, p1, m0, m1, v0a, v1a;
+    float* ap = nullptr;
+    if (ADAM) {
+        ap = SEL(adam_p);
+        if (active && ap != nullptr && sg.w < 0) {
+            const long long o = (long long)sg.x * 64;
+            const float4* pp = reinterpret_cast<const float4*>(ap + o) + gl;
+            const float4* mp = reinterpret_cast<const float4*>(SEL(adam_m) + o) + gl;
+            const float4* vp = reinterpret_cast<const float4*>(SEL(adam_v) + o) + gl;
+            p0 = pp[0]; p1 = pp[8]; m0 = mp[0]; m1 = mp[8]; v0a = vp[0]; v1a = vp[8];
+        }
     }
     const int beg = active ? sg.y : 0, end = active ? sg.z : 0;
     int n_it = (end - beg + 7) >> 3;
@@ -175,23 +218,24 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
                 add4(acc1, __ldg(g + 8));
             }
         }
-        float* ap = SEL(adam_p);
-        if (ap != nullptr) {
+        if (ADAM && ap != nullptr) {
             const float step_size = (float)adam.consts[0], bc2s = (float)adam.consts[1];
             const long long o = (long long)sg.x * 64;
             float4* pp = reinterpret_cast<float4*>(ap + o) + gl;
             float4* mp = reinterpret_cast<float4*>(SEL(adam_m) + o) + gl;
             float4* vp = reinterpret_cast<float4*>(SEL(adam_v) + o) + gl;
-            float4 p0 = pp[0], p1 = pp[8], m0 = mp[0], m1 = mp[8], v0 = vp[0], v1 = vp[8];
+            if (sg.w >= 0) {      // split row, finished by its last-arriving item: fetched here
+                p0 = pp[0]; p1 = pp[8]; m0 = mp[0]; m1 = mp[8]; v0a = vp[0]; v1a = vp[8];
+            }
             float* oldp = SEL(adam_old);
             if (oldp != nullptr) {
                 float4* op = reinterpret_cast<float4*>(oldp + o) + gl;
                 op[0] = p0;
                 op[8] = p1;
             }
-            adam4(p0, acc0, m0, v0, adam, step_size, bc2s);
-            adam4(p1, acc1, m1, v1, adam, step_size, bc2s);
-            pp[0] = p0; pp[8] = p1; mp[0] = m0; mp[8] = m1; vp[0] = v0; vp[8] = v1;
+            adam4(p0, acc0, m0, v0a, adam, step_size, bc2s);
+            adam4(p1, acc1, m1, v1a, adam, step_size, bc2s);
+            pp[0] = p0; pp[8] = p1; mp[0] = m0; mp[8] = m1; vp[0] = v0a; vp[8] = v1a;
         } else {
             float4* y = reinterpret_cast<float4*>(SEL(Y) + (long long)sg.x * SEL(ldy)) + gl;
             y[0] = acc0;
@@ -251,12 +295,20 @@ ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimre
     if (items <= 0) return 0;
     const unsigned blocks = (unsigned)((items + 31) / 32);      // 8 warps x 4 items per CTA
     cudaStream_t st = er_stream(stream);
-    switch (variant) {
-        case 1: spmm64_pair_kernel<8, 2><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-        case 2: spmm64_pair_kernel<4, 3><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-        case 3: spmm64_pair_kernel<2, 6><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-        case 4: spmm64_pair_kernel<8, 3><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-        default: spmm64_pair_kernel<4, 4><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+    const bool compact = ha.row_mask != nullptr || hb.row_mask != nullptr;
+    if (fused) {
+        ER_CHECK_ARG(!compact, "fused Adam runs on the dense last hop (no row mask)");
+        spmm64_pair_kernel<4, 2, false, true><<<blocks, 256, 0, st>>>(ha, hb, ac);
+    } else if (compact) {
+        spmm64_pair_kernel<4, 4, true, false><<<blocks, 256, 0, st>>>(ha, hb, ac);
+    } else {
+        switch (variant) {
+            case 1: spmm64_pair_kernel<8, 2, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+            case 2: spmm64_pair_kernel<4, 3, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+            case 3: spmm64_pair_kernel<2, 6, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+            case 4: spmm64_pair_kernel<8, 3, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+            default: spmm64_pair_kernel<4, 4, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
+        }
     }
     ER_LAUNCH_CHECK();
     return 0;

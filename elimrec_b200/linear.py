@@ -305,28 +305,33 @@ class LinearSchedule:
             ops.zero_rows(rows, 0, U + I, 0, GA, D)
             ops.zero_rows(rows, 0, U + I, 0, GB, D)
         ops.lin_seed2(rows, dOin, nm, inv, GA, GB)
-        pending = None if split else weights(True)      # queued behind the seeds: the chain must not wait for its big grid
         mask, need2 = ws["mask"], ws["need2"]
         g_u = lambda k: (GA if k % 2 == 0 else GB)[:U]
         g_i = lambda k: (GA if k % 2 == 1 else GB)[U:]
         h_u, h_i, flip = g_u(L), g_i(L), 0
-        for k in range(L, 0, -1):
-            nxt = ws["H"][flip]
-            # h_L is valid on the instance rows only, h_{L-1} on need2 only: the first two hops drop every other column
-            cm = mask if k == L else (need2 if k == L - 1 else None)
-            rm = need2 if (k == L and L >= 2) else None
-            kw = {}
-            if k == 1 and fuse_adam:
-                ad = self._adam
-                Eu, Ei = P["embedding_user.weight"], P["embedding_item.weight"]
-                kw = dict(adam_u=(Eu.data, *ad._st("embedding_user.weight", Eu), ws["E0"][:U]),
-                          adam_i=(Ei.data, *ad._st("embedding_item.weight", Ei), ws["E0"][U:]),
-                          adam_consts=(ad.consts, ad.betas[0], ad.betas[1], ad.eps, ad.wd))
-            ops.spmm64_pair(g.ui_t, g.iu_t, h_i, h_u, nxt[:U], nxt[U:],
-                            row_mask_u=rm[:U] if rm is not None else None, row_mask_i=rm[U:] if rm is not None else None,
-                            col_mask_u=cm[U:] if cm is not None else None, col_mask_i=cm[:U] if cm is not None else None,
-                            addend_u=g_u(k - 1), addend_i=g_i(k - 1), add_mask_u=mask[:U], add_mask_i=mask[U:], **kw)
-            h_u, h_i, flip = nxt[:U], nxt[U:], flip ^ 1
+        # The chain is the critical path: it runs on a HIGH-PRIORITY stream, the weight gradients (one big grid that nothing
+        # but Adam waits for) on the current one - their CTAs fill what the propagation launches leave free.
+        chain = ops.fork_side(8, high_priority=True)
+        with torch.cuda.stream(chain):
+            for k in range(L, 0, -1):
+                nxt = ws["H"][flip]
+                # h_L is valid on the instance rows only, h_{L-1} on need2 only: the first two hops drop every other column
+                cm = mask if k == L else (need2 if k == L - 1 else None)
+                rm = need2 if (k == L and L >= 2) else None
+                kw = {}
+                if k == 1 and fuse_adam:
+                    ad = self._adam
+                    Eu, Ei = P["embedding_user.weight"], P["embedding_item.weight"]
+                    kw = dict(adam_u=(Eu.data, *ad._st("embedding_user.weight", Eu), ws["E0"][:U]),
+                              adam_i=(Ei.data, *ad._st("embedding_item.weight", Ei), ws["E0"][U:]),
+                              adam_consts=(ad.consts, ad.betas[0], ad.betas[1], ad.eps, ad.wd))
+                ops.spmm64_pair(g.ui_t, g.iu_t, h_i, h_u, nxt[:U], nxt[U:],
+                                row_mask_u=rm[:U] if rm is not None else None, row_mask_i=rm[U:] if rm is not None else None,
+                                col_mask_u=cm[U:] if cm is not None else None, col_mask_i=cm[:U] if cm is not None else None,
+                                addend_u=g_u(k - 1), addend_i=g_i(k - 1), add_mask_u=mask[:U], add_mask_i=mask[U:], **kw)
+                h_u, h_i, flip = nxt[:U], nxt[U:], flip ^ 1
+        pending = None if split else weights(False)
+        ops.join_side(chain)
         grads = {} if fuse_adam else {"embedding_user.weight": h_u, "embedding_item.weight": h_i}
         ws["bw_pending"] = (weights, pending)
         if split:
@@ -339,9 +344,6 @@ class LinearSchedule:
         weights, pending = ws.pop("bw_pending")
         if pending is None:
             weights(False)
-        else:
-            for st in pending:
-                ops.join_side(st)
         dead = self._dead_params()
         return {n: gv for n, gv in ws["g"].items() if n not in dead} if dead else ws["g"]
 
