@@ -61,9 +61,11 @@ def parse():
     ap.add_argument("--fused-layer-grad", type=int, default=0,
                     help="1: layer-mean gradient added in the backward SpMM epilogues; 0 (default, measured faster): a scatter "
                          "kernel after each SpMM, hidden under the other stream's SpMM")
-    ap.add_argument("--parallel", default="dp", choices=["dp", "rowshard"],
-                    help="N>1: data-parallel replicas (weak scaling, default) or the row-sharded all-gather design "
-                         "(strong scaling: every rank works on the SAME batch)")
+    ap.add_argument("--parallel", default="colshard", choices=["colshard", "dp", "rowshard"],
+                    help="N>1: colshard (default) = column-sharded linear schedule: every rank owns 64/N embedding columns, draws "
+                         "its own batch, propagation needs no communication (weak scaling); dp = data-parallel replicas with "
+                         "averaged gradients (weak scaling); rowshard = the row-sharded all-gather design (strong scaling: every "
+                         "rank works on the SAME batch)")
     return ap.parse_args()
 
 
@@ -329,13 +331,17 @@ def main():
                      "linear_schedule": bool(args.linear)})
     torch.manual_seed(2022)
     rowshard = world > 1 and args.parallel == "rowshard"
+    colshard = world > 1 and args.parallel == "colshard" and bool(args.linear) and bool(args.lazy_tables)
     if rowshard:
         from elimrec_b200.sharded import ShardedEliMRec
         model = ShardedEliMRec(conf, ds).to(dev)
+    elif colshard:
+        from elimrec_b200.colshard import ColShardedEliMRec
+        model = ColShardedEliMRec(conf, ds).to(dev)
     else:
         model = EliMRec(conf, ds).to(dev)
     model.make_optimizer()
-    if world > 1 and not rowshard:
+    if world > 1 and not (rowshard or colshard):
         model.enable_data_parallel()
     log(f"[bench] rank {rank}/{world}: model ready")
     # data-parallel: every rank draws its own triples; row-sharded: all ranks work on the same batch
@@ -456,7 +462,7 @@ def main():
     # ---- per-kernel CUDA-event profile + roofline of the wide SpMM -------------------------------
     kernels = {}
     roofline, rooflines = None, []
-    if rank == 0 and not rowshard:
+    if rank == 0 and not (rowshard or colshard):
         # rank-local, serialised launches, NO collective (the other ranks do not take part in this pass)
         dp_saved, model._dp = getattr(model, "_dp", False), False
         _lib.PROFILE["on"], _lib.PROFILE["events"] = True, []
@@ -474,7 +480,7 @@ def main():
         roofline, rooflines = rooflines_of(model, agg, args.workload, BATCH)
     clk = clocks.stop() if rank == 0 else None
     sync_all()
-    if world > 1:   # the profile pass above stepped rank 0 only: put every replica back on the same weights
+    if world > 1 and not (rowshard or colshard):   # the profile pass above stepped rank 0 only: put every replica back on the same weights
         for prm in model.parameters():
             dist.broadcast(prm.data, src=0)
 
@@ -579,7 +585,10 @@ def main():
                 "dtype": "f32 (fp32 propagation / loss / Adam; 3xTF32 tensor-core GEMMs = fp32 accuracy class)", "data": "synthetic",
                 "config": {"workload": f"{args.workload}-shape EliMRec train step (sample + fwd + bwd + Adam), batch {BATCH}/GPU, "
                                        f"layer_num 3, recdim 64, U={ds.num_users} I={ds.num_items} E_train={ds.train_matrix.nnz}",
-                           "parallelism": (f"rowshard{world} (all-gather per GCN layer)" if rowshard else f"dp{world}") if world > 1 else "single",
+                           "parallelism": ((f"rowshard{world} (all-gather per GCN layer)" if rowshard else
+                                            (f"colshard{world} (each rank: 64/{world} embedding columns of every row, its own batch; "
+                                             "propagation without communication; 2 all-to-alls of the instance rows + 1 small "
+                                             "all-reduce per step)" if colshard else f"dp{world}")) if world > 1 else "single"),
                            "l2_policy": f"no flush: the per-step working set ({ws_mb:.0f} MB: embedding tables + Adam moments + "
                                         "propagation / gradient slabs + gathered constant rows) exceeds the 126 MB L2",
                            "cuda_graph": bool(runner is not None), "lazy_tables": bool(args.lazy_tables),

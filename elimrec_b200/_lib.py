@@ -79,7 +79,7 @@ _SIGS = {
     "elimrec_spmm": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp],
     "elimrec_spmm_masked": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, C.POINTER(MeanEpilogue), vp, vp, i32,
                             vp, i64, vp, vp],
-    "elimrec_spmm64_pair": [C.POINTER(Spmm64Half), C.POINTER(Spmm64Half), C.POINTER(AdamConsts), i32, vp],
+    "elimrec_spmm64_pair": [C.POINTER(Spmm64Half), C.POINTER(Spmm64Half), C.POINTER(AdamConsts), i32, i32, vp],
     "elimrec_mark_rows": [i32, vp, i64, vp, vp],
     "elimrec_inst_rows": [i32, vp, vp, vp, i32, vp, i64, vp, vp, vp],
     "elimrec_mark_neighbors": [i32, vp, vp, vp, vp, vp],
@@ -130,6 +130,17 @@ _SIGS = {
     "elimrec_split_fp16": [i64, vp, f32, vp, vp, vp],
     "elimrec_rank_tc": [C.POINTER(RankTcTables), i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "elimrec_metric_rows": [i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp],
+    "elimrec_cs_inst_rows": [i32, i32, vp, i32, vp, i64, vp, vp, vp],
+    "elimrec_cs_pack": [i64, vp, i32, C.POINTER(LinLayers), f32, i32, vp, vp],
+    "elimrec_cs_unpack": [i32, i64, i32, vp, i32, vp, i64, vp],
+    "elimrec_cs_seed_pack": [i64, i32, i32, vp, i64, i32, f32, vp, vp],
+    "elimrec_cs_seed_scatter": [i64, vp, i32, vp, vp, vp, i64, vp],
+    "elimrec_comm_unique_id": [vp],
+    "elimrec_comm_init": [vp, i32, i32, C.POINTER(vp)],
+    "elimrec_comm_destroy": [vp],
+    "elimrec_comm_allreduce": [vp, vp, vp, i64, i32, vp],
+    "elimrec_comm_allgather": [vp, vp, vp, i64, vp],
+    "elimrec_comm_alltoall": [vp, vp, vp, i64, vp],
 }
 _I64_RET = {
     "elimrec_gemm_workspace_floats": [i64, i64, i32],

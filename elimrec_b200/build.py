@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 print(log)
     objs = [os.path.join(objdir, s[:-3] + ".o") for s in _sources()]
     if force or jobs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

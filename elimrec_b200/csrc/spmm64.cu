@@ -23,7 +23,7 @@ struct Half64 {
     int n_item;
     const int2* hrow;      // split row h: {first item, number of items}
     int* counter;          // per split row, zero on entry, left zero
-    float* partial;        // [n_split_items x 64]
+    float* partial;        // [n_split_items x W]
     const int* col;
     const float* val;
     const float* X;
@@ -48,17 +48,83 @@ struct AdamC {
     float b2, omb1, omb2, eps, wd;
 };
 
-// torch.optim.Adam single-tensor math, as in adam_multi_kernel (csrc/bpr.cu)
-__device__ __forceinline__ void adam4(float4& p, const float4 g, float4& m, float4& v, const AdamC& c, float step_size, float bc2s) {
-#define ADAM1(f)                                                  \
-    {                                                             \
-        const float gr = fmaf(c.wd, p.f, g.f);                    \
-        m.f = m.f + (gr - m.f) * c.omb1;                          \
-        v.f = fmaf(c.omb2 * gr, gr, v.f * c.b2);                  \
-        p.f = p.f - step_size * (m.f / (sqrtf(v.f) / bc2s + c.eps)); \
+// The slice of a W = 8 * FPL wide row that one lane of an 8-lane group holds.  FPL = 8: columns [4l, 4l+4) and [32+4l, 32+4l+4)
+// (two 128-byte lines per row, a warp-level LDG.128 covers whole lines); FPL = 4 / 2 / 1: columns [FPL*l, FPL*(l+1)) - the
+// column-sharded multi-GPU mode, where a rank propagates 64 / world columns of every row.
+template <int FPL>
+struct RowVec {
+    float f[FPL];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < FPL; ++i) f[i] = 0.f;
     }
-    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
-#undef ADAM1
+    template <bool CG>
+    __device__ __forceinline__ void load(const float* row, int gl) {
+        if (FPL == 8) {
+            const float4* p = reinterpret_cast<const float4*>(row) + gl;
+            const float4 a = CG ? __ldcg(p) : __ldg(p), b = CG ? __ldcg(p + 8) : __ldg(p + 8);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4 % FPL] = b.x; f[5 % FPL] = b.y; f[6 % FPL] = b.z; f[7 % FPL] = b.w;
+        } else if (FPL == 4) {
+            const float4* p = reinterpret_cast<const float4*>(row) + gl;
+            const float4 a = CG ? __ldcg(p) : __ldg(p);
+            f[0] = a.x; f[1 % FPL] = a.y; f[2 % FPL] = a.z; f[3 % FPL] = a.w;
+        } else if (FPL == 2) {
+            const float2* p = reinterpret_cast<const float2*>(row) + gl;
+            const float2 a = CG ? __ldcg(p) : __ldg(p);
+            f[0] = a.x; f[1 % FPL] = a.y;
+        } else {
+            f[0] = CG ? __ldcg(row + gl) : __ldg(row + gl);
+        }
+    }
+    __device__ __forceinline__ void load_plain(const float* row, int gl) {      // read-write memory (Adam state)
+        if (FPL == 8) {
+            const float4* p = reinterpret_cast<const float4*>(row) + gl;
+            const float4 a = p[0], b = p[8];
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4 % FPL] = b.x; f[5 % FPL] = b.y; f[6 % FPL] = b.z; f[7 % FPL] = b.w;
+        } else if (FPL == 4) {
+            const float4 a = reinterpret_cast<const float4*>(row)[gl];
+            f[0] = a.x; f[1 % FPL] = a.y; f[2 % FPL] = a.z; f[3 % FPL] = a.w;
+        } else if (FPL == 2) {
+            const float2 a = reinterpret_cast<const float2*>(row)[gl];
+            f[0] = a.x; f[1 % FPL] = a.y;
+        } else {
+            f[0] = row[gl];
+        }
+    }
+    __device__ __forceinline__ void store(float* row, int gl) const {
+        if (FPL == 8) {
+            float4* p = reinterpret_cast<float4*>(row) + gl;
+            p[0] = make_float4(f[0], f[1], f[2], f[3]);
+            p[8] = make_float4(f[4 % FPL], f[5 % FPL], f[6 % FPL], f[7 % FPL]);
+        } else if (FPL == 4) {
+            reinterpret_cast<float4*>(row)[gl] = make_float4(f[0], f[1 % FPL], f[2 % FPL], f[3 % FPL]);
+        } else if (FPL == 2) {
+            reinterpret_cast<float2*>(row)[gl] = make_float2(f[0], f[1 % FPL]);
+        } else {
+            row[gl] = f[0];
+        }
+    }
+    __device__ __forceinline__ void fma(float w, const RowVec& v) {
+#pragma unroll
+        for (int i = 0; i < FPL; ++i) f[i] = fmaf(w, v.f[i], f[i]);
+    }
+    __device__ __forceinline__ void add(const RowVec& v) {
+#pragma unroll
+        for (int i = 0; i < FPL; ++i) f[i] += v.f[i];
+    }
+};
+
+// torch.optim.Adam single-tensor math, as in adam_multi_kernel (csrc/bpr.cu)
+template <int FPL>
+__device__ __forceinline__ void adam_vec(RowVec<FPL>& p, const RowVec<FPL>& g, RowVec<FPL>& m, RowVec<FPL>& v, const AdamC& c,
+                                         float step_size, float bc2s) {
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) {
+        const float gr = fmaf(c.wd, p.f[i], g.f[i]);
+        m.f[i] = m.f[i] + (gr - m.f[i]) * c.omb1;
+        v.f[i] = fmaf(c.omb2 * gr, gr, v.f[i] * c.b2);
+        p.f[i] = p.f[i] - step_size * (m.f[i] / (sqrtf(v.f[i]) / bc2s + c.eps));
+    }
 }
 
 // COMPACT (launches with a row mask): the CTA first looks at its 32 items, keeps the marked ones (order preserved) and deals
@@ -66,9 +132,11 @@ __device__ __forceinline__ void adam4(float4& p, const float4 g, float4& m, floa
 // items of a warp would otherwise finish only when the slowest unmasked one does).
 // ADAM (fused optimizer epilogue): the table / moment rows are fetched BEFORE the gather loop, so their HBM latency hides
 // under the L2 gathers instead of adding a dependent round trip per row.
-template <int UNR, int MINB, bool COMPACT, bool ADAM>
+template <int FPL, int UNR, int MINB, bool COMPACT, bool ADAM>
 __global__ void __launch_bounds__(256, MINB)
 spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
+    constexpr int W = 8 * FPL;
+    typedef RowVec<FPL> Vec;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, gl = lane & 7;
     long long it_all = (((long long)blockIdx.x * 256 + threadIdx.x) >> 5) * 4 + (lane >> 3);
@@ -113,23 +181,23 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
         }
     }
     // fused Adam: table / moment rows of a whole-row item, in flight while the neighbours are gathered
-    float4 p0, p1, m0, m1, v0a, v1a;
+    Vec pv, mv, vv;
     float* ap = nullptr;
     if (ADAM) {
         ap = SEL(adam_p);
         if (active && ap != nullptr && sg.w < 0) {
-            const long long o = (long long)sg.x * 64;
-            const float4* pp = reinterpret_cast<const float4*>(ap + o) + gl;
-            const float4* mp = reinterpret_cast<const float4*>(SEL(adam_m) + o) + gl;
-            const float4* vp = reinterpret_cast<const float4*>(SEL(adam_v) + o) + gl;
-            p0 = pp[0]; p1 = pp[8]; m0 = mp[0]; m1 = mp[8]; v0a = vp[0]; v1a = vp[8];
+            const long long o = (long long)sg.x * W;
+            pv.load_plain(ap + o, gl);
+            mv.load_plain(SEL(adam_m) + o, gl);
+            vv.load_plain(SEL(adam_v) + o, gl);
         }
     }
     const int beg = active ? sg.y : 0, end = active ? sg.z : 0;
     int n_it = (end - beg + 7) >> 3;
     n_it = __reduce_max_sync(full, n_it);       // shuffles below need all four groups in step
 
-    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    Vec acc;
+    acc.zero();
     for (int it = 0; it < n_it; ++it) {
         const int e = beg + it * 8 + gl;
         int c = 0;
@@ -145,7 +213,7 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
 #pragma unroll
         for (int u0 = 0; u0 < 8; u0 += UNR) {
             if (u0 > 0 && ((alive >> u0) & (0x01010101u * ((1u << (8 - u0)) - 1u))) == 0) break;   // nothing left in any group
-            float4 v0[UNR], v1[UNR];
+            Vec v[UNR];
             float ww[UNR];
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
@@ -153,15 +221,11 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
                 const float wv = __shfl_sync(full, w, u0 + u, 8);
                 const bool ok = (mine >> (u0 + u)) & 1u;
                 ww[u] = ok ? wv : 0.f;
-                const float4* p = reinterpret_cast<const float4*>(X + (long long)cc * ldx) + gl;
-                v0[u] = ok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v1[u] = ok ? __ldg(p + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) v[u].template load<false>(X + (long long)cc * ldx, gl);
+                else v[u].zero();
             }
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                fma4(acc0, ww[u], v0[u]);
-                fma4(acc1, ww[u], v1[u]);
-            }
+            for (int u = 0; u < UNR; ++u) acc.fma(ww[u], v[u]);
         }
     }
 
@@ -171,9 +235,7 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
     float* partial = SEL(partial);
     int* counter = SEL(counter);
     if (split) {
-        float4* pp = reinterpret_cast<float4*>(partial + idx * 64) + gl;
-        pp[0] = acc0;
-        pp[8] = acc1;
+        acc.store(partial + idx * W, gl);
         __threadfence();
     }
     if (__any_sync(full, split)) {
@@ -186,23 +248,18 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
             active = false;                       // somebody else finishes this row
         } else {
             __threadfence();
-            acc0 = make_float4(0.f, 0.f, 0.f, 0.f);
-            acc1 = acc0;
-            const float4* ps = reinterpret_cast<const float4*>(partial + (long long)hr.x * 64) + gl;
+            acc.zero();
+            const float* ps = partial + (long long)hr.x * W;
             constexpr int RU = 4;
             for (int s = 0; s < hr.y; s += RU) {
-                float4 t0[RU], t1[RU];
+                Vec t[RU];
 #pragma unroll
                 for (int u = 0; u < RU; ++u) {
-                    const bool ok = s + u < hr.y;
-                    t0[u] = ok ? __ldcg(ps + (long long)(s + u) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    t1[u] = ok ? __ldcg(ps + (long long)(s + u) * 16 + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s + u < hr.y) t[u].template load<true>(ps + (long long)(s + u) * W, gl);
+                    else t[u].zero();
                 }
 #pragma unroll
-                for (int u = 0; u < RU; ++u) {
-                    add4(acc0, t0[u]);
-                    add4(acc1, t1[u]);
-                }
+                for (int u = 0; u < RU; ++u) acc.add(t[u]);
             }
             if (gl == 0) counter[sg.w] = 0;     // ready for the next launch
         }
@@ -213,43 +270,37 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
         if (addend != nullptr) {      // the layer-mean gradient entering this layer of the backward chain (instance rows)
             const unsigned char* am = SEL(add_mask);
             if (am == nullptr || __ldg(am + sg.x) != 0) {
-                const float4* g = reinterpret_cast<const float4*>(addend + (long long)sg.x * SEL(ld_add)) + gl;
-                add4(acc0, __ldg(g));
-                add4(acc1, __ldg(g + 8));
+                Vec g;
+                g.template load<false>(addend + (long long)sg.x * SEL(ld_add), gl);
+                acc.add(g);
             }
         }
         if (ADAM && ap != nullptr) {
             const float step_size = (float)adam.consts[0], bc2s = (float)adam.consts[1];
-            const long long o = (long long)sg.x * 64;
-            float4* pp = reinterpret_cast<float4*>(ap + o) + gl;
-            float4* mp = reinterpret_cast<float4*>(SEL(adam_m) + o) + gl;
-            float4* vp = reinterpret_cast<float4*>(SEL(adam_v) + o) + gl;
+            const long long o = (long long)sg.x * W;
             if (sg.w >= 0) {      // split row, finished by its last-arriving item: fetched here
-                p0 = pp[0]; p1 = pp[8]; m0 = mp[0]; m1 = mp[8]; v0a = vp[0]; v1a = vp[8];
+                pv.load_plain(ap + o, gl);
+                mv.load_plain(SEL(adam_m) + o, gl);
+                vv.load_plain(SEL(adam_v) + o, gl);
             }
             float* oldp = SEL(adam_old);
-            if (oldp != nullptr) {
-                float4* op = reinterpret_cast<float4*>(oldp + o) + gl;
-                op[0] = p0;
-                op[8] = p1;
-            }
-            adam4(p0, acc0, m0, v0a, adam, step_size, bc2s);
-            adam4(p1, acc1, m1, v1a, adam, step_size, bc2s);
-            pp[0] = p0; pp[8] = p1; mp[0] = m0; mp[8] = m1; vp[0] = v0a; vp[8] = v1a;
+            if (oldp != nullptr) pv.store(oldp + o, gl);
+            adam_vec<FPL>(pv, acc, mv, vv, adam, step_size, bc2s);
+            pv.store(ap + o, gl);
+            mv.store(SEL(adam_m) + o, gl);
+            vv.store(SEL(adam_v) + o, gl);
         } else {
-            float4* y = reinterpret_cast<float4*>(SEL(Y) + (long long)sg.x * SEL(ldy)) + gl;
-            y[0] = acc0;
-            y[8] = acc1;
+            acc.store(SEL(Y) + (long long)sg.x * SEL(ldy), gl);
         }
     }
 #undef SEL
 }
 
-int fill_half(Half64& h, const elimrec_spmm64_half_t* s, const char** err) {
+int fill_half(Half64& h, const elimrec_spmm64_half_t* s, int align, const char** err) {
     h = Half64{};
     if (s == nullptr) return 0;
     if (s->n_split_item < 0 || s->n_split_item > s->n_item) { *err = "n_split_item out of range"; return -1; }
-    if (s->ldx % 4 != 0 || s->ldy % 4 != 0) { *err = "row strides must be multiples of 4 floats"; return -1; }
+    if (s->ldx % align != 0 || s->ldy % align != 0) { *err = "row strides must be multiples of the lane vector width"; return -1; }
     h.item = reinterpret_cast<const int4*>(s->item);
     h.n_item = s->n_item;
     h.hrow = reinterpret_cast<const int2*>(s->split_rows);
@@ -258,7 +309,7 @@ int fill_half(Half64& h, const elimrec_spmm64_half_t* s, const char** err) {
     h.col = s->col; h.val = s->val; h.X = s->X; h.ldx = s->ldx; h.Y = s->Y; h.ldy = s->ldy;
     h.row_mask = s->row_mask; h.col_mask = s->col_mask;
     h.addend = s->addend; h.ld_add = s->ld_add; h.add_mask = s->add_mask;
-    if (s->addend != nullptr && s->ld_add % 4 != 0) { *err = "addend stride must be a multiple of 4 floats"; return -1; }
+    if (s->addend != nullptr && s->ld_add % align != 0) { *err = "addend stride must be a multiple of the lane vector width"; return -1; }
     h.adam_p = s->adam_param; h.adam_m = s->adam_exp_avg; h.adam_v = s->adam_exp_avg_sq; h.adam_old = s->adam_old_out;
     if (h.adam_p != nullptr && (h.adam_m == nullptr || h.adam_v == nullptr)) { *err = "fused Adam needs exp_avg / exp_avg_sq"; return -1; }
     if (h.n_item > 0 && (h.X == nullptr || (h.Y == nullptr && h.adam_p == nullptr) || h.item == nullptr)) { *err = "NULL buffer"; return -1; }
@@ -272,8 +323,9 @@ int fill_half(Half64& h, const elimrec_spmm64_half_t* s, const char** err) {
 }  // namespace
 
 ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimrec_spmm64_half_t* b,
-                                    const elimrec_adam_consts_t* adam, int variant, elimrec_stream_t stream) {
+                                    const elimrec_adam_consts_t* adam, int width, int variant, elimrec_stream_t stream) {
     ER_CHECK_ARG(a != nullptr, "first half required");
+    ER_CHECK_ARG(width == 64 || width == 32 || width == 16 || width == 8, "width must be 64, 32, 16 or 8");
     AdamC ac{};
     const bool fused = (a->adam_param != nullptr) || (b != nullptr && b->adam_param != nullptr);
     ER_CHECK_ARG(!fused || (adam != nullptr && adam->consts_dev != nullptr), "fused Adam needs the optimizer constants");
@@ -287,7 +339,8 @@ ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimre
     }
     Half64 ha, hb;
     const char* err = nullptr;
-    if (fill_half(ha, a, &err) != 0 || fill_half(hb, b, &err) != 0) {
+    const int align = width >= 32 ? 4 : (width == 16 ? 2 : 1);
+    if (fill_half(ha, a, align, &err) != 0 || fill_half(hb, b, align, &err) != 0) {
         elimrec_set_error("elimrec_spmm64_pair: %s", err);
         return -1;
     }
@@ -296,20 +349,21 @@ ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimre
     const unsigned blocks = (unsigned)((items + 31) / 32);      // 8 warps x 4 items per CTA
     cudaStream_t st = er_stream(stream);
     const bool compact = ha.row_mask != nullptr || hb.row_mask != nullptr;
-    if (fused) {
-        ER_CHECK_ARG(!compact, "fused Adam runs on the dense last hop (no row mask)");
-        spmm64_pair_kernel<4, 2, false, true><<<blocks, 256, 0, st>>>(ha, hb, ac);
-    } else if (compact) {
-        spmm64_pair_kernel<4, 4, true, false><<<blocks, 256, 0, st>>>(ha, hb, ac);
-    } else {
-        switch (variant) {
-            case 1: spmm64_pair_kernel<8, 2, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-            case 2: spmm64_pair_kernel<4, 3, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-            case 3: spmm64_pair_kernel<2, 6, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-            case 4: spmm64_pair_kernel<8, 3, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-            default: spmm64_pair_kernel<4, 4, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac); break;
-        }
-    }
+    ER_CHECK_ARG(!(fused && compact), "fused Adam runs on the dense last hop (no row mask)");
+#define PAIR_LAUNCH(FPL)                                                                                                   \
+    do {                                                                                                                   \
+        if (fused) spmm64_pair_kernel<FPL, 4, 2, false, true><<<blocks, 256, 0, st>>>(ha, hb, ac);                         \
+        else if (compact) spmm64_pair_kernel<FPL, 4, 4, true, false><<<blocks, 256, 0, st>>>(ha, hb, ac);                  \
+        else if (variant == 1) spmm64_pair_kernel<FPL, 8, 2, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac);            \
+        else if (variant == 2) spmm64_pair_kernel<FPL, 4, 3, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac);            \
+        else if (variant == 4) spmm64_pair_kernel<FPL, 8, 3, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac);            \
+        else spmm64_pair_kernel<FPL, 4, 4, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac);                              \
+    } while (0)
+    if (width == 64) PAIR_LAUNCH(8);
+    else if (width == 32) PAIR_LAUNCH(4);
+    else if (width == 16) PAIR_LAUNCH(2);
+    else PAIR_LAUNCH(1);
+#undef PAIR_LAUNCH
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -44,6 +44,7 @@ class LinearSchedule:
     def _lin_init(self):
         want = bool(_cfg(self.config, "linear_schedule", True))
         self.linear = bool(want and self.lazy_tables and not self._generic and not (self.tiktok and self.word_grad))
+        self._lin_w = getattr(self, "_lin_w", D)        # columns of the propagated slabs held here (64; 64 / world when column-sharded)
         if self.proj_precision == "auto":
             self.proj_precision = "x3" if self.linear else "tf32"
         if not self.linear:
@@ -103,11 +104,12 @@ class LinearSchedule:
         dev, U, I, L = self.device_, self.num_users, self.num_items, self.n_layers
         N = U + I
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        ws["P"] = [None] + [e(N, D) for _ in range(L)]      # p_1 .. p_L (users first); p_0 are the embedding tables themselves
-        ws["H"] = [e(N, D), e(N, D)]                        # backward chain, ping-pong
+        w = self._lin_w
+        ws["P"] = [None] + [e(N, w) for _ in range(L)]      # p_1 .. p_L (users first); p_0 are the embedding tables themselves
+        ws["H"] = [e(N, w), e(N, w)]                        # backward chain, ping-pong
         # the two seed vectors of the chain (lin_seed2), valid on the instance rows of the current step only
-        ws["GA"], ws["GB"] = torch.zeros(N, D, dtype=torch.float32, device=dev), torch.zeros(N, D, dtype=torch.float32, device=dev)
-        ws["E0"] = e(N, D)                                  # [E_u ; E_i] as THIS forward saw them (Adam overwrites the tables)
+        ws["GA"], ws["GB"] = torch.zeros(N, w, dtype=torch.float32, device=dev), torch.zeros(N, w, dtype=torch.float32, device=dev)
+        ws["E0"] = e(N, w)                                  # [E_u ; E_i] as THIS forward saw them (Adam overwrites the tables)
         ws["Wp"] = {m: e(D, kp) for m, kp in zip(self.mods, self._lin_Kp)}     # [W_m | b_m | 0] of this forward
         if self.proj_precision == "x3":
             ws["Wp_split"] = {m: (e(D, kp), e(D, kp)) for m, kp in zip(self.mods, self._lin_Kp)}   # its TF32 hi / lo parts

@@ -992,6 +992,11 @@ class EliMRec(LinearSchedule, BasicModel):
         return {n: views[n] for n in grads}      # heads the loss does not use stay without a gradient
 
     # -- whole step as one CUDA graph (launch-bound otherwise: ~60 small launches per step) ------------
+    def _extra_state(self):
+        """trainable state kept outside the nn.Module parameters / FusedAdam (sharded modes): tensors that building a graphed
+        step must leave unchanged"""
+        return []
+
     def make_graphed_step(self, batch_size=None, device_sampler=None):
         """The whole training step as a CUDA graph.  ``device_sampler`` (a ``PairwiseSamplerV2``): the graph starts with the
         Philox batch sampler reading its position from the optimizer's device step counter, so ``runner()`` with no
@@ -1010,6 +1015,7 @@ class EliMRec(LinearSchedule, BasicModel):
         # parameters, Adam moments and the device step counter are put back afterwards: building the runner changes nothing.
         ad = self._adam
         saved_p = {n: p.detach().clone() for n, p in self.named_parameters()}
+        saved_x = [t.clone() for t in self._extra_state()]
         saved_st = {n: (m.clone(), v.clone()) for n, (m, v) in ad.state.items()}
         saved_step, saved_consts = ad.step_dev.clone(), ad.consts.clone()
         with torch.cuda.stream(side):
@@ -1024,7 +1030,9 @@ class EliMRec(LinearSchedule, BasicModel):
                 else:
                     m.zero_(); v.zero_()
             ad.step_dev.copy_(saved_step); ad.consts.copy_(saved_consts)
-        del saved_p, saved_st
+            for t, old in zip(self._extra_state(), saved_x):
+                t.copy_(old)
+        del saved_p, saved_st, saved_x
         torch.cuda.synchronize()
         dp = getattr(self, "_dp", False)
         dead = self._dead_params()

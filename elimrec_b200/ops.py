@@ -95,16 +95,16 @@ def spmm64_half(h, X, Y, row_mask=None, col_mask=None, addend=None, add_mask=Non
     if adam is not None:
         p, m, v, old = adam
         for t in (p, m, v) + ((old,) if old is not None else ()):
-            if not t.is_contiguous() or t.shape[-1] != 64:
-                raise _lib.ElimrecError("fused Adam takes contiguous [rows x 64] tensors")
+            if not t.is_contiguous():
+                raise _lib.ElimrecError("fused Adam takes contiguous [rows x width] tensors")
         d.adam_param, d.adam_exp_avg, d.adam_exp_avg_sq, d.adam_old_out = ptr(p, F32), ptr(m, F32), ptr(v, F32), ptr(old, F32, True)
     return d
 
 
 def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row_mask_i=None, col_mask_u=None, col_mask_i=None,
                 addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, adam_u=None, adam_i=None, adam_consts=None,
-                variant=0):
-    """Both halves of a 64-wide propagation layer in ONE launch (elimrec_spmm64_pair): Y_u = half_u @ X_for_u (user rows gather
+                variant=0, width=64):
+    """Both halves of a 64-wide (``width``: 64 / 32 / 16 / 8 columns per rank when column-sharded) propagation layer in ONE launch (elimrec_spmm64_pair): Y_u = half_u @ X_for_u (user rows gather
     item rows), Y_i = half_i @ X_for_i.  ``col_mask_u``: mask over the COLUMNS of half_u (item rows), etc.  ``addend_*`` /
     ``add_mask_*``: Y[row] += addend[row] on the marked rows (the gradient entering this layer of the backward chain).
     ``adam_u`` / ``adam_i`` = (param, exp_avg, exp_avg_sq, old_out or None) with ``adam_consts`` = (consts_dev, beta1, beta2, eps,
@@ -116,7 +116,9 @@ def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row
         ac = _lib.AdamConsts()
         ac.consts_dev, ac.beta1, ac.beta2, ac.eps, ac.weight_decay = (ptr(adam_consts[0], torch.float64), adam_consts[1], adam_consts[2],
                                                                      adam_consts[3], adam_consts[4])
-    call("elimrec_spmm64_pair", C.byref(da), C.byref(db), (C.byref(ac) if ac is not None else None), int(variant), stream(),
+    if X_for_u.shape[-1] < width or X_for_i.shape[-1] < width:
+        raise _lib.ElimrecError("spmm64_pair: operand narrower than the propagated width")
+    call("elimrec_spmm64_pair", C.byref(da), C.byref(db), (C.byref(ac) if ac is not None else None), int(width), int(variant), stream(),
          tag="spmm64_pair" + ("+adam" if ac is not None else ""))
 
 
@@ -491,3 +493,28 @@ def sample_batch_device(seed, epoch, batch_index_dev, n, user_ids, row_ptr, item
     call("elimrec_sample_batch_device", seed, epoch, ptr(batch_index_dev, torch.int64), n, user_ids.numel(),
          ptr(user_ids, torch.int32), ptr(row_ptr, torch.int64), ptr(items, torch.int32), num_items, ptr(ou, torch.int64),
          ptr(op, torch.int64), ptr(on, torch.int64), stream())
+
+
+# ---- column-sharded multi-GPU step (csrc/colshard.cu) --------------------------------------------------------------------
+def cs_pack(rows, num_users, layers, scale, w, out, n_rows=None):
+    n = rows.numel() if rows is not None else n_rows
+    call("elimrec_cs_pack", n, ptr(rows, torch.int32, True), num_users, C.byref(layers), scale, w, ptr(out, F32), stream())
+
+
+def cs_unpack(world, n, w, recv, n_mod, O):
+    call("elimrec_cs_unpack", world, n, w, ptr(recv, F32), n_mod, ptr(O, F32), O.stride(0), stream())
+
+
+def cs_seed_pack(n, world, w, dO, n_mod, scale, send):
+    call("elimrec_cs_seed_pack", n, world, w, ptr(dO, F32), dO.stride(0), n_mod, scale, ptr(send, F32), stream())
+
+
+def cs_seed_scatter(rows_all, w, recv, GA, GB):
+    call("elimrec_cs_seed_scatter", rows_all.numel(), ptr(rows_all, torch.int32), w, ptr(recv, F32), ptr(GA, F32), ptr(GB, F32),
+         GA.stride(0), stream())
+
+
+def cs_inst_rows(world, B, triples, num_users, rows, mask=None, mask2=None):
+    call("elimrec_cs_inst_rows", world, B, ptr(triples, torch.int64), num_users, ptr(rows, torch.int32),
+         (mask.numel() if mask is not None else 0), ptr(mask, torch.uint8, True), ptr(mask2, torch.uint8, True), stream(),
+         launches=1 + (mask is not None) + (mask2 is not None))

@@ -124,8 +124,10 @@ typedef struct {
     double beta1, beta2;
     float eps, weight_decay;
 } elimrec_adam_consts_t;
+/* width: 64 (one GPU) or 32 / 16 / 8 (column-sharded multi-GPU mode: a rank propagates 64 / world columns of every row; X, Y,
+ * addend, partial and the Adam tensors are then `width` columns wide) */
 int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimrec_spmm64_half_t* b, const elimrec_adam_consts_t* adam /* may be NULL */,
-                        int variant, elimrec_stream_t stream);
+                        int width, int variant, elimrec_stream_t stream);
 /* mask[0:n_nodes] = 0; mask[rows[r]] = 1 */
 int elimrec_mark_rows(int n_rows, const int32_t* rows, int64_t n_nodes, uint8_t* mask, elimrec_stream_t stream);
 /* rows[0:3B] = [users | num_users + pos | num_users + neg]  (node ids of the batch, models/EliMRec.py:120-122 gathers
@@ -461,6 +463,44 @@ int elimrec_topk_matrix(int n_rows, int n_cols, const float* scores, int K, int3
 int elimrec_metric_rows(int n_eval, int K, const int32_t* topk_idx, const int64_t* truth_ptr,
                         const int32_t* truth_items, int n_metrics, const int32_t* metric_ids_host,
                         const double* inv_log2_host, float* rows, double* sums, elimrec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * comm - NCCL collectives of the multi-GPU modes (csrc/comm.cu).  The reference is single-device
+ * (device hard-wired to cuda:0, main.py:36): these have no reference counterpart, they are what shards its step.
+ * One communicator per process / GPU, built from a unique id the caller distributes (rank 0: elimrec_comm_unique_id, then
+ * e.g. one torch.distributed broadcast of the ELIMREC_COMM_ID_BYTES).  Every collective is enqueued on the caller's stream,
+ * in order with the kernels around it; none synchronises the host; all are capturable in a CUDA graph.  NCCL is resolved
+ * at run time from the libnccl.so.2 already loaded in the process.  Buffers are device pointers.
+ *   allreduce : recv[i] = sum (or mean) over ranks of send[i]            (send == recv allowed)
+ *   allgather : recv[q * bytes : (q+1) * bytes] = rank q's send[0 : bytes]
+ *   alltoall  : recv[q * bytes : (q+1) * bytes] = rank q's send[me * bytes : (me+1) * bytes]
+ * ------------------------------------------------------------------------------------------------ */
+#define ELIMREC_COMM_ID_BYTES 128
+/* Column-sharded ("feature-sharded") step, csrc/colshard.cu: rank r of `world` owns columns [r w, (r+1) w), w = 64 / world,
+ * of both embedding tables and of every 64-wide slab of the linear schedule; propagation then needs no communication, and
+ * only the instance rows of the batches cross NVLink (two all-to-alls per step).  Buffers [world][n][2w] are what
+ * elimrec_comm_alltoall sends / receives (n = 3B rows of one rank's batch).
+ *   cs_pack        out[j, 0:w] = scale * sum_k p_k[rows[j], 0:w], out[j, w:2w] = scale * parity sum   (layers: w-wide tables)
+ *   cs_unpack      O[j, q w + c] = recv[q][j][c];  O[j, 64 (1+m) + q w + c] += recv[q][j][w + c], m < n_mod
+ *   cs_seed_pack   send[q][j][c] = scale * sum_b dO[j, 64 b + q w + c];  send[q][j][w + c] = scale * dO[j, q w + c]
+ *   cs_seed_scatter GA[rows[j], c] += recv[j][c];  GB[rows[j], c] += recv[j][w + c]      (atomic; rows = all world * n rows) */
+/* triples [world][3][B] int64 (users | pos | neg of every rank's batch) -> rows [world][3][B] node ids (items offset by
+ * num_users); mask / mask2 (each may be NULL): zeroed over n_nodes, then 1 at every instance row of every batch */
+int elimrec_cs_inst_rows(int world, int B, const int64_t* triples, int32_t num_users, int32_t* rows, int64_t n_nodes, uint8_t* mask,
+                         uint8_t* mask2, elimrec_stream_t stream);
+int elimrec_cs_pack(int64_t n_rows, const int32_t* rows /* may be NULL: row j = node j */, int32_t num_users,
+                    const elimrec_lin_layers_t* layers, float scale, int w, float* out, elimrec_stream_t stream);
+int elimrec_cs_unpack(int world, int64_t n, int w, const float* recv, int n_mod, float* O, int64_t ldo, elimrec_stream_t stream);
+int elimrec_cs_seed_pack(int64_t n, int world, int w, const float* dO, int64_t ldo, int n_mod, float scale, float* send,
+                         elimrec_stream_t stream);
+int elimrec_cs_seed_scatter(int64_t n_all, const int32_t* rows, int w, const float* recv, float* GA, float* GB, int64_t ldg,
+                            elimrec_stream_t stream);
+int elimrec_comm_unique_id(void* unique_id_out_host);
+int elimrec_comm_init(const void* unique_id_host, int rank, int world, void** comm_out);
+int elimrec_comm_destroy(void* comm);
+int elimrec_comm_allreduce(void* comm, const float* send, float* recv, int64_t n, int average, elimrec_stream_t stream);
+int elimrec_comm_allgather(void* comm, const void* send, void* recv, int64_t bytes_per_rank, elimrec_stream_t stream);
+int elimrec_comm_alltoall(void* comm, const void* send, void* recv, int64_t bytes_per_pair, elimrec_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -73,14 +73,14 @@ def spmm(half, X, Y, width, epi=None, row_mask=None, col_mask=None, density=50, 
 
 def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row_mask_i=None, col_mask_u=None, col_mask_i=None,
                 addend_u=None, addend_i=None, add_mask_u=None, add_mask_i=None, adam_u=None, adam_i=None, adam_consts=None,
-                variant=0):
+                variant=0, width=64):
     for half, X, Y, rm, cm, ad, am, adam in ((half_u, X_for_u, Y_u, row_mask_u, col_mask_u, addend_u, add_mask_u, adam_u),
                                              (half_i, X_for_i, Y_i, row_mask_i, col_mask_i, addend_i, add_mask_i, adam_i)):
         if adam is None:
-            spmm(half, X, Y, 64, row_mask=rm, col_mask=cm, addend=ad, add_mask=am)
+            spmm(half, X, Y, width, row_mask=rm, col_mask=cm, addend=ad, add_mask=am)
             continue
-        grad = torch.zeros(half.n_rows, 64)
-        spmm(half, X, grad, 64, row_mask=rm, col_mask=cm, addend=ad, add_mask=am)
+        grad = torch.zeros(half.n_rows, width)
+        spmm(half, X, grad, width, row_mask=rm, col_mask=cm, addend=ad, add_mask=am)
         p, m, v, old = adam
         if old is not None:
             old.copy_(p)
@@ -451,3 +451,55 @@ def metric_rows(topk_idx, truth_ptr, truth_items, metric_ids, K, rows, sums):
     rows[:out.shape[0]] = torch.from_numpy(out)
     if sums is not None:
         sums += torch.from_numpy(out.astype(np.float64).sum(0))
+
+
+# ---- column-sharded multi-GPU step ---------------------------------------------------------------------------------------
+def cs_pack(rows, num_users, layers, scale, w, out, n_rows=None):
+    _log("cs_pack")
+    node = rows.long() if rows is not None else torch.arange(n_rows)
+    is_user = node < num_users
+    sa = sp = None
+    for k, (tu, ti) in enumerate(layers):
+        v = torch.where(is_user.unsqueeze(1), tu[torch.where(is_user, node, 0), :w], ti[torch.where(is_user, 0, node - num_users), :w])
+        sa = v.clone() if sa is None else sa + v
+        par = torch.where(is_user, k % 2 == 0, k % 2 == 1).unsqueeze(1)
+        pv = torch.where(par, v, torch.zeros_like(v))
+        sp = pv if sp is None else sp + pv
+    out.view(-1, 2 * w)[:, :w] = sa * scale
+    out.view(-1, 2 * w)[:, w:] = sp * scale
+
+
+def cs_unpack(world, n, w, recv, n_mod, O):
+    _log("cs_unpack")
+    r = recv.view(world, n, 2 * w)
+    O[:n, :64] = r[:, :, :w].permute(1, 0, 2).reshape(n, 64)
+    par = r[:, :, w:].permute(1, 0, 2).reshape(n, 64)
+    for m in range(n_mod):
+        O[:n, 64 * (m + 1):64 * (m + 2)] += par
+
+
+def cs_seed_pack(n, world, w, dO, n_mod, scale, send):
+    _log("cs_seed_pack")
+    b = dO[:n, :64]
+    a = dO[:n, :64 * (1 + n_mod)].reshape(n, 1 + n_mod, 64).sum(1)
+    s = send.view(world, n, 2 * w)
+    s[:, :, :w] = (scale * a).reshape(n, world, w).permute(1, 0, 2)
+    s[:, :, w:] = (scale * b).reshape(n, world, w).permute(1, 0, 2)
+
+
+def cs_seed_scatter(rows_all, w, recv, GA, GB):
+    _log("cs_seed_scatter")
+    r = recv.view(-1, 2 * w)
+    GA[:, :w].index_add_(0, rows_all.long(), r[:, :w])
+    GB[:, :w].index_add_(0, rows_all.long(), r[:, w:])
+
+
+def cs_inst_rows(world, B, triples, num_users, rows, mask=None, mask2=None):
+    _log("cs_inst_rows")
+    t = triples.view(world, 3, B).clone()
+    t[:, 1:] += num_users
+    rows.copy_(t.reshape(-1).to(torch.int32))
+    for m in (mask, mask2):
+        if m is not None:
+            m.zero_()
+            m[rows.long()] = 1

@@ -87,6 +87,7 @@ def _install_sim():
     import elimrec_b200.linear as ln
     import elimrec_b200.model as md
     import elimrec_b200.optim as op
+    import elimrec_b200.colshard as csm
     import elimrec_b200.sharded as sh
 
     class _Ev:
@@ -99,7 +100,7 @@ def _install_sim():
     class _St:
         def wait_event(self, *a):
             pass
-    for mod in (md, ev, op, sh, ln):
+    for mod in (md, ev, op, sh, ln, csm):
         mod.ops = sim_ops
     md._require_cuda = lambda dev: None
     torch.cuda.Event = _Ev
@@ -183,3 +184,89 @@ def test_data_parallel_and_row_sharded_models_world2():
         assert p.exitcode == 0
     for rank, worst_dp, ok_eval, ok_seval, ok_loss, worst_sh in res:
         assert worst_dp < 1e-4 and ok_eval and ok_seval and ok_loss and worst_sh < 1e-4, res
+
+
+def _colshard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from conftest import load_golden
+        from helpers import golden_dataset, golden_params
+        from elimrec_b200.colshard import ColShardedEliMRec
+        from elimrec_b200.data import Config
+        from elimrec_b200.model import EliMRec
+        _install_sim()
+        out = []
+        for gname, dsname in (("generic", "synthg"), ("kwai", "kwai")):
+            g = load_golden(gname)
+            g["_name"] = gname
+            ds = golden_dataset(g)
+            cfg = lambda **kw: Config(**{"data.input.dataset": dsname, "topks": [20], "device": torch.device("cpu"), "alpha": 0.5,
+                                         "test_batch_size": 16, "rank_backend": "fp32", "proj_precision": "fp32", **kw})
+            load = lambda m: m.load_state_dict({k: torch.as_tensor(v) for k, v in golden_params(g).items()}, strict=False)
+            batch = lambda i: tuple(torch.as_tensor(g[f"batch{i}_{k}"]) for k in ("users", "pos", "neg"))
+            rel = lambda a, b: float((a.double() - torch.as_tensor(b).double()).abs().max() / torch.as_tensor(b).double().abs().max())
+            # (1) the same batch on every rank: mean loss / mean gradient == the single-process step -> golden trajectory
+            m = ColShardedEliMRec(cfg(), ds)
+            load(m)
+            m.make_optimizer(lr=1e-3, weight_decay=1e-4)
+            losses = [float(m.train_step(*batch(i))) for i in range(3)]
+            ok_loss = bool(np.allclose(losses, g["losses"], rtol=2e-5))
+            m.eval()
+            ok_eval = True
+            worst = max(rel(v, g["sd3/" + k]) for k, v in m.state_dict().items())      # gathers the column shards
+            # (2) a different batch per rank == one process stepping on the MEAN of the per-batch gradients; evaluation after it
+            m = ColShardedEliMRec(cfg(), ds)
+            load(m)
+            m.make_optimizer(lr=1e-3, weight_decay=1e-4)
+            lm = float(m.train_step(*batch(rank)))
+            ref = EliMRec(cfg(), ds)
+            load(ref)
+            opt = ref.make_optimizer(lr=1e-3, weight_decay=1e-4)
+            lr_ = 0.0
+            for i in range(world):
+                li = ref.bpr_loss(*batch(i)) / world
+                li.backward()
+                lr_ += float(li)
+            opt.step()
+            ok_mean = abs(lm - lr_) < 2e-5 * abs(lr_)
+            worst2 = max(rel(a, b) for a, b in zip(m.state_dict().values(), ref.state_dict().values()))
+            # tables of that forward (pre-update weights) through the all-gather of the column shards: user-sharded evaluation
+            m.eval()
+            ref0 = EliMRec(cfg(), ds)
+            load(ref0)
+            ref0.bpr_loss(*batch(rank))
+            ok_tab = rel(m.all_users, ref0.all_users.detach().numpy()) < 2e-5 and rel(m.all_items, ref0.all_items.detach().numpy()) < 2e-5
+            ev = m.evaluate()[0]
+            out.append((gname, ok_loss, ok_eval, worst, ok_mean, worst2, ok_tab, bool(np.isfinite(ev).all())))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_sharded_model_world2():
+    """column-sharded multi-GPU mode on 2 gloo ranks (32 columns each): all-gather of the triples, the two all-to-alls of the
+    instance rows, the all-reduce of the small gradients, column-local fused Adam, state_dict / table gathers."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + (os.getpid() % 300)
+    procs = [ctx.Process(target=_colshard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res, t0 = [], time.time()
+    while len(res) < len(procs):
+        try:
+            res.append(q.get(timeout=2))
+        except _queue.Empty:
+            if any(not p.is_alive() and p.exitcode not in (0, None) for p in procs) or time.time() - t0 > 400:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError(f"worker failed (exit codes {[p.exitcode for p in procs]})")
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in res:
+        for gname, ok_loss, ok_eval, worst, ok_mean, worst2, ok_tab, fin in out:
+            assert ok_loss and ok_eval and ok_mean and ok_tab and fin and worst < 1e-4 and worst2 < 1e-4, (rank, out)

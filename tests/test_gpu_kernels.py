@@ -715,3 +715,84 @@ def test_spmm64_pair_matches_fp64(dev, variant):
     Xz = (X * cm.unsqueeze(1)).double().cpu().numpy()
     ref4 = np.concatenate([A_ui @ Xz[U:], A_iu @ Xz[:U]]) + (add * am.unsqueeze(1)).double().cpu().numpy()
     assert rel_err(Y4, ref4) < FP32_TOL
+
+
+@pytest.mark.parametrize("width", [32, 16, 8])
+def test_spmm64_pair_narrow_widths(dev, width):
+    """the column-sharded widths (64 / world columns per rank): dense, masked, additive epilogue, fused Adam; vs fp64 / torch"""
+    from elimrec_b200 import ops
+    from elimrec_b200.graph import BipartiteGraph
+    U, I = 700, 500
+    g = BipartiteGraph(_rand_graph(U, I, 6000, [(3, 480), (10, 130), (11, 65)], seed=width), dev)
+    X = torch.randn(U + I, width, device=dev)
+    A_ui = sp.csr_matrix((g.ui.vals_host.astype(np.float64), g.ui.indices_host, g.ui.indptr_host), shape=(U, I))
+    A_iu = sp.csr_matrix((g.iu.vals_host.astype(np.float64), g.iu.indices_host, g.iu.indptr_host), shape=(I, U))
+    Xd = X.double().cpu().numpy()
+    ref = np.concatenate([A_ui @ Xd[U:], A_iu @ Xd[:U]])
+    Y = torch.full((U + I, width), float("nan"), device=dev)
+    ops.spmm64_pair(g.ui, g.iu, X[U:], X[:U], Y[:U], Y[U:], width=width)
+    assert rel_err(Y, ref) < FP32_TOL
+    rm = (torch.rand(U + I, device=dev) < 0.4).to(torch.uint8)
+    cm = (torch.rand(U + I, device=dev) < 0.5).to(torch.uint8)
+    add = torch.randn(U + I, width, device=dev)
+    Y2 = torch.full_like(Y, 3.0)
+    ops.spmm64_pair(g.ui, g.iu, X[U:], X[:U], Y2[:U], Y2[U:], row_mask_u=rm[:U], row_mask_i=rm[U:], col_mask_u=cm[U:],
+                    col_mask_i=cm[:U], addend_u=add[:U], addend_i=add[U:], add_mask_u=rm[:U], add_mask_i=rm[U:], width=width)
+    Xz = (X * cm.unsqueeze(1)).double().cpu().numpy()
+    ref2 = np.concatenate([A_ui @ Xz[U:], A_iu @ Xz[:U]]) + add.double().cpu().numpy()
+    sel = rm.bool().cpu().numpy()
+    assert rel_err(Y2[rm.bool()], ref2[sel]) < FP32_TOL and (Y2[~rm.bool()] == 3.0).all()
+    # fused Adam on the finished rows == torch.optim.Adam on the gradient
+    p0 = torch.randn(U + I, width, device=dev)
+    prm = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([prm], lr=1e-3, weight_decay=1e-4)
+    prm.grad = Y.clone()
+    opt.step()
+    consts, step = torch.zeros(2, dtype=torch.float64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)
+    ops.adam_tick(step, consts, 1e-3, 0.9, 0.999)
+    pu, pi = p0[:U].clone(), p0[U:].clone()
+    mu, vu, mi, vi = (torch.zeros_like(t) for t in (pu, pu, pi, pi))
+    old = torch.empty_like(p0)
+    ops.spmm64_pair(g.ui, g.iu, X[U:], X[:U], None, None, adam_u=(pu, mu, vu, old[:U]), adam_i=(pi, mi, vi, old[U:]),
+                    adam_consts=(consts, 0.9, 0.999, 1e-8, 1e-4), width=width)
+    assert rel_err(torch.cat([pu, pi]), prm.detach()) < 2e-6 and torch.equal(old, p0)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_colshard_glue_kernels_match_restatement(dev, world):
+    import sim_ops
+    from elimrec_b200 import ops
+    w, U, I, B, L, nm = 64 // world, 50, 70, 33, 3, 3
+    g = torch.Generator().manual_seed(world)
+    T = torch.stack([torch.stack([torch.randint(0, U, (B,), generator=g), torch.randint(0, I, (B,), generator=g),
+                                  torch.randint(0, I, (B,), generator=g)]) for _ in range(world)]).reshape(-1)
+    rows_w, m1w, m2w = torch.zeros(world * 3 * B, dtype=torch.int32), torch.ones(U + I, dtype=torch.uint8), torch.ones(U + I, dtype=torch.uint8)
+    sim_ops.cs_inst_rows(world, B, T, U, rows_w, m1w, m2w)
+    rows, m1, m2 = torch.zeros_like(rows_w, device=dev), torch.ones(U + I, dtype=torch.uint8, device=dev), torch.ones(U + I, dtype=torch.uint8, device=dev)
+    ops.cs_inst_rows(world, B, T.to(dev), U, rows, m1, m2)
+    assert torch.equal(rows.cpu(), rows_w) and torch.equal(m1.cpu(), m1w) and torch.equal(m2.cpu(), m2w)
+    tabs = [(torch.randn(U, w, generator=g), torch.randn(I, w, generator=g)) for _ in range(L + 1)]
+    want = torch.zeros(world * 3 * B, 2 * w)
+    sim_ops.cs_pack(rows_w, U, sim_ops.lin_layers(tabs), 0.25, w, want)
+    got = torch.zeros(world * 3 * B, 2 * w, device=dev)
+    ops.cs_pack(rows, U, ops.lin_layers([(a.to(dev), b.to(dev)) for a, b in tabs]), 0.25, w, got)
+    assert rel_err(got, want) < 1e-6
+    recv = torch.randn(world, 3 * B, 2 * w, generator=g)
+    O0 = torch.randn(3 * B, 64 * (1 + nm), generator=g)
+    want = O0.clone()
+    sim_ops.cs_unpack(world, 3 * B, w, recv, nm, want)
+    got = O0.to(dev)
+    ops.cs_unpack(world, 3 * B, w, recv.to(dev), nm, got)
+    assert rel_err(got, want) < 1e-6
+    dO = torch.randn(3 * B, 64 * (1 + nm), generator=g)
+    want = torch.zeros(world, 3 * B, 2 * w)
+    sim_ops.cs_seed_pack(3 * B, world, w, dO, nm, 0.125, want)
+    got = torch.zeros(world, 3 * B, 2 * w, device=dev)
+    ops.cs_seed_pack(3 * B, world, w, dO.to(dev), nm, 0.125, got)
+    assert rel_err(got, want) < 1e-6
+    GA0, GB0 = torch.randn(U + I, w, generator=g), torch.randn(U + I, w, generator=g)
+    wa, wb = GA0.clone(), GB0.clone()
+    sim_ops.cs_seed_scatter(rows_w, w, recv, wa, wb)
+    ga, gb = GA0.to(dev), GB0.to(dev)
+    ops.cs_seed_scatter(rows, w, recv.to(dev), ga, gb)
+    assert rel_err(ga, wa) < 2e-6 and rel_err(gb, wb) < 2e-6

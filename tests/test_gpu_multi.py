@@ -139,3 +139,74 @@ def test_row_sharded_allgather_training_nccl():
     for rank, out in res:
         for gname, ok_eval, ok_loss, worst in out:
             assert ok_eval and ok_loss and worst < 1e-4, (rank, gname, ok_eval, ok_loss, worst)
+
+
+def _colshard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from conftest import load_golden
+    from gpu_util import rel_err
+    from helpers import golden_dataset, golden_params
+    from elimrec_b200.colshard import ColShardedEliMRec
+    from elimrec_b200.data import Config
+    from elimrec_b200.model import EliMRec
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        out = []
+        for gname, dsname in (("generic", "synthg"), ("kwai", "kwai")):
+            g = load_golden(gname)
+            g["_name"] = gname
+            ds = golden_dataset(g)
+            cfg = lambda: Config(**{"data.input.dataset": dsname, "topks": [20], "device": dev, "alpha": 0.5, "test_batch_size": 16})
+            load = lambda m: m.load_state_dict({k: torch.as_tensor(v) for k, v in golden_params(g).items()}, strict=False)
+            batch = lambda i: (g[f"batch{i}_users"], g[f"batch{i}_pos"], g[f"batch{i}_neg"])
+            # (1) the same batch on both ranks == the single-GPU (= reference) trajectory; through the CUDA-graph runner,
+            #     i.e. with the NCCL collectives of the C-ABI comm family captured inside the graph
+            m = ColShardedEliMRec(cfg(), ds).to(dev)
+            load(m)
+            m.make_optimizer(lr=1e-3, weight_decay=1e-4)
+            run = m.make_graphed_step(len(batch(0)[0]))
+            losses = [float(run(*batch(i))) for i in range(3)]
+            ok_loss = bool(np.allclose(losses, g["losses"], rtol=2e-5))
+            worst = max(rel_err(v, g["sd3/" + k]) for k, v in m.state_dict().items())
+            # (2) a different batch per rank == one GPU stepping on the mean gradient; tables + sharded evaluation of that forward
+            m = ColShardedEliMRec(cfg(), ds).to(dev)
+            load(m)
+            m.make_optimizer(lr=1e-3, weight_decay=1e-4)
+            m.train_step(*batch(rank))
+            ref = EliMRec(cfg(), ds).to(dev)
+            load(ref)
+            opt = ref.make_optimizer(lr=1e-3, weight_decay=1e-4)
+            for i in range(world):
+                (ref.bpr_loss(*[torch.tensor(x) for x in batch(i)]) / world).backward()
+            opt.step()
+            worst2 = max(rel_err(a, b) for a, b in zip(m.state_dict().values(), ref.state_dict().values()))
+            m.eval()
+            res, _ = m.evaluate()
+            ref0 = EliMRec(cfg(), ds).to(dev)
+            load(ref0)
+            ref0.bpr_loss(*[torch.tensor(x) for x in batch(rank)])
+            ok_tab = rel_err(m.all_items, ref0.all_items) < 2e-5 and rel_err(m.all_users, ref0.all_users) < 2e-5
+            out.append((gname, ok_loss, worst, worst2, bool(ok_tab), bool(np.isfinite(res).all())))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_column_sharded_training_nccl():
+    """column-sharded mode on 2 GPUs (32 embedding columns each), NCCL through the C-ABI comm family, step captured as one
+    CUDA graph: golden trajectory, mean-of-batches step, table completion through the all-gather."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 150)
+    procs = [ctx.Process(target=_colshard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = _collect(procs, q)
+    for rank, out in res:
+        for gname, ok_loss, worst, worst2, ok_tab, fin in out:
+            assert ok_loss and ok_tab and fin and worst < 1e-4 and worst2 < 1e-4, (rank, out)
