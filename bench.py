@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="exploratory runs only: skip the host-sampler arm (e2e = null)")
     ap.add_argument("--eval-users", type=int, default=0, help="0 = all test users")
     ap.add_argument("--cuda-graph", type=int, default=1)
     ap.add_argument("--lazy-tables", type=int, default=1,
@@ -427,32 +428,35 @@ def main():
         return n
 
     e2e_epochs = max(1, -(-args.steps // steps_per_epoch))
-    np.random.seed(2022 + (0 if rowshard else rank))
-    sampler_pf = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat", prefetch=True, pin=True)
-    sampler_pf.rng.seed(1 + (0 if rowshard else rank))        # replicas draw different triples
-    run_epochs(sampler_pf, 1)                     # warm-up epoch; leaves the next epoch being sampled on the thread
-    sync_all()
-    t0 = time.perf_counter()
-    n_e2e = run_epochs(sampler_pf, e2e_epochs)
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    if sampler_pf._next is not None:
-        sampler_pf._next[0].join()
-    sampler_se = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat", prefetch=False, pin=True)
-    sampler_se.rng.seed(101 + (0 if rowshard else rank))
-    sync_all()
-    t0 = time.perf_counter()
-    n_ser = run_epochs(sampler_se, e2e_epochs)
-    sync_all()
-    ser_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s, ser_s], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = units * n_e2e / float(te[0])
-    e2e_serial = units * n_ser / float(te[1])
-    e2e_steps = e2e_epochs * steps_per_epoch
-    log(f"[bench] rank {rank}: e2e arm done ({e2e_steps} steps: {1e3 * float(te[0]) / e2e_steps:.3f} ms/step overlapped, "
-        f"{1e3 * float(te[1]) / e2e_steps:.3f} serial)")
+    e2e_value = e2e_serial = None
+    e2e_steps = 0
+    if not args.no_e2e:
+        np.random.seed(2022 + (0 if rowshard else rank))
+        sampler_pf = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat", prefetch=True, pin=True)
+        sampler_pf.rng.seed(1 + (0 if rowshard else rank))        # replicas draw different triples
+        run_epochs(sampler_pf, 1)                     # warm-up epoch; leaves the next epoch being sampled on the thread
+        sync_all()
+        t0 = time.perf_counter()
+        n_e2e = run_epochs(sampler_pf, e2e_epochs)
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        if sampler_pf._next is not None:
+            sampler_pf._next[0].join()
+        sampler_se = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat", prefetch=False, pin=True)
+        sampler_se.rng.seed(101 + (0 if rowshard else rank))
+        sync_all()
+        t0 = time.perf_counter()
+        n_ser = run_epochs(sampler_se, e2e_epochs)
+        sync_all()
+        ser_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s, ser_s], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = units * n_e2e / float(te[0])
+        e2e_serial = units * n_ser / float(te[1])
+        e2e_steps = e2e_epochs * steps_per_epoch
+        log(f"[bench] rank {rank}: e2e arm done ({e2e_steps} steps: {1e3 * float(te[0]) / e2e_steps:.3f} ms/step overlapped, "
+            f"{1e3 * float(te[1]) / e2e_steps:.3f} serial)")
 
     # fixed batches for the per-kernel profile and the reference-schedule comparison
     u, p, n = sampler_dev.sample_epoch_device((args.warmup + args.steps) * BATCH)
@@ -494,7 +498,9 @@ def main():
         if args.eval_users:
             users = users[:args.eval_users]
         kw = dict(test_users=users) if args.eval_users else {}
+        log(f"[bench] rank {rank}: evaluation warm-up")
         evalr.evaluate(model, **kw)  # warm-up (device CSR upload, smem opt-in)
+        log(f"[bench] rank {rank}: evaluation warm-up done")
 
         def timed_eval():
             sync_all()
@@ -513,6 +519,7 @@ def main():
         # (masked layers over every row, modality blocks, fusion Linear + heads), normalised and split inside the timed call
         step_sampled()
         t_dev, t_wall, res = timed_eval()
+        log(f"[bench] rank {rank}: evaluation after a step {1e3 * t_dev:.2f} ms")
         c_dev, c_wall, _ = timed_eval()          # again without a step in between: cached tables
         M_ = len(model.mods)
         flops = 2.0 * len(users) * ds.num_items * 64 * ((1 + M_) * 3 + 3)      # fp16 hi/lo: 3 MMA terms per dot product; + row-mean pass
@@ -596,7 +603,7 @@ def main():
                            "triples_per_optimizer_step": BATCH * units,
                            "sampler": "value: device Philox sampler inside every step's graph; e2e: host compat sampler (bit-exact "
                                       "libc stream) + numpy shuffle, whole epochs, inside the timed region"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4,
+                "e2e": None if args.no_e2e else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4,
                         "steps": e2e_steps, "epochs": e2e_epochs, "serial_sampler_value": e2e_serial,
                         "note": "main.py:92-102 loop over whole epochs; value: next epoch sampled on a prefetch thread while this one "
                                 "trains; serial_sampler_value: each epoch sampled + shuffled before its first step (as the "
@@ -605,7 +612,17 @@ def main():
                 "eval": ev, "sampler": samp, "kernels": kernels, "final_loss": final_loss, "dense_schedule": dense}
         emit(line)
     if world > 1:
+        # orderly teardown: graphs that captured collectives first, then the library's communicator, then torch's
+        runner = runner_h = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        log(f"[bench] rank {rank}: teardown")
+        if getattr(model, "comm", None) is not None:
+            model.comm.close()
         dist.destroy_process_group()
+        log(f"[bench] rank {rank}: done")
     return 0
 
 

@@ -120,13 +120,16 @@ class ColShardedEliMRec(EliMRec):
         T_own, T_all, rows_all = ws["T_own"], ws["T_all"], ws["rows_all"]
         rows = rows_all[self.rank * 3 * B:(self.rank + 1) * 3 * B]            # this rank's instance rows
         ws["inst_rows"] = rows
-        # every rank needs every batch's instance rows (it propagates its columns for all of them)
-        if users.data_ptr() != T_own.data_ptr():
-            T_own[:B].copy_(users); T_own[B:2 * B].copy_(pos); T_own[2 * B:].copy_(neg)
-        self.comm.all_gather(T_all, T_own)
-        ops.cs_inst_rows(G, B, T_all, U, rows_all, mask, need2)
+        # Layer 1 does not depend on the batch: it starts at once on the current stream.  Everything about the instance rows
+        # runs beside it on a high-priority stream: every rank needs every batch's rows (it propagates its columns for all).
         side = ops.fork_side(0, high_priority=True)
         with torch.cuda.stream(side):
+            if users.data_ptr() != T_own.data_ptr():
+                T_own[:B].copy_(users); T_own[B:2 * B].copy_(pos); T_own[2 * B:].copy_(neg)
+            self.comm.all_gather(T_all, T_own)
+            ops.cs_inst_rows(G, B, T_all, U, rows_all, mask, need2)
+            ev_rows = torch.cuda.Event()
+            ev_rows.record(side)
             if L >= 2:
                 ops.mark_neighbors(g.ui, mask[:U], need2[U:])
                 ops.mark_neighbors(g.iu, mask[U:], need2[:U])
@@ -139,6 +142,7 @@ class ColShardedEliMRec(EliMRec):
             if getattr(self, "_tick_early", False):
                 self._adam.tick()
             self._snapshot(P, ws)
+            torch.cuda.current_stream().wait_event(ev_rows)
             ops.zero_rows(rows_all, 0, U + I, 0, ws["GA"], w)
             ops.zero_rows(rows_all, 0, U + I, 0, ws["GB"], w)
             ws["seed_zeroed"] = True
@@ -151,11 +155,12 @@ class ColShardedEliMRec(EliMRec):
         for k in range(1, L + 1):
             out = ws["P"][k]
             rm = mask if k == L else (need2 if k == L - 1 else None)
-            if k == L - 1:
-                cur.wait_event(ev_masks)
+            if rm is not None:
+                cur.wait_event(ev_rows if k == L else ev_masks)
             ops.spmm64_pair(g.ui, g.iu, in_i, in_u, out[:U], out[U:], row_mask_u=rm[:U] if rm is not None else None,
                             row_mask_i=rm[U:] if rm is not None else None, width=w)
             in_u, in_i = out[:U], out[U:]
+        cur.wait_event(ev_rows)
         # exchange: my columns of everybody's instance rows  ->  all 64 columns of my instance rows
         lay = ops.lin_layers(self._lin_tables(ws, Eu, Ei))
         ops.cs_pack(rows_all, U, lay, 1.0 / (L + 1), w, ws["cs_send"])

@@ -38,15 +38,12 @@ class Comm:
             self._h = h
 
     def close(self):
+        """destroy the communicator.  Call it explicitly, after every CUDA graph that captured its collectives is gone and
+        the device is idle; at interpreter exit the communicator is simply left to the process teardown (destroying it from a
+        finaliser, in whatever order the garbage collector picks, can block on the peer)."""
         if self._h is not None:
             _lib.lib().elimrec_comm_destroy(self._h)
             self._h = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
 
     # ---- the three collectives -----------------------------------------------------------------------------------------
     def all_reduce(self, t: torch.Tensor, average: bool = False):

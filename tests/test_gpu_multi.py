@@ -153,6 +153,7 @@ def _colshard_worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    comms = []
     try:
         out = []
         for gname, dsname in (("generic", "synthg"), ("kwai", "kwai")):
@@ -171,6 +172,7 @@ def _colshard_worker(rank, world, port, q):
             losses = [float(run(*batch(i))) for i in range(3)]
             ok_loss = bool(np.allclose(losses, g["losses"], rtol=2e-5))
             worst = max(rel_err(v, g["sd3/" + k]) for k, v in m.state_dict().items())
+            comms.append(m.comm)
             # (2) a different batch per rank == one GPU stepping on the mean gradient; tables + sharded evaluation of that forward
             m = ColShardedEliMRec(cfg(), ds).to(dev)
             load(m)
@@ -190,8 +192,17 @@ def _colshard_worker(rank, world, port, q):
             ref0.bpr_loss(*[torch.tensor(x) for x in batch(rank)])
             ok_tab = rel_err(m.all_items, ref0.all_items) < 2e-5 and rel_err(m.all_users, ref0.all_users) < 2e-5
             out.append((gname, ok_loss, worst, worst2, bool(ok_tab), bool(np.isfinite(res).all())))
+            comms.append(m.comm)
         q.put((rank, out))
     finally:
+        # orderly teardown: the graphs that captured collectives, then the library's communicators, then torch's
+        run = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        for c in comms:
+            c.close()
         dist.destroy_process_group()
 
 
