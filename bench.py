@@ -224,7 +224,19 @@ def rooflines_of(model, agg, workload, B, prefix=""):
         pass
     fam = sum(sum(v) for k, v in agg.items() if k.startswith("spmm"))
     common = dict(traffic=traffic, peak_source=which, spmm_family_share_of_step=fam / tot)
-    if f"spmm{Fw}w" in agg and half is not None:
+    if model.linear and "spmm64_pair" in agg:
+        # linear schedule: ONE launch per propagation layer covers both CSR halves (elimrec_spmm64_pair); timed on the
+        # unmasked launches (forward layer 1).  Algorithmic bytes: both halves' indices + values, the [N x 64] slab in and out.
+        alg = alg_of(g.ui) + alg_of(g.iu)
+        head = add("spmm64_pair_kernel (one 64-wide propagation layer, both CSR halves in one launch, unmasked)", "spmm64_pair", "hbm",
+                   alg, hbm, "GB/s", gathered_bytes_per_launch=float(g.nnz * 256), **common)
+        if head is not None:
+            head["l2_gather_gbps"] = g.nnz * 256 / (head["avg_launch_us"] * 1e-6) / 1e9
+        if "spmm64_pair+adam" in agg:      # last backward hop with the optimizer in its epilogue: + 7 Adam streams, - the slab store
+            add("spmm64_pair_kernel + fused Adam epilogue (last backward hop: propagation + optimizer on both embedding tables)",
+                "spmm64_pair+adam", "hbm", alg - (U + I) * 64 * 4 + 7.0 * (U + I) * 64 * 4 + (U + I) * 64 * 4, hbm, "GB/s",
+                peak_source=which, note="algorithmic bytes = indices + gathered slab + 7 Adam streams + the pre-update snapshot")
+    elif f"spmm{Fw}w" in agg and half is not None:
         head = add(f"spmm_seg_kernel<{Fw}> (whole rows, {'user' if half is g.ui else 'item'}-row half, unmasked)", f"spmm{Fw}w",
                    "hbm", alg_of(half), hbm, "GB/s", **common)
         other = g.iu if half is g.ui else g.ui
@@ -235,13 +247,14 @@ def rooflines_of(model, agg, workload, B, prefix=""):
                    "hbm", 0.5 * (alg_of(g.ui) + alg_of(g.iu)), hbm, "GB/s", **common)
     if head is not None:
         slab_mb = (U + I) * Fw * 4 / 1e6
-        head["note"] = (f"operand slab {slab_mb:.0f} MB " + ("fits the 126 MB L2: the gather is bound by L2->SM bandwidth, DRAM carries "
-                        "only the compulsory bytes" if slab_mb < 100 else "exceeds the 126 MB L2: the gather misses to HBM at "
-                        "row granularity") + "; achieved = algorithmic bytes / launch time (DESIGN.md 3.1)")
+        head["note"] = (f"operand slab {slab_mb:.0f} MB " + ("fits the 126 MB L2: the gather is bound by L2->SM bandwidth (~12.4 TB/s "
+                        "cap, B300_MICROARCH.md), DRAM carries only the compulsory bytes" if slab_mb < 100 else "exceeds the 126 MB L2: "
+                        "the gather misses to HBM at row granularity") + "; achieved = algorithmic bytes / launch time (DESIGN.md 3.1)")
     # Adam: 7 streams x 4 B per parameter element (read p, g, m, v; write p, m, v)
-    n_par = sum(p.numel() for p in model._params().values())
-    add("adam_multi_kernel (all parameters, one launch)", "elimrec_adam_apply_multi", "hbm", 28.0 * n_par, hbm, "GB/s",
-        peak_source=which)
+    n_par = sum(p.numel() for n_, p in model._params().items()
+                if not (model.linear and "spmm64_pair+adam" in agg and n_.startswith(("embedding_user.w", "embedding_item.w"))))
+    add("adam_multi_kernel (" + ("small weights; the tables ride in the last hop" if "spmm64_pair+adam" in agg else "all parameters") +
+        ", one launch)", "elimrec_adam_apply_multi", "hbm", 28.0 * n_par, hbm, "GB/s", peak_source=which)
     if model.linear:
         Kt = model._lin_Ktot
         add("gather_rows_kernel (Zbar rows at the 3B instance rows)", "elimrec_gather_rows", "hbm", 2.0 * 3 * B * Kt * 4, hbm, "GB/s",

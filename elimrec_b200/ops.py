@@ -119,7 +119,8 @@ def spmm64_pair(half_u, half_i, X_for_u, X_for_i, Y_u, Y_i, row_mask_u=None, row
     if X_for_u.shape[-1] < width or X_for_i.shape[-1] < width:
         raise _lib.ElimrecError("spmm64_pair: operand narrower than the propagated width")
     call("elimrec_spmm64_pair", C.byref(da), C.byref(db), (C.byref(ac) if ac is not None else None), int(width), int(variant), stream(),
-         tag="spmm64_pair" + ("+adam" if ac is not None else ""))
+         tag="spmm64_pair" + ("+adam" if ac is not None else ("_masked" if any(m is not None for m in (
+             row_mask_u, row_mask_i, col_mask_u, col_mask_i)) else "")))
 
 
 def mark_rows(rows, mask):
