@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-10x", action="store_true", help="skip the tiktok-10x scaling section (scale_10x)")
     ap.add_argument("--no-e2e", action="store_true", help="exploratory runs only: skip the host-sampler arm (e2e = null)")
     ap.add_argument("--eval-users", type=int, default=0, help="0 = all test users")
     ap.add_argument("--cuda-graph", type=int, default=1)
@@ -292,6 +293,101 @@ def rooflines_of(model, agg, workload, B, prefix=""):
     return head, out
 
 
+def measure_10x(args, rank, world, dev, log):
+    """BASELINE.json configs[4]: the 10x-scaled Tiktok-shape graph.  At N > 1 both multi-GPU designs, device-timed, max over
+    ranks: `colshard` (column-sharded linear schedule, every rank its own batch: weak scaling) and `rowshard` (the design the
+    north star names: users / items row-sharded, an NCCL all-gather of the propagated shards per GCN layer, every rank the SAME
+    batch: strong scaling) with its time split into compute and collectives.  At N = 1 the single-GPU step they scale from."""
+    import torch
+    import torch.distributed as dist
+    from elimrec_b200.data import Config
+    from elimrec_b200.model import EliMRec
+    from elimrec_b200.sampler import PairwiseSamplerV2
+    ds, name = build_dataset("tiktok10x")
+    out = {"workload": f"tiktok10x-shape EliMRec train step, batch {BATCH}/GPU, U={ds.num_users} I={ds.num_items} "
+                       f"E_train={ds.train_matrix.nnz}", "n_gpus": world}
+
+    def timed(step, n_warm, n_steps):
+        for _ in range(n_warm):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_steps):
+            step()
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / n_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    conf = lambda: Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH})
+    torch.manual_seed(2022)
+    if world == 1:
+        model = EliMRec(conf(), ds).to(dev)
+        model.make_optimizer()
+        smp = PairwiseSamplerV2(ds, batch_size=BATCH, mode="device", device=dev, seed=2022)
+        run = model.make_graphed_step(device_sampler=smp)
+        ms = timed(run, 3, 10)
+        out["single_gpu"] = {"ms_per_step": ms, "value": BATCH / (ms / 1e3), "unit": UNIT, "schedule": "linear, CUDA graph, device sampler"}
+        return out
+    from elimrec_b200.colshard import ColShardedEliMRec
+    from elimrec_b200.sharded import ShardedEliMRec
+    model = ColShardedEliMRec(conf(), ds).to(dev)
+    model.make_optimizer()
+    smp = PairwiseSamplerV2(ds, batch_size=BATCH, mode="device", device=dev, seed=2022 + rank)
+    run = model.make_graphed_step(device_sampler=smp)
+    ms = timed(run, 3, 10)
+    out["colshard"] = {"ms_per_step": ms, "value": world * BATCH / (ms / 1e3), "unit": UNIT, "scaling": "weak",
+                       "triples_per_optimizer_step": world * BATCH,
+                       "collectives_per_step": "1 all-gather of the triples, 2 all-to-alls of the instance rows "
+                                               f"({world * 3 * BATCH * 2 * (64 // world) * 4 / 1e6:.1f} MB per rank each), 1 all-reduce of the "
+                                               "small weight gradients; no collective in the propagation"}
+    log(f"[bench] rank {rank}: 10x colshard {ms:.3f} ms/step")
+    run = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    model.comm.close()
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+    model = ShardedEliMRec(conf(), ds).to(dev)
+    model.make_optimizer()
+    smp = PairwiseSamplerV2(ds, batch_size=BATCH, mode="device", device=dev, seed=2022)      # the same batch on every rank
+    bu, bp, bn = (torch.empty(BATCH, dtype=torch.int64, device=dev) for _ in range(3))
+
+    def step():
+        smp.sample_batch_device(model._adam.step_dev, bu, bp, bn)
+        model.train_step(bu, bp, bn)
+    ms_full = timed(step, 2, 5)
+    # the same step with every collective turned into a no-op: what is left is compute (results are garbage, timing is not)
+    model._ag = lambda slab, blk: None
+    model._ar = lambda t: None
+    try:
+        ms_comp = timed(step, 1, 5)
+    finally:
+        del model._ag, model._ar
+    N = ds.num_users + ds.num_items
+    out["rowshard"] = {"ms_per_step": ms_full, "value": BATCH / (ms_full / 1e3), "unit": UNIT, "scaling": "strong",
+                       "ms_without_collectives": ms_comp, "collective_ms": ms_full - ms_comp,
+                       "collectives_per_step": f"10 all-gathers of propagated slabs (5 x [N x 256] = {N * 256 * 4 / 1e6:.0f} MB and 5 x [N x 64] = "
+                                               f"{N * 64 * 4 / 1e6:.0f} MB each, fp32), 1 all-reduce of the instance rows, 1 of the "
+                                               "projection weight gradients",
+                       "bound_by": "the per-layer all-gathers (NVLink), not the sharded SpMM"}
+    log(f"[bench] rank {rank}: 10x rowshard {ms_full:.3f} ms/step ({ms_comp:.3f} without collectives)")
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     # stdout carries exactly ONE JSON line: route everything else a library may print there (e.g. NCCL's version
@@ -311,6 +407,10 @@ def main():
         if rank != 0:
             return 0
         import torch
+        try:      # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every core this process may run on
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+        except Exception:
+            pass
         ds, name = build_dataset(args.workload)
         r = cpu_port_run(ds, name, args.steps, args.warmup, budget_s=200.0)
         v = BATCH / r["step_s"]
@@ -589,6 +689,13 @@ def main():
         rooflines += rls_d
         del md, rd
 
+    tenx = None
+    if not args.no_10x and args.workload == "tiktok" and bool(args.linear) and bool(args.lazy_tables) and not rowshard:
+        try:
+            tenx = measure_10x(args, rank, world, dev, log)
+        except Exception as exc:      # the headline must survive a failure of the extra section
+            tenx = {"error": f"{type(exc).__name__}: {exc}"}
+            log(f"[bench] rank {rank}: scale_10x failed: {tenx['error']}")
     if rank == 0:
         N_ = ds.num_users + ds.num_items
         if model.linear:
@@ -622,7 +729,7 @@ def main():
                                 "trains; serial_sampler_value: each epoch sampled + shuffled before its first step (as the "
                                 "reference does), both inside the timed region"},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu,
-                "eval": ev, "sampler": samp, "kernels": kernels, "final_loss": final_loss, "dense_schedule": dense}
+                "eval": ev, "sampler": samp, "kernels": kernels, "final_loss": final_loss, "dense_schedule": dense, "scale_10x": tenx}
         emit(line)
     if world > 1:
         # orderly teardown: graphs that captured collectives first, then the library's communicator, then torch's

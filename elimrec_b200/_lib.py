@@ -127,6 +127,7 @@ _SIGS = {
     "elimrec_rank_scores": [C.POINTER(RankTables), i32, vp, vp, vp, vp],
     "elimrec_rank_topk": [C.POINTER(RankTables), i32, vp, vp, vp, vp, i32, vp, vp, vp],
     "elimrec_topk_matrix": [i32, i32, vp, i32, vp, vp, vp],
+    "elimrec_mask_train": [i32, i32, vp, vp, vp, vp, vp],
     "elimrec_split_fp16": [i64, vp, f32, vp, vp, vp],
     "elimrec_rank_tc": [C.POINTER(RankTcTables), i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "elimrec_metric_rows": [i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp],

@@ -297,11 +297,143 @@ __global__ void topk_matrix_kernel(int n_rows, int n_cols, const float* __restri
     }
 }
 
+// The same for 32 < K <= 128: NL = ceil(K / 32) list entries per lane, lane l holds the sorted positions [l NL, (l+1) NL).
+// Strict `>` against the current K-th value in increasing column order => ties keep the lowest index, like the K <= 32 path.
+template <int NL>
+__global__ void topk_matrix_big_kernel(int n_rows, int n_cols, const float* __restrict__ scores, int K,
+                                       int* __restrict__ idx, float* __restrict__ val) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    if (r >= n_rows) return;
+    float lv[NL];
+    int li[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { lv[j] = -INFINITY; li[j] = -1; }
+    const int kl = (K - 1) / NL, kj = (K - 1) % NL;      // where the K-th entry lives
+    const float* row = scores + (long long)r * n_cols;
+    auto kth = [&]() {
+        float t = lv[0];
+#pragma unroll
+        for (int j = 1; j < NL; ++j) if (j == kj) t = lv[j];
+        return __shfl_sync(full, t, kl);
+    };
+    for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        const float v = (c0 + lane < n_cols) ? __ldg(row + c0 + lane) : -INFINITY;
+        float thr = kth();
+        unsigned m = __ballot_sync(full, v > thr);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const float cv = __shfl_sync(full, v, b);
+            if (cv > thr) {
+                int cnt = 0;                              // entries (among the first K) that stay in front of the candidate
+#pragma unroll
+                for (int j = 0; j < NL; ++j) cnt += (lane * NL + j < K && lv[j] >= cv) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(full, cnt, o);
+                const int pos = cnt;
+                const float pv = __shfl_up_sync(full, lv[NL - 1], 1);
+                const int pi = __shfl_up_sync(full, li[NL - 1], 1);
+#pragma unroll
+                for (int j = NL - 1; j >= 0; --j) {
+                    const int p = lane * NL + j;
+                    if (p > pos) {
+                        lv[j] = (j > 0) ? lv[j - 1] : pv;
+                        li[j] = (j > 0) ? li[j - 1] : pi;
+                    } else if (p == pos) {
+                        lv[j] = cv;
+                        li[j] = c0 + b;
+                    }
+                }
+                thr = kth();
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        const int p = lane * NL + j;
+        if (p < K) {
+            idx[(long long)r * K + p] = li[j];
+            val[(long long)r * K + p] = lv[j];
+        }
+    }
+}
+
+// scores[r, train items of users[r]] = -inf   (uni_evaluator.py:149-154), for the explicit-matrix path
+__global__ void mask_train_kernel(int n_rows, int n_cols, const int* __restrict__ users, const long long* __restrict__ tptr,
+                                  const int* __restrict__ titems, float* __restrict__ scores) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const int u = __ldg(users + r);
+    for (long long e = __ldg(tptr + u) + lane; e < __ldg(tptr + u + 1); e += 32) {
+        const int it = __ldg(titems + e);
+        if (it >= 0 && it < n_cols) scores[(long long)r * n_cols + it] = -INFINITY;
+    }
+}
+
+constexpr int METRIC_MAX_K = 128;
+
 struct MetricArgs {
     int n_metrics;
     int ids[5];
-    double inv_log2[32];
+    double inv_log2[METRIC_MAX_K];
 };
+
+// metric.h:17-114 for 32 < K <= 128: same accumulator types and order, hit flags in ceil(K / 32) ballots, curves by lane 0
+__global__ void metric_rows_big_kernel(int n_eval, int K, const int* __restrict__ topk, const long long* __restrict__ tptr,
+                                       const int* __restrict__ titems, MetricArgs ma, float* __restrict__ rows) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    if (r >= n_eval) return;
+    const long long b = __ldg(tptr + r), e = __ldg(tptr + r + 1);
+    const int tl = (int)(e - b);
+    unsigned hm[METRIC_MAX_K / 32];
+#pragma unroll
+    for (int c = 0; c < METRIC_MAX_K / 32; ++c) {
+        bool hit = false;
+        const int i = c * 32 + lane;
+        if (i < K) {
+            const int id = __ldg(topk + (long long)r * K + i);
+            long long lo = b, hi = e;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if (__ldg(titems + mid) < id) lo = mid + 1; else hi = mid;
+            }
+            hit = (lo < e) && (__ldg(titems + lo) == id);
+        }
+        hm[c] = __ballot_sync(full, hit);
+    }
+    if (lane != 0) return;
+    float* out = rows + (long long)r * ma.n_metrics * K;
+    for (int j = 0; j < ma.n_metrics; ++j) {
+        const int id = ma.ids[j];
+        float* o = out + j * K;
+        int hits = 0, first = K;
+        float dcg = 0.f, idcg = 0.f, sum_pre = 0.f;
+        for (int i = 0; i < K; ++i) {
+            const bool h = (hm[i >> 5] >> (i & 31)) & 1u;
+            if (h) {
+                hits += 1;
+                if (first == K) first = i;
+            }
+            if (id == 1) o[i] = (float)(1.0 * hits / (i + 1));
+            else if (id == 2) o[i] = (float)(1.0 * hits / (double)tl);
+            else if (id == 4) {
+                if (h) dcg = (float)((double)dcg + ma.inv_log2[i]);
+                if (i < tl) idcg = (float)((double)idcg + ma.inv_log2[i]);
+                o[i] = dcg / idcg;
+            } else if (id == 3) {
+                if (h) sum_pre += (float)(1.0 * hits / (i + 1));
+                o[i] = (hits == 0) ? 0.f : sum_pre / (float)hits;
+            } else {
+                o[i] = (i >= first) ? (float)(1.0 / (first + 1)) : 0.f;
+            }
+        }
+    }
+}
 
 // metric.h:17-114 with the reference's accumulator types (int hits, float DCG/iDCG/sum_pre, double
 // addends, float stores).  One warp per evaluated user; lane i owns rank i.
@@ -453,9 +585,23 @@ ELIMREC_API int elimrec_rank_topk(const elimrec_rank_tables_t* t, int n_eval, co
 
 ELIMREC_API int elimrec_topk_matrix(int n_rows, int n_cols, const float* scores, int K, int32_t* topk_idx,
                                     float* topk_val, elimrec_stream_t stream) {
-    ER_CHECK_ARG(K >= 1 && K <= 32, "K must be in [1, 32]");
+    ER_CHECK_ARG(K >= 1 && K <= METRIC_MAX_K, "K must be in [1, 128]");
     if (n_rows <= 0) return 0;
-    topk_matrix_kernel<<<(n_rows + 7) / 8, 256, 0, er_stream(stream)>>>(n_rows, n_cols, scores, K, topk_idx, topk_val);
+    cudaStream_t st = er_stream(stream);
+    const int blocks = (n_rows + 7) / 8;
+    if (K <= 32) topk_matrix_kernel<<<blocks, 256, 0, st>>>(n_rows, n_cols, scores, K, topk_idx, topk_val);
+    else if (K <= 64) topk_matrix_big_kernel<2><<<blocks, 256, 0, st>>>(n_rows, n_cols, scores, K, topk_idx, topk_val);
+    else topk_matrix_big_kernel<4><<<blocks, 256, 0, st>>>(n_rows, n_cols, scores, K, topk_idx, topk_val);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_mask_train(int n_rows, int n_cols, const int32_t* users, const int64_t* train_ptr,
+                                   const int32_t* train_items, float* scores, elimrec_stream_t stream) {
+    ER_CHECK_ARG(users != nullptr && train_ptr != nullptr && scores != nullptr, "NULL buffer");
+    if (n_rows <= 0) return 0;
+    mask_train_kernel<<<(n_rows + 7) / 8, 256, 0, er_stream(stream)>>>(n_rows, n_cols, users, (const long long*)train_ptr, train_items,
+                                                                      scores);
     ER_LAUNCH_CHECK();
     return 0;
 }
@@ -463,7 +609,7 @@ ELIMREC_API int elimrec_topk_matrix(int n_rows, int n_cols, const float* scores,
 ELIMREC_API int elimrec_metric_rows(int n_eval, int K, const int32_t* topk_idx, const int64_t* truth_ptr,
                                     const int32_t* truth_items, int n_metrics, const int32_t* metric_ids_host,
                                     const double* inv_log2_host, float* rows, double* sums, elimrec_stream_t stream) {
-    ER_CHECK_ARG(K >= 1 && K <= 32, "K must be in [1, 32]");
+    ER_CHECK_ARG(K >= 1 && K <= METRIC_MAX_K, "K must be in [1, 128]");
     ER_CHECK_ARG(n_metrics >= 1 && n_metrics <= 5, "n_metrics must be in [1, 5]");
     if (n_eval <= 0) return 0;
     MetricArgs ma{};
@@ -474,8 +620,11 @@ ELIMREC_API int elimrec_metric_rows(int n_eval, int K, const int32_t* topk_idx, 
     }
     for (int i = 0; i < K; ++i) ma.inv_log2[i] = inv_log2_host[i];
     cudaStream_t st = er_stream(stream);
-    metric_rows_kernel<<<(n_eval + 7) / 8, 256, 0, st>>>(n_eval, K, topk_idx, (const long long*)truth_ptr, truth_items,
-                                                         ma, rows);
+    if (K <= 32)
+        metric_rows_kernel<<<(n_eval + 7) / 8, 256, 0, st>>>(n_eval, K, topk_idx, (const long long*)truth_ptr, truth_items, ma, rows);
+    else
+        metric_rows_big_kernel<<<(n_eval + 7) / 8, 256, 0, st>>>(n_eval, K, topk_idx, (const long long*)truth_ptr, truth_items, ma,
+                                                                 rows);
     ER_LAUNCH_CHECK();
     if (sums != nullptr) {
         metric_colsum_kernel<<<n_metrics * K, 256, 0, st>>>(n_eval, n_metrics * K, rows, sums);

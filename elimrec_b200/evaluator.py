@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
+from ._lib import ElimrecError
 
 metric_dict = {"Precision": 1, "Recall": 2, "MAP": 3, "NDCG": 4, "MRR": 5}
 re_metric_dict = {v: k for k, v in metric_dict.items()}
@@ -126,7 +127,23 @@ class UniEvaluator(AbstractEvaluator):
             backend = model.config["rank_backend"] if "rank_backend" in model.config else "tc"
             if getattr(model, "fusion_mode", "rubi") != "rubi":
                 backend = "fp32"     # the hm / sum score fusions are epilogues of the exact-fp32 rank kernel
-            if backend == "tc":      # tensor cores, fp16 hi/lo operand pairs (fp32-class accuracy)
+            if K > 128:
+                raise ElimrecError(f"top_k = {K}: the evaluator supports cut-offs up to 128")
+            if K > 32:
+                # the fused rank kernels keep one top-K entry per lane (K <= 32).  Larger cut-offs (UniEvaluator's own default is
+                # 50, uni_evaluator.py:38): exact fp32 scores of a chunk of users -> train mask -> top-K of the explicit matrix
+                tables = model.rank_tables()
+                if mean is not None:
+                    ops.rank_rowmean(tables, u, mean)
+                chunk = max(1, min(n, (1 << 28) // max(1, model.num_items)))
+                sc = torch.empty(chunk, model.num_items, dtype=torch.float32, device=dev)
+                for c0 in range(0, n, chunk):
+                    c1 = min(n, c0 + chunk)
+                    ops.rank_scores(tables, u[c0:c1], mean[c0:c1] if mean is not None else None, sc[:c1 - c0])
+                    if self.user_neg_test is None:
+                        ops.mask_train(sc[:c1 - c0], u[c0:c1], st["train_ptr"], st["train_items"])
+                    ops.topk_matrix(sc[:c1 - c0], K, idx[c0:c1], val[c0:c1])
+            elif backend == "tc":    # tensor cores, fp16 hi/lo operand pairs (fp32-class accuracy)
                 tables = model.rank_tc_tables()
                 if mean is not None:
                     ops.rank_tc(tables, 0, u, None, None, None, K, None, None, mean)

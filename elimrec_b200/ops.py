@@ -475,6 +475,12 @@ def topk_matrix(scores, K, idx, val):
          ptr(val, F32), stream())
 
 
+def mask_train(scores, users, train_ptr, train_items):
+    """scores[r, train items of users[r]] = -inf"""
+    call("elimrec_mask_train", scores.shape[0], scores.shape[1], ptr(users, torch.int32), ptr(train_ptr, torch.int64),
+         ptr(train_items, torch.int32), ptr(scores, F32), stream())
+
+
 def metric_rows(topk_idx, truth_ptr, truth_items, metric_ids, K, rows, sums):
     ids = np.ascontiguousarray(metric_ids, dtype=np.int32)
     inv = np.ascontiguousarray(1.0 / np.log2(np.arange(K, dtype=np.float64) + 2.0))

@@ -73,6 +73,9 @@ class ShardedEliMRec(EliMRec):
         r = self.rank
         dist.all_gather_into_tensor(slab, slab[r * blk:(r + 1) * blk])
 
+    def _ar(self, t):
+        dist.all_reduce(t)
+
     def _workspace(self, B):
         ws = self._ws
         if ws is not None and ws["B"] == B:
@@ -198,7 +201,7 @@ class ShardedEliMRec(EliMRec):
         ops.gather_rows(rows[:B], ws["O_u"], Oin[:B], Fw)
         item_idx = (rows[B:] - U).contiguous()
         ops.gather_rows(item_idx, ws["O_i"], Oin[B:], Fw)
-        dist.all_reduce(Oin)
+        self._ar(Oin)
         self._fuse_heads(P, ws, Oin[:B], ws["F_c"][:B], [s_[:B] for s_ in ws["S_c"]], "u")
         self._fuse_heads(P, ws, Oin[B:], ws["F_c"][B:], [s_[B:] for s_ in ws["S_c"]], "i")
         if self.kwai:
@@ -272,7 +275,7 @@ class ShardedEliMRec(EliMRec):
             flat[o_:o_ + n_] = gr[f"{m}_dense.weight"].reshape(-1)
             o_ += n_
         flat[o_:] = ws["g_proj_bias"]
-        dist.all_reduce(flat)
+        self._ar(flat)
         o_ = 0
         for m in self.mods:
             n_ = gr[f"{m}_dense.weight"].numel()

@@ -454,10 +454,15 @@ int elimrec_rank_tc(const elimrec_rank_tc_tables_t* t, int what, int n_eval, con
                     const int64_t* train_ptr, const int32_t* train_items, int K, int32_t* topk_idx, float* topk_val,
                     float* mean_out, void* workspace, elimrec_stream_t stream);
 int64_t elimrec_rank_tc_workspace_bytes(int n_eval);
-/* top-K of an explicit score matrix (arg_top_k_2d, util/cython/include/arg_topk.h:15-45) */
+/* top-K of an explicit score matrix (arg_top_k_2d, util/cython/include/arg_topk.h:15-45), K <= 128; ties: lowest index.
+ * With elimrec_rank_scores + elimrec_mask_train it is also the evaluator's path for 32 < K <= 128 (the fused rank kernels
+ * keep one list entry per lane; UniEvaluator's default is top_k = 50, uni_evaluator.py:38). */
 int elimrec_topk_matrix(int n_rows, int n_cols, const float* scores, int K, int32_t* topk_idx, float* topk_val,
                         elimrec_stream_t stream);
-/* metric curves: rows[r, j*K + i] for metric_ids[j] in {1 Precision, 2 Recall, 3 MAP, 4 NDCG, 5 MRR}; truth CSR is
+/* scores[r, train items of users[r]] = -inf (uni_evaluator.py:149-154); train CSR indexed by user id */
+int elimrec_mask_train(int n_rows, int n_cols, const int32_t* users, const int64_t* train_ptr, const int32_t* train_items,
+                       float* scores, elimrec_stream_t stream);
+/* metric curves (K <= 128): rows[r, j*K + i] for metric_ids[j] in {1 Precision, 2 Recall, 3 MAP, 4 NDCG, 5 MRR}; truth CSR is
  * indexed by POSITION r (already gathered for the evaluated users), items sorted ascending.
  * inv_log2_host: K doubles 1/log2(i+2).  sums: [n_metrics*K] doubles, accumulated (zero it first). */
 int elimrec_metric_rows(int n_eval, int K, const int32_t* topk_idx, const int64_t* truth_ptr,

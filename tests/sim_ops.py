@@ -443,6 +443,21 @@ def rank_topk(t, eval_users, ui_mean, train_ptr, train_items, K, idx, val):
     val.copy_(torch.from_numpy(np.take_along_axis(sc, top.astype(np.int64), 1)))
 
 
+def mask_train(scores, users, train_ptr, train_items):
+    _log("mask_train")
+    tp, ti = train_ptr.numpy(), train_items.numpy()
+    for r, u in enumerate(users.tolist()):
+        scores[r, torch.from_numpy(ti[tp[u]:tp[u + 1]].astype(np.int64))] = -np.inf
+
+
+def topk_matrix(scores, K, idx, val):
+    _log("topk_matrix")
+    sc = scores.numpy()
+    top = ref_eval.topk_lowest_index(sc, K)
+    idx.copy_(torch.from_numpy(top))
+    val.copy_(torch.from_numpy(np.take_along_axis(sc, top.astype(np.int64), 1)))
+
+
 def metric_rows(topk_idx, truth_ptr, truth_items, metric_ids, K, rows, sums):
     _log("metric_rows")
     tp, ti = truth_ptr.numpy(), truth_items.numpy()

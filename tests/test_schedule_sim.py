@@ -397,8 +397,8 @@ def test_double_backward_and_predict_type_normal(sim, golden):
             assert rel(prm.grad, og[nm].numpy()) < TOL, nm
 
 
-@pytest.mark.parametrize("top_k", [1, [1, 7, 32], 32])
-def test_evaluator_edge_cases(sim, golden, top_k):
+@pytest.mark.parametrize("top_k", [1, [1, 7, 32], 32, 50, [20, 50, 56]])
+def test_evaluator_edge_cases(backend, golden, top_k):
     """users without any training item (uni_evaluator.py:150-153), users whose train list covers most items, K = 1 and the
     largest supported K, every metric; against the oracle evaluator on the same dicts."""
     from oracle import ref_eval
