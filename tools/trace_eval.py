@@ -32,6 +32,21 @@ def main():
     run()
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
+    # host-side phases of the same call, without the profiler
+    def phase(fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t)
+    run()
+    p1 = phase(lambda: model.all_users)
+    p2 = phase(lambda: model.rank_tables())
+    p3 = phase(lambda: model.rank_tc_tables())
+    p4 = phase(lambda: ev.evaluate(model))
+    print(f"# phases (ms, host wall incl. sync): complete tables {p1:.2f} | normalise heads {p2:.2f} | fp16 hi/lo split {p3:.2f} | rank + metrics {p4:.2f}")
+    run()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         ev.evaluate(model)
