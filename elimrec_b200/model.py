@@ -1106,8 +1106,12 @@ class EliMRec(LinearSchedule, BasicModel):
                 else:
                     if device_sampler is not None:
                         raise ElimrecError("this runner samples its own batches; call it without arguments")
-                    u, p, n = model._triples(users, pos, neg)
-                    su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
+                    if all(torch.is_tensor(x) and x.dtype == torch.int64 and x.numel() == B for x in (users, pos, neg)):
+                        # (pinned) host or device int64 tensors: straight into the graph's static inputs, no temporaries
+                        su.copy_(users, non_blocking=True); sp_.copy_(pos, non_blocking=True); sn.copy_(neg, non_blocking=True)
+                    else:
+                        u, p, n = model._triples(users, pos, neg)
+                        su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
                 graphs[0].replay()
                 if dp:
                     bucket = model._ws["cache"]["bucket"]
