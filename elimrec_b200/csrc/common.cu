@@ -11,4 +11,4 @@ void elimrec_set_error(const char* fmt, ...) {
 }
 
 ELIMREC_API const char* elimrec_last_error(void) { return g_err; }
-ELIMREC_API int elimrec_abi_version(void) { return 1; }
+ELIMREC_API int elimrec_abi_version(void) { return 2; }

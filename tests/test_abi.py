@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_channel():
     l = _lib.lib()
-    assert l.elimrec_abi_version() == 1
+    assert l.elimrec_abi_version() == 2
     # argument validation happens before any CUDA call, so this is safe without a GPU
     rc = l.elimrec_spmm(100, 0, 1, 0, None, None, None, None, None, None, 4, None, 4, None, None, None)
     assert rc == -1 and b"width" in l.elimrec_last_error()
