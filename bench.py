@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--linear", type=int, default=1,
                     help="1 (default): linear schedule - modality graphs by linearity from one 64-wide propagation + constant "
                          "tables; 0: the row-sparse slab schedule of round 1")
+    ap.add_argument("--two-hop-masks", type=int, default=1, help="linear schedule: layer L-1 / first backward hop under the two-hop row masks (1) or dense (0)")
     ap.add_argument("--fused-layer-grad", type=int, default=0,
                     help="1: layer-mean gradient added in the backward SpMM epilogues; 0 (default, measured faster): a scatter "
                          "kernel after each SpMM, hidden under the other stream's SpMM")
@@ -474,7 +475,7 @@ def main():
     ds, name = build_dataset(args.workload)
     conf = Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH,
                      "lazy_tables": bool(args.lazy_tables), "fused_layer_grad": bool(args.fused_layer_grad),
-                     "linear_schedule": bool(args.linear)})
+                     "linear_schedule": bool(args.linear), "two_hop_masks": bool(args.two_hop_masks)})
     torch.manual_seed(2022)
     rowshard = world > 1 and args.parallel == "rowshard"
     colshard = world > 1 and args.parallel == "colshard" and bool(args.linear) and bool(args.lazy_tables)

@@ -130,7 +130,7 @@ class ColShardedEliMRec(EliMRec):
             ops.cs_inst_rows(G, B, T_all, U, rows_all, mask, need2)
             ev_rows = torch.cuda.Event()
             ev_rows.record(side)
-            if L >= 2:
+            if L >= 2 and self._lin_need2:
                 ops.mark_neighbors(g.ui, mask[:U], need2[U:])
                 ops.mark_neighbors(g.iu, mask[U:], need2[:U])
             ev_masks = torch.cuda.Event()
@@ -154,7 +154,7 @@ class ColShardedEliMRec(EliMRec):
         cur = torch.cuda.current_stream()
         for k in range(1, L + 1):
             out = ws["P"][k]
-            rm = mask if k == L else (need2 if k == L - 1 else None)
+            rm = mask if k == L else (need2 if (k == L - 1 and self._lin_need2) else None)
             if rm is not None:
                 cur.wait_event(ev_rows if k == L else ev_masks)
             ops.spmm64_pair(g.ui, g.iu, in_i, in_u, out[:U], out[U:], row_mask_u=rm[:U] if rm is not None else None,
@@ -210,8 +210,8 @@ class ColShardedEliMRec(EliMRec):
         with torch.cuda.stream(chain):
             for k in range(L, 0, -1):
                 nxt = ws["H"][flip]
-                cm = mask if k == L else (need2 if k == L - 1 else None)
-                rm = need2 if (k == L and L >= 2) else None
+                cm = mask if k == L else (need2 if (k == L - 1 and self._lin_need2) else None)
+                rm = need2 if (k == L and L >= 2 and self._lin_need2) else None
                 kw = {}
                 if k == 1:
                     kw = dict(adam_u=(cs["eu"], cs["mu"], cs["vu"], ws["E0"][:U]), adam_i=(cs["ei"], cs["mi"], cs["vi"], ws["E0"][U:]),
@@ -259,7 +259,7 @@ class ColShardedEliMRec(EliMRec):
         U, I, L, G, w = self.num_users, self.num_items, self.n_layers, self.world, self._lin_w
         N, g = U + I, self.graph
         E0 = ws["E0"]
-        for k in range(max(1, L - 1), L + 1):
+        for k in range(max(1, L - 1 if self._lin_need2 else L), L + 1):
             src = E0 if k == 1 else ws["P"][k - 1]
             out = ws["P"][k]
             ops.spmm64_pair(g.ui, g.iu, src[U:], src[:U], out[:U], out[U:], width=w)

@@ -8,13 +8,14 @@
 // These are "skinny" reductions (1.2 GFLOP at the Tiktok shape, 6 K rows) that used to take ten launches (chunked outer
 // products + reductions, hi/lo operand splits + three tensor-core weight-gradient launches + their reductions) and ~200 us
 // of kernel time beside the propagation backward.  Exact fp32 FFMA, deterministic: a CTA owns a 64 x 64 output tile and one
-// of `splits` row ranges (register-staged double buffering, 4 x 4 micro-tile), partial tiles go to scratch and are summed in
-// split order.
+// of `splits` row ranges (register-staged double buffering, 64 x 128 tile, 8 x 8 micro-tile), partial tiles go to scratch and are
+// summed in split order.
 #include "common.cuh"
 
 namespace {
 
 constexpr int WG_BR = 16;          // rows per staged chunk
+constexpr int WG_TN = 128;         // output columns per tile (B columns); 64 output rows (A columns)
 
 struct WgProblem {
     const float* A;
@@ -35,7 +36,7 @@ struct WgArgs {
     WgProblem p[ELIMREC_WGRAD_MAX_PROBLEMS];
     int n_tiles;
     int splits;
-    float* ws;          // [n_tiles][splits][64 x 64] partial tiles, then [n_tiles][splits][64] partial column sums
+    float* ws;          // [n_tiles][splits][64 x 128] partial tiles, then [n_tiles][splits][64] partial column sums
     const float* gscale;
 };
 
@@ -45,49 +46,66 @@ __device__ __forceinline__ int wg_find(const WgArgs& a, int tile) {
     return q;
 }
 
-__global__ void __launch_bounds__(256) wgrad_multi_kernel(const __grid_constant__ WgArgs a) {
-    __shared__ float As[2][WG_BR][64 + 4];
-    __shared__ float Bs[2][WG_BR][64 + 4];
+// 128 threads, 8 x 8 outputs per thread: thread (ty, tx) owns output rows {4 ty .. 4 ty + 3, 32 + 4 ty ..} (A columns) and output
+// columns {4 tx .. 4 tx + 3, 64 + 4 tx ..} (B columns) - two conflict-free LDS.128 per operand and 64 FMAs per staged row, so the loop is
+// bound by the FP32 pipe and not by shared-memory bandwidth (a 4 x 4 micro-tile spends as many cycles loading as multiplying).
+__global__ void __launch_bounds__(128) wgrad_multi_kernel(const __grid_constant__ WgArgs a) {
+    __shared__ __align__(16) float As[2][WG_BR][64];
+    __shared__ __align__(16) float Bs[2][WG_BR][WG_TN];
     const int tile = blockIdx.x, split = blockIdx.y;
     const WgProblem& pr = a.p[wg_find(a, tile)];
-    const int c0 = (tile - pr.tile0) * 64;                 // first column of B / out handled here
+    const int c0 = (tile - pr.tile0) * WG_TN;              // first column of B / out handled here
     const int rows = pr.r1 - pr.r0;
     int chunk = (rows + a.splits - 1) / a.splits;
     chunk = (chunk + WG_BR - 1) / WG_BR * WG_BR;
     const int rb = pr.r0 + split * chunk, re = min(pr.r1, rb + chunk);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int lr = tid >> 4, lc = (tid & 15) * 4;          // this thread's float4 of a staged chunk: row lr, columns lc..lc+3
-    float acc[4][4];
+    float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float bsum = 0.f;
     const bool want_bias = pr.bias != nullptr && c0 == 0;
-    const bool b_vec = (pr.ldb % 4 == 0) && ((reinterpret_cast<unsigned long long>(pr.B) & 15) == 0) && (c0 + 64 <= pr.K);
+    const bool b_vec = (pr.ldb % 4 == 0) && ((reinterpret_cast<unsigned long long>(pr.B) & 15) == 0);
 
-    float4 ra, rbv;
+    // staging: A chunk = 16 x 64 floats = 256 float4 (2 per thread), B chunk = 16 x 128 = 512 float4 (4 per thread)
+    float4 ra[2], rbv[4];
     auto load = [&](int r) {
-        const int row = r + lr;
-        ra = make_float4(0.f, 0.f, 0.f, 0.f);
-        rbv = ra;
-        if (row < re) {
-            ra = __ldg(reinterpret_cast<const float4*>(pr.A + (long long)row * pr.lda + lc));
-            const float* bp = pr.B + (long long)row * pr.ldb + c0 + lc;
-            if (b_vec) {
-                rbv = __ldg(reinterpret_cast<const float4*>(bp));
-            } else {
-                const int left = pr.K - (c0 + lc);
-                if (left > 0) rbv.x = __ldg(bp);
-                if (left > 1) rbv.y = __ldg(bp + 1);
-                if (left > 2) rbv.z = __ldg(bp + 2);
-                if (left > 3) rbv.w = __ldg(bp + 3);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int f = tid + 128 * q, row = r + (f >> 4), col = (f & 15) * 4;
+            ra[q] = (row < re) ? __ldg(reinterpret_cast<const float4*>(pr.A + (long long)row * pr.lda + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int f = tid + 128 * q, row = r + (f >> 5), col = c0 + (f & 31) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < re && col < pr.K) {
+                const float* bp = pr.B + (long long)row * pr.ldb + col;
+                if (b_vec && col + 4 <= pr.K) {
+                    v = __ldg(reinterpret_cast<const float4*>(bp));
+                } else {
+                    v.x = __ldg(bp);
+                    if (col + 1 < pr.K) v.y = __ldg(bp + 1);
+                    if (col + 2 < pr.K) v.z = __ldg(bp + 2);
+                    if (col + 3 < pr.K) v.w = __ldg(bp + 3);
+                }
             }
+            rbv[q] = v;
         }
     };
     auto store = [&](int buf) {
-        *reinterpret_cast<float4*>(&As[buf][lr][lc]) = ra;
-        *reinterpret_cast<float4*>(&Bs[buf][lr][lc]) = rbv;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int f = tid + 128 * q;
+            *reinterpret_cast<float4*>(&As[buf][f >> 4][(f & 15) * 4]) = ra[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int f = tid + 128 * q;
+            *reinterpret_cast<float4*>(&Bs[buf][f >> 5][(f & 31) * 4]) = rbv[q];
+        }
     };
 
     if (rb < re) {
@@ -100,14 +118,16 @@ __global__ void __launch_bounds__(256) wgrad_multi_kernel(const __grid_constant_
             if (more) load(r + WG_BR);
 #pragma unroll
             for (int kk = 0; kk < WG_BR; ++kk) {
-                const float4 av = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-                const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-                const float a4[4] = {av.x, av.y, av.z, av.w};
-                const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][32 + ty * 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
             }
             if (want_bias && tid < 64) {
 #pragma unroll
@@ -120,37 +140,43 @@ __global__ void __launch_bounds__(256) wgrad_multi_kernel(const __grid_constant_
             }
         }
     }
-    float* part = a.ws + ((long long)tile * a.splits + split) * 4096;
+    // partial tile, row-major [64][128]
+    float* part = a.ws + ((long long)tile * a.splits + split) * (64 * WG_TN);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(part + (ty * 4 + i) * 64 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    if (want_bias && tid < 64) a.ws[(long long)a.n_tiles * a.splits * 4096 + ((long long)tile * a.splits + split) * 64 + tid] = bsum;
+    for (int i = 0; i < 8; ++i) {
+        const int o = (i < 4) ? ty * 4 + i : 32 + ty * 4 + (i - 4);
+        *reinterpret_cast<float4*>(part + o * WG_TN + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(part + o * WG_TN + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    if (want_bias && tid < 64)
+        a.ws[(long long)a.n_tiles * a.splits * (64 * WG_TN) + ((long long)tile * a.splits + split) * 64 + tid] = bsum;
 }
 
-// grid (tiles, 16): CTA y sums 256 elements of the tile over the splits, in split order
+// grid (tiles, 32): CTA y sums 256 elements of the tile over the splits, in split order
 __global__ void __launch_bounds__(256) wgrad_multi_reduce_kernel(const __grid_constant__ WgArgs a) {
+    constexpr int TE = 64 * WG_TN;
     const int tile = blockIdx.x;
     const WgProblem& pr = a.p[wg_find(a, tile)];
-    const int c0 = (tile - pr.tile0) * 64;
+    const int c0 = (tile - pr.tile0) * WG_TN;
     const float g = (pr.scale_by_g && a.gscale != nullptr) ? __ldg(a.gscale) : 1.f;
-    const float* part = a.ws + (long long)tile * a.splits * 4096;
+    const float* part = a.ws + (long long)tile * a.splits * TE;
     {
         const int e = blockIdx.y * 256 + threadIdx.x;
-        const int o = e >> 6, c = e & 63;
+        const int o = e / WG_TN, c = e % WG_TN;
         if (c0 + c < pr.K) {
             float s = 0.f;
             int z = 0;
             for (; z + 4 <= a.splits; z += 4) {
-                const float t0 = part[(long long)z * 4096 + e], t1 = part[(long long)(z + 1) * 4096 + e];
-                const float t2 = part[(long long)(z + 2) * 4096 + e], t3 = part[(long long)(z + 3) * 4096 + e];
+                const float t0 = part[(long long)z * TE + e], t1 = part[(long long)(z + 1) * TE + e];
+                const float t2 = part[(long long)(z + 2) * TE + e], t3 = part[(long long)(z + 3) * TE + e];
                 s = (((s + t0) + t1) + t2) + t3;
             }
-            for (; z < a.splits; ++z) s += part[(long long)z * 4096 + e];
+            for (; z < a.splits; ++z) s += part[(long long)z * TE + e];
             pr.out[(long long)o * pr.ldo + c0 + c] = g * s;
         }
     }
     if (pr.bias != nullptr && c0 == 0 && blockIdx.y == 0 && threadIdx.x < 64) {
-        const float* bp = a.ws + (long long)a.n_tiles * a.splits * 4096 + (long long)tile * a.splits * 64 + threadIdx.x;
+        const float* bp = a.ws + (long long)a.n_tiles * a.splits * TE + (long long)tile * a.splits * 64 + threadIdx.x;
         float s = 0.f;
         for (int z = 0; z < a.splits; ++z) s += bp[z * 64];
         pr.bias[threadIdx.x] = g * s;
@@ -159,7 +185,7 @@ __global__ void __launch_bounds__(256) wgrad_multi_reduce_kernel(const __grid_co
 
 int wg_tiles(int n, const elimrec_wgrad_problem_t* p) {
     int t = 0;
-    for (int i = 0; i < n; ++i) t += (int)((p[i].K + 63) / 64);
+    for (int i = 0; i < n; ++i) t += (int)((p[i].K + WG_TN - 1) / WG_TN);
     return t;
 }
 
@@ -167,7 +193,7 @@ int wg_tiles(int n, const elimrec_wgrad_problem_t* p) {
 
 ELIMREC_API int64_t elimrec_wgrad_multi_workspace_floats(int n, const elimrec_wgrad_problem_t* problems, int splits) {
     if (n <= 0 || problems == nullptr || splits <= 0) return 0;
-    return (int64_t)wg_tiles(n, problems) * splits * (4096 + 64);
+    return (int64_t)wg_tiles(n, problems) * splits * (64 * WG_TN + 64);
 }
 
 ELIMREC_API int elimrec_wgrad_multi(int n, const elimrec_wgrad_problem_t* problems, int splits, float* workspace,
@@ -184,16 +210,16 @@ ELIMREC_API int elimrec_wgrad_multi(int n, const elimrec_wgrad_problem_t* proble
         ER_CHECK_ARG(q.lda % 4 == 0 && (reinterpret_cast<unsigned long long>(q.A) & 15) == 0, "A must be 16-byte aligned rows");
         a.p[i] = WgProblem{q.A, q.lda, q.B, q.ldb, (int)q.K, (int)q.row_begin, (int)q.row_end, q.out, q.ldo, q.bias_out,
                            q.scale_by_g, tiles};
-        tiles += (int)((q.K + 63) / 64);
+        tiles += (int)((q.K + WG_TN - 1) / WG_TN);
     }
     a.n_tiles = tiles;
     a.splits = splits;
     a.ws = workspace;
     a.gscale = gscale_dev;
     cudaStream_t st = er_stream(stream);
-    wgrad_multi_kernel<<<dim3(tiles, splits), 256, 0, st>>>(a);
+    wgrad_multi_kernel<<<dim3(tiles, splits), 128, 0, st>>>(a);
     ER_LAUNCH_CHECK();
-    wgrad_multi_reduce_kernel<<<dim3(tiles, 16), 256, 0, st>>>(a);
+    wgrad_multi_reduce_kernel<<<dim3(tiles, 32), 256, 0, st>>>(a);
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -44,6 +44,9 @@ class LinearSchedule:
     def _lin_init(self):
         want = bool(_cfg(self.config, "linear_schedule", True))
         self.linear = bool(want and self.lazy_tables and not self._generic and not (self.tiktok and self.word_grad))
+        # two_hop_masks (default on): layer L-1 / the first backward hop only at the rows the instance rows reach (need2).  Off: those
+        # layers run dense (no mark_neighbors launches, no dependency of layer L-1 on the batch) - measured per shape, bench.py --two-hop-masks
+        self._lin_need2 = bool(_cfg(self.config, "two_hop_masks", True))
         self._lin_w = getattr(self, "_lin_w", D)        # columns of the propagated slabs held here (64; 64 / world when column-sharded)
         if self.proj_precision == "auto":
             self.proj_precision = "x3" if self.linear else "tf32"
@@ -217,7 +220,7 @@ class LinearSchedule:
             ops.inst_rows(users, pos, neg, U, rows, mask, need2)
             ev_rows = torch.cuda.Event()
             ev_rows.record(side)
-            if L >= 2:    # layer L-1 is read at the graph neighbours of the instance rows
+            if L >= 2 and self._lin_need2:    # layer L-1 is read at the graph neighbours of the instance rows
                 ops.mark_neighbors(g.ui, mask[:U], need2[U:])
                 ops.mark_neighbors(g.iu, mask[U:], need2[:U])
             ev_masks = torch.cuda.Event()
@@ -244,7 +247,7 @@ class LinearSchedule:
         cur = torch.cuda.current_stream()
         for k in range(1, L + 1):
             out = ws["P"][k]
-            rm = mask if k == L else (need2 if k == L - 1 else None)
+            rm = mask if k == L else (need2 if (k == L - 1 and self._lin_need2) else None)
             if rm is not None:
                 cur.wait_event(ev_rows if k == L else ev_masks)
             ops.spmm64_pair(g.ui, g.iu, in_i, in_u, out[:U], out[U:], row_mask_u=rm[:U] if rm is not None else None,
@@ -318,8 +321,10 @@ class LinearSchedule:
             for k in range(L, 0, -1):
                 nxt = ws["H"][flip]
                 # h_L is valid on the instance rows only, h_{L-1} on need2 only: the first two hops drop every other column
-                cm = mask if k == L else (need2 if k == L - 1 else None)
-                rm = need2 if (k == L and L >= 2) else None
+                # (without the two-hop masks the first hop writes every row - exact zeros where nothing arrives - and the
+                # second one runs dense)
+                cm = mask if k == L else (need2 if (k == L - 1 and self._lin_need2) else None)
+                rm = need2 if (k == L and L >= 2 and self._lin_need2) else None
                 kw = {}
                 if k == 1 and fuse_adam:
                     ad = self._adam
@@ -357,7 +362,7 @@ class LinearSchedule:
         U, I, L = self.num_users, self.num_items, self.n_layers
         N, g = U + I, self.graph
         E0 = ws["E0"]
-        for k in range(max(1, L - 1), L + 1):
+        for k in range(max(1, L - 1 if self._lin_need2 else L), L + 1):      # the layers the step computed under a row mask
             src = E0 if k == 1 else ws["P"][k - 1]
             out = ws["P"][k]
             ops.spmm64_pair(g.ui, g.iu, src[U:], src[:U], out[:U], out[U:])

@@ -114,7 +114,7 @@ def check_steps(model, g, pre, steps=3, subset=None, worst=1e-4, frac=1e-3):
 
 
 # ---- the default configuration: every schedule -------------------------------------------------------------------------------
-SCHEDULES = {"linear": dict(), "rowsparse": dict(linear_schedule=False), "rowsparse_fused": dict(linear_schedule=False, fused_layer_grad=True),
+SCHEDULES = {"linear": dict(), "linear_dense_hops": dict(two_hop_masks=False), "rowsparse": dict(linear_schedule=False), "rowsparse_fused": dict(linear_schedule=False, fused_layer_grad=True),
              "reference": dict(lazy_tables=False)}
 
 
@@ -123,7 +123,7 @@ def test_default_schedule_vs_golden(backend, golden, sched):
     name = "kwai" if golden["_name"] == "kwai" else "synthg"
     kw = SCHEDULES[sched]
     model = build(golden_dataset(golden), golden_params(golden), name, **kw)
-    assert model.linear == (sched == "linear")
+    assert model.linear == sched.startswith("linear")
     loss = model.bpr_loss(*batch(golden, 0))
     loss.backward(retain_graph=True)
     assert abs(float(loss) - float(golden["loss0"])) < TOL * abs(float(golden["loss0"]))
