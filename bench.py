@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--linear", type=int, default=1,
                     help="1 (default): linear schedule - modality graphs by linearity from one 64-wide propagation + constant "
                          "tables; 0: the row-sparse slab schedule of round 1")
-    ap.add_argument("--two-hop-masks", type=int, default=1, help="linear schedule: layer L-1 / first backward hop under the two-hop row masks (1) or dense (0)")
+    ap.add_argument("--two-hop-masks", type=int, default=0, help="linear schedule: layer L-1 / first backward hop under the two-hop row masks (1) or dense (0)")
     ap.add_argument("--fused-layer-grad", type=int, default=0,
                     help="1: layer-mean gradient added in the backward SpMM epilogues; 0 (default, measured faster): a scatter "
                          "kernel after each SpMM, hidden under the other stream's SpMM")

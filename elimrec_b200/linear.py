@@ -44,9 +44,11 @@ class LinearSchedule:
     def _lin_init(self):
         want = bool(_cfg(self.config, "linear_schedule", True))
         self.linear = bool(want and self.lazy_tables and not self._generic and not (self.tiktok and self.word_grad))
-        # two_hop_masks (default on): layer L-1 / the first backward hop only at the rows the instance rows reach (need2).  Off: those
-        # layers run dense (no mark_neighbors launches, no dependency of layer L-1 on the batch) - measured per shape, bench.py --two-hop-masks
-        self._lin_need2 = bool(_cfg(self.config, "two_hop_masks", True))
+        # two_hop_masks: layer L-1 / the first backward hop only at the rows the instance rows reach (need2).  Off (default): those
+        # layers run dense - no mark_neighbors launches, no dependency of layer L-1 on the batch.  Measured on B200, ms/step with
+        # masks | dense: tiktok 0.410 | 0.399, kwai 0.481 | 0.446, movielens 0.549 | 0.550 (need2 covers most rows anyway: the
+        # positives are popular items, and their neighbours are most users)
+        self._lin_need2 = bool(_cfg(self.config, "two_hop_masks", False))
         self._lin_w = getattr(self, "_lin_w", D)        # columns of the propagated slabs held here (64; 64 / world when column-sharded)
         if self.proj_precision == "auto":
             self.proj_precision = "x3" if self.linear else "tf32"
@@ -314,10 +316,17 @@ class LinearSchedule:
         g_u = lambda k: (GA if k % 2 == 0 else GB)[:U]
         g_i = lambda k: (GA if k % 2 == 1 else GB)[U:]
         h_u, h_i, flip = g_u(L), g_i(L), 0
-        # The chain is the critical path: it runs on a HIGH-PRIORITY stream, the weight gradients (one big grid that nothing
-        # but Adam waits for) on the current one - their CTAs fill what the propagation launches leave free.
-        chain = ops.fork_side(8, high_priority=True)
-        with torch.cuda.stream(chain):
+        # The weight gradients (one FMA-bound grid that nothing but Adam waits for) run BEFORE the chain, not beside it: both
+        # want every SM (the propagation launch its whole register file for gather parallelism), and measured side by side
+        # they take longer than back to back (backward section 192 us beside, ~160 us in sequence).  wgrad_overlap=True keeps the
+        # side-by-side form (chain on a high-priority stream, weight gradients on the current one).
+        overlap = bool(_cfg(self.config, "wgrad_overlap", False))
+        pending = None
+        if not split and not overlap:
+            pending = weights(False)
+
+        def hops():
+            nonlocal h_u, h_i, flip
             for k in range(L, 0, -1):
                 nxt = ws["H"][flip]
                 # h_L is valid on the instance rows only, h_{L-1} on need2 only: the first two hops drop every other column
@@ -337,8 +346,16 @@ class LinearSchedule:
                                 col_mask_u=cm[U:] if cm is not None else None, col_mask_i=cm[:U] if cm is not None else None,
                                 addend_u=g_u(k - 1), addend_i=g_i(k - 1), add_mask_u=mask[:U], add_mask_i=mask[U:], **kw)
                 h_u, h_i, flip = nxt[:U], nxt[U:], flip ^ 1
-        pending = None if split else weights(False)
-        ops.join_side(chain)
+
+        if overlap:
+            chain = ops.fork_side(8, high_priority=True)
+            with torch.cuda.stream(chain):
+                hops()
+            if not split:
+                pending = weights(False)
+            ops.join_side(chain)
+        else:
+            hops()
         grads = {} if fuse_adam else {"embedding_user.weight": h_u, "embedding_item.weight": h_i}
         ws["bw_pending"] = (weights, pending)
         if split:
