@@ -93,6 +93,7 @@ _SIGS = {
     "elimrec_axpy_rows": [i64, i32, vp, vp, i64, vp, i64, vp],
     "elimrec_layer_mean": [i64, i32, i32, C.POINTER(vp), C.POINTER(i64), f32, vp, i64, vp],
     "elimrec_wgrad_multi": [i32, C.POINTER(WgradProblem), i32, vp, vp, vp],
+    "elimrec_wgrad_multi_x3": [i32, C.POINTER(WgradProblem), i32, vp, vp, vp],
     "elimrec_lin_assemble": [i64, vp, i32, C.POINTER(LinLayers), f32, i32, i32, vp, i64, vp],
     "elimrec_lin_seed": [i32, vp, i32, i32, vp, i64, i32, f32, vp, i64, vp],
     "elimrec_lin_seed2": [i32, vp, vp, i64, i32, f32, vp, vp, i64, vp],

@@ -222,7 +222,7 @@ class ColShardedEliMRec(EliMRec):
                                 addend_u=g_u(k - 1), addend_i=g_i(k - 1), add_mask_u=mask[:U], add_mask_i=mask[U:], width=w, **kw)
                 h_u, h_i, flip = nxt[:U], nxt[U:], flip ^ 1
         # small weights: gradients of my batch, averaged over the ranks (the loss value rides along)
-        ops.wgrad_multi(self._lin_wgrad_problems(ws, gWu, gWi), ws["wg_splits"], ws["wg_ws"], None)
+        ops.wgrad_multi(self._lin_wgrad_problems(ws, gWu, gWi), ws["wg_splits"], ws["wg_ws"], None, x3=self._lin_wgrad_x3())
         if tied:
             ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], ws["G"], 1.0 / ws["G"])
             ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], ws["G"], 1.0 / ws["G"])

@@ -291,6 +291,27 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+// N float4 per thread (stride `nt` threads): every load is issued before the first store - hi and lo may alias as far as the
+// compiler knows, so a load-convert-store loop is one dependent shared-memory round trip per element
+template <int N>
+__device__ __forceinline__ void split_f4(float4* hi, float4* lo, int t, int nt, int n_valid) {
+    float4 x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (i < n_valid) x[i] = hi[i * nt + t];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i < n_valid) {
+            float4 h, l;
+            h.x = tf32_rna(x[i].x); h.y = tf32_rna(x[i].y); h.z = tf32_rna(x[i].z); h.w = tf32_rna(x[i].w);
+            l.x = tf32_rna(x[i].x - h.x); l.y = tf32_rna(x[i].y - h.y); l.z = tf32_rna(x[i].z - h.z); l.w = tf32_rna(x[i].w - h.w);
+            hi[i * nt + t] = h;
+            lo[i * nt + t] = l;
+        }
+    }
+}
+
+
 __global__ void __launch_bounds__(192)
 linear_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                      const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ bias, float* __restrict__ Y,
@@ -372,16 +393,7 @@ linear_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&full_bar[s], ph);
             float4* hi = reinterpret_cast<float4*>(smem + s * X_STAGE);
             float4* lo = reinterpret_cast<float4*>(smem + s * X_STAGE + F_A_BYTES);
-#pragma unroll
-            for (int i = 0; i < F_A_BYTES / 16 / 128; ++i) {
-                const int idx = i * 128 + t;
-                const float4 x = hi[idx];
-                float4 h, l;
-                h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-                l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-                hi[idx] = h;
-                lo[idx] = l;
-            }
+            split_f4<F_A_BYTES / 16 / 128>(hi, lo, t, 128, F_A_BYTES / 16 / 128);
             fence_proxy_async();           // generic-proxy writes -> visible to the tensor core (async proxy)
             mbar_arrive(&split_bar[s]);
         }
@@ -530,16 +542,7 @@ fuse_heads_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&full_bar[s], ph);
             float4* hi = reinterpret_cast<float4*>(smem + s * H_STAGE);
             float4* lo = reinterpret_cast<float4*>(smem + s * H_STAGE + F_A_BYTES);
-#pragma unroll
-            for (int i = 0; i < F_A_BYTES / 16 / 128; ++i) {
-                const int idx = i * 128 + t;
-                const float4 x = hi[idx];
-                float4 h, l;
-                h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-                l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-                hi[idx] = h;
-                lo[idx] = l;
-            }
+            split_f4<F_A_BYTES / 16 / 128>(hi, lo, t, 128, F_A_BYTES / 16 / 128);
             fence_proxy_async();
             mbar_arrive(&split_bar[s]);
         }
@@ -701,16 +704,7 @@ fuse_heads_x3_all_kernel(const __grid_constant__ FuseAllMaps mp, FuseAllOut ho, 
                 mbar_wait(&full_bar[s], ph);
                 float4* hi = reinterpret_cast<float4*>(smem + s * H_STAGE);
                 float4* lo = reinterpret_cast<float4*>(smem + s * H_STAGE + F_A_BYTES);
-#pragma unroll
-                for (int i = 0; i < F_A_BYTES / 16 / 128; ++i) {
-                    const int idx = i * 128 + t;
-                    const float4 x = hi[idx];
-                    float4 h, l;
-                    h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-                    l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-                    hi[idx] = h;
-                    lo[idx] = l;
-                }
+                split_f4<F_A_BYTES / 16 / 128>(hi, lo, t, 128, F_A_BYTES / 16 / 128);
                 fence_proxy_async();
                 mbar_arrive(&split_bar[s]);
             }
@@ -1049,6 +1043,237 @@ ELIMREC_API int elimrec_linear_tf32_fwd(int64_t M, int64_t K, const float* X, in
 }
 
 
+
+
+// ---------------------------------------------------------------------------------------------
+// Batched 3xTF32 weight gradients (the tensor-core twin of csrc/wgrad_multi.cu, same problems / workspace / reduction):
+//   partial[tile][split][n][c] = sum over the split's rows of  A_p[m, n] * B_p[m, c0 + c]     (+ column sums of A_p)
+// computed like linear_tf32_wgrad_kernel as D^T[c, n] with both operands MN-major straight from row-major memory, but on
+// fp32-accurate operands: four split warps turn every landed TMA stage into TF32 hi (in place) + lo (twin buffer) and the
+// MMA thread issues lo*hi + hi*lo + hi*hi into one TMEM accumulator.  The bias gradient (column sums of A) rides along as
+// two more MMAs against a constant all-ones A' tile into a second 64-column accumulator.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int X3_BR = 32;                        // rows per stage (4 MMA k-steps of 8 rows)
+constexpr int X3_STAGES = 4;
+constexpr int X3_BOX = X3_BR * 128;              // one TMA box: [32 rows x 32 floats] = 4 KB
+constexpr int X3_G = 2 * X3_BOX;                 // A_p block: 64 columns
+constexpr int X3_X = 4 * X3_BOX;                 // B_p tile: 128 columns
+constexpr int X3_STAGE = 2 * X3_G + 2 * X3_X;    // [G hi | G lo | X hi | X lo] = 48 KB
+constexpr int X3_ONES = 4096;
+constexpr int X3_SMEM = X3_STAGES * X3_STAGE + X3_ONES + 1024;
+constexpr int X3_TMEM_COLS = 512;              // 4 rotating [128 x 64] accumulators + 4 for the bias sums
+constexpr int X3_SPLIT = 256;                    // split / epilogue threads (warps 2..9)
+constexpr int X3_THREADS = 64 + X3_SPLIT;
+
+struct X3Args {
+    CUtensorMap A[ELIMREC_WGRAD_MAX_PROBLEMS], B[ELIMREC_WGRAD_MAX_PROBLEMS];
+    int K[ELIMREC_WGRAD_MAX_PROBLEMS], rows[ELIMREC_WGRAD_MAX_PROBLEMS], has_bias[ELIMREC_WGRAD_MAX_PROBLEMS];
+    int tile0[ELIMREC_WGRAD_MAX_PROBLEMS + 1];
+    int n_prob, n_tiles, splits;
+    float* ws;
+};
+
+__global__ void __launch_bounds__(X3_THREADS, 1) wgrad_x3_multi_kernel(const __grid_constant__ X3Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[X3_STAGES];
+    __shared__ __align__(8) uint64_t split_bar[X3_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[X3_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    int p = 0;
+    while (p + 1 < a.n_prob && tile >= a.tile0[p + 1]) ++p;
+    const int c0 = (tile - a.tile0[p]) * 128;              // first B column of this tile
+    const int K = a.K[p], rows = a.rows[p];
+    const int n_boxes = (min(K - c0, 128) + 31) / 32;      // B boxes holding any valid column
+    int chunk = (rows + a.splits - 1) / a.splits;
+    chunk = (chunk + X3_BR - 1) / X3_BR * X3_BR;
+    const int rb0 = split * chunk;
+    const int rb1 = min(rows, rb0 + chunk);
+    const int n_it = rb1 > rb0 ? (rb1 - rb0 + X3_BR - 1) / X3_BR : 0;    // the last stage's rows past `rows` arrive as zeros
+    const bool want_bias = a.has_bias[p] != 0 && c0 == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&a.A[p]);
+        tma_prefetch_desc(&a.B[p]);
+        for (int s = 0; s < X3_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&split_bar[s], X3_SPLIT);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, X3_TMEM_COLS);
+    if (warp >= 2 && want_bias) {                          // the all-ones A' tile of the bias accumulator
+        float4* ones = reinterpret_cast<float4*>(smem + X3_STAGES * X3_STAGE);
+        for (int i = threadIdx.x - 64; i < X3_ONES / 16; i += X3_SPLIT) ones[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % X3_STAGES;
+                const uint32_t ph = (it / X3_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], (uint32_t)(n_boxes + 2) * X3_BOX);
+                uint8_t* base = smem + s * X3_STAGE;
+                const int row = rb0 + it * X3_BR;
+                tma_load_2d(&a.A[p], &full_bar[s], base, 0, row);
+                tma_load_2d(&a.A[p], &full_bar[s], base + X3_BOX, 32, row);
+                for (int b = 0; b < n_boxes; ++b) tma_load_2d(&a.B[p], &full_bar[s], base + 2 * X3_G + b * X3_BOX, c0 + b * 32, row);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(128, 64, 1, 1);   // A' = B_p^T and B' = A_p are both MN-major
+            const uint32_t ones = smem_u32(smem + X3_STAGES * X3_STAGE);
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % X3_STAGES;
+                const uint32_t ph = (it / X3_STAGES) & 1;
+                mbar_wait(&split_bar[s], ph);
+                tc_fence_after();
+                const uint32_t gh = smem_u32(smem + s * X3_STAGE), gl = gh + X3_G;
+                const uint32_t xh = gl + X3_G, xl = xh + X3_X;
+#pragma unroll
+                for (int j = 0; j < X3_BR / 8; ++j) {      // one MMA = 8 rows = two 4-row (512-byte) swizzle atoms per 32-column group
+                    const uint64_t dxh = umma_desc(xh + j * 1024, X3_BOX, 512, 1), dxl = umma_desc(xl + j * 1024, X3_BOX, 512, 1);
+                    const uint64_t dgh = umma_desc(gh + j * 1024, X3_BOX, 512, 1), dgl = umma_desc(gl + j * 1024, X3_BOX, 512, 1);
+                    // k-step j of every stage goes to accumulator j: the tensor core's fp32 accumulate is not a rounded fp32 add
+                    // (measured: ~2^-24 of the running sum lost per MMA, same sign), so four shorter chains summed once in
+                    // registers carry a quarter of the error of one long chain
+                    const uint32_t dj = tmem_d + j * 64;
+                    umma_tf32(dj, dxl, dgh, idesc, it != 0);
+                    umma_tf32(dj, dxh, dgl, idesc, 1);
+                    umma_tf32(dj, dxh, dgh, idesc, 1);
+                    if (want_bias) {
+                        const uint64_t d1 = umma_desc(ones, 1024, 512, 1);
+                        umma_tf32(dj + 256, d1, dgl, idesc, it != 0);
+                        umma_tf32(dj + 256, d1, dgh, idesc, 1);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        const int t = threadIdx.x - 64;
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % X3_STAGES;
+            const uint32_t ph = (it / X3_STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            uint8_t* base = smem + s * X3_STAGE;
+            float4* ghi = reinterpret_cast<float4*>(base);
+            float4* glo = reinterpret_cast<float4*>(base + X3_G);
+            float4* xhi = reinterpret_cast<float4*>(base + 2 * X3_G);
+            float4* xlo = reinterpret_cast<float4*>(base + 2 * X3_G + X3_X);
+            split_f4<X3_G / 16 / X3_SPLIT>(ghi, glo, t, X3_SPLIT, X3_G / 16 / X3_SPLIT);
+            split_f4<X3_X / 16 / X3_SPLIT>(xhi, xlo, t, X3_SPLIT, n_boxes * (X3_BOX / 16 / X3_SPLIT));
+            fence_proxy_async();
+            mbar_arrive(&split_bar[s]);
+        }
+        const int q = warp & 3, half = (warp - 2) >> 2;        // TMEM lane quadrant of this warp, and which 32 of the 64 columns it drains
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        float* out = a.ws + ((long long)tile * a.splits + split) * (64 * 128);     // [64 x 128] like wgrad_multi's partial tiles
+        float v[32];
+        auto drain4 = [&](uint32_t taddr) {      // (acc0 + acc1) + (acc2 + acc3) of the four rotating accumulators
+            float w[32];
+            tmem_ld_32x32(taddr, v);
+            tmem_ld_32x32(taddr + 64, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int n = 0; n < 32; ++n) v[n] += w[n];
+            float x[32];
+            tmem_ld_32x32(taddr + 128, w);
+            tmem_ld_32x32(taddr + 192, x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int n = 0; n < 32; ++n) v[n] += w[n] + x[n];
+        };
+        if (n_it > 0) {
+            drain4(tmem_d + ((uint32_t)(q * 32) << 16) + half * 32);
+        } else {
+#pragma unroll
+            for (int n = 0; n < 32; ++n) v[n] = 0.f;
+        }
+#pragma unroll
+        for (int n = 0; n < 32; ++n) out[(half * 32 + n) * 128 + q * 32 + lane] = v[n];   // 32 consecutive c per warp store
+        if (want_bias && q == 0) {
+            if (n_it > 0) drain4(tmem_d + 256 + half * 32);
+            if (lane == 0) {
+                float* bp = a.ws + (long long)a.n_tiles * a.splits * (64 * 128) + ((long long)tile * a.splits + split) * 64 + half * 32;
+#pragma unroll
+                for (int n = 0; n < 32; ++n) bp[n] = v[n];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, X3_TMEM_COLS);
+}
+}  // namespace
+
+int er_wgrad_multi_reduce(int n, const elimrec_wgrad_problem_t* problems, int splits, float* workspace, const float* gscale_dev,
+                          cudaStream_t st);   // csrc/wgrad_multi.cu
+
+ELIMREC_API int elimrec_wgrad_multi_x3(int n, const elimrec_wgrad_problem_t* problems, int splits, float* workspace,
+                                       const float* gscale_dev, elimrec_stream_t stream) {
+    ER_CHECK_ARG(n >= 0 && n <= ELIMREC_WGRAD_MAX_PROBLEMS && (n == 0 || problems != nullptr), "too many problems");
+    ER_CHECK_ARG(splits >= 1 && splits <= 64 && workspace != nullptr, "splits in [1, 64] and a workspace required");
+    if (n == 0) return 0;
+    X3Args a{};
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        const elimrec_wgrad_problem_t& q = problems[i];
+        ER_CHECK_ARG(q.K > 0 && q.row_begin >= 0 && q.row_end >= q.row_begin && q.row_end <= 0x7fffffff, "bad problem shape");
+        const float* A = q.A + q.row_begin * q.lda;
+        const float* B = q.B + q.row_begin * q.ldb;
+        if (q.lda % 4 != 0 || q.ldb % 4 != 0 || !aligned16(A) || !aligned16(B)) {
+            elimrec_set_error("elimrec_wgrad_multi_x3: operands must be 16-byte aligned with row strides that are multiples of 4 "
+                              "(problem %d: lda=%lld ldb=%lld)", i, (long long)q.lda, (long long)q.ldb);
+            return -2;
+        }
+        const int64_t rows = q.row_end - q.row_begin;
+        if (rows > 0 && (make_map(&a.A[i], A, rows, 64, q.lda, X3_BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) != 0 ||
+                         make_map(&a.B[i], B, rows, q.K, q.ldb, X3_BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) != 0)) {
+            elimrec_set_error("elimrec_wgrad_multi_x3: cuTensorMapEncodeTiled failed (problem %d)", i);
+            return -3;
+        }
+        a.K[i] = (int)q.K;
+        a.rows[i] = (int)rows;
+        a.has_bias[i] = q.bias_out != nullptr;
+        a.tile0[i] = tiles;
+        tiles += (int)((q.K + 127) / 128);
+    }
+    a.tile0[n] = tiles;
+    a.n_prob = n;
+    a.n_tiles = tiles;
+    a.splits = splits;
+    a.ws = workspace;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_x3_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM);
+        if (e != cudaSuccess) {
+            elimrec_set_error("elimrec_wgrad_multi_x3: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            return -3;
+        }
+        configured = true;
+    }
+    cudaStream_t st = er_stream(stream);
+    wgrad_x3_multi_kernel<<<dim3(tiles, splits), X3_THREADS, X3_SMEM, st>>>(a);
+    ER_LAUNCH_CHECK();
+    return er_wgrad_multi_reduce(n, problems, splits, workspace, gscale_dev, st);
+}
 
 namespace {
 struct PrepMulti {

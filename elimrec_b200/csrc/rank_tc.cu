@@ -61,6 +61,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// the same box delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -78,6 +93,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrives on the barrier at this offset in every CTA of `mask` once the issuing thread's earlier MMAs have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -112,6 +132,7 @@ constexpr int T_ITEMS = 128;                   // items per tile  = MMA M = TMEM
 constexpr int T_USERS = 64;                    // users per CTA   = MMA N = TMEM columns per table
 constexpr int I_PART = T_ITEMS * 128;          // one [128 items x 64 dims] fp16 tile = 16 KB
 constexpr int U_PART = T_USERS * 128;          // one [ 64 users x 64 dims] fp16 tile =  8 KB
+constexpr int TC_CLUSTER = 2;                  // CTAs (user tiles) per cluster: every item tile is fetched from L2 once per cluster
 constexpr int N_DRAIN = 16;                    // drain warps: 4 TMEM lane quadrants x 4 groups of 16 user columns
 constexpr int TC_THREADS = 32 * (2 + N_DRAIN);
 enum { TC_MEAN = 0, TC_NORMAL = 1, TC_TE = 2, TC_TIE = 3 };
@@ -148,8 +169,12 @@ __device__ __noinline__ bool train_row_tail_has(const int* eval_users, const lon
     return lo < end && __ldg(train_items + lo) == item;
 }
 
+// Clusters of TC_CLUSTER = 2 CTAs (two user tiles on the two SMs of a TPC) share the item stream: per ring slot CTA 0 fetches the
+// hi box and CTA 1 the lo box, each multicast into BOTH CTAs' shared memory, so the L2 -> SM traffic of the kernel (every CTA
+// used to stream all (1+M) item tables: 44.6 GB per evaluation at Tiktok shape, the kernel's co-limiter next to MUFU) halves.
+// A slot is refilled only when the MMA warps of both CTAs have released it (the commit is multicast to both empty barriers).
 template <int MODE, int NT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1)
 rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NTMAX], empty_bar[NTMAX], tfull_bar[2], tempty_bar[2];
@@ -168,7 +193,7 @@ rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
     if (warp == 0 && lane == 0) {
         for (int b = 0; b < NTMAX; ++b) {
             mbar_init(&full_bar[b], 1);
-            mbar_init(&empty_bar[b], 1);
+            mbar_init(&empty_bar[b], TC_CLUSTER);      // one release per CTA of the cluster
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
@@ -205,8 +230,11 @@ rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                          // the peer's barriers exist before anything of mine can reach them
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_smem;
+    const uint32_t crank = cluster_ctarank();
+    constexpr uint16_t CMASK = (1u << TC_CLUSTER) - 1;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -214,10 +242,10 @@ rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
             for (int j = 0; j < n_tiles; ++j) {
                 for (int t = 0; t < nt; ++t, ++it) {
                     const int s = it & (NTMAX - 1);
-                    mbar_wait(&empty_bar[s], ((it / NTMAX) & 1) ^ 1);
-                    mbar_expect_tx(&full_bar[s], (uint32_t)(2 * I_PART));
-                    tma_load_2d(&mp.hi[t], &full_bar[s], smI + (s * 2 + 0) * I_PART, 0, j * T_ITEMS);
-                    tma_load_2d(&mp.lo[t], &full_bar[s], smI + (s * 2 + 1) * I_PART, 0, j * T_ITEMS);
+                    mbar_wait(&empty_bar[s], ((it / NTMAX) & 1) ^ 1);      // released by BOTH CTAs
+                    mbar_expect_tx(&full_bar[s], (uint32_t)(2 * I_PART));  // my box + the peer's
+                    tma_load_2d_mc(crank == 0 ? &mp.hi[t] : &mp.lo[t], &full_bar[s], smI + (s * 2 + crank) * I_PART, 0, j * T_ITEMS,
+                                   CMASK);
                 }
             }
         }
@@ -240,7 +268,7 @@ rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
                         umma_f16(d, umma_desc_sw128(ih + k * 32), umma_desc_sw128(ul + k * 32), IDESC_F16_128x64, 1);
                         umma_f16(d, umma_desc_sw128(ih + k * 32), umma_desc_sw128(uh + k * 32), IDESC_F16_128x64, 1);
                     }
-                    umma_commit(&empty_bar[s]);  // ring slot consumed
+                    umma_commit_mc(&empty_bar[s], CMASK);  // ring slot consumed here: tell both producers
                 }
                 umma_commit(&tfull_bar[buf]);   // accumulators of tile j complete
             }
@@ -401,6 +429,7 @@ rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_d, 512);
+    cluster_sync_all();                          // no CTA leaves while the peer's releases / boxes can still land in it
 }
 
 constexpr int RANK_TC_SMEM = NTMAX * 2 * I_PART + NTMAX * 2 * U_PART + T_USERS * 32 * 4 + N_DRAIN * 16 * 8 + 1024;
@@ -492,7 +521,7 @@ int launch_rank_tc(const RankTcMaps& mp, const RankTcArgs& a, cudaStream_t st) {
         }
         configured = true;
     }
-    const int blocks = (a.n_eval + T_USERS - 1) / T_USERS;
+    const int blocks = ((a.n_eval + T_USERS - 1) / T_USERS + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER;   // padding CTAs rank nothing
     rank_tc_kernel<MODE, NT><<<blocks, TC_THREADS, RANK_TC_SMEM, st>>>(mp, a);
     return 0;
 }

@@ -196,18 +196,23 @@ ELIMREC_API int64_t elimrec_wgrad_multi_workspace_floats(int n, const elimrec_wg
     return (int64_t)wg_tiles(n, problems) * splits * (64 * WG_TN + 64);
 }
 
-ELIMREC_API int elimrec_wgrad_multi(int n, const elimrec_wgrad_problem_t* problems, int splits, float* workspace,
-                                    const float* gscale_dev, elimrec_stream_t stream) {
-    ER_CHECK_ARG(n >= 0 && n <= ELIMREC_WGRAD_MAX_PROBLEMS && (n == 0 || problems != nullptr), "too many problems");
-    ER_CHECK_ARG(splits >= 1 && splits <= 64 && workspace != nullptr, "splits in [1, 64] and a workspace required");
-    if (n == 0) return 0;
-    WgArgs a{};
+namespace {
+int wg_args(const char* who, int n, const elimrec_wgrad_problem_t* problems, int splits, float* workspace, const float* gscale_dev,
+            WgArgs* out) {
+    WgArgs& a = *out;
+    a = WgArgs{};
     a.n_prob = n;
     int tiles = 0;
     for (int i = 0; i < n; ++i) {
         const elimrec_wgrad_problem_t& q = problems[i];
-        ER_CHECK_ARG(q.K > 0 && q.row_begin >= 0 && q.row_end >= q.row_begin, "bad problem shape");
-        ER_CHECK_ARG(q.lda % 4 == 0 && (reinterpret_cast<unsigned long long>(q.A) & 15) == 0, "A must be 16-byte aligned rows");
+        if (!(q.K > 0 && q.row_begin >= 0 && q.row_end >= q.row_begin)) {
+            elimrec_set_error("%s: bad problem shape", who);
+            return -1;
+        }
+        if (!(q.lda % 4 == 0 && (reinterpret_cast<unsigned long long>(q.A) & 15) == 0)) {
+            elimrec_set_error("%s: A must be 16-byte aligned rows", who);
+            return -1;
+        }
         a.p[i] = WgProblem{q.A, q.lda, q.B, q.ldb, (int)q.K, (int)q.row_begin, (int)q.row_end, q.out, q.ldo, q.bias_out,
                            q.scale_by_g, tiles};
         tiles += (int)((q.K + WG_TN - 1) / WG_TN);
@@ -216,10 +221,33 @@ ELIMREC_API int elimrec_wgrad_multi(int n, const elimrec_wgrad_problem_t* proble
     a.splits = splits;
     a.ws = workspace;
     a.gscale = gscale_dev;
-    cudaStream_t st = er_stream(stream);
-    wgrad_multi_kernel<<<dim3(tiles, splits), 128, 0, st>>>(a);
+    return 0;
+}
+}  // namespace
+
+// the fixed-order reduction of the partial tiles, shared with the tensor-core twin (csrc/linear_tc.cu: elimrec_wgrad_multi_x3)
+int er_wgrad_multi_reduce(int n, const elimrec_wgrad_problem_t* problems, int splits, float* workspace, const float* gscale_dev,
+                          cudaStream_t st) {
+    WgArgs a;
+    int rc = wg_args("elimrec_wgrad_multi_x3", n, problems, splits, workspace, gscale_dev, &a);
+    if (rc != 0) return rc;
+    wgrad_multi_reduce_kernel<<<dim3(a.n_tiles, 32), 256, 0, st>>>(a);
     ER_LAUNCH_CHECK();
-    wgrad_multi_reduce_kernel<<<dim3(tiles, 32), 256, 0, st>>>(a);
+    return 0;
+}
+
+ELIMREC_API int elimrec_wgrad_multi(int n, const elimrec_wgrad_problem_t* problems, int splits, float* workspace,
+                                    const float* gscale_dev, elimrec_stream_t stream) {
+    ER_CHECK_ARG(n >= 0 && n <= ELIMREC_WGRAD_MAX_PROBLEMS && (n == 0 || problems != nullptr), "too many problems");
+    ER_CHECK_ARG(splits >= 1 && splits <= 64 && workspace != nullptr, "splits in [1, 64] and a workspace required");
+    if (n == 0) return 0;
+    WgArgs a;
+    int rc = wg_args("elimrec_wgrad_multi", n, problems, splits, workspace, gscale_dev, &a);
+    if (rc != 0) return rc;
+    cudaStream_t st = er_stream(stream);
+    wgrad_multi_kernel<<<dim3(a.n_tiles, splits), 128, 0, st>>>(a);
+    ER_LAUNCH_CHECK();
+    wgrad_multi_reduce_kernel<<<dim3(a.n_tiles, 32), 256, 0, st>>>(a);
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -147,7 +147,17 @@ class LinearSchedule:
             gWu, gWi = ws["g_eff"]["u"], ws["g_eff"]["i"]
         else:
             gWu, gWi = ws["g"]["embedding_user_after_GCN.weight"], ws["g"]["embedding_item_after_GCN.weight"]
-        ws["wg_ws"] = e(max(1, ops.wgrad_multi_ws_floats(self._lin_wgrad_problems(ws, gWu, gWi), ws["wg_splits"])))
+        probs = self._lin_wgrad_problems(ws, gWu, gWi)
+        if self._lin_wgrad_x3():
+            # tensor-core form: one CTA per SM (four 48 KB stages each), so the row ranges are sized to fill the SMs once
+            tiles = sum((p[4] + 127) // 128 for p in probs)
+            ws["wg_splits"] = max(1, min(64, 148 // max(1, tiles), (3 * B + 31) // 32))
+        ws["wg_ws"] = e(max(1, ops.wgrad_multi_ws_floats(probs, ws["wg_splits"])))
+
+    def _lin_wgrad_x3(self):
+        """weight gradients on the tensor cores (3xTF32) in the default accuracy class; exact FFMA with proj_precision='fp32'
+        (and in 'tf32' mode, whose weight gradients were always exact) or wgrad_precision='fp32'"""
+        return self.proj_precision == "x3" and str(_cfg(self.config, "wgrad_precision", "x3")) == "x3"
 
     def _lin_tc(self):
         return self.proj_precision == "tf32"
@@ -289,7 +299,7 @@ class LinearSchedule:
             Linears and heads from the instance gradients, d[W_m | b_m] = dO_m[inst]^T Zbar_m[inst] (weight AND bias: the ones
             column of Zbar) - none of it waits for the propagation backward.  Returns what must be joined before Adam."""
             def go():
-                ops.wgrad_multi(self._lin_wgrad_problems(ws, gWu, gWi), ws["wg_splits"], ws["wg_ws"], gscale)
+                ops.wgrad_multi(self._lin_wgrad_problems(ws, gWu, gWi), ws["wg_splits"], ws["wg_ws"], gscale, x3=self._lin_wgrad_x3())
                 if tied:
                     ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
                     ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)

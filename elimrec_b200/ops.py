@@ -378,13 +378,18 @@ def wgrad_multi_ws_floats(problems, splits):
     return int(_lib.lib().elimrec_wgrad_multi_workspace_floats(len(problems), _wgrad_problems(problems), splits))
 
 
-def wgrad_multi(problems, splits, ws, gscale=None):
+def wgrad_multi(problems, splits, ws, gscale=None, x3=False):
     """problems: list of (A, a_col, B, b_col, K, row_begin, row_end, out [64 x K], bias_out or None, scale_by_g):
     out = g * A[r0:r1, a_col:a_col+64]^T B[r0:r1, b_col:b_col+K], bias_out = g * column sums of that A block - all problems in
-    one launch + one fixed-order reduction (elimrec_wgrad_multi)."""
+    one launch + one fixed-order reduction.  x3=False: exact fp32 FFMA (elimrec_wgrad_multi); x3=True: 3xTF32 on the tensor
+    cores (elimrec_wgrad_multi_x3, fp32-class accuracy)."""
     arr = _wgrad_problems(problems)
-    call("elimrec_wgrad_multi", len(problems), arr, splits, ptr(ws, F32), ptr(gscale, F32, True), stream(), launches=2,
-         tag="wgrad_multi")
+    if x3:
+        call("elimrec_wgrad_multi_x3", len(problems), arr, splits, ptr(ws, F32), ptr(gscale, F32, True), stream(), launches=2,
+             tag="wgrad_multi_x3")
+    else:
+        call("elimrec_wgrad_multi", len(problems), arr, splits, ptr(ws, F32), ptr(gscale, F32, True), stream(), launches=2,
+             tag="wgrad_multi")
 
 
 def adam_apply_multi(items, consts_dev, b1, b2, eps, wd):

@@ -354,6 +354,12 @@ typedef struct {
 int64_t elimrec_wgrad_multi_workspace_floats(int n, const elimrec_wgrad_problem_t* problems_host, int splits);
 int elimrec_wgrad_multi(int n, const elimrec_wgrad_problem_t* problems_host, int splits /* row ranges per tile, <= 64 */,
                         float* workspace, const float* gscale_dev /* may be NULL */, elimrec_stream_t stream);
+/* The same contract on the tensor cores (csrc/linear_tc.cu): tcgen05 kind::tf32 on hi / lo split operands (3xTF32: lo*hi +
+ * hi*lo + hi*hi in one TMEM accumulator, the bias sums as two more MMAs against an all-ones tile), fp32-class accuracy
+ * (relative error ~1e-6 of sum |a||b|) instead of exact FFMA order; same workspace size, same fixed-order reduction of the row-range
+ * partials.  B and ldb must additionally be 16-byte aligned / a multiple of 4. */
+int elimrec_wgrad_multi_x3(int n, const elimrec_wgrad_problem_t* problems_host, int splits, float* workspace,
+                           const float* gscale_dev /* may be NULL */, elimrec_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * adam - replaces torch.optim.Adam(lr, weight_decay) .step() (main.py:49,101): coupled L2,

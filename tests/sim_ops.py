@@ -350,7 +350,7 @@ def wgrad_multi_ws_floats(problems, splits):
     return 1
 
 
-def wgrad_multi(problems, splits, ws, gscale=None):
+def wgrad_multi(problems, splits, ws, gscale=None, x3=False):
     _log("wgrad_multi")
     for A, a_col, B, b_col, K, r0, r1, out, bias, by_g in problems:
         g = float(gscale) if (by_g and gscale is not None) else 1.0

@@ -677,6 +677,48 @@ def test_wgrad_multi_matches_fp64(dev):
         assert all(torch.equal(a, b) for a, b in zip(first, outs))
 
 
+def test_wgrad_multi_x3_matches_fp64(dev):
+    """elimrec_wgrad_multi_x3 (tcgen05 3xTF32, MN-major operands split hi / lo in shared memory, bias sums through an all-ones
+    tile): the same problem family as the exact kernel - row ranges that are not multiples of the 32-row stage, column blocks,
+    K = 64 / 100 / 132 / 256 / 772 tiles, more row ranges than rows - against fp64 in the fp32 class, against the exact kernel,
+    deterministic; a misaligned B is refused."""
+    from elimrec_b200 import ops
+    from elimrec_b200._lib import ElimrecError
+    g = torch.Generator().manual_seed(2)
+    R = 1000
+    A = torch.randn(R, 256, generator=g).to(dev)
+    Bm = torch.randn(R, 300, generator=g).to(dev)
+    Z = (torch.randn(R, 780, generator=g) * torch.logspace(-3, 2, 780)).to(dev)
+    gs = torch.tensor([0.37], device=dev)
+    outs = [torch.full((64, 256), float("nan"), device=dev), torch.full((64, 64), float("nan"), device=dev),
+            torch.full((64, 132), float("nan"), device=dev), torch.full((64, 100), float("nan"), device=dev),
+            torch.full((64, 772), float("nan"), device=dev)]
+    b0, b1 = torch.full((64,), float("nan"), device=dev), torch.full((64,), float("nan"), device=dev)
+    pr = [(A, 0, Bm, 0, 256, 0, 400, outs[0], b0, True), (A, 64, Bm, 64, 64, 0, R, outs[1], b1, True),
+          (A, 128, Z, 4, 132, 0, R, outs[2], None, False), (A, 192, Bm, 8, 100, 123, 777, outs[3], None, False),
+          (A, 64, Z, 8, 772, 5, 995, outs[4], None, False)]
+    exact = [torch.empty_like(o) for o in outs]
+    ws = torch.empty(ops.wgrad_multi_ws_floats(pr, 7), device=dev)
+    ops.wgrad_multi([(*q[:7], e, None, q[9]) for q, e in zip(pr, exact)], 7, ws, gs)
+    for splits in (1, 7, 11, 40):
+        ws = torch.empty(ops.wgrad_multi_ws_floats(pr, splits), device=dev)
+        ops.wgrad_multi(pr, splits, ws, gs, x3=True)
+        first = [o.clone() for o in outs]
+        for (A_, ac, B_, bc, K, r0, r1, out, bias, by_g), ex in zip(pr, exact):
+            sc = 0.37 if by_g else 1.0
+            a64, b64 = A_[r0:r1, ac:ac + 64].double(), B_[r0:r1, bc:bc + K].double()
+            want = sc * (a64.t() @ b64)
+            bound = sc * (a64.abs().t() @ b64.abs())                 # per element: error relative to sum |a||b|
+            assert float(((out[:, :K].double() - want).abs() / bound).max()) < 4e-6
+            assert rel_err(out[:, :K], want) < 5e-6 and rel_err(out[:, :K], ex[:, :K]) < 5e-6
+            if bias is not None:
+                assert rel_err(bias, sc * a64.sum(0)) < 2e-6
+        ops.wgrad_multi(pr, splits, ws, gs, x3=True)
+        assert all(torch.equal(a, b) for a, b in zip(first, outs))
+    with pytest.raises(ElimrecError):
+        ops.wgrad_multi([(A, 192, Bm, 1, 100, 123, 777, outs[3], None, False)], 4, ws, gs, x3=True)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 3])
 def test_spmm64_pair_matches_fp64(dev, variant):
     """elimrec_spmm64_pair (both halves in one launch, 8-lane groups, split rows with last-arriver reduction): dense, row- and
