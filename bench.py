@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--linear", type=int, default=1,
                     help="1 (default): linear schedule - modality graphs by linearity from one 64-wide propagation + constant "
                          "tables; 0: the row-sparse slab schedule of round 1")
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
+                    help="exploratory runs only: extra model config entries (python literals), e.g. --set wgrad_groups=\"late\"")
     ap.add_argument("--two-hop-masks", type=int, default=0, help="linear schedule: layer L-1 / first backward hop under the two-hop row masks (1) or dense (0)")
     ap.add_argument("--fused-layer-grad", type=int, default=0,
                     help="1: layer-mean gradient added in the backward SpMM epilogues; 0 (default, measured faster): a scatter "
@@ -476,6 +478,10 @@ def main():
     conf = Config(**{"data.input.dataset": name, "topks": [TOPK], "device": dev, "alpha": 0.5, "batch_size": BATCH,
                      "lazy_tables": bool(args.lazy_tables), "fused_layer_grad": bool(args.fused_layer_grad),
                      "linear_schedule": bool(args.linear), "two_hop_masks": bool(args.two_hop_masks)})
+    for kv in args.set:
+        import ast
+        k, v = kv.split("=", 1)
+        conf[k] = ast.literal_eval(v)
     torch.manual_seed(2022)
     rowshard = world > 1 and args.parallel == "rowshard"
     colshard = world > 1 and args.parallel == "colshard" and bool(args.linear) and bool(args.lazy_tables)

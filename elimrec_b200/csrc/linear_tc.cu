@@ -30,8 +30,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// true in exactly one lane of a converged warp.  TMA / tensor-core instructions are warp-level ("uniform") instructions: under
+// `if (lane == 0)` ptxas wraps each of them in an elect-and-loop sequence (ELECT / PLOP3 / BRA.U.ANY, ~100 cycles of issue
+// latency per MMA - more than a 128x64 MMA itself takes); under elect.sync, with the whole warp walking the loop in step so
+// that every operand is warp-uniform, it emits the bare predicated instruction.  The producer and MMA warps below therefore
+// run their loops (barrier waits included) on all 32 lanes and the issuing primitives elect their lane themselves.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {      // one elected lane
+    if (elect_one())
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -49,7 +60,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {   // one elected lane
+    if (elect_one())
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
@@ -65,8 +77,9 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by ONE thread
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by one elected lane of a converged warp
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one())
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -75,7 +88,8 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // mbarrier arrives when every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {      // one elected lane (the one that issued the MMAs)
+    if (elect_one())
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (32*(warp%4) + t)
@@ -90,6 +104,11 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -187,7 +206,7 @@ linear_tf32_fwd_kernel(const __grid_constant__ FwdMulti mp) {
     const uint32_t tmem_d = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             int it = 0;                          // k-blocks issued so far (ring position), across tiles
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int p = fwd_problem_of(mp, tile);
@@ -203,7 +222,7 @@ linear_tf32_fwd_kernel(const __grid_constant__ FwdMulti mp) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
             int it = 0, j = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
@@ -346,7 +365,7 @@ linear_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t tmem_d = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % X_STAGES;
                 const uint32_t ph = (kb / X_STAGES) & 1;
@@ -359,7 +378,7 @@ linear_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % X_STAGES;
@@ -482,7 +501,7 @@ fuse_heads_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t tmem_d = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % H_STAGES;
                 const uint32_t ph = (kb / H_STAGES) & 1;
@@ -501,7 +520,7 @@ fuse_heads_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % H_STAGES;
@@ -629,7 +648,7 @@ fuse_heads_x3_all_kernel(const __grid_constant__ FuseAllMaps mp, FuseAllOut ho, 
     const uint32_t tmem_d = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int who = tile < n_user_tiles ? 0 : 1;
@@ -653,7 +672,7 @@ fuse_heads_x3_all_kernel(const __grid_constant__ FuseAllMaps mp, FuseAllOut ho, 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc_tf32(F_BM, F_BN, 0, 0);
             int it = 0, tc = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc) {
@@ -852,7 +871,7 @@ linear_tf32_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     const uint32_t tmem_d = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % G_STAGES;
                 const uint32_t ph = (it / G_STAGES) & 1;
@@ -866,7 +885,7 @@ linear_tf32_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc_tf32(128, 64, 1, 1);  // A = X^T and B = dY are both MN-major
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % G_STAGES;
@@ -1074,7 +1093,7 @@ struct X3Args {
     float* ws;
 };
 
-__global__ void __launch_bounds__(X3_THREADS, 1) wgrad_x3_multi_kernel(const __grid_constant__ X3Args a) {
+__global__ void __launch_bounds__(X3_THREADS, 3) wgrad_x3_multi_kernel(const __grid_constant__ X3Args a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[X3_STAGES];
     __shared__ __align__(8) uint64_t split_bar[X3_STAGES];
@@ -1120,7 +1139,7 @@ __global__ void __launch_bounds__(X3_THREADS, 1) wgrad_x3_multi_kernel(const __g
     const uint32_t tmem_d = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % X3_STAGES;
                 const uint32_t ph = (it / X3_STAGES) & 1;
@@ -1134,7 +1153,7 @@ __global__ void __launch_bounds__(X3_THREADS, 1) wgrad_x3_multi_kernel(const __g
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp in step, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc_tf32(128, 64, 1, 1);   // A' = B_p^T and B' = A_p are both MN-major
             const uint32_t ones = smem_u32(smem + X3_STAGES * X3_STAGE);
             for (int it = 0; it < n_it; ++it) {
@@ -1185,36 +1204,39 @@ __global__ void __launch_bounds__(X3_THREADS, 1) wgrad_x3_multi_kernel(const __g
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
         float* out = a.ws + ((long long)tile * a.splits + split) * (64 * 128);     // [64 x 128] like wgrad_multi's partial tiles
-        float v[32];
-        auto drain4 = [&](uint32_t taddr) {      // (acc0 + acc1) + (acc2 + acc3) of the four rotating accumulators
-            float w[32];
-            tmem_ld_32x32(taddr, v);
-            tmem_ld_32x32(taddr + 64, w);
-            tmem_ld_wait();
+        // eight columns at a time: the kernel runs beside the propagation launches, which want the register file - a lean
+        // drain keeps this CTA at 64 registers per thread so that two propagation CTAs fit on the SM next to it
+        auto drain4 = [&](uint32_t taddr, float* dst, int stride) {   // (acc0 + acc1) + (acc2 + acc3) of the rotating accumulators
+#pragma unroll 1
+            for (int c = 0; c < 32; c += 8) {
+                float v[8], w[8];
+                if (n_it > 0) {
+                    tmem_ld_32x8(taddr + c, v);
+                    tmem_ld_32x8(taddr + c + 64, w);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int n = 0; n < 32; ++n) v[n] += w[n];
-            float x[32];
-            tmem_ld_32x32(taddr + 128, w);
-            tmem_ld_32x32(taddr + 192, x);
-            tmem_ld_wait();
+                    for (int n = 0; n < 8; ++n) v[n] += w[n];
+                    float x[8];
+                    tmem_ld_32x8(taddr + c + 128, w);
+                    tmem_ld_32x8(taddr + c + 192, x);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int n = 0; n < 32; ++n) v[n] += w[n] + x[n];
-        };
-        if (n_it > 0) {
-            drain4(tmem_d + ((uint32_t)(q * 32) << 16) + half * 32);
-        } else {
+                    for (int n = 0; n < 8; ++n) v[n] += w[n] + x[n];
+                } else {
 #pragma unroll
-            for (int n = 0; n < 32; ++n) v[n] = 0.f;
-        }
+                    for (int n = 0; n < 8; ++n) v[n] = 0.f;
+                }
+                if (dst != nullptr) {
 #pragma unroll
-        for (int n = 0; n < 32; ++n) out[(half * 32 + n) * 128 + q * 32 + lane] = v[n];   // 32 consecutive c per warp store
-        if (want_bias && q == 0) {
-            if (n_it > 0) drain4(tmem_d + 256 + half * 32);
-            if (lane == 0) {
-                float* bp = a.ws + (long long)a.n_tiles * a.splits * (64 * 128) + ((long long)tile * a.splits + split) * 64 + half * 32;
-#pragma unroll
-                for (int n = 0; n < 32; ++n) bp[n] = v[n];
+                    for (int n = 0; n < 8; ++n) dst[(c + n) * stride] = v[n];
+                }
             }
+        };
+        // partial tile [64 x 128] like wgrad_multi's: 32 consecutive c per warp store
+        drain4(tmem_d + ((uint32_t)(q * 32) << 16) + half * 32, out + (half * 32) * 128 + q * 32 + lane, 128);
+        if (want_bias && q == 0) {
+            float* bp = a.ws + (long long)a.n_tiles * a.splits * (64 * 128) + ((long long)tile * a.splits + split) * 64 + half * 32;
+            drain4(tmem_d + 256 + half * 32, lane == 0 ? bp : nullptr, 1);
         }
     }
     tc_fence_before();

@@ -76,6 +76,15 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// true in exactly one lane of a converged warp.  The tensor-core / TMA instructions are warp-level ("uniform") instructions:
+// issued under `if (lane == 0)` ptxas wraps every one of them in its own elect-and-loop sequence (ELECT / PLOP3 / BRA.U.ANY,
+// ~100 cycles of issue latency per MMA - more than the MMA itself); issued under elect.sync by a warp that runs the loop in
+// step it emits the bare instruction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -133,6 +142,7 @@ constexpr int T_USERS = 64;                    // users per CTA   = MMA N = TMEM
 constexpr int I_PART = T_ITEMS * 128;          // one [128 items x 64 dims] fp16 tile = 16 KB
 constexpr int U_PART = T_USERS * 128;          // one [ 64 users x 64 dims] fp16 tile =  8 KB
 constexpr int TC_CLUSTER = 2;                  // CTAs (user tiles) per cluster: every item tile is fetched from L2 once per cluster
+constexpr int TC_PIECE = 2 * T_ITEMS / TC_CLUSTER;   // rows of the [hi ; lo] slot (2 x 128) that one CTA of the cluster fetches
 constexpr int N_DRAIN = 16;                    // drain warps: 4 TMEM lane quadrants x 4 groups of 16 user columns
 constexpr int TC_THREADS = 32 * (2 + N_DRAIN);
 enum { TC_MEAN = 0, TC_NORMAL = 1, TC_TE = 2, TC_TIE = 3 };
@@ -169,10 +179,10 @@ __device__ __noinline__ bool train_row_tail_has(const int* eval_users, const lon
     return lo < end && __ldg(train_items + lo) == item;
 }
 
-// Clusters of TC_CLUSTER = 2 CTAs (two user tiles on the two SMs of a TPC) share the item stream: per ring slot CTA 0 fetches the
-// hi box and CTA 1 the lo box, each multicast into BOTH CTAs' shared memory, so the L2 -> SM traffic of the kernel (every CTA
-// used to stream all (1+M) item tables: 44.6 GB per evaluation at Tiktok shape, the kernel's co-limiter next to MUFU) halves.
-// A slot is refilled only when the MMA warps of both CTAs have released it (the commit is multicast to both empty barriers).
+// Clusters of TC_CLUSTER CTAs (user tiles) share the item stream: of every ring slot ([hi ; lo] boxes = 2 x 128 rows) each CTA
+// fetches TC_PIECE rows and multicasts them into the shared memory of ALL CTAs of the cluster, so an item tile leaves L2 once
+// per cluster instead of once per CTA (every CTA used to stream all (1+M) item tables: 44.6 GB per evaluation at Tiktok shape).
+// A slot is refilled only when the MMA warps of every CTA have released it (the commit is multicast to all empty barriers).
 template <int MODE, int NT>
 __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1)
 rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
@@ -237,31 +247,35 @@ rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
     constexpr uint16_t CMASK = (1u << TC_CLUSTER) - 1;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;                          // running (tile, table) counter: slot = it % NTMAX
-            for (int j = 0; j < n_tiles; ++j) {
-                for (int t = 0; t < nt; ++t, ++it) {
-                    const int s = it & (NTMAX - 1);
-                    mbar_wait(&empty_bar[s], ((it / NTMAX) & 1) ^ 1);      // released by BOTH CTAs
-                    mbar_expect_tx(&full_bar[s], (uint32_t)(2 * I_PART));  // my box + the peer's
-                    tma_load_2d_mc(crank == 0 ? &mp.hi[t] : &mp.lo[t], &full_bar[s], smI + (s * 2 + crank) * I_PART, 0, j * T_ITEMS,
-                                   CMASK);
+        int it = 0;                          // running (tile, table) counter: slot = it % NTMAX
+        constexpr int PPP = T_ITEMS / TC_PIECE;                // pieces per part
+        const int part = (int)crank / PPP, r0 = ((int)crank % PPP) * TC_PIECE;
+        for (int j = 0; j < n_tiles; ++j) {
+            for (int t = 0; t < nt; ++t, ++it) {
+                const int s = it & (NTMAX - 1);
+                mbar_wait(&empty_bar[s], ((it / NTMAX) & 1) ^ 1);      // released by EVERY CTA of the cluster
+                if (elect_one()) {
+                    mbar_expect_tx(&full_bar[s], (uint32_t)(2 * I_PART));  // my piece + the peers'
+                    tma_load_2d_mc(part == 0 ? &mp.hi[t] : &mp.lo[t], &full_bar[s], smI + (s * 2 + part) * I_PART + r0 * 128, 0,
+                                   j * T_ITEMS + r0, CMASK);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int it = 0;
-            for (int j = 0; j < n_tiles; ++j) {
-                const int buf = j & 1;
-                mbar_wait(&tempty_bar[buf], ((j >> 1) & 1) ^ 1);
-                for (int t = 0; t < nt; ++t, ++it) {
-                    const int s = it & (NTMAX - 1);
-                    mbar_wait(&full_bar[s], (it / NTMAX) & 1);
-                    tc_fence_after();
-                    const uint32_t ih = smem_u32(smI + (s * 2) * I_PART), il = ih + I_PART;
-                    const uint32_t uh = smem_u32(smU + (t * 2) * U_PART), ul = uh + U_PART;
-                    const uint32_t d = tmem_d + buf * 256 + t * 64;
+        // the whole warp walks the loop (waits included) so that every address below is warp-uniform; one elected lane issues
+        int it = 0;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int buf = j & 1;
+            mbar_wait(&tempty_bar[buf], ((j >> 1) & 1) ^ 1);
+            for (int t = 0; t < nt; ++t, ++it) {
+                const int s = it & (NTMAX - 1);
+                mbar_wait(&full_bar[s], (it / NTMAX) & 1);
+                tc_fence_after();
+                const uint32_t ih = smem_u32(smI + (s * 2) * I_PART), il = ih + I_PART;
+                const uint32_t uh = smem_u32(smU + (t * 2) * U_PART), ul = uh + U_PART;
+                const uint32_t d = tmem_d + buf * 256 + t * 64;
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {   // K = 64 = 4 x 16 halves (32 bytes inside the 128-byte atom)
                         umma_f16(d, umma_desc_sw128(il + k * 32), umma_desc_sw128(uh + k * 32), IDESC_F16_128x64, k != 0);
@@ -269,8 +283,9 @@ rank_tc_kernel(const __grid_constant__ RankTcMaps mp, const RankTcArgs a) {
                         umma_f16(d, umma_desc_sw128(ih + k * 32), umma_desc_sw128(uh + k * 32), IDESC_F16_128x64, 1);
                     }
                     umma_commit_mc(&empty_bar[s], CMASK);  // ring slot consumed here: tell both producers
+                    if (t == nt - 1) umma_commit(&tfull_bar[buf]);   // accumulators of tile j complete
                 }
-                umma_commit(&tfull_bar[buf]);   // accumulators of tile j complete
+                __syncwarp();
             }
         }
     } else {
@@ -497,12 +512,12 @@ EncodeTiledFn get_encode() {
     }
     return fn;
 }
-int make_map_f16(CUtensorMap* map, const void* base, int64_t rows) {   // [rows x 64] fp16, box [64 dims x 128 items]
+int make_map_f16(CUtensorMap* map, const void* base, int64_t rows) {   // [rows x 64] fp16, box [64 dims x TC_PIECE items]
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) return -1;
     cuuint64_t dims[2] = {64, (cuuint64_t)rows};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64u, (cuuint32_t)T_ITEMS};
+    cuuint32_t box[2] = {64u, (cuuint32_t)TC_PIECE};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -148,11 +148,17 @@ class LinearSchedule:
         else:
             gWu, gWi = ws["g"]["embedding_user_after_GCN.weight"], ws["g"]["embedding_item_after_GCN.weight"]
         probs = self._lin_wgrad_problems(ws, gWu, gWi)
+        n0 = 2 + len(self.mods)          # problems [:n0] contract the instance gradients, [n0:] contract dO[inst]
+        groups = (probs, probs[:n0], probs[n0:])
         if self._lin_wgrad_x3():
             # tensor-core form: one CTA per SM (four 48 KB stages each), so the row ranges are sized to fill the SMs once
-            tiles = sum((p[4] + 127) // 128 for p in probs)
-            ws["wg_splits"] = max(1, min(64, 148 // max(1, tiles), (3 * B + 31) // 32))
-        ws["wg_ws"] = e(max(1, ops.wgrad_multi_ws_floats(probs, ws["wg_splits"])))
+            fill = lambda pr: max(1, min(64, 148 // max(1, sum((p[4] + 127) // 128 for p in pr)), (3 * B + 31) // 32))
+            ws["wg_splits"] = fill(probs)
+            ws["wg_splits_g"] = (fill(groups[1]), fill(groups[2]))
+        else:
+            ws["wg_splits_g"] = (ws["wg_splits"], ws["wg_splits"])
+        need = [ops.wgrad_multi_ws_floats(pr, sp) for pr, sp in zip(groups, (ws["wg_splits"],) + ws["wg_splits_g"]) if pr]
+        ws["wg_ws"] = e(max(1, *need))
 
     def _lin_wgrad_x3(self):
         """weight gradients on the tensor cores (3xTF32) in the default accuracy class; exact FFMA with proj_precision='fp32'
@@ -294,24 +300,48 @@ class LinearSchedule:
             gWu, gWi, gr["embedding_user_after_GCN.bias"], gr["embedding_item_after_GCN.bias"],
             [gr[f"s_dense_{m}.weight"] for m in self.mods], [gr[f"s_dense_{m}.bias"] for m in self.mods], ws["inst_ws"], part=part)
 
-        def weights(fork):
-            """every gradient that is not an embedding table's, in ONE launch + its reduction (elimrec_wgrad_multi): fusion
-            Linears and heads from the instance gradients, d[W_m | b_m] = dO_m[inst]^T Zbar_m[inst] (weight AND bias: the ones
-            column of Zbar) - none of it waits for the propagation backward.  Returns what must be joined before Adam."""
-            def go():
-                ops.wgrad_multi(self._lin_wgrad_problems(ws, gWu, gWi), ws["wg_splits"], ws["wg_ws"], gscale, x3=self._lin_wgrad_x3())
-                if tied:
-                    ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
-                    ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
-            if not fork:
-                go()
-                return []
-            s1 = ops.fork_side(5)
-            with torch.cuda.stream(s1):
-                go()
-            return [s1]
+        def weights(group=None):
+            """every gradient that is not an embedding table's (elimrec_wgrad_multi: one launch + its reduction per call) - none
+            of it waits for the propagation backward.  group 0: fusion Linears and heads (they contract the instance
+            gradients and can start before d O[inst] exists); group 1: d[W_m | b_m] = dO_m[inst]^T Zbar_m[inst] (weight AND
+            bias: the ones column of Zbar); None: both in one launch."""
+            probs = self._lin_wgrad_problems(ws, gWu, gWi)
+            n0 = 2 + len(self.mods)
+            sel = probs if group is None else (probs[:n0] if group == 0 else probs[n0:])
+            splits = ws["wg_splits"] if group is None else ws["wg_splits_g"][group]
+            if sel:
+                ops.wgrad_multi(sel, splits, ws["wg_ws"], gscale, x3=self._lin_wgrad_x3())
+            if tied and group != 1:
+                ops.fold_blocks(gWu, gr["embedding_user_after_GCN.weight"], G, 1.0 / G)
+                ops.fold_blocks(gWi, gr["embedding_item_after_GCN.weight"], G, 1.0 / G)
 
+        # wgrad_overlap (default): the weight gradients run on a side stream beside the backward chain (the chain itself on a
+        # high-priority stream).  Measured on tiktok-shape with the 54-register tensor-core kernel (ms/step): one launch after
+        # d O[inst] 0.375 (default, wgrad_groups="one"); two launches, the instance-gradient problems already beside the
+        # d O[inst] kernel 0.384 ("early": that kernel is on the critical path and slows down by what the hop gains); two
+        # launches after d O[inst] 0.384 ("late"); in sequence before the chain 0.386 (wgrad_overlap=False).
+        overlap = bool(_cfg(self.config, "wgrad_overlap", True)) and not split
+        early = str(_cfg(self.config, "wgrad_groups", "one"))      # "one" | "early" | "late"
+        sw = None
+        if overlap and early == "early":
+            sw = ops.fork_side(5)
+            with torch.cuda.stream(sw):
+                weights(0)
         ib(1)
+        pending = None
+        if overlap:
+            sw = ops.fork_side(5)      # the same side stream, now also behind d O[inst]
+            with torch.cuda.stream(sw):
+                if early == "one":
+                    weights(None)
+                else:
+                    if early != "early":
+                        weights(0)
+                    weights(1)
+            pending = []
+        elif not split:
+            weights(None)      # in sequence, before the chain (measured with the exact FFMA kernel: 0.417 vs 0.399 ms/step)
+            pending = []
         # the 64-wide backward chain: h_L = g_L, h_{k-1} = A_hat^T h_k + g_{k-1}.  g_k lives on the instance rows and takes two
         # values per row: GA (all blocks of dO) where layer k carries the modality graphs' E_u part (users: k even, items:
         # k odd), GB (id block) elsewhere.  h_L is read straight from the G slabs through the column mask; every later g_k is the
@@ -326,15 +356,6 @@ class LinearSchedule:
         g_u = lambda k: (GA if k % 2 == 0 else GB)[:U]
         g_i = lambda k: (GA if k % 2 == 1 else GB)[U:]
         h_u, h_i, flip = g_u(L), g_i(L), 0
-        # The weight gradients (one FMA-bound grid that nothing but Adam waits for) run BESIDE the chain: the chain on a
-        # high-priority stream, the weight gradients on the current one, filling the SM time the latency-bound propagation
-        # launches leave.  Measured on tiktok-shape (B200): 0.399 ms/step beside, 0.417 ms/step with the weight gradients in
-        # sequence before the chain (wgrad_overlap=False; each kernel alone is faster, their sum is not).
-        overlap = bool(_cfg(self.config, "wgrad_overlap", True))
-        pending = None
-        if not split and not overlap:
-            pending = weights(False)
-
         def hops():
             nonlocal h_u, h_i, flip
             for k in range(L, 0, -1):
@@ -361,9 +382,8 @@ class LinearSchedule:
             chain = ops.fork_side(8, high_priority=True)
             with torch.cuda.stream(chain):
                 hops()
-            if not split:
-                pending = weights(False)
             ops.join_side(chain)
+            ops.join_side(sw)
         else:
             hops()
         grads = {} if fuse_adam else {"embedding_user.weight": h_u, "embedding_item.weight": h_i}
@@ -377,7 +397,7 @@ class LinearSchedule:
         ws = self._ws
         weights, pending = ws.pop("bw_pending")
         if pending is None:
-            weights(False)
+            weights(None)
         dead = self._dead_params()
         return {n: gv for n, gv in ws["g"].items() if n not in dead} if dead else ws["g"]
 

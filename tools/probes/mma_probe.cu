@@ -61,13 +61,20 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int reps, int n_acc, long
         if (MODE == 0) idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         else idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((MODE == 2 ? 1u : 0u) << 15) | ((MODE == 2 ? 1u : 0u) << 16) |
                      ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        uint64_t da[4], db[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (MODE == 2) { da[k] = desc(a0 + k * 1024, 4096, 512, 1); db[k] = desc(b0 + k * 1024, 4096, 512, 1); }
+            else { da[k] = desc(a0 + k * 32, 16, 1024, 2); db[k] = desc(b0 + k * 32, 16, 1024, 2); }
+        }
+        const uint32_t amask = (uint32_t)n_acc - 1;      // n_acc is a power of two
         const long long t0 = clock64();
-        for (int r = 0; r < reps; ++r) {
-            const int k = r & 3;
-            uint64_t da, db;
-            if (MODE == 2) { da = desc(a0 + k * 1024, 4096, 512, 1); db = desc(b0 + k * 1024, 4096, 512, 1); }
-            else { da = desc(a0 + k * 32, 16, 1024, 2); db = desc(b0 + k * 32, 16, 1024, 2); }
-            mma<MODE == 0 ? 0 : 1>(d + (uint32_t)((r % n_acc) * N), da, db, idesc, r >= n_acc);
+        for (int r = 0; r < reps; r += 4) {              // descriptors precomputed, four MMAs per trip: nothing but the issue
+            const uint32_t dd = d + ((uint32_t)(r >> 2) & amask) * (uint32_t)N;
+            mma<MODE == 0 ? 0 : 1>(dd, da[0], db[0], idesc, r >= 4 * n_acc);
+            mma<MODE == 0 ? 0 : 1>(dd, da[1], db[1], idesc, 1);
+            mma<MODE == 0 ? 0 : 1>(dd, da[2], db[2], idesc, 1);
+            mma<MODE == 0 ? 0 : 1>(dd, da[3], db[3], idesc, 1);
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
         mbar_wait(&bar, 0);
