@@ -130,9 +130,12 @@ __device__ __forceinline__ void adam_vec(RowVec<FPL>& p, const RowVec<FPL>& g, R
 // COMPACT (launches with a row mask): the CTA first looks at its 32 items, keeps the marked ones (order preserved) and deals
 // them to its first groups - warps left without work exit, so a 50 % mask costs half the time instead of all of it (the four
 // items of a warp would otherwise finish only when the slowest unmasked one does).
-// ADAM (fused optimizer epilogue): the table / moment rows are fetched BEFORE the gather loop, so their HBM latency hides
-// under the L2 gathers instead of adding a dependent round trip per row.
-template <int FPL, int UNR, int MINB, bool COMPACT, bool ADAM>
+// ADAM (fused optimizer epilogue): Adam of a row right after its gradient is complete, on the registers that hold it.
+// PREF fetches the table / moment rows BEFORE the gather loop (their HBM latency then hides under the L2 gathers, at 104
+// registers and 2 CTAs per SM); without it they are fetched after the loop at 64 registers and 4 CTAs per SM - measured on the
+// Tiktok-shape graph (tools/spmm64_bench.py): 76.9 us with, 59.1 us without (the shipped form), 58.1 us at <UNR 2, 4 CTAs>;
+// variants that spill to reach 5 CTAs per SM take 70-83 us.
+template <int FPL, int UNR, int MINB, bool COMPACT, bool ADAM, int PREF = 1>
 __global__ void __launch_bounds__(256, MINB)
 spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
     constexpr int W = 8 * FPL;
@@ -185,7 +188,13 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
     float* ap = nullptr;
     if (ADAM) {
         ap = SEL(adam_p);
-        if (active && ap != nullptr && sg.w < 0) {
+        if (PREF == 2 && active && ap != nullptr && sg.w < 0) {      // no registers held: the rows are only pulled into L2
+            const long long o = (long long)sg.x * W + gl * (FPL >= 4 ? 4 : FPL);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(SEL(adam_m) + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(SEL(adam_v) + o));
+        }
+        if (PREF == 1 && active && ap != nullptr && sg.w < 0) {
             const long long o = (long long)sg.x * W;
             pv.load_plain(ap + o, gl);
             mv.load_plain(SEL(adam_m) + o, gl);
@@ -278,7 +287,7 @@ spmm64_pair_kernel(const Half64 a, const Half64 b, const AdamC adam) {
         if (ADAM && ap != nullptr) {
             const float step_size = (float)adam.consts[0], bc2s = (float)adam.consts[1];
             const long long o = (long long)sg.x * W;
-            if (sg.w >= 0) {      // split row, finished by its last-arriving item: fetched here
+            if (PREF != 1 || sg.w >= 0) {      // split row, finished by its last-arriving item: fetched here (PREF != 1: every row)
                 pv.load_plain(ap + o, gl);
                 mv.load_plain(SEL(adam_m) + o, gl);
                 vv.load_plain(SEL(adam_v) + o, gl);
@@ -352,7 +361,9 @@ ELIMREC_API int elimrec_spmm64_pair(const elimrec_spmm64_half_t* a, const elimre
     ER_CHECK_ARG(!(fused && compact), "fused Adam runs on the dense last hop (no row mask)");
 #define PAIR_LAUNCH(FPL)                                                                                                   \
     do {                                                                                                                   \
-        if (fused) spmm64_pair_kernel<FPL, 4, 2, false, true><<<blocks, 256, 0, st>>>(ha, hb, ac);                         \
+        if (fused && variant == 1) spmm64_pair_kernel<FPL, 4, 2, false, true, 1><<<blocks, 256, 0, st>>>(ha, hb, ac);   \
+        else if (fused && variant == 2) spmm64_pair_kernel<FPL, 4, 4, false, true, 2><<<blocks, 256, 0, st>>>(ha, hb, ac); \
+        else if (fused) spmm64_pair_kernel<FPL, 4, 4, false, true, 0><<<blocks, 256, 0, st>>>(ha, hb, ac);             \
         else if (compact) spmm64_pair_kernel<FPL, 4, 4, true, false><<<blocks, 256, 0, st>>>(ha, hb, ac);                  \
         else if (variant == 1) spmm64_pair_kernel<FPL, 8, 2, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac);            \
         else if (variant == 2) spmm64_pair_kernel<FPL, 4, 3, false, false><<<blocks, 256, 0, st>>>(ha, hb, ac);            \

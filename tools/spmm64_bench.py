@@ -92,6 +92,18 @@ def main():
         e1 = float((Y1 - refm)[sel].abs().max() / refm.abs().max())
         out[name] = {"spmm_seg_kernel us": round(t0, 2), "spmm64_pair us": round(t1, 2), "err": [e0, e1],
                      "untouched_rows_ok": bool((Y1[~sel] == 0).all())}
+    # the last backward hop with the fused Adam epilogue, at its tuning points (variant 0 = the shipped one)
+    P = torch.randn(U + I, 64, device=dev)
+    M, V = torch.zeros_like(P), torch.zeros_like(P)
+    E0 = torch.empty_like(P)
+    consts = torch.tensor([1e-3, 1.0], dtype=torch.float64, device=dev)
+    adam_bytes = alg - 2 * (U + I) * 64 * 4 + 8 * (U + I) * 64 * 4      # source slab + p, m, v read + p, m, v, snapshot written
+    for v in range(3):      # 0 = shipped (<UNR 4, 4 CTAs/SM>, rows fetched after the gathers), 1 = prefetched rows, 2 = <UNR 2, 4>
+        fn = lambda: ops.spmm64_pair(g.ui, g.iu, X[U:], X[:U], Y1[:U], Y1[U:], variant=v,
+                                     adam_u=(P[:U], M[:U], V[:U], E0[:U]), adam_i=(P[U:], M[U:], V[U:], E0[U:]),
+                                     adam_consts=(consts, 0.9, 0.999, 1e-8, 0.0))
+        t = timeit(fn)
+        out[f"fused Adam hop v{v}"] = {"us": round(t, 2), "alg_GBps": round(adam_bytes / t / 1e3, 1)}
     print(json.dumps(out, indent=1))
 
 
