@@ -115,6 +115,7 @@ _SIGS = {
     "elimrec_bpr_forward_backward": [i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "elimrec_inst_backward": [i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, vp, C.POINTER(vp),
                               C.POINTER(vp), vp, vp],
+    "elimrec_inst_forward": [i32, i32, i32, vp, vp, vp, C.POINTER(vp), vp, vp, C.POINTER(vp), vp, C.POINTER(vp), vp],
     "elimrec_inst_backward_part": [i32, i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, vp, C.POINTER(vp),
                               C.POINTER(vp), vp, vp],
     "elimrec_adam_apply_multi": [i32, C.POINTER(AdamTensor), vp, f64, f64, f32, f32, vp],

@@ -136,6 +136,11 @@ class EliMRec(LinearSchedule, BasicModel):
         self.fuse_precision = _cfg(cfg, "fuse_precision", "x3")
         if self.fuse_precision not in ("x3", "fp32"):
             raise ElimrecError("fuse_precision must be 'x3' or 'fp32'")
+        # the same two layers on the 3B instance rows of a row-sparse step: 'x3' = the tensor-core kernel on 128-row tiles, users
+        # and items side by side (default: 21 us at Tiktok shape), 'ffma' = one exact-fp32 launch over 3B/16 CTAs (29 us)
+        self.inst_fuse = _cfg(cfg, "inst_fuse", "x3")
+        if self.inst_fuse not in ("ffma", "x3"):
+            raise ElimrecError("inst_fuse must be 'ffma' or 'x3'")
         # lazy_tables (default on): a training step computes exactly what its loss and gradients read.  The BPR loss
         # indexes the fused / single-modal tables with the <= 3B sampled rows (EliMRec.py:120-128), so the step produces
         #   * the last propagation layer and its layer mean at those rows only (row-masked SpMM),
@@ -547,11 +552,19 @@ class EliMRec(LinearSchedule, BasicModel):
             rows = ws["inst_rows"]
             if not gathered:
                 ops.gather_rows(rows, O, ws["O_inst"], Fw)
-            su_ = ops.fork_side(6)
-            with torch.cuda.stream(su_):
-                self._fuse_heads_rows(ws, ws["O_inst"][:B], ws["F_c"][:B], [s_[:B] for s_ in ws["S_c"]], "u")
-            self._fuse_heads_rows(ws, ws["O_inst"][B:], ws["F_c"][B:], [s_[B:] for s_ in ws["S_c"]], "i")
-            ops.join_side(su_)
+            if self.inst_fuse == "ffma":
+                # exact fp32 on 3B/16 CTAs (measured slower than the tensor-core form: instruction-issue bound)
+                Wu, Wi = self._fusion_weights(P, ws)
+                ops.inst_forward(B, 1 + len(self.mods), Fw, ws["O_inst"], Wu, Wi,
+                                 [P[f"s_dense_{m}.weight"].detach() for m in self.mods],
+                                 P["embedding_user_after_GCN.bias"].detach(), P["embedding_item_after_GCN.bias"].detach(),
+                                 [P[f"s_dense_{m}.bias"].detach() for m in self.mods], ws["F_c"], ws["S_c"])
+            else:
+                su_ = ops.fork_side(6)
+                with torch.cuda.stream(su_):
+                    self._fuse_heads_rows(ws, ws["O_inst"][:B], ws["F_c"][:B], [s_[:B] for s_ in ws["S_c"]], "u")
+                self._fuse_heads_rows(ws, ws["O_inst"][B:], ws["F_c"][B:], [s_[B:] for s_ in ws["S_c"]], "i")
+                ops.join_side(su_)
             ops.bpr([ws["F_c"]] + ws["S_c"], weights, ws["c_users"], ws["c_pos"], ws["c_neg"], B, ws["loss"], ws["inst_dummy"],
                     ws["inst_grad"], ws["terms"])
             self._tables_pending = True

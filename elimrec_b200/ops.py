@@ -364,6 +364,14 @@ def inst_backward(B, nt, F, inst_grad, O_inst, gscale, Wu, Wi, Ws, dO_inst, dWu,
          dbp, ptr(ws, F32), stream(), launches={1: 1, 2: 2, 3: 3}[part], tag=f"inst_backward{part}")
 
 
+def inst_forward(B, nt, F, O_inst, Wu, Wi, Ws, bu, bi, bs, F_out, S_out):
+    """fusion Linear + heads on the 3B instance rows (users first), exact fp32, one launch (elimrec_inst_forward)"""
+    n = nt - 1
+    arr = lambda ts: (C.c_void_p * max(n, 1))(*[ptr(t, F32) for t in ts])
+    call("elimrec_inst_forward", B, nt, F, ptr(O_inst, F32), ptr(Wu, F32), ptr(Wi, F32), arr(Ws), ptr(bu, F32), ptr(bi, F32),
+         arr(bs), ptr(F_out, F32), arr(S_out), stream(), launches=1, tag="inst_forward")
+
+
 def _wgrad_problems(problems):
     arr = (_lib.WgradProblem * len(problems))()
     for k, (A, a_col, B, b_col, K, r0, r1, out, bias, by_g) in enumerate(problems):

@@ -326,6 +326,13 @@ int elimrec_inst_backward(int B, int n_tables, int F, const float* inst_grad, co
                           const float* gscale_dev /* may be NULL */, const float* Wu, const float* Wi,
                           const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu, float* dbi,
                           float* const* dWs_host, float* const* dbs_host, float* workspace, elimrec_stream_t stream);
+/* Forward of the same two layers on the 3B instance rows of a row-sparse step, exact fp32, one launch (csrc/bpr.cu):
+ *   F_out[r] = O_inst[r, 0:F] @ W_{u|i}^T + b_{u|i}  (rows 0..B-1 take the user fusion Linear, B..3B-1 the item one;
+ *   models/EliMRec.py:261-270),  S_out[m][r] = O_inst[r, 64(m+1) : 64(m+2)] @ Ws[m]^T + bs[m]  (models/EliMRec.py:146-151).
+ * F = 64 * n_tables; every pointer 16-byte aligned. */
+int elimrec_inst_forward(int B, int n_tables, int F, const float* O_inst, const float* Wu, const float* Wi,
+                         const float* const* Ws_host, const float* bu, const float* bi, const float* const* bs_host,
+                         float* F_out, float* const* S_out_host, elimrec_stream_t stream);
 /* The same in two independent parts, so that the weight gradients (part 2: they only feed Adam) can run on another
  * stream while d O[inst] (part 1) seeds the backward propagation.  part 3 = both, in this order. */
 int elimrec_inst_backward_part(int part, int B, int n_tables, int F, const float* inst_grad, const float* O_inst,

@@ -293,6 +293,14 @@ def fuse_heads_x3(O_rows, Wf_hi, Wf_lo, bf, Ws_hi, Ws_lo, bs, F_out, S_out, tag=
         S_out[m].copy_(O_rows[:, 64 * (m + 1):64 * (m + 2)] @ (Ws_hi[m] + Ws_lo[m]).t() + bs[m])
 
 
+def inst_forward(B, nt, F, O_inst, Wu, Wi, Ws, bu, bi, bs, F_out, S_out):
+    _log("inst_forward")
+    F_out[:B] = O_inst[:B] @ Wu.t() + bu
+    F_out[B:3 * B] = O_inst[B:3 * B] @ Wi.t() + bi
+    for m in range(nt - 1):
+        S_out[m][:3 * B] = O_inst[:3 * B, 64 * (m + 1):64 * (m + 2)] @ Ws[m].t() + bs[m]
+
+
 def fuse_heads_x3_all(U, I, O, Wu, bu, Wi, bi, Ws_hi, Ws_lo, bs, F_out, S_out, tag="fuse_heads_x3_all"):
     fuse_heads_x3(O[:U], Wu[0], Wu[1], bu, Ws_hi, Ws_lo, bs, F_out[:U], [s[:U] for s in S_out], tag)
     fuse_heads_x3(O[U:U + I], Wi[0], Wi[1], bi, Ws_hi, Ws_lo, bs, F_out[U:U + I], [s[U:U + I] for s in S_out], tag)

@@ -677,6 +677,32 @@ def test_wgrad_multi_matches_fp64(dev):
         assert all(torch.equal(a, b) for a, b in zip(first, outs))
 
 
+@pytest.mark.parametrize("B,n_heads", [(2048, 3), (77, 3), (500, 2), (33, 0)])
+def test_inst_forward_matches_fp64(dev, B, n_heads):
+    """elimrec_inst_forward: fusion Linear (users / items take different weights) + heads on the 3B instance rows, exact
+    fp32, against fp64 and deterministic; row counts that are not multiples of the 16-row CTA tile."""
+    from elimrec_b200 import ops
+    g = torch.Generator().manual_seed(B)
+    nt = 1 + n_heads
+    Fw = 64 * nt
+    O = torch.randn(3 * B, Fw, generator=g).to(dev)
+    Wu, Wi = (torch.randn(64, Fw, generator=g) * 0.1).to(dev), (torch.randn(64, Fw, generator=g) * 0.1).to(dev)
+    bu, bi = torch.randn(64, generator=g).to(dev), torch.randn(64, generator=g).to(dev)
+    Ws = [(torch.randn(64, 64, generator=g) * 0.1).to(dev) for _ in range(n_heads)]
+    bs = [torch.randn(64, generator=g).to(dev) for _ in range(n_heads)]
+    Fo = torch.full((3 * B, 64), float("nan"), device=dev)
+    So = [torch.full((3 * B, 64), float("nan"), device=dev) for _ in range(n_heads)]
+    ops.inst_forward(B, nt, Fw, O, Wu, Wi, Ws, bu, bi, bs, Fo, So)
+    Od = O.double()
+    want = torch.cat([Od[:B] @ Wu.double().t() + bu.double(), Od[B:] @ Wi.double().t() + bi.double()])
+    assert rel_err(Fo, want) < 1e-6
+    for m in range(n_heads):
+        assert rel_err(So[m], Od[:, 64 * (m + 1):64 * (m + 2)] @ Ws[m].double().t() + bs[m].double()) < 1e-6
+    first = Fo.clone()
+    ops.inst_forward(B, nt, Fw, O, Wu, Wi, Ws, bu, bi, bs, Fo, So)
+    assert torch.equal(first, Fo)
+
+
 def test_wgrad_multi_x3_matches_fp64(dev):
     """elimrec_wgrad_multi_x3 (tcgen05 3xTF32, MN-major operands split hi / lo in shared memory, bias sums through an all-ones
     tile): the same problem family as the exact kernel - row ranges that are not multiples of the 32-row stage, column blocks,
