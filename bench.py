@@ -565,7 +565,7 @@ def main():
         del hu_, hp_, hn_, perm
 
     # ---- e2e arm: main.py:92-102 as written - host sampler, per-batch H2D, loss.item() every step ---------------------------
-    runner_h = model.make_graphed_step() if use_graph else None
+    runner_h = model.make_graphed_step(host_loss=True) if use_graph else None      # loss lands in pinned memory inside the graph
     steps_per_epoch = len(sampler_host)
 
     def run_epochs(sampler, n_epochs):

@@ -1010,15 +1010,21 @@ class EliMRec(LinearSchedule, BasicModel):
         step must leave unchanged"""
         return []
 
-    def make_graphed_step(self, batch_size=None, device_sampler=None):
+    def make_graphed_step(self, batch_size=None, device_sampler=None, host_loss=False):
         """The whole training step as a CUDA graph.  ``device_sampler`` (a ``PairwiseSamplerV2``): the graph starts with the
         Philox batch sampler reading its position from the optimizer's device step counter, so ``runner()`` with no
-        arguments draws a new batch and trains on it - sampling + forward + backward + Adam in one replay."""
+        arguments draws a new batch and trains on it - sampling + forward + backward + Adam in one replay.
+        ``host_loss``: the graph ends with the copy of the loss into pinned host memory and ``runner(...)`` returns a host
+        scalar tensor AFTER synchronising the stream - for loops that read the loss every step anyway (main.py:102) this
+        replaces the separate device-to-host copy + sync of ``loss.item()``."""
         B = int(batch_size or self.config["batch_size"])
         if self._adam is None:
             self.make_optimizer()
         dev = self.device_
-        su, sp_, sn = (torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3))
+        s3 = torch.zeros(3, B, dtype=torch.int64, device=dev)      # one buffer: a packed host batch arrives in ONE copy
+        su, sp_, sn = s3[0], s3[1], s3[2]
+        s3_flat = s3.view(-1)
+        loss_host = torch.zeros((), dtype=torch.float32).pin_memory() if host_loss else None
         if device_sampler is not None:
             device_sampler.ensure_device(dev)
         model = self
@@ -1061,6 +1067,8 @@ class EliMRec(LinearSchedule, BasicModel):
             with torch.cuda.graph(graph):
                 draw()
                 loss = self.train_step(su, sp_, sn)
+                if host_loss:
+                    loss_host.copy_(loss.reshape(()), non_blocking=True)
             graphs = (graph,)
         elif single:
             # EXPERIMENTAL (dp_single_graph=True, not yet run on hardware - DESIGN.md section 8 item 1): the same schedule with
@@ -1120,8 +1128,16 @@ class EliMRec(LinearSchedule, BasicModel):
                     if device_sampler is not None:
                         raise ElimrecError("this runner samples its own batches; call it without arguments")
                     if all(torch.is_tensor(x) and x.dtype == torch.int64 and x.numel() == B for x in (users, pos, neg)):
-                        # (pinned) host or device int64 tensors: straight into the graph's static inputs, no temporaries
-                        su.copy_(users, non_blocking=True); sp_.copy_(pos, non_blocking=True); sn.copy_(neg, non_blocking=True)
+                        # (pinned) host or device int64 tensors: straight into the graph's static inputs, no temporaries -
+                        # and in ONE copy when the three are adjacent slices of one buffer (PairwiseSamplerV2 packs its
+                        # pinned epochs [batch][users | pos | neg] for exactly this)
+                        pu = users.data_ptr()
+                        if (pos.data_ptr() == pu + 8 * B and neg.data_ptr() == pu + 16 * B and users.is_contiguous()
+                                and pos.is_contiguous() and neg.is_contiguous()
+                                and users.untyped_storage().data_ptr() == neg.untyped_storage().data_ptr()):
+                            s3_flat.copy_(users.as_strided((3 * B,), (1,)), non_blocking=True)
+                        else:
+                            su.copy_(users, non_blocking=True); sp_.copy_(pos, non_blocking=True); sn.copy_(neg, non_blocking=True)
                     else:
                         u, p, n = model._triples(users, pos, neg)
                         su.copy_(u, non_blocking=True); sp_.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
@@ -1143,6 +1159,9 @@ class EliMRec(LinearSchedule, BasicModel):
                 model._tables_version = getattr(model, "_tables_version", 0) + 1
                 if model.lazy_tables:
                     model._tables_pending = True
+                if host_loss and not dp:
+                    torch.cuda.current_stream().synchronize()
+                    return loss_host
                 return loss
 
         return _Runner()

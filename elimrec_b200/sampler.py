@@ -113,13 +113,18 @@ class PairwiseSamplerV2:
         total = u.size
         perm = np.random.permutation(total) if self.shuffle else None
         if self.pin:
-            out = [torch.empty(total, dtype=torch.int64).pin_memory() for _ in range(3)]
-            for src, dst in zip((u, p, n), out):
-                if perm is None:
-                    dst.numpy()[:] = src
-                else:
-                    np.take(src, perm, out=dst.numpy())
-            return tuple(out), total
+            # pinned and PACKED: full batch b is [users | pos | neg] in 3 * batch_size consecutive words, so that a consumer can
+            # move it to the device in one copy (EliMRec.make_graphed_step does); the short last batch follows, same layout
+            bs = self.batch_size
+            nb, tail = divmod(total, bs)
+            buf = torch.empty(3 * total, dtype=torch.int64).pin_memory()
+            full = buf[:3 * nb * bs].view(nb, 3, bs).numpy()
+            rest = buf[3 * nb * bs:].view(3, tail).numpy()
+            for j, src in enumerate((u, p, n)):
+                src = src if perm is None else src[perm]
+                full[:, j, :] = src[:nb * bs].reshape(nb, bs)
+                rest[j, :] = src[nb * bs:]
+            return ("packed", buf, None), total
         if perm is not None:
             u, p, n = u[perm], p[perm], n[perm]
         return (u, p, n), total
@@ -154,6 +159,16 @@ class PairwiseSamplerV2:
             u, p, n = self.sample_epoch_device()
             total = u.numel()  # i.i.d. draws: already in random order, no shuffle pass needed
         self.epoch += 1
+        if isinstance(u, str):      # packed pinned epoch (see _host_epoch): views, no copies
+            buf = p
+            nb, tail = divmod(total, bs)
+            for b in range(nb):
+                blk = buf[3 * b * bs:3 * (b + 1) * bs]
+                yield blk[:bs], blk[bs:2 * bs], blk[2 * bs:]
+            if tail and not self.drop_last:
+                blk = buf[3 * nb * bs:]
+                yield blk[:tail], blk[tail:2 * tail], blk[2 * tail:]
+            return
         for b in range(0, total, bs):
             if self.drop_last and b + bs > total:
                 break

@@ -258,6 +258,39 @@ def test_linear_schedule_matches_reference_schedule(golden):
         np.testing.assert_allclose(eager.evaluate()[0], lin.evaluate()[0], atol=5e-5)
 
 
+def test_graphed_step_packed_batches_and_host_loss(golden):
+    """The pinned epochs of PairwiseSamplerV2 are packed [batch][users | pos | neg]: the graph runner moves such a batch in ONE
+    host-to-device copy, and with host_loss=True hands back the loss from pinned memory after synchronising - the same
+    losses and parameters, bit for bit, as three separate copies + a device loss."""
+    from elimrec_b200.sampler import PairwiseSamplerV2
+    a, _ = _golden_model(golden)
+    b, _ = _golden_model(golden)
+    for m in (a, b):
+        m.make_optimizer(lr=1e-3, weight_decay=1e-4)
+    ds = golden_dataset(golden)
+    B = 64
+    np.random.seed(3)
+    sm = PairwiseSamplerV2(ds, batch_size=B, mode="compat", pin=True)
+    batches = [t for t in sm]
+    full = [t for t in batches if t[0].numel() == B]
+    assert len(full) >= 3 and all(t[0].is_pinned() for t in full)
+    u0, p0, n0 = full[0]
+    assert p0.data_ptr() == u0.data_ptr() + 8 * B and n0.data_ptr() == u0.data_ptr() + 16 * B
+    ra = a.make_graphed_step(B, host_loss=True)
+    rb = b.make_graphed_step(B)
+    for u, p_, n in full[:4]:
+        la = ra(u, p_, n)
+        assert la.device.type == "cpu"
+        lb = rb(u.clone(), p_.clone(), n.clone())
+        assert float(la) == float(lb)
+        assert all(torch.equal(x, y) for x, y in zip(ra.triples, rb.triples))
+    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(v, w), k
+    # every sampled triple is there exactly once, in epoch order (the short last batch included)
+    total = sum(t[0].numel() for t in batches)
+    assert total == sm.num_trainings and batches[-1][0].numel() == (total % B or B)
+
+
 @pytest.mark.parametrize("linear", [True, False])
 def test_graphed_train_eval_train_eval(golden, linear):
     """CUDA-graph runner: every replay is a new training forward, so tables cached for evaluation (all_users / all_items /
