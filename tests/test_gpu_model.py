@@ -261,7 +261,7 @@ def test_linear_schedule_matches_reference_schedule(golden):
 def test_graphed_step_packed_batches_and_host_loss(golden):
     """The pinned epochs of PairwiseSamplerV2 are packed [batch][users | pos | neg]: the graph runner moves such a batch in ONE
     host-to-device copy, and with host_loss=True hands back the loss from pinned memory after synchronising - the same
-    losses and parameters, bit for bit, as three separate copies + a device loss."""
+    batches, losses and parameters as three separate copies + a device loss."""
     from elimrec_b200.sampler import PairwiseSamplerV2
     a, _ = _golden_model(golden)
     b, _ = _golden_model(golden)
@@ -282,10 +282,11 @@ def test_graphed_step_packed_batches_and_host_loss(golden):
         la = ra(u, p_, n)
         assert la.device.type == "cpu"
         lb = rb(u.clone(), p_.clone(), n.clone())
-        assert float(la) == float(lb)
+        assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(lb))
         assert all(torch.equal(x, y) for x, y in zip(ra.triples, rb.triples))
+    # (not bit-equal: the backward seeds of a node sampled three or more times in one batch are summed with float atomics)
     for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
-        assert torch.equal(v, w), k
+        assert rel_err(v, w) < 1e-6, k
     # every sampled triple is there exactly once, in epoch order (the short last batch included)
     total = sum(t[0].numel() for t in batches)
     assert total == sm.num_trainings and batches[-1][0].numel() == (total % B or B)
