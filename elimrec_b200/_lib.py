@@ -113,8 +113,10 @@ _SIGS = {
     "elimrec_fuse_heads_x3": [i64, i32, vp, i64, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(vp), vp],
     "elimrec_linear_x3_fwd": [i64, i64, vp, i64, vp, vp, vp, vp, i64, vp],
     "elimrec_bpr_forward_backward": [i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],
+    "elimrec_bpr_forward_backward_part": [i32, i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "elimrec_inst_backward": [i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, vp, C.POINTER(vp),
                               C.POINTER(vp), vp, vp],
+    "elimrec_inst_dout_seed": [i32, i32, i32, vp, vp, vp, vp, C.POINTER(vp), vp, vp, i32, f32, vp, vp, i64, vp],
     "elimrec_inst_forward": [i32, i32, i32, vp, vp, vp, C.POINTER(vp), vp, vp, C.POINTER(vp), vp, C.POINTER(vp), vp],
     "elimrec_inst_backward_part": [i32, i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, vp, C.POINTER(vp),
                               C.POINTER(vp), vp, vp],
@@ -190,7 +192,8 @@ def lib():
 # kernels launched through the C-ABI (bench.py reports `gpu_launches` from this) and an optional
 # per-family CUDA-event profile (bench.py --profile-kernels; events sit on the launching stream)
 CALLS = {"n": 0, "launches": 0}
-_LAUNCHES = {"elimrec_rank_tc": 2, "elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2, "elimrec_inst_backward": 3, "elimrec_inst_backward_part": 0}
+_LAUNCHES = {"elimrec_rank_tc": 2, "elimrec_colsum": 2, "elimrec_bpr_forward_backward": 2, "elimrec_metric_rows": 2, "elimrec_inst_backward": 3, "elimrec_inst_backward_part": 0,
+             "elimrec_bpr_forward_backward_part": 0}
 PROFILE = {"on": False, "events": []}
 
 

@@ -137,9 +137,20 @@ struct InstW {
 
 constexpr int IRB = 16;  // rows per CTA in inst_dO
 
+// backward seeds of the linear schedule fused into inst_dO (what elimrec_lin_seed2 does in a launch of its own):
+//   GA[rows[j]] += scale * (sum of all 64-column blocks of dO[j]),  GB[rows[j]] += scale * dO[j, 0:64]
+struct InstSeed {
+    const int* rows;    // NULL: no seeds
+    float* GA;
+    float* GB;
+    long long ldg;
+    float scale;
+    int n_mod;
+};
+
 __global__ void __launch_bounds__(256)
 inst_dO_kernel(int B, int nt, int F, InstW w, const float* __restrict__ ig, const float* __restrict__ gscale,
-               float* __restrict__ dO) {
+               float* __restrict__ dO, InstSeed sd) {
     __shared__ __align__(16) float gs[IRB][64 * (1 + ELIMREC_MAX_MODS)];
     const int nbu = (B + IRB - 1) / IRB;
     const bool user = (int)blockIdx.x < nbu;
@@ -184,6 +195,24 @@ inst_dO_kernel(int B, int nt, int F, InstW w, const float* __restrict__ ig, cons
 #pragma unroll
         for (int r = 0; r < IRB; ++r)
             if (r0 + r < r1) dO[(long long)(r0 + r) * F + c] = g * acc[r];
+        if (sd.rows != nullptr) {      // the tile goes back through shared memory for the cross-block sums of the seeds
+            __syncthreads();           // (F = blockDim.x columns: every thread is here exactly once; gs is no longer read)
+#pragma unroll
+            for (int r = 0; r < IRB; ++r) gs[r][c] = g * acc[r];
+        }
+    }
+    if (sd.rows != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < IRB * 64; i += blockDim.x) {
+            const int r = i >> 6, col = i & 63;
+            if (r0 + r >= r1) continue;
+            const float b = gs[r][col];
+            float a = b;
+            for (int m = 0; m < sd.n_mod; ++m) a += gs[r][64 * (m + 1) + col];
+            const long long node = __ldg(sd.rows + r0 + r);
+            atomicAdd(sd.GA + node * sd.ldg + col, sd.scale * a);
+            atomicAdd(sd.GB + node * sd.ldg + col, sd.scale * b);
+        }
     }
 }
 
@@ -401,6 +430,16 @@ ELIMREC_API int elimrec_bpr_forward_backward(int B, int n_tables, const float* c
                                              const int64_t* neg, int32_t num_users, float* loss_out,
                                              int32_t* inst_rows, float* inst_grad, float* workspace,
                                              elimrec_stream_t stream) {
+    return elimrec_bpr_forward_backward_part(3, B, n_tables, tables_host, weight_host, users, pos, neg, num_users, loss_out,
+                                             inst_rows, inst_grad, workspace, stream);
+}
+
+ELIMREC_API int elimrec_bpr_forward_backward_part(int part, int B, int n_tables, const float* const* tables_host,
+                                                  const float* weight_host, const int64_t* users, const int64_t* pos,
+                                                  const int64_t* neg, int32_t num_users, float* loss_out,
+                                                  int32_t* inst_rows, float* inst_grad, float* workspace,
+                                                  elimrec_stream_t stream) {
+    ER_CHECK_ARG(part >= 1 && part <= 3, "part is 1 (terms + instance gradients), 2 (loss reduction) or 3 (both)");
     ER_CHECK_ARG(B > 0, "empty batch");
     ER_CHECK_ARG(n_tables >= 1 && n_tables <= 1 + ELIMREC_MAX_MODS, "n_tables out of range");
     BprTables tb{};
@@ -410,12 +449,16 @@ ELIMREC_API int elimrec_bpr_forward_backward(int B, int n_tables, const float* c
     }
     cudaStream_t st = er_stream(stream);
     const long long warps = (long long)B * n_tables;
-    bpr_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(B, n_tables, tb, (const long long*)users, (const long long*)pos,
-                                                             (const long long*)neg, num_users, inst_rows, inst_grad,
-                                                             workspace);
-    ER_LAUNCH_CHECK();
-    bpr_loss_reduce_kernel<<<1, 256, 0, st>>>(B, n_tables, tb, workspace, loss_out);
-    ER_LAUNCH_CHECK();
+    if (part & 1) {
+        bpr_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(B, n_tables, tb, (const long long*)users, (const long long*)pos,
+                                                                 (const long long*)neg, num_users, inst_rows, inst_grad,
+                                                                 workspace);
+        ER_LAUNCH_CHECK();
+    }
+    if (part & 2) {
+        bpr_loss_reduce_kernel<<<1, 256, 0, st>>>(B, n_tables, tb, workspace, loss_out);
+        ER_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -475,7 +518,7 @@ ELIMREC_API int elimrec_inst_backward_part(int part, int B, int n_tables, int F,
     cudaStream_t st = er_stream(stream);
     if (part & 1) {
         const int nb = (B + IRB - 1) / IRB + (2 * B + IRB - 1) / IRB;
-        inst_dO_kernel<<<nb, 256, 0, st>>>(B, n_tables, F, w, inst_grad, gscale_dev, dO_inst);
+        inst_dO_kernel<<<nb, 256, 0, st>>>(B, n_tables, F, w, inst_grad, gscale_dev, dO_inst, InstSeed{});
         ER_LAUNCH_CHECK();
     }
     if (!(part & 2)) return 0;
@@ -529,6 +572,23 @@ ELIMREC_API int elimrec_inst_forward(int B, int n_tables, int F, const float* O_
     }
     const int nb = (B + IRB - 1) / IRB + (2 * B + IRB - 1) / IRB;
     inst_fwd_kernel<<<nb, 64 * n_tables, 0, er_stream(stream)>>>(B, n_tables, F, w, O_inst);
+    ER_LAUNCH_CHECK();
+    return 0;
+}
+
+ELIMREC_API int elimrec_inst_dout_seed(int B, int n_tables, int F, const float* inst_grad, const float* gscale_dev, const float* Wu,
+                                     const float* Wi, const float* const* Ws_host, float* dO_inst, const int32_t* rows, int n_mod,
+                                     float scale, float* GA, float* GB, int64_t ldg, elimrec_stream_t stream) {
+    ER_CHECK_ARG(B >= 0 && n_tables >= 1 && n_tables <= 1 + ELIMREC_MAX_MODS && F == 64 * n_tables, "F must be 64 * n_tables");
+    ER_CHECK_ARG(F == 256, "the fused seed epilogue needs one thread per column (F = 256: three modalities)");
+    ER_CHECK_ARG(n_mod >= 0 && n_mod <= n_tables - 1 && rows != nullptr && GA != nullptr && GB != nullptr, "bad seed arguments");
+    if (B == 0) return 0;
+    InstW w{};
+    w.Wu = Wu; w.Wi = Wi;
+    for (int m = 0; m < n_tables - 1; ++m) w.Ws[m] = Ws_host[m];
+    const int nb = (B + IRB - 1) / IRB + (2 * B + IRB - 1) / IRB;
+    inst_dO_kernel<<<nb, 256, 0, er_stream(stream)>>>(B, n_tables, F, w, inst_grad, gscale_dev, dO_inst,
+                                                       InstSeed{rows, GA, GB, (long long)ldg, scale, n_mod});
     ER_LAUNCH_CHECK();
     return 0;
 }

@@ -327,7 +327,16 @@ class LinearSchedule:
             sw = ops.fork_side(5)
             with torch.cuda.stream(sw):
                 weights(0)
-        ib(1)
+        # d O[inst] and the backward seeds (two vectors per instance row, see below) in one launch when the shapes allow
+        fused_seed = bool(_cfg(self.config, "fused_seed", True)) and Fw == 256
+        if fused_seed:
+            if not ws.pop("seed_zeroed", False):
+                ops.zero_rows(rows, 0, U + I, 0, ws["GA"], D)
+                ops.zero_rows(rows, 0, U + I, 0, ws["GB"], D)
+            ops.inst_dO_seed(B, nt, Fw, ig, gscale, Wu, Wi, [P[f"s_dense_{m}.weight"].detach() for m in self.mods], dOin, rows,
+                             len(self.mods), 1.0 / (L + 1), ws["GA"], ws["GB"])
+        else:
+            ib(1)
         pending = None
         if overlap:
             sw = ops.fork_side(5)      # the same side stream, now also behind d O[inst]
@@ -348,10 +357,11 @@ class LinearSchedule:
         # additive epilogue of the propagation launch.
         inv, nm = 1.0 / (L + 1), len(self.mods)
         GA, GB = ws["GA"], ws["GB"]
-        if not ws.pop("seed_zeroed", False):      # normally done by the forward, off the critical path
-            ops.zero_rows(rows, 0, U + I, 0, GA, D)
-            ops.zero_rows(rows, 0, U + I, 0, GB, D)
-        ops.lin_seed2(rows, dOin, nm, inv, GA, GB)
+        if not fused_seed:
+            if not ws.pop("seed_zeroed", False):      # normally done by the forward, off the critical path
+                ops.zero_rows(rows, 0, U + I, 0, GA, D)
+                ops.zero_rows(rows, 0, U + I, 0, GB, D)
+            ops.lin_seed2(rows, dOin, nm, inv, GA, GB)
         mask, need2 = ws["mask"], ws["need2"]
         g_u = lambda k: (GA if k % 2 == 0 else GB)[:U]
         g_i = lambda k: (GA if k % 2 == 1 else GB)[U:]

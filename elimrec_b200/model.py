@@ -565,8 +565,18 @@ class EliMRec(LinearSchedule, BasicModel):
                     self._fuse_heads_rows(ws, ws["O_inst"][:B], ws["F_c"][:B], [s_[:B] for s_ in ws["S_c"]], "u")
                 self._fuse_heads_rows(ws, ws["O_inst"][B:], ws["F_c"][B:], [s_[B:] for s_ in ws["S_c"]], "i")
                 ops.join_side(su_)
-            ops.bpr([ws["F_c"]] + ws["S_c"], weights, ws["c_users"], ws["c_pos"], ws["c_neg"], B, ws["loss"], ws["inst_dummy"],
-                    ws["inst_grad"], ws["terms"])
+            bpr_args = ([ws["F_c"]] + ws["S_c"], weights, ws["c_users"], ws["c_pos"], ws["c_neg"], B, ws["loss"], ws["inst_dummy"],
+                        ws["inst_grad"], ws["terms"])
+            if getattr(self, "_defer_loss", False):
+                # train_step: nothing in the backward reads the loss scalar - its reduction leaves the critical path (joined
+                # before train_step returns)
+                ops.bpr(*bpr_args, part=1)
+                sl = ops.fork_side(9)
+                with torch.cuda.stream(sl):
+                    ops.bpr(*bpr_args, part=2)
+                self._loss_side = sl
+            else:
+                ops.bpr(*bpr_args)
             self._tables_pending = True
         return ws["loss"][0]
 
@@ -967,10 +977,12 @@ class EliMRec(LinearSchedule, BasicModel):
             # ... and, on one GPU, Adam on the two embedding tables is the epilogue of the last backward hop (fused_adam=False
             # keeps the separate optimizer pass; data-parallel replicas must average the gradients first)
             fuse = self._fuse_adam_now = bool(self.linear and not getattr(self, "_dp", False) and _cfg(self.config, "fused_adam", True))
+            self._defer_loss = bool(self.linear and self.lazy_tables and not getattr(self, "_dp", False))
+            self._loss_side = None
             try:
                 loss = self._forward(users, pos, neg)
             finally:
-                self._tick_early = self._fuse_adam_now = False
+                self._tick_early = self._fuse_adam_now = self._defer_loss = False
             if fuse:      # moments of the tables must exist before the backward hands them to the kernel
                 P = self._params()
                 for n in ("embedding_user.weight", "embedding_item.weight"):
@@ -979,6 +991,9 @@ class EliMRec(LinearSchedule, BasicModel):
             if getattr(self, "_dp", False):
                 grads = self._allreduce_grads(grads)
             self._adam.apply(grads, tick=not early)
+            if self._loss_side is not None:
+                ops.join_side(self._loss_side)
+                self._loss_side = None
         return loss
 
     # -- data-parallel replicas: each rank draws its own triples, gradients are averaged (NCCL) ----

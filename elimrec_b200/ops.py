@@ -339,13 +339,23 @@ def colsum_ws_floats(M, N):
     return int(_lib.lib().elimrec_colsum_workspace_floats(M, N))
 
 
-def bpr(tables, weights, users, pos, neg, num_users, loss_out, inst_rows, inst_grad, ws):
+def bpr(tables, weights, users, pos, neg, num_users, loss_out, inst_rows, inst_grad, ws, part=3):
+    """part 1 = per-triple terms + instance gradients, part 2 = their fixed-order reduction to the loss scalar, 3 = both"""
     n = len(tables)
     tp = (C.c_void_p * n)(*[ptr(t, F32) for t in tables])
     wp = (C.c_float * n)(*weights)
-    call("elimrec_bpr_forward_backward", users.numel(), n, tp, wp, ptr(users, torch.int64), ptr(pos, torch.int64),
+    call("elimrec_bpr_forward_backward_part", part, users.numel(), n, tp, wp, ptr(users, torch.int64), ptr(pos, torch.int64),
          ptr(neg, torch.int64), num_users, ptr(loss_out, F32), ptr(inst_rows, torch.int32), ptr(inst_grad, F32),
-         ptr(ws, F32), stream())
+         ptr(ws, F32), stream(), launches={1: 1, 2: 1, 3: 2}[part], tag="elimrec_bpr_forward_backward")
+
+
+def inst_dO_seed(B, nt, F, inst_grad, gscale, Wu, Wi, Ws, dO_inst, rows, n_mod, scale, GA, GB):
+    """d O[inst] with the linear schedule's backward seeds in its epilogue (elimrec_inst_dout_seed): inst_backward(part=1)
+    followed by lin_seed2, in one launch"""
+    wsp = (C.c_void_p * max(nt - 1, 1))(*[ptr(t, F32) for t in Ws])
+    call("elimrec_inst_dout_seed", B, nt, F, ptr(inst_grad, F32), ptr(gscale, F32, True), ptr(Wu, F32), ptr(Wi, F32), wsp,
+         ptr(dO_inst, F32), ptr(rows, torch.int32), n_mod, scale, ptr(GA, F32), ptr(GB, F32), GA.stride(0), stream(), launches=1,
+         tag="inst_dO_seed")
 
 
 def inst_backward_ws_floats(B, nt, F):

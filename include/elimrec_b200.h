@@ -316,6 +316,13 @@ int elimrec_bpr_forward_backward(int B, int n_tables, const float* const* tables
                                  float* loss_out, int32_t* inst_rows, float* inst_grad, float* workspace,
                                  elimrec_stream_t stream);
 
+/* The same in parts: 1 = per-triple terms + instance gradients (what the backward waits for), 2 = the fixed-order reduction of
+ * the terms to the loss scalar (nothing but the caller's read of the loss waits for it), 3 = both. */
+int elimrec_bpr_forward_backward_part(int part, int B, int n_tables, const float* const* tables_host, const float* weight_host,
+                                      const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t num_users,
+                                      float* loss_out, int32_t* inst_rows, float* inst_grad, float* workspace,
+                                      elimrec_stream_t stream);
+
 /* Backward of embedding_{user,item}_after_GCN and s_dense_* (models/EliMRec.py:261-270,146-151) restricted to
  * the 3B instance rows, where alone their gradient is non-zero:
  *   dO_inst [3B x F]   = g * (dF @ W_{u|i} + per-block dS_m @ Ws_m)        (rows < B use Wu, the rest Wi)
@@ -326,6 +333,13 @@ int elimrec_inst_backward(int B, int n_tables, int F, const float* inst_grad, co
                           const float* gscale_dev /* may be NULL */, const float* Wu, const float* Wi,
                           const float* const* Ws_host, float* dO_inst, float* dWu, float* dWi, float* dbu, float* dbi,
                           float* const* dWs_host, float* const* dbs_host, float* workspace, elimrec_stream_t stream);
+/* d O[inst] (part 1 of elimrec_inst_backward) with the backward seeds of the linear schedule in its epilogue - what
+ * elimrec_lin_seed2 does in a launch of its own: GA[rows[j]] += scale * (sum of the 1 + n_mod 64-column blocks of dO_inst[j]),
+ * GB[rows[j]] += scale * dO_inst[j, 0:64]  (float atomics; rows = the 3B instance nodes).  F = 256 only. */
+int elimrec_inst_dout_seed(int B, int n_tables, int F, const float* inst_grad, const float* gscale_dev /* may be NULL */,
+                         const float* Wu, const float* Wi, const float* const* Ws_host, float* dO_inst, const int32_t* rows,
+                         int n_mod, float scale, float* GA, float* GB, int64_t ldg, elimrec_stream_t stream);
+
 /* Forward of the same two layers on the 3B instance rows of a row-sparse step, exact fp32, one launch (csrc/bpr.cu):
  *   F_out[r] = O_inst[r, 0:F] @ W_{u|i}^T + b_{u|i}  (rows 0..B-1 take the user fusion Linear, B..3B-1 the item one;
  *   models/EliMRec.py:261-270),  S_out[m][r] = O_inst[r, 64(m+1) : 64(m+2)] @ Ws[m]^T + bs[m]  (models/EliMRec.py:146-151).

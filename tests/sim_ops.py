@@ -314,7 +314,14 @@ def colsum(M, N, A, ld, out, ws, accumulate=False, scale=None, a_off=0):
     out[:N] = out[:N] + s if accumulate else s
 
 
-def bpr(tables, weights, users, pos, neg, num_users, loss_out, inst_rows_out, inst_grad, terms):
+def inst_dO_seed(B, nt, F, inst_grad, gscale, Wu, Wi, Ws, dO_inst, rows, n_mod, scale, GA, GB):
+    inst_backward(B, nt, F, inst_grad, None, gscale, Wu, Wi, Ws, dO_inst, None, None, None, None, None, None, None, part=1)
+    lin_seed2(rows, dO_inst, n_mod, scale, GA, GB)
+
+
+def bpr(tables, weights, users, pos, neg, num_users, loss_out, inst_rows_out, inst_grad, terms, part=3):
+    if part == 2:       # (the simulator computes the loss with the terms: nothing left to reduce)
+        return
     """1 + M normalised-cosine BPR losses (EliMRec.py:291-297) and their gradient w.r.t. the gathered rows."""
     _log("bpr")
     B = users.numel()

@@ -703,6 +703,45 @@ def test_inst_forward_matches_fp64(dev, B, n_heads):
     assert torch.equal(first, Fo)
 
 
+def test_inst_dO_seed_equals_two_launches(dev):
+    """elimrec_inst_dout_seed = elimrec_inst_backward_part(1) + elimrec_lin_seed2 in one launch: the same d O[inst] bit for bit,
+    the same seeds (float atomics: duplicates of a node may add in another order); bpr in two parts = bpr in one."""
+    from elimrec_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, nt, Fw, N = 300, 4, 256, 500
+    ig = torch.randn(3 * B, Fw, generator=g).to(dev) * 1e-3
+    Wu, Wi = (torch.randn(64, Fw, generator=g) * 0.1).to(dev), (torch.randn(64, Fw, generator=g) * 0.1).to(dev)
+    Ws = [(torch.randn(64, 64, generator=g) * 0.1).to(dev) for _ in range(3)]
+    rows = torch.randint(0, N, (3 * B,), generator=g).to(torch.int32).to(dev)       # plenty of duplicates
+    gs = torch.tensor([0.7], device=dev)
+    dO1, dO2 = torch.empty(3 * B, Fw, device=dev), torch.empty(3 * B, Fw, device=dev)
+    GA1, GB1, GA2, GB2 = (torch.zeros(N, 64, device=dev) for _ in range(4))
+    dummy = torch.empty(1, device=dev)
+    wsz = torch.empty(ops.inst_backward_ws_floats(B, nt, Fw), device=dev)
+    ops.inst_backward(B, nt, Fw, ig, dO1, gs, Wu, Wi, Ws, dO1, dummy, dummy, dummy, dummy, [dummy] * 3, [dummy] * 3, wsz, part=1)
+    ops.lin_seed2(rows, dO1, 3, 0.25, GA1, GB1)
+    ops.inst_dO_seed(B, nt, Fw, ig, gs, Wu, Wi, Ws, dO2, rows, 3, 0.25, GA2, GB2)
+    assert torch.equal(dO1, dO2)
+    assert rel_err(GA2, GA1) < 1e-6 and rel_err(GB2, GB1) < 1e-6 and float(GA1.abs().max()) > 0
+    # reference of the seeds in fp64
+    want = torch.zeros(N, 64, dtype=torch.float64, device=dev)
+    want.index_add_(0, rows.long(), 0.25 * dO1.double().reshape(3 * B, 4, 64).sum(1))
+    assert rel_err(GA2, want) < 1e-6
+    # bpr: parts 1 + 2 = 3
+    T = [torch.randn(N, 64, generator=g).to(dev) for _ in range(4)]
+    u = torch.randint(0, 200, (B,), generator=g).to(dev)
+    p_ = torch.randint(0, 300, (B,), generator=g).to(dev)
+    n = torch.randint(0, 300, (B,), generator=g).to(dev)
+    outs = []
+    for parts in ((3,), (1, 2)):
+        loss, ir = torch.zeros(1, device=dev), torch.zeros(3 * B, dtype=torch.int32, device=dev)
+        igo, terms = torch.zeros(3 * B, Fw, device=dev), torch.zeros(4 * B, device=dev)
+        for part in parts:
+            ops.bpr(T, [1.0, 0.5, 0.5, 0.5], u, p_, n, 200, loss, ir, igo, terms, part=part)
+        outs.append((loss, ir, igo))
+    assert all(torch.equal(a, b) for a, b in zip(*outs)) and float(outs[0][0]) > 0
+
+
 def test_wgrad_multi_x3_matches_fp64(dev):
     """elimrec_wgrad_multi_x3 (tcgen05 3xTF32, MN-major operands split hi / lo in shared memory, bias sums through an all-ones
     tile): the same problem family as the exact kernel - row ranges that are not multiples of the 32-row stage, column blocks,
