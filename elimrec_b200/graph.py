@@ -38,7 +38,19 @@ if os.environ.get("ELIMREC_SEG"):   # tuning sweeps: "seg_len,heavy_seg_len,bala
 
 
 SEG64_LEN = 64      # work items of the 64-wide pair kernel (csrc/spmm64.cu): rows of at most this many edges are one item, longer
-                    # rows are dealt evenly over ceil(deg / SEG64_LEN) items whose partial sums the last-arriving item adds up
+                    # rows are dealt evenly over ceil(deg / seg_len) items whose partial sums the last-arriving item adds up
+SEG64_LEN_DENSE = 128       # ... for a CSR half whose MEAN degree exceeds SEG64_DENSE_DEGREE (most of its rows would be split at 64:
+SEG64_DENSE_DEGREE = 32     # Movielens items 169, Kwai users 149): measured per dense launch 61.1 -> 56.1 us (Movielens shape),
+                            # 41.8 -> 39.3 us (Kwai); the Tiktok shape (means 17 / 8) stays at 64 (36.9 us; 39.7 at 128, 55.6 at 256)
+
+
+def seg64_len_for(indptr: np.ndarray, row_lo: int = 0, row_hi: int | None = None) -> int:
+    """segment length of a CSR half's work list (ELIMREC_SEG64_LEN overrides, for experiments)"""
+    if "ELIMREC_SEG64_LEN" in os.environ:
+        return int(os.environ["ELIMREC_SEG64_LEN"])
+    row_hi = indptr.size - 1 if row_hi is None else row_hi
+    n = max(1, row_hi - row_lo)
+    return SEG64_LEN_DENSE if (int(indptr[row_hi]) - int(indptr[row_lo])) / n > SEG64_DENSE_DEGREE else SEG64_LEN
 
 
 def build_segments64(indptr: np.ndarray, seg_len: int = SEG64_LEN, row_lo: int = 0, row_hi: int | None = None):
@@ -96,7 +108,8 @@ class CsrHalf:
         self.val = torch.from_numpy(self.vals_host).to(device)
         self.indptr = torch.from_numpy(self.indptr_host).to(device)
         # work list of the 64-wide pair kernel (its own split: 8-lane groups, no CTA padding)
-        it, hrow, n_hit = build_segments64(self.indptr_host, SEG64_LEN, row_lo, self.n_rows if row_hi is None else row_hi)
+        it, hrow, n_hit = build_segments64(self.indptr_host, seg64_len_for(self.indptr_host, row_lo, row_hi), row_lo,
+                                           self.n_rows if row_hi is None else row_hi)
         self.n_item64, self.n_split64 = int(it.shape[0]), int(n_hit)
         self.item64 = torch.from_numpy(it if it.size else np.zeros((1, 4), np.int32)).to(device)
         self.hrow64 = torch.from_numpy(hrow if hrow.size else np.zeros((1, 2), np.int32)).to(device)
