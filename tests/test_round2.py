@@ -171,3 +171,26 @@ def test_fused_adam_epilogue_matches_separate_pass(backend, golden):
     assert rel(fused.all_users, plain.all_users.detach().cpu().numpy()) < 1e-6
     assert rel(fused.all_items, plain.all_items.detach().cpu().numpy()) < 1e-6
     check_steps(build(golden_dataset(golden), golden_params(golden), name), golden, "")
+
+
+def test_work_list_segment_length_follows_the_mean_degree(monkeypatch):
+    """graph.py: a CSR half is cut into work items of 64 edges, 128 when its mean degree exceeds 32 (most rows would be split
+    at 64); every edge is in exactly one item either way and ELIMREC_SEG64_LEN overrides the choice."""
+    from elimrec_b200 import graph
+    monkeypatch.delenv("ELIMREC_SEG64_LEN", raising=False)
+    rng = np.random.default_rng(0)
+    for mean, want in ((8, 64), (150, 128)):
+        deg = rng.poisson(mean, size=400)
+        deg[:3] = (1000, 0, 65)
+        indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+        seg = graph.seg64_len_for(indptr)
+        assert seg == want
+        items, hrow, n_hit = graph.build_segments64(indptr, seg)
+        covered = np.zeros(indptr[-1], dtype=np.int32)
+        for r, b, e, h in items:
+            assert 0 <= e - b <= seg and indptr[r] <= b and e <= indptr[r + 1]      # (an empty row is an item too: it writes zeros)
+            covered[b:e] += 1
+        assert (covered == 1).all()
+        assert n_hit == int(hrow[:, 1].sum()) and (items[:n_hit, 3] >= 0).all() and (items[n_hit:, 3] < 0).all()
+    monkeypatch.setenv("ELIMREC_SEG64_LEN", "256")
+    assert graph.seg64_len_for(indptr) == 256
