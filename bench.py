@@ -601,6 +601,39 @@ def main():
         n_ser = run_epochs(sampler_se, e2e_epochs)
         sync_all()
         ser_s = time.perf_counter() - t0
+        # the same loop with the loss of step i read while step i+1 runs (make_graphed_step(host_loss="deferred")): same copies,
+        # same per-step result on the host, one step late - what the per-step launch + sync latency of main.py:102 costs
+        def_s = None
+        if use_graph and not (rowshard or colshard) and world == 1:
+            runner_d = model.make_graphed_step(host_loss="deferred")
+            sampler_pf2 = PairwiseSamplerV2(ds, batch_size=BATCH, mode="compat", prefetch=True, pin=True)
+            sampler_pf2.rng.seed(7)
+
+            def run_deferred(n_epochs):
+                n = 0
+                for _ in range(n_epochs):
+                    for hu, hp, hn in sampler_pf2:
+                        if hu.numel() != BATCH:
+                            runner_d.flush()
+                            float(model.train_step(hu, hp, hn))
+                        else:
+                            prev = runner_d(hu, hp, hn)
+                            if prev is not None:
+                                float(prev)
+                        n += int(hu.numel())
+                last = runner_d.flush()
+                if last is not None:
+                    float(last)
+                return n
+            run_deferred(1)
+            sync_all()
+            t0 = time.perf_counter()
+            n_def = run_deferred(e2e_epochs)
+            sync_all()
+            def_s = time.perf_counter() - t0
+            if sampler_pf2._next is not None:
+                sampler_pf2._next[0].join()
+            log(f"[bench] rank {rank}: e2e with the loss read one step late: {1e3 * def_s / (e2e_epochs * steps_per_epoch):.3f} ms/step")
         te = torch.tensor([e2e_s, ser_s], device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -771,6 +804,7 @@ def main():
                                       "libc stream) + numpy shuffle, whole epochs, inside the timed region"},
                 "e2e": None if args.no_e2e else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 4,
                         "steps": e2e_steps, "epochs": e2e_epochs, "serial_sampler_value": e2e_serial,
+                        "deferred_loss_value": (units * n_def / def_s) if def_s else None,
                         "note": "main.py:92-102 loop over whole epochs; value: next epoch sampled on a prefetch thread while this one "
                                 "trains; serial_sampler_value: each epoch sampled + shuffled before its first step (as the "
                                 "reference does), both inside the timed region"},

@@ -1031,7 +1031,10 @@ class EliMRec(LinearSchedule, BasicModel):
         arguments draws a new batch and trains on it - sampling + forward + backward + Adam in one replay.
         ``host_loss``: the graph ends with the copy of the loss into pinned host memory and ``runner(...)`` returns a host
         scalar tensor AFTER synchronising the stream - for loops that read the loss every step anyway (main.py:102) this
-        replaces the separate device-to-host copy + sync of ``loss.item()``."""
+        replaces the separate device-to-host copy + sync of ``loss.item()``.  ``host_loss="deferred"``: ``runner(...)`` launches
+        step i and returns the loss of step i-1 (``None`` on the first call; ``runner.flush()`` returns the last one): the host
+        then prepares and launches the next step while this one runs, instead of idling the GPU for the launch + sync latency
+        of every step."""
         B = int(batch_size or self.config["batch_size"])
         if self._adam is None:
             self.make_optimizer()
@@ -1040,6 +1043,8 @@ class EliMRec(LinearSchedule, BasicModel):
         su, sp_, sn = s3[0], s3[1], s3[2]
         s3_flat = s3.view(-1)
         loss_host = torch.zeros((), dtype=torch.float32).pin_memory() if host_loss else None
+        deferred = host_loss == "deferred"
+        done_ev = [torch.cuda.Event(), torch.cuda.Event()] if deferred else None
         if device_sampler is not None:
             device_sampler.ensure_device(dev)
         model = self
@@ -1134,6 +1139,14 @@ class EliMRec(LinearSchedule, BasicModel):
             launches_per_step = n_launch
 
             triples = (su, sp_, sn)          # the batch the last replay trained on
+            _n_calls = 0
+
+            def flush(self):
+                """deferred host loss: wait for the last launched step and return its loss (None if there is none)"""
+                if not deferred or self._n_calls == 0:
+                    return None
+                done_ev[(self._n_calls - 1) & 1].synchronize()
+                return loss_host.clone()
 
             def __call__(self, users=None, pos=None, neg=None):
                 if users is None:
@@ -1174,6 +1187,16 @@ class EliMRec(LinearSchedule, BasicModel):
                 model._tables_version = getattr(model, "_tables_version", 0) + 1
                 if model.lazy_tables:
                     model._tables_pending = True
+                if deferred and not dp:
+                    # step i is on its way; hand back the loss of step i-1, which the graph left in pinned memory (step i
+                    # overwrites it only at its very end, a full step after the event we wait for here)
+                    k = self._n_calls
+                    done_ev[k & 1].record()
+                    self._n_calls = k + 1
+                    if k == 0:
+                        return None
+                    done_ev[(k - 1) & 1].synchronize()
+                    return loss_host.clone()
                 if host_loss and not dp:
                     torch.cuda.current_stream().synchronize()
                     return loss_host

@@ -292,6 +292,29 @@ def test_graphed_step_packed_batches_and_host_loss(golden):
     assert total == sm.num_trainings and batches[-1][0].numel() == (total % B or B)
 
 
+def test_graphed_step_deferred_host_loss(golden):
+    """host_loss="deferred": runner(batch_i) launches step i and returns the loss of step i-1 (None first, flush() for the
+    last) - the same sequence of losses as the synchronous runner, one call late."""
+    a, _ = _golden_model(golden)
+    b, _ = _golden_model(golden)
+    for m in (a, b):
+        m.make_optimizer(lr=1e-3, weight_decay=1e-4)
+    B = len(_batch(golden, 0)[0])
+    ra = a.make_graphed_step(B, host_loss=True)
+    rb = b.make_graphed_step(B, host_loss="deferred")
+    assert rb.flush() is None
+    sync, late = [], []
+    for i in range(5):
+        sync.append(float(ra(*_batch(golden, i % 3))))
+        out = rb(*_batch(golden, i % 3))
+        assert (out is None) == (i == 0)
+        if out is not None:
+            late.append(float(out))
+    late.append(float(rb.flush()))
+    assert len(late) == 5 and all(abs(x - y) <= 1e-6 * abs(x) for x, y in zip(sync, late))
+    assert len(set(sync)) == 5
+
+
 @pytest.mark.parametrize("linear", [True, False])
 def test_graphed_train_eval_train_eval(golden, linear):
     """CUDA-graph runner: every replay is a new training forward, so tables cached for evaluation (all_users / all_items /
