@@ -30,6 +30,8 @@ from .model import D, EliMRec, ElimrecError
 
 
 class ColShardedEliMRec(EliMRec):
+    _lin_prefork = False      # (its own _lin_forward)
+
     def _init_weight(self):
         if not (dist.is_available() and dist.is_initialized()):
             raise ElimrecError("ColShardedEliMRec needs an initialised torch.distributed process group")

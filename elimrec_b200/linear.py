@@ -39,6 +39,7 @@ def _cfg(config, key, default):
 
 class LinearSchedule:
     """Mixin of ``EliMRec`` (model.py): everything specific to the linear schedule."""
+    _lin_prefork = True      # _lin_forward consumes a stream forked at the start of a captured step (see there)
 
     # ---- construction ---------------------------------------------------------------------------------------------------
     def _lin_init(self):
@@ -262,15 +263,21 @@ class LinearSchedule:
             self._lin_modal_gemm(ws, ws["Zg"], ws["O_inst"], 3 * B)
         # the propagation: p_k = A_hat p_{k-1}, both halves 64 wide in one launch
         in_u, in_i = Eu, Ei
-        cur = torch.cuda.current_stream()
-        for k in range(1, L + 1):
-            out = ws["P"][k]
-            rm = mask if k == L else (need2 if (k == L - 1 and self._lin_need2) else None)
-            if rm is not None:
-                cur.wait_event(ev_rows if k == L else ev_masks)
-            ops.spmm64_pair(g.ui, g.iu, in_i, in_u, out[:U], out[U:], row_mask_u=rm[:U] if rm is not None else None,
-                            row_mask_i=rm[U:] if rm is not None else None)
-            in_u, in_i = out[:U], out[U:]
+        # make_graphed_step forks a stream at the very start of the captured step (before the batch is drawn): the unmasked
+        # layers depend on the tables only, so they start at t = 0 instead of behind the sampler and the first small nodes
+        prop, self._prop_stream = getattr(self, "_prop_stream", None), None
+        cur = prop if prop is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(prop):      # (None: the current stream)
+            for k in range(1, L + 1):
+                out = ws["P"][k]
+                rm = mask if k == L else (need2 if (k == L - 1 and self._lin_need2) else None)
+                if rm is not None:
+                    cur.wait_event(ev_rows if k == L else ev_masks)
+                ops.spmm64_pair(g.ui, g.iu, in_i, in_u, out[:U], out[U:], row_mask_u=rm[:U] if rm is not None else None,
+                                row_mask_i=rm[U:] if rm is not None else None)
+                in_u, in_i = out[:U], out[U:]
+        if prop is not None:
+            ops.join_side(prop)
         ops.join_side(side)
         lay = ops.lin_layers(self._lin_tables(ws, Eu, Ei))
         ops.lin_assemble(rows, U, lay, 1.0 / (L + 1), len(self.mods), True, ws["O_inst"])

@@ -1085,6 +1085,8 @@ class EliMRec(LinearSchedule, BasicModel):
         if not dp:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
+                if self.linear and self._lin_prefork and bool(_cfg(self.config, "prefork_propagation", True)):
+                    self._prop_stream = ops.fork_side(11)      # before the batch exists: the dense layers start at t = 0
                 draw()
                 loss = self.train_step(su, sp_, sn)
                 if host_loss:
