@@ -780,7 +780,8 @@ def main():
         if model.linear:
             ws_mb = (N_ * 64 * 4 * (1 + 2 + 1 + model.n_layers + 2) + 2 * 3 * BATCH * model._lin_Ktot * 4) / 1e6
             sched = ("linear: the modality graphs by linearity from ONE 64-wide propagation + constant Zbar tables (built once); "
-                     "layers L-1 / L and the fusion / head tables only at the rows the loss reads; identical loss / gradients / "
+                     + ("layers L-1 / L" if args.two_hop_masks else "layer L") +
+                     " and the fusion / head tables only at the rows the loss reads; identical loss / gradients / "
                      "parameters up to fp32 reassociation; full tables completed at evaluation")
         else:
             ws_mb = 900.0
