@@ -194,3 +194,17 @@ def test_work_list_segment_length_follows_the_mean_degree(monkeypatch):
         assert n_hit == int(hrow[:, 1].sum()) and (items[:n_hit, 3] >= 0).all() and (items[n_hit:, 3] < 0).all()
     monkeypatch.setenv("ELIMREC_SEG64_LEN", "256")
     assert graph.seg64_len_for(indptr) == 256
+
+
+@pytest.mark.parametrize("knobs", [dict(wgrad_groups="early"), dict(wgrad_groups="late"), dict(wgrad_overlap=False),
+                                   dict(fused_seed=False), dict(inst_fuse="ffma"), dict(wgrad_precision="fp32"),
+                                   dict(fused_adam=False), dict(two_hop_masks=True)],
+                         ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
+def test_linear_schedule_knobs_leave_the_trajectory_alone(sim, golden, knobs):
+    """Every scheduling knob of the linear step (how the weight gradients are launched, where the seeds and the loss
+    reduction run, which kernel does fusion + heads on the instance rows, Adam fused or separate, two-hop masks) reorders or
+    regroups launches only: three Adam steps reproduce the reference's losses and parameters."""
+    from test_schedule_sim import check_steps
+    model = build(golden_dataset(golden), golden_params(golden), _name(golden), proj_precision="x3", **knobs)
+    assert model.linear
+    check_steps(model, golden, "")
