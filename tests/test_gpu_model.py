@@ -284,9 +284,11 @@ def test_graphed_step_packed_batches_and_host_loss(golden):
         lb = rb(u.clone(), p_.clone(), n.clone())
         assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(lb))
         assert all(torch.equal(x, y) for x, y in zip(ra.triples, rb.triples))
-    # (not bit-equal: the backward seeds of a node sampled three or more times in one batch are summed with float atomics)
+    # (not bit-equal: the backward seeds of a node sampled three or more times in one batch are summed with float atomics, and
+    # Adam turns the last bits of a near-zero gradient into a visible fraction of lr - same criterion as check_steps)
     for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
-        assert rel_err(v, w) < 1e-6, k
+        d = (v.double() - w.double()).abs() / w.double().abs().max()
+        assert float(d.max()) < 1e-4 and float((d > 1e-5).double().mean()) < 1e-3, k
     # every sampled triple is there exactly once, in epoch order (the short last batch included)
     total = sum(t[0].numel() for t in batches)
     assert total == sm.num_trainings and batches[-1][0].numel() == (total % B or B)
